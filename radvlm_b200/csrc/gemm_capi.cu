@@ -1,0 +1,126 @@
+// C-ABI launchers for the tcgen05 GEMM (see gemm_sm100.cuh).
+#include "gemm_sm100.cuh"
+#include "host_util.h"
+
+namespace rv {
+
+template <int BN, int EPI>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                            cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    RV_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_tiles = ((args.M + kGemmBM - 1) / kGemmBM) * ((args.N + BN - 1) / BN);
+  const int sms = device_sm_count();
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  gemm_bf16_tn_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+template <int EPI>
+static int launch_gemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                          cudaStream_t stream) {
+  switch (bn) {
+    case 128: return launch_gemm_inst<128, EPI>(ta, tb, args, stream);
+    case 192: return launch_gemm_inst<192, EPI>(ta, tb, args, stream);
+    case 256: return launch_gemm_inst<256, EPI>(ta, tb, args, stream);
+  }
+  set_error("block_n must be 128, 192 or 256 (got %d)", bn);
+  return RADVLM_ERR_BAD_ARGUMENT;
+}
+
+// Wave-quantisation aware tile-width choice: cost = waves * BN (MMA cycles per K step scale with BN).
+int gemm_pick_block_n(int M, int N) {
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+  const int num_m = (M + kGemmBM - 1) / kGemmBM;
+  int best = 256;
+  long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long tiles = static_cast<long>(num_m) * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cost = waves * bn;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
+                  int epilogue, int block_n, cudaStream_t stream) {
+  int st = require_sm100();
+  if (st != RADVLM_OK) return st;
+  RV_CHECK_ARG(A != nullptr && W != nullptr, "gemm: null operand");
+  RV_CHECK_ARG(args.M > 0 && args.N > 0 && args.K > 0, "gemm: bad shape M=%d N=%d K=%d", args.M,
+               args.N, args.K);
+  RV_CHECK_ARG(lda >= args.K && ldw >= args.K, "gemm: row pitch smaller than K");
+  const int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N);
+  CUtensorMap ta, tb;
+  st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M),
+                         static_cast<uint64_t>(lda) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
+                         static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(bn),
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+  if (st != RADVLM_OK) return st;
+  switch (epilogue) {
+    case EPI_BIAS_BF16: return launch_gemm_bn<EPI_BIAS_BF16>(bn, ta, tb, args, stream);
+    case EPI_GELU_TANH_BF16: return launch_gemm_bn<EPI_GELU_TANH_BF16>(bn, ta, tb, args, stream);
+    case EPI_GELU_ERF_BF16: return launch_gemm_bn<EPI_GELU_ERF_BF16>(bn, ta, tb, args, stream);
+    case EPI_RESID_F32: return launch_gemm_bn<EPI_RESID_F32>(bn, ta, tb, args, stream);
+    case EPI_POS_F32: return launch_gemm_bn<EPI_POS_F32>(bn, ta, tb, args, stream);
+    case EPI_QKV_SPLIT: return launch_gemm_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
+    case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
+  }
+  set_error("gemm: unknown epilogue %d", epilogue);
+  return RADVLM_ERR_BAD_ARGUMENT;
+}
+
+}  // namespace rv
+
+extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N,
+                                int K, const float* bias, int epilogue, void* out, int64_t ldo,
+                                const float* aux, int aux_period, int block_n, void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
+  RV_CHECK_ARG(out != nullptr && ldo >= N, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
+  RV_CHECK_ARG((ldo % 8) == 0, "gemm: ldo must be a multiple of 8 elements");
+  RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");
+  RV_CHECK_ARG(epilogue != EPI_POS_F32 || (aux != nullptr && aux_period > 0 && (N % 4) == 0),
+               "gemm: position epilogue needs aux/aux_period and N % 4 == 0");
+  GemmArgs a{};
+  a.M = M; a.N = N; a.K = K;
+  a.bias = bias;
+  a.out = out;
+  a.ldo = static_cast<int>(ldo);
+  a.aux = aux;
+  a.aux_period = aux_period;
+  return gemm_dispatch(A, lda, W, ldw, a, epilogue, block_n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
+                                     int K, const float* bias, void* q, void* k, void* vt, int seq,
+                                     int seq_pad, int heads, int hd, int hd_pad, int block_n,
+                                     void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(q && k && vt, "qkv: null output");
+  RV_CHECK_ARG(seq > 0 && seq_pad >= seq && hd_pad >= hd && (hd % 8) == 0 && (hd_pad % 8) == 0 &&
+                   (seq_pad % 8) == 0 && (M % seq) == 0,
+               "qkv: bad geometry seq=%d seq_pad=%d hd=%d hd_pad=%d M=%d", seq, seq_pad, hd, hd_pad, M);
+  GemmArgs a{};
+  a.M = M; a.N = 3 * heads * hd; a.K = K;
+  a.bias = bias;
+  a.q = static_cast<__nv_bfloat16*>(q);
+  a.k = static_cast<__nv_bfloat16*>(k);
+  a.vt = static_cast<__nv_bfloat16*>(vt);
+  a.seq = seq; a.seq_pad = seq_pad; a.heads = heads; a.hd = hd; a.hd_pad = hd_pad;
+  return gemm_dispatch(A, lda, W, ldw, a, EPI_QKV_SPLIT, block_n, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,320 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   * A (activations, row-major [M,K]) and W (nn.Linear weight, row-major [N,K]) are both K-major,
+//     fetched by TMA (128B swizzle, 64-element K slabs) into a multi-stage shared-memory ring.
+//   * One elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1); fp32 accumulators
+//     live in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * Four epilogue warps read TMEM with tcgen05.ld (one output row per thread) and apply the fused
+//     epilogue: bias, GELU (tanh / erf), fp32 residual add, position-embedding add, or the QKV
+//     head-split scatter (Q,K -> [tile,head,seq_pad,hd_pad];  V -> transposed [tile,head,hd_pad,seq_pad]).
+//
+// Replaces the cuBLASLt / ATen elementwise launches behind nn.Linear / nn.Conv2d(k=14,s=14) in
+//   finetuning/llava/model/multimodal_encoder/siglip_encoder.py:156-173,192-194,207-209,237,252-254
+//   finetuning/llava/model/multimodal_projector/builder.py:44-48
+#pragma once
+
+#include "common.cuh"
+
+namespace rv {
+
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // out_bf16 = acc + bias
+  EPI_GELU_TANH_BF16 = 1,  // out_bf16 = gelu_tanh(acc + bias)           (SigLipMLP.fc1, siglip_encoder.py:252-253)
+  EPI_GELU_ERF_BF16 = 2,   // out_bf16 = gelu_erf(acc + bias)            (mm_projector.0/1, builder.py:44-46)
+  EPI_RESID_F32 = 3,       // out_f32  = acc + bias + resid_f32          (residual adds, siglip_encoder.py:293,298)
+  EPI_POS_F32 = 4,         // out_f32  = acc + bias + pos[row % period]  (siglip_encoder.py:170-173)
+  EPI_QKV_SPLIT = 5,       // head split scatter of q/k/v                (siglip_encoder.py:207-213)
+  EPI_BIAS_F32 = 6,        // out_f32  = acc + bias
+};
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;  // [N] or nullptr
+  void* out;          // [M, ldo] bf16 or f32 depending on the epilogue
+  int ldo;
+  const float* aux;  // EPI_RESID_F32: residual [M, ldo];  EPI_POS_F32: table [aux_period, N]
+  int aux_period;
+  // EPI_QKV_SPLIT
+  __nv_bfloat16* q;   // [tiles, heads, seq_pad, hd_pad]
+  __nv_bfloat16* k;   // [tiles, heads, seq_pad, hd_pad]
+  __nv_bfloat16* vt;  // [tiles, heads, hd_pad, seq_pad]
+  int seq, seq_pad, heads, hd, hd_pad;
+};
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, int col0,
+                                                    const uint32_t* acc) {
+  // acc: 32 fp32 accumulators for (row, col0 .. col0+31)
+  if (row >= a.M || col0 >= a.N) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  const bool full = (col0 + 32 <= a.N);
+
+  if (a.bias != nullptr) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(a.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < a.N) v[j] += __ldg(a.bias + col0 + j);
+    }
+  }
+
+  if constexpr (EPI == EPI_GELU_TANH_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  }
+  if constexpr (EPI == EPI_GELU_ERF_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
+    if (full) {
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 p;
+        p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        o4[j] = p;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < a.N) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32) {
+    float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
+    const float* x = nullptr;
+    if constexpr (EPI == EPI_RESID_F32) x = a.aux + static_cast<size_t>(row) * a.ldo + col0;
+    if constexpr (EPI == EPI_POS_F32) x = a.aux + static_cast<size_t>(row % a.aux_period) * a.N + col0;
+    if (full) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+      if constexpr (EPI != EPI_BIAS_F32) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4 xr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[j] = x4[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j + 0] += xr[j].x;
+          v[4 * j + 1] += xr[j].y;
+          v[4 * j + 2] += xr[j].z;
+          v[4 * j + 3] += xr[j].w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < a.N) {
+          float r = v[j];
+          if constexpr (EPI != EPI_BIAS_F32) r += x[j];
+          o[j] = r;
+        }
+    }
+  } else if constexpr (EPI == EPI_QKV_SPLIT) {
+    const int D = a.heads * a.hd;
+    const int tile = row / a.seq;
+    const int t = row - tile * a.seq;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = col0 + 8 * g;
+      if (c >= a.N) break;
+      const int which = c / D;
+      const int rem = c - which * D;
+      const int head = rem / a.hd;
+      const int d = rem - head * a.hd;
+      const size_t th = static_cast<size_t>(tile) * a.heads + head;
+      if (which < 2) {
+        __nv_bfloat16* base = (which == 0 ? a.q : a.k) + (th * a.seq_pad + t) * a.hd_pad + d;
+        uint4 p;
+        p.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+        p.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+        p.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+        p.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+        *reinterpret_cast<uint4*>(base) = p;
+      } else {
+        __nv_bfloat16* base = a.vt + (th * a.hd_pad + d) * a.seq_pad + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) base[static_cast<size_t>(j) * a.seq_pad] = __float2bfloat16_rn(v[8 * g + j]);
+      }
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  // barrier map (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (args.M + kGemmBM - 1) / kGemmBM;
+  const int num_n = (args.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (args.K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n;
+        const int n_blk = tile - m_blk * num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kGemmBK, m_blk * kGemmBM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kGemmBK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * 32, 1024, kLayoutSw128);
+            const uint64_t bdesc = make_smem_desc(sb + k * 32, 1024, kLayoutSw128);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == num_k - 1) umma_commit(tfull_bar(acc));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n;
+      const int n_blk = tile - m_blk * num_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kGemmBM + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_wait_ld();
+        gemm_epilogue_chunk<EPI>(args, row, n_blk * BN + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace rv

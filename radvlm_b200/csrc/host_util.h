@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: status codes, thread-local error string,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/radvlm_b200.h"
+
+namespace rv {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define RV_CHECK_ARG(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      rv::set_error(__VA_ARGS__);      \
+      return RADVLM_ERR_BAD_ARGUMENT;  \
+    }                                  \
+  } while (0)
+
+#define RV_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      rv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                    __LINE__);                                                         \
+      return RADVLM_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+// Returns 0 when the current device is sm_100 (B200); otherwise sets the error and returns a status.
+int require_sm100();
+int device_sm_count();
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows, row pitch in bytes.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                      CUtensorMapSwizzle swizzle);
+
+}  // namespace rv

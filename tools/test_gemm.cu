@@ -1,0 +1,181 @@
+// Standalone bring-up test for the tcgen05 GEMM through the C ABI (no torch needed on the GPU box).
+//   build: see Makefile (`make tools`)     run: ./build/test_gemm [quick]
+// Compares against a naive CUDA-core fp32 GEMM on the same bf16 inputs.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../include/radvlm_b200.h"
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+__global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* C,
+                         int M, int N, int K) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc += __bfloat162float(A[(size_t)m * K + k]) * __bfloat162float(W[(size_t)n * K + k]);
+  C[(size_t)m * N + n] = acc + (bias ? bias[n] : 0.f);
+}
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+
+static float gelu_tanh_h(float x) {
+  return 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+static float gelu_erf_h(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+
+struct Case {
+  int M, N, K, epi, bn;
+};
+
+static int run_case(const Case& c) {
+  const int M = c.M, N = c.N, K = c.K;
+  std::vector<__nv_bfloat16> hA((size_t)M * K), hW((size_t)N * K);
+  std::vector<float> hb(N), haux;
+  for (auto& v : hA) v = __float2bfloat16(frand());
+  for (auto& v : hW) v = __float2bfloat16(frand());
+  for (auto& v : hb) v = frand();
+  const int period = 7;
+  if (c.epi == RADVLM_EPI_RESID_F32) haux.resize((size_t)M * N);
+  if (c.epi == RADVLM_EPI_POS_F32) haux.resize((size_t)period * N);
+  for (auto& v : haux) v = frand();
+
+  __nv_bfloat16 *dA, *dW;
+  float *db, *dref, *daux = nullptr;
+  void* dout;
+  const bool out_f32 = (c.epi == RADVLM_EPI_RESID_F32 || c.epi == RADVLM_EPI_POS_F32 ||
+                        c.epi == RADVLM_EPI_BIAS_F32);
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dW, hW.size() * 2));
+  CK(cudaMalloc(&db, N * 4));
+  CK(cudaMalloc(&dref, (size_t)M * N * 4));
+  CK(cudaMalloc(&dout, (size_t)M * N * 4));
+  CK(cudaMemset(dout, 0xFF, (size_t)M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, hb.data(), N * 4, cudaMemcpyHostToDevice));
+  if (!haux.empty()) {
+    CK(cudaMalloc(&daux, haux.size() * 4));
+    CK(cudaMemcpy(daux, haux.data(), haux.size() * 4, cudaMemcpyHostToDevice));
+  }
+  ref_gemm<<<dim3((N + 127) / 128, M), 128>>>(dA, dW, db, dref, M, N, K);
+  CK(cudaGetLastError());
+
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int st = 0;
+  const int reps = (M >= 4096) ? 5 : 1;
+  // for the residual epilogue run out-of-place (aux != out) so repetitions stay idempotent
+  for (int i = 0; i < reps + 1; ++i) {
+    if (i == 1) cudaEventRecord(e0);
+    st = radvlm_gemm_bf16(dA, K, dW, K, M, N, K, db, c.epi, dout, N, daux, period, c.bn, nullptr);
+    if (st != 0) break;
+  }
+  cudaEventRecord(e1);
+  if (st != 0) {
+    printf("case M=%d N=%d K=%d epi=%d bn=%d: API error %d: %s\n", M, N, K, c.epi, c.bn, st,
+           radvlm_last_error());
+    return 1;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("case M=%d N=%d K=%d epi=%d bn=%d: kernel failed: %s\n", M, N, K, c.epi, c.bn,
+           cudaGetErrorString(e));
+    exit(3);
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= (reps > 0 ? reps : 1);
+
+  std::vector<float> href((size_t)M * N), hout((size_t)M * N);
+  CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));
+  if (out_f32) {
+    CK(cudaMemcpy(hout.data(), dout, hout.size() * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<__nv_bfloat16> tmp((size_t)M * N);
+    CK(cudaMemcpy(tmp.data(), dout, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) hout[i] = __bfloat162float(tmp[i]);
+  }
+  double max_err = 0, max_ref = 0;
+  size_t bad = 0, worst = 0;
+  for (size_t i = 0; i < href.size(); ++i) {
+    float r = href[i];
+    const int row = (int)(i / N), col = (int)(i % N);
+    if (c.epi == RADVLM_EPI_GELU_TANH_BF16) r = gelu_tanh_h(r);
+    if (c.epi == RADVLM_EPI_GELU_ERF_BF16) r = gelu_erf_h(r);
+    if (c.epi == RADVLM_EPI_RESID_F32) r += haux[i];
+    if (c.epi == RADVLM_EPI_POS_F32) r += haux[(size_t)(row % period) * N + col];
+    const double tol = out_f32 ? 2e-3 : (2e-3 + fabs(r) * 8e-3);
+    const double err = fabs((double)hout[i] - (double)r);
+    if (!(err <= tol)) ++bad;
+    if (err > max_err || isnan(hout[i])) {
+      max_err = err;
+      worst = i;
+    }
+    if (fabs(r) > max_ref) max_ref = fabs(r);
+  }
+  const double tflops = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
+  printf("case M=%5d N=%5d K=%5d epi=%d bn=%3d : max_err=%.3e max_ref=%.3e bad=%zu/%zu  %.3f ms %.1f TFLOP/s %s\n",
+         M, N, K, c.epi, c.bn, max_err, max_ref, bad, href.size(), ms, tflops, bad ? "FAIL" : "ok");
+  if (bad) {
+    printf("  worst at (%zu,%zu): got %f want %f\n", worst / N, worst % N, hout[worst], href[worst]);
+    printf("  got[0,0..7]:");
+    for (int j = 0; j < 8 && j < N; ++j) printf(" %8.4f", hout[j]);
+    printf("\n  ref[0,0..7]:");
+    for (int j = 0; j < 8 && j < N; ++j) printf(" %8.4f", href[j]);
+    printf("\n");
+  }
+  cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dref); cudaFree(dout);
+  if (daux) cudaFree(daux);
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  std::vector<Case> cases = {
+      {128, 128, 64, RADVLM_EPI_BIAS_F32, 128},    // one tile, one K slab
+      {128, 128, 256, RADVLM_EPI_BIAS_F32, 128},   // K loop within one stage ring
+      {128, 256, 1152, RADVLM_EPI_BIAS_F32, 256},  // ring wrap-around
+      {128, 192, 1152, RADVLM_EPI_BIAS_F32, 192},
+      {300, 200, 136, RADVLM_EPI_BIAS_F32, 128},   // ragged M/N/K tails
+      {729, 1152, 588 + 4, RADVLM_EPI_POS_F32, 0},
+      {1458, 1152, 1152, RADVLM_EPI_RESID_F32, 0},
+      {1458, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 0},
+      {1458, 1152, 4304, RADVLM_EPI_BIAS_BF16, 0},
+      {1458, 3584, 1152, RADVLM_EPI_GELU_ERF_BF16, 0},
+  };
+  if (!quick) {
+    cases.push_back({7290, 3456, 1152, RADVLM_EPI_BIAS_BF16, 256});
+    cases.push_back({7290, 3456, 1152, RADVLM_EPI_BIAS_BF16, 192});
+    cases.push_back({7290, 3456, 1152, RADVLM_EPI_BIAS_BF16, 128});
+    cases.push_back({7290, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 0});
+    cases.push_back({7290, 1152, 4304, RADVLM_EPI_RESID_F32, 0});
+    cases.push_back({7290, 3584, 3584, RADVLM_EPI_BIAS_BF16, 0});
+    cases.push_back({29160, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 256});
+    cases.push_back({29160, 1152, 4304, RADVLM_EPI_RESID_F32, 0});
+  }
+  int fails = 0;
+  for (const auto& c : cases) fails += run_case(c);
+  printf("%s (%d failing cases)\n", fails ? "GEMM TEST FAILED" : "GEMM TEST PASSED", fails);
+  return fails ? 1 : 0;
+}
