@@ -65,6 +65,15 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
                           const float* bias, void* q, void* k, void* vt, int seq, int seq_pad,
                           int heads, int hd, int hd_pad, int block_n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused non-causal attention for one ViT block (siglip_encoder.py:216-235: q k^T * scale ->
+ * softmax(fp32) -> p v -> transpose/reshape).  Inputs in the layout radvlm_gemm_qkv_split writes;
+ * out: bf16 [tiles*seq, heads*hd] token-major (A operand of out_proj).
+ * Supported geometry: hd_pad == 80, hd % 8 == 0, seq_pad % 128 == 0, seq_pad - 128 < seq <= seq_pad.
+ * ---------------------------------------------------------------------------------------------- */
+int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
+                         int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,56 @@
+// C-ABI launcher for the fused SigLIP attention kernel (attention_sm100.cuh).
+#include "attention_sm100.cuh"
+#include "host_util.h"
+
+namespace rv {
+
+int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
+                     int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream) {
+  int st = require_sm100();
+  if (st != RADVLM_OK) return st;
+  RV_CHECK_ARG(q && k && vt && out, "attention: null pointer");
+  RV_CHECK_ARG(tiles > 0 && heads > 0, "attention: bad batch (tiles=%d heads=%d)", tiles, heads);
+  if (hd_pad != kAttnHdPad || hd > hd_pad || (hd % 8) != 0 || (seq_pad % kAttnBKV) != 0 ||
+      seq > seq_pad || seq <= seq_pad - kAttnBKV) {
+    set_error("attention: unsupported geometry seq=%d seq_pad=%d hd=%d hd_pad=%d (need hd_pad=80, "
+              "hd%%8==0, seq_pad%%128==0, seq_pad-128 < seq <= seq_pad)", seq, seq_pad, hd, hd_pad);
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  }
+  static thread_local bool configured = false;
+  if (!configured) {
+    RV_CUDA(cudaFuncSetAttribute(siglip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kAttnSmemBytes));
+    configured = true;
+  }
+  const uint64_t th = static_cast<uint64_t>(tiles) * heads;
+  CUtensorMap tq, tk, tv;
+  st = make_tmap_bf16_2d(&tq, q, hd_pad, th * seq_pad, static_cast<uint64_t>(hd_pad) * 2, 16, kAttnBQ,
+                         CU_TENSOR_MAP_SWIZZLE_32B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tk, k, hd_pad, th * seq_pad, static_cast<uint64_t>(hd_pad) * 2, 16, kAttnBKV,
+                         CU_TENSOR_MAP_SWIZZLE_32B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64,
+                         kAttnHdPad, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (st != RADVLM_OK) return st;
+  AttnArgs a;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.seq = seq;
+  a.seq_pad = seq_pad;
+  a.heads = heads;
+  a.hd = hd;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  dim3 grid((seq + kAttnBQ - 1) / kAttnBQ, heads, tiles);
+  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tk, tv, a);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+}  // namespace rv
+
+extern "C" int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles,
+                                    int heads, int seq, int seq_pad, int hd, int hd_pad, float scale,
+                                    void* stream) {
+  return rv::attention_launch(q, k, vt, out, tiles, heads, seq, seq_pad, hd, hd_pad, scale,
+                              static_cast<cudaStream_t>(stream));
+}
