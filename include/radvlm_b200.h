@@ -74,6 +74,198 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
 int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                          int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound tower helpers.
+ *   radvlm_layernorm_f32_bf16 : nn.LayerNorm(eps) over the fp32 residual stream, bf16 result
+ *                               (siglip_encoder.py:264,266,287,296)
+ *   radvlm_patch_im2col       : pixel tiles [n,C,S,S] (RADVLM_DT_*) -> bf16 [n*P*P, k_pad] patch rows,
+ *                               column order == patch_embedding.weight.flatten(1) (siglip_encoder.py:156-171)
+ *   radvlm_cast_f32_bf16      : tower output -> projector operand
+ * ---------------------------------------------------------------------------------------------- */
+int radvlm_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows,
+                              int D, float eps, void* stream);
+int radvlm_patch_im2col(const void* pixels, int dtype, void* out, int n_tiles, int channels,
+                        int image_size, int patch_size, int k_pad, void* stream);
+int radvlm_cast_f32_bf16(const float* x, void* y, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-path entry points: SigLIP tower (SigLipVisionTower.forward, siglip_encoder.py:576-589,
+ * i.e. embeddings + the executed encoder layers, hidden_states[-1], no post_layernorm) and the
+ * mlp2x_gelu projector (llava_arch.py:192-196 encode_images; builder.py:41-48).
+ *
+ * Weight blocks hold DEVICE pointers to bf16 matrices in nn.Linear layout [out, in] and fp32 vectors;
+ * the structs themselves live in HOST memory.  The host side (radvlm_b200/encoder.py) packs them
+ * from the reference's Parameters (state-dict names in SURVEY.md section 5) and caches by version.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct radvlm_vit_layer_weights {
+  const float* ln1_gamma;
+  const float* ln1_beta;
+  const void* qkv_w;   /* bf16 [3*hidden, hidden] = rows of q_proj; k_proj; v_proj */
+  const float* qkv_b;  /* [3*hidden] */
+  const void* out_w;   /* bf16 [hidden, hidden] */
+  const float* out_b;
+  const float* ln2_gamma;
+  const float* ln2_beta;
+  const void* fc1_w;   /* bf16 [intermediate, hidden] */
+  const float* fc1_b;
+  const void* fc2_w;   /* bf16 [hidden, intermediate] */
+  const float* fc2_b;
+} radvlm_vit_layer_weights;
+
+typedef struct radvlm_siglip_weights {
+  int hidden;       /* 1152 */
+  int intermediate; /* 4304 */
+  int heads;        /* 16 */
+  int num_layers;   /* executed layers: 26 (siglip_encoder.py:570 drops the 27th) */
+  int image_size;   /* 384 */
+  int patch_size;   /* 14 */
+  int channels;     /* 3 */
+  int patch_k_pad;  /* 640: 3*14*14 = 588 zero padded to a multiple of 64 */
+  float ln_eps;     /* 1e-6 */
+  const void* patch_w;    /* bf16 [hidden, patch_k_pad] = patch_embedding.weight.flatten(1), zero padded */
+  const float* patch_b;   /* [hidden] */
+  const float* pos_embed; /* fp32 [P*P, hidden] */
+  const radvlm_vit_layer_weights* layers; /* host array [num_layers] */
+} radvlm_siglip_weights;
+
+typedef struct radvlm_projector_weights {
+  int in_dim; /* 1152 */
+  int hidden; /* 3584 */
+  const void* w1;  /* bf16 [hidden, in_dim] */
+  const float* b1;
+  const void* w2;  /* bf16 [hidden, hidden] */
+  const float* b2;
+} radvlm_projector_weights;
+
+/* scratch needed by radvlm_encode_images for n_tiles tiles (0 on bad arguments) */
+size_t radvlm_encode_workspace_bytes(const radvlm_siglip_weights* tw, const radvlm_projector_weights* pw,
+                                     int n_tiles);
+
+/* pixels: [n_tiles, C, S, S] of pixel_dtype -> hidden_out: fp32 [n_tiles*P*P, hidden] */
+int radvlm_siglip_tower_forward(const radvlm_siglip_weights* tw, const void* pixels, int pixel_dtype,
+                                int n_tiles, float* hidden_out, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* hidden: fp32 [rows, in_dim] -> features_out: [rows, hidden] of out_dtype (RADVLM_DT_BF16 | RADVLM_DT_F32) */
+int radvlm_projector_forward(const radvlm_projector_weights* pw, const float* hidden, int rows,
+                             void* features_out, int out_dtype, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* encode_images: tower + projector.  features_out: [n_tiles*P*P, projector hidden] of out_dtype */
+int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvlm_projector_weights* pw,
+                         const void* pixels, int pixel_dtype, int n_tiles, void* features_out,
+                         int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Planner (CPU only, no CUDA): every integer decision of the path with the reference's Python
+ * float64/int semantics, bit-exact.
+ *   radvlm_plan_select_best_resolution : mm_utils.py:119-149 (candidates are (width,height) pairs)
+ *   radvlm_plan_image                  : mm_utils.py:152-188,213-240 ; llava_arch.py:127-159,386-390
+ *   radvlm_plan_splice                 : llava_arch.py:428-531
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct radvlm_image_plan {
+  int32_t width, height;          /* original size, PIL order (W,H)  (llava_arch.py:138) */
+  int32_t best_w, best_h;         /* select_best_resolution */
+  int32_t grid_w, grid_h;         /* (num_patch_width, num_patch_height) */
+  int32_t resized_w, resized_h;   /* aspect-preserving resize inside the canvas */
+  int32_t paste_x, paste_y;       /* centred paste offset */
+  int32_t n_tiles;                /* 1 + grid_w*grid_h (base tile first) */
+  int32_t crop_r0, crop_c0, crop_h, crop_w; /* unpad window in the (S*grid_h, S*grid_w) feature map */
+  int32_t pool;                   /* 1 when times > 1.1 (bilinear resize to out_h x out_w) */
+  int32_t out_h, out_w;           /* feature rows / cols before the newline column */
+  int32_t n_tokens;               /* S*S + out_h*(out_w+1) */
+} radvlm_image_plan;
+
+int radvlm_plan_select_best_resolution(int W, int H, const int32_t* pinpoints, int n, int* best_w,
+                                       int* best_h);
+int radvlm_plan_image(int W, int H, const int32_t* pinpoints, int n_pinpoints, int tile_size,
+                      int patches_per_side, int max_num_patches /* <=0: never pool */,
+                      radvlm_image_plan* out);
+
+#define RADVLM_SEG_PAD 0
+#define RADVLM_SEG_TEXT 1
+#define RADVLM_SEG_IMAGE 2
+typedef struct radvlm_splice_segment {
+  int64_t dst_row;  /* first output row, b*max_len + position */
+  int32_t length;   /* rows */
+  int32_t kind;     /* RADVLM_SEG_* */
+  int32_t src_off;  /* TEXT: offset into text_src[];  IMAGE: first visual token (0) */
+  int32_t image;    /* IMAGE: index into the merge-image table */
+  int32_t pos0;     /* position id of the first row */
+  int32_t reserved;
+} radvlm_splice_segment;
+
+/* input_ids: host int64 [B,L]; attention_mask: host uint8 [B,L] or NULL (all ones);
+ * image_tokens[n_images]: visual tokens each image contributes (in consumption order).
+ * Outputs: segments (sorted by dst_row, covering all B*max_len rows), text_src (flat b*L+i source
+ * positions of kept text tokens), lengths[B], max_len.  A text-only sample consumes one image
+ * (llava_arch.py:452-459); when the list runs out inside a sample the previous image is reused
+ * (llava_arch.py:478-481); otherwise RADVLM_ERR_BAD_ARGUMENT ("IndexError"). */
+int radvlm_plan_splice(const int64_t* input_ids, const uint8_t* attention_mask, int B, int L,
+                       int image_token_index, const int32_t* image_tokens, int n_images,
+                       int64_t max_length, int left_pad, radvlm_splice_segment* segments,
+                       int segment_capacity, int* n_segments, int32_t* text_src, int text_capacity,
+                       int* n_text, int32_t* lengths, int* max_len_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Merge + splice gather kernel: spatial unpad / anyres_max bilinear pool / image_newline / base-tile
+ * prepend (llava_arch.py:350-412), embed_tokens gather + interleave (llava_arch.py:449-493) and
+ * truncate / pad / stack with labels, attention_mask, position_ids (llava_arch.py:495-531) in ONE pass:
+ * every output row [b, p, :] is produced once, directly in the padded [B, max_len, H] tensor.
+ * ---------------------------------------------------------------------------------------------- */
+#define RADVLM_MERGE_ANYRES 0  /* base tile + unpadded (optionally pooled) grid with newline column */
+#define RADVLM_MERGE_SINGLE 1  /* one tile + one newline token (llava_arch.py:407-412) */
+#define RADVLM_MERGE_FLAT 2    /* tiles*T tokens, no newline ("flat", or a 4-D image batch) */
+typedef struct radvlm_merge_image {
+  int32_t tile_base; /* index of the image's first (base) tile in the feature buffer */
+  int32_t mode;      /* RADVLM_MERGE_* */
+  int32_t grid_w;
+  int32_t crop_r0, crop_c0, crop_h, crop_w;
+  int32_t pool, out_h, out_w;
+  int32_t n_tokens;
+  int32_t reserved;
+} radvlm_merge_image;
+
+/* All pointers are DEVICE pointers.  dtype: element type of features / newline / embed table / out.
+ *   features [tiles, T, H]; newline [H]; embed_table [vocab, H]; input_ids int64 [B*L];
+ *   labels_in int64 [B*L] or NULL (=> all IGNORE_INDEX); segments / images / text_src: tables from the planner.
+ *   out_embeds [B*max_len, H]; out_labels int64; out_mask uint8; out_pos int64 (each [B*max_len]; may be NULL) */
+int radvlm_merge_splice(const void* features, const void* newline, const void* embed_table, int dtype,
+                        int hidden, int tokens_per_tile, int patches_per_side, const int64_t* input_ids,
+                        const int64_t* labels_in, const int32_t* text_src,
+                        const radvlm_splice_segment* segments, int n_segments,
+                        const radvlm_merge_image* images, int n_images, int64_t total_rows,
+                        void* out_embeds, int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
+                        int64_t ignore_index, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused anyres preprocessing (uint8 -> resize -> pad -> tile -> normalise), bit-exact with
+ * process_anyres_image + SigLipImageProcessor.preprocess (mm_utils.py:152-210,243-293;
+ * siglip_encoder.py:47-67; Pillow 8bpc BICUBIC ImagingResample restated on the device).
+ *
+ * src: device buffer holding the uint8 images (HWC, 3 channels, or HW single channel that is
+ * replicated to RGB).  Per image a descriptor (same content on host and device): geometry from
+ * radvlm_plan_image, the first output tile index, and byte offsets into src / scratch.
+ * tiles_out: [total_tiles, 3, tile_size, tile_size] of out_dtype; tile order per image = base tile
+ * first, then the crops row-major (mm_utils.py:204-208,291).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct radvlm_preprocess_image {
+  int64_t src_offset;     /* byte offset of this image in src */
+  int64_t scratch_offset; /* byte offset of this image's scratch region (16-byte aligned) */
+  int32_t width, height, channels; /* channels: 3 (HWC) or 1 (grayscale, replicated) */
+  int32_t grid_w, grid_h;
+  int32_t resized_w, resized_h;
+  int32_t paste_x, paste_y;
+  int32_t tile_base;
+} radvlm_preprocess_image;
+
+size_t radvlm_preprocess_scratch_bytes(int width, int height, int channels, int resized_w, int resized_h,
+                                       int tile_size);
+int radvlm_preprocess_anyres(const uint8_t* src, const radvlm_preprocess_image* images_dev,
+                             const radvlm_preprocess_image* images_host, int n_images, int tile_size,
+                             void* tiles_out, int out_dtype, void* scratch, size_t scratch_bytes,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

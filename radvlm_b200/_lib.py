@@ -1,0 +1,156 @@
+"""ctypes binding of ``libradvlm_b200.so`` (the C ABI declared in ``include/radvlm_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, importing the product path raises with the
+build instruction.  The planner entry points are CPU-only and work without a GPU; every GPU entry
+point returns ``RADVLM_ERR_UNSUPPORTED_DEVICE`` when the current device is not sm_100.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libradvlm_b200.so")
+
+OK = 0
+ERR_BAD_ARGUMENT = 1
+ERR_UNSUPPORTED_SHAPE = 2
+ERR_CUDA = 3
+ERR_WORKSPACE_TOO_SMALL = 4
+ERR_UNSUPPORTED_DEVICE = 5
+
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+
+EPI_BIAS_BF16 = 0
+EPI_GELU_TANH_BF16 = 1
+EPI_GELU_ERF_BF16 = 2
+EPI_RESID_F32 = 3
+EPI_POS_F32 = 4
+EPI_BIAS_F32 = 6
+
+SEG_PAD, SEG_TEXT, SEG_IMAGE = 0, 1, 2
+MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT = 0, 1, 2
+
+
+class RadvlmError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("radvlm_b200 status %d: %s" % (status, message))
+        self.status = status
+        self.message = message
+
+
+class VitLayerWeights(C.Structure):
+    _fields_ = [
+        ("ln1_gamma", C.c_void_p), ("ln1_beta", C.c_void_p),
+        ("qkv_w", C.c_void_p), ("qkv_b", C.c_void_p),
+        ("out_w", C.c_void_p), ("out_b", C.c_void_p),
+        ("ln2_gamma", C.c_void_p), ("ln2_beta", C.c_void_p),
+        ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
+        ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+    ]
+
+
+class SiglipWeights(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_int), ("intermediate", C.c_int), ("heads", C.c_int), ("num_layers", C.c_int),
+        ("image_size", C.c_int), ("patch_size", C.c_int), ("channels", C.c_int), ("patch_k_pad", C.c_int),
+        ("ln_eps", C.c_float),
+        ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("pos_embed", C.c_void_p),
+        ("layers", C.POINTER(VitLayerWeights)),
+    ]
+
+
+class ProjectorWeights(C.Structure):
+    _fields_ = [
+        ("in_dim", C.c_int), ("hidden", C.c_int),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+    ]
+
+
+class ImagePlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "best_w", "best_h", "grid_w", "grid_h", "resized_w", "resized_h",
+        "paste_x", "paste_y", "n_tiles", "crop_r0", "crop_c0", "crop_h", "crop_w", "pool",
+        "out_h", "out_w", "n_tokens")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SpliceSegment(C.Structure):
+    _fields_ = [
+        ("dst_row", C.c_int64), ("length", C.c_int32), ("kind", C.c_int32), ("src_off", C.c_int32),
+        ("image", C.c_int32), ("pos0", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class MergeImage(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "tile_base", "mode", "grid_w", "crop_r0", "crop_c0", "crop_h", "crop_w", "pool", "out_h",
+        "out_w", "n_tokens", "reserved")]
+
+
+class PreprocessImage(C.Structure):
+    _fields_ = [
+        ("src_offset", C.c_int64), ("scratch_offset", C.c_int64),
+        ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+        ("grid_w", C.c_int32), ("grid_h", C.c_int32), ("resized_w", C.c_int32), ("resized_h", C.c_int32),
+        ("paste_x", C.c_int32), ("paste_y", C.c_int32), ("tile_base", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/radvlm_b200.h declares
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_pi = C.POINTER(C.c_int)
+SIGNATURES = {
+    "radvlm_last_error": (C.c_char_p, []),
+    "radvlm_abi_version": (_i, []),
+    "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
+    "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "radvlm_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "radvlm_layernorm_f32_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "radvlm_patch_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "radvlm_cast_f32_bf16": (_i, [_vp, _vp, _sz, _vp]),
+    "radvlm_encode_workspace_bytes": (_sz, [C.POINTER(SiglipWeights), C.POINTER(ProjectorWeights), _i]),
+    "radvlm_siglip_tower_forward": (_i, [C.POINTER(SiglipWeights), _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "radvlm_projector_forward": (_i, [C.POINTER(ProjectorWeights), _vp, _i, _vp, _i, _vp, _sz, _vp]),
+    "radvlm_encode_images": (_i, [C.POINTER(SiglipWeights), C.POINTER(ProjectorWeights), _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "radvlm_plan_select_best_resolution": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _pi, _pi]),
+    "radvlm_plan_image": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _i, _i, _i, C.POINTER(ImagePlan)]),
+    "radvlm_plan_splice": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _i64, _i,
+                                C.POINTER(SpliceSegment), _i, _pi, C.POINTER(C.c_int32), _i, _pi,
+                                C.POINTER(C.c_int32), _pi]),
+    "radvlm_merge_splice": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64,
+                                 _vp, _vp, _vp, _vp, _i64, _vp]),
+    "radvlm_preprocess_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "radvlm_preprocess_anyres": (_i, [_vp, _vp, C.POINTER(PreprocessImage), _i, _i, _vp, _i, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the argument types.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "radvlm_b200: %s is missing.  Build it with `make` (or `python -c 'import __graft_entry__ as g; "
+            "g.build()'`).  There is no CPU or PyTorch fallback for the encode path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().radvlm_last_error().decode("utf-8", "replace")
+
+
+def check(status: int):
+    if status != OK:
+        raise RadvlmError(status, last_error())

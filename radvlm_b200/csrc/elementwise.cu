@@ -1,0 +1,209 @@
+// HBM-bound helper kernels of the tower: LayerNorm (fp32 residual stream -> bf16 GEMM operand),
+// patch im2col (pixel tiles -> patch-major bf16 rows for the patch-embed GEMM), fp32 -> bf16 cast.
+//
+//   LayerNorm : siglip_encoder.py:264,266,287,296 (nn.LayerNorm(1152, eps=1e-6))
+//   im2col    : siglip_encoder.py:156-171 (Conv2d k=14 s=14 "valid" == GEMM over 14x14x3 patches;
+//               the 6 trailing rows / columns of the 384-px tile are not covered by any patch)
+#include "common.cuh"
+#include "host_util.h"
+
+#include <cuda_fp16.h>
+
+namespace rv {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (two-pass mean / variance like ATen).
+// ---------------------------------------------------------------------------------------------
+template <int NV>  // float4 vectors per lane
+__global__ void __launch_bounds__(256)
+layernorm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
+                             int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = (idx < nvec) ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(warp) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g = __ldg(g4 + idx);
+      const float4 b = __ldg(b4 + idx);
+      uint2 o;
+      o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      yr[idx] = o;
+    }
+  }
+}
+
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
+                     float eps, cudaStream_t stream) {
+  RV_CHECK_ARG(x && gamma && beta && y && rows > 0, "layernorm: bad arguments");
+  if ((D % 4) != 0 || D > 12 * 128) {
+    set_error("layernorm: D=%d unsupported (need D %% 4 == 0 and D <= 1536)", D);
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  }
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int nv = (D / 4 + 31) / 32;
+  __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
+  if (nv <= 3)
+    layernorm_f32_to_bf16_kernel<3><<<blocks, threads, 0, stream>>>(x, gamma, beta, yy, rows, D, eps);
+  else if (nv <= 9)
+    layernorm_f32_to_bf16_kernel<9><<<blocks, threads, 0, stream>>>(x, gamma, beta, yy, rows, D, eps);
+  else
+    layernorm_f32_to_bf16_kernel<12><<<blocks, threads, 0, stream>>>(x, gamma, beta, yy, rows, D, eps);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (tower output -> projector A operand)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, size_t nvec) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < nvec; i += stride) {
+    const float4 v = x[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    y[i] = o;
+  }
+}
+
+int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream) {
+  RV_CHECK_ARG(x && y && (n % 4) == 0, "cast: bad arguments (n must be a multiple of 4)");
+  const size_t nvec = n / 4;
+  size_t blocks = (nvec + 255) / 256;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return RADVLM_OK;
+  cast_f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), nvec);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col for the 14x14 stride-14 patch embedding.
+//   in : pixels [n, C, S, S]  (fp32 / bf16 / fp16)
+//   out: A [n * P * P, Kpad] bf16,  column k = c*ps*ps + ky*ps + kx  (== conv weight.flatten(1)),
+//        columns [C*ps*ps, Kpad) zero.
+// One CTA per (patch row py, tile): the 3 x 14 x (P*14) strip is read with coalesced row loads.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_patch_kernel(const T* __restrict__ px, __nv_bfloat16* __restrict__ out, int C, int S, int ps,
+                    int P, int Kpad) {
+  const int py = blockIdx.x;
+  const int tile = blockIdx.y;
+  const int K = C * ps * ps;
+  const int strip_w = P * ps;  // 378
+  const T* base = px + static_cast<size_t>(tile) * C * S * S;
+  __nv_bfloat16* orow = out + (static_cast<size_t>(tile) * P * P + static_cast<size_t>(py) * P) * Kpad;
+  // real columns
+  const int total = C * ps * strip_w;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int x = i % strip_w;
+    const int cy = i / strip_w;  // c*ps + ky
+    const int c = cy / ps;
+    const int ky = cy - c * ps;
+    const float v = to_f32<T>(base[(static_cast<size_t>(c) * S + (py * ps + ky)) * S + x]);
+    const int pxi = x / ps;
+    const int kx = x - pxi * ps;
+    orow[static_cast<size_t>(pxi) * Kpad + cy * ps + kx] = __float2bfloat16_rn(v);
+  }
+  // zero padding columns
+  const int padw = Kpad - K;
+  for (int i = threadIdx.x; i < P * padw; i += blockDim.x) {
+    const int pxi = i / padw;
+    orow[static_cast<size_t>(pxi) * Kpad + K + (i - pxi * padw)] = __float2bfloat16_rn(0.f);
+  }
+}
+
+int im2col_launch(const void* pixels, int dtype, void* out, int n_tiles, int C, int S, int ps,
+                  int Kpad, cudaStream_t stream) {
+  RV_CHECK_ARG(pixels && out && n_tiles > 0, "im2col: bad arguments");
+  const int P = S / ps;
+  RV_CHECK_ARG(P > 0 && Kpad >= C * ps * ps && (Kpad % 8) == 0, "im2col: bad geometry");
+  dim3 grid(P, n_tiles);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  switch (dtype) {
+    case RADVLM_DT_F32:
+      im2col_patch_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(pixels), o, C, S, ps, P, Kpad);
+      break;
+    case RADVLM_DT_BF16:
+      im2col_patch_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(pixels), o, C, S, ps, P, Kpad);
+      break;
+    case RADVLM_DT_F16:
+      im2col_patch_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(pixels), o, C, S, ps, P, Kpad);
+      break;
+    default:
+      set_error("im2col: unknown dtype %d", dtype);
+      return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+}  // namespace rv
+
+extern "C" int radvlm_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* y,
+                                         int rows, int D, float eps, void* stream) {
+  int st = rv::require_sm100();
+  if (st != RADVLM_OK) return st;
+  return rv::layernorm_launch(x, gamma, beta, y, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_cast_f32_bf16(const float* x, void* y, size_t n, void* stream) {
+  int st = rv::require_sm100();
+  if (st != RADVLM_OK) return st;
+  return rv::cast_f32_bf16_launch(x, y, n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_patch_im2col(const void* pixels, int dtype, void* out, int n_tiles, int channels,
+                                   int image_size, int patch_size, int k_pad, void* stream) {
+  int st = rv::require_sm100();
+  if (st != RADVLM_OK) return st;
+  return rv::im2col_launch(pixels, dtype, out, n_tiles, channels, image_size, patch_size, k_pad,
+                           static_cast<cudaStream_t>(stream));
+}

@@ -14,32 +14,9 @@
 #pragma once
 
 #include "common.cuh"
+#include "gemm_args.h"
 
 namespace rv {
-
-enum GemmEpilogue : int {
-  EPI_BIAS_BF16 = 0,       // out_bf16 = acc + bias
-  EPI_GELU_TANH_BF16 = 1,  // out_bf16 = gelu_tanh(acc + bias)           (SigLipMLP.fc1, siglip_encoder.py:252-253)
-  EPI_GELU_ERF_BF16 = 2,   // out_bf16 = gelu_erf(acc + bias)            (mm_projector.0/1, builder.py:44-46)
-  EPI_RESID_F32 = 3,       // out_f32  = acc + bias + resid_f32          (residual adds, siglip_encoder.py:293,298)
-  EPI_POS_F32 = 4,         // out_f32  = acc + bias + pos[row % period]  (siglip_encoder.py:170-173)
-  EPI_QKV_SPLIT = 5,       // head split scatter of q/k/v                (siglip_encoder.py:207-213)
-  EPI_BIAS_F32 = 6,        // out_f32  = acc + bias
-};
-
-struct GemmArgs {
-  int M, N, K;
-  const float* bias;  // [N] or nullptr
-  void* out;          // [M, ldo] bf16 or f32 depending on the epilogue
-  int ldo;
-  const float* aux;  // EPI_RESID_F32: residual [M, ldo];  EPI_POS_F32: table [aux_period, N]
-  int aux_period;
-  // EPI_QKV_SPLIT
-  __nv_bfloat16* q;   // [tiles, heads, seq_pad, hd_pad]
-  __nv_bfloat16* k;   // [tiles, heads, seq_pad, hd_pad]
-  __nv_bfloat16* vt;  // [tiles, heads, hd_pad, seq_pad]
-  int seq, seq_pad, heads, hd, hd_pad;
-};
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;

@@ -1,0 +1,22 @@
+// Internal launch functions shared between translation units of the library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gemm_args.h"
+
+namespace rv {
+
+int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
+                  int epilogue, int block_n, cudaStream_t stream);
+int gemm_pick_block_n(int M, int N);
+int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
+                     int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
+                     float eps, cudaStream_t stream);
+int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream);
+int im2col_launch(const void* pixels, int dtype, void* out, int n_tiles, int C, int S, int ps,
+                  int Kpad, cudaStream_t stream);
+
+}  // namespace rv

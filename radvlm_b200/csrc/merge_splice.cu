@@ -1,0 +1,259 @@
+// Merge + splice gather kernel (HBM-bound): one warp produces one output row of the padded
+// [B, max_len, H] inputs_embeds tensor, reading its source exactly once.
+//
+//   spatial unpad / anyres_max pool / newline / base prepend   llava_arch.py:350-412 (unpad_image 127-159)
+//   text embedding gather + interleave with image tokens       llava_arch.py:449-493
+//   truncate / pad / stack, labels, attention_mask, position   llava_arch.py:495-531
+//
+// Row -> source resolution: warp-uniform binary search in the (sorted) segment table, then closed-form
+// index arithmetic.  The bilinear branch follows ATen upsample_bilinear2d
+// (align_corners=False): scale = in/out in fp32, src = max(scale*(i+0.5)-0.5, 0), 4-tap lerp in fp32.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace rv {
+
+template <typename T>
+struct Vec16;  // 16-byte vector of T <-> float[]
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                      pack_bf16x2(f[6], f[7]));
+  }
+};
+template <>
+struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 p = __half22float2(h);
+      f[2 * i] = p.x;
+      f[2 * i + 1] = p.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+struct MergeSpliceArgs {
+  const uint4* features;
+  const uint4* newline;
+  const uint4* embed;
+  int nvec;  // 16-byte vectors per row
+  int T;     // tokens per tile (729)
+  int S;     // patches per side (27)
+  const int64_t* input_ids;
+  const int64_t* labels_in;
+  const int32_t* text_src;
+  const radvlm_splice_segment* segments;
+  int n_segments;
+  const radvlm_merge_image* images;
+  int64_t total_rows;
+  uint4* out;
+  int64_t* out_labels;
+  uint8_t* out_mask;
+  int64_t* out_pos;
+  int64_t ignore_index;
+};
+
+constexpr int kMsUnroll = 7;
+
+__device__ __forceinline__ void copy_row(const uint4* __restrict__ src, uint4* __restrict__ dst, int nvec,
+                                         int lane) {
+  int i = lane;
+  for (; i + 32 * (kMsUnroll - 1) < nvec; i += 32 * kMsUnroll) {
+    uint4 v[kMsUnroll];
+#pragma unroll
+    for (int u = 0; u < kMsUnroll; ++u) v[u] = ld_stream(src + i + 32 * u);
+#pragma unroll
+    for (int u = 0; u < kMsUnroll; ++u) st_stream(dst + i + 32 * u, v[u]);
+  }
+  for (; i < nvec; i += 32) st_stream(dst + i, ld_stream(src + i));
+}
+
+// feature row (in 16-byte vectors) of grid position (R, C) of the un-cropped S*gh x S*gw map
+__device__ __forceinline__ size_t grid_src_row(const radvlm_merge_image& im, int R, int C, int S, int T) {
+  const int tr = R / S, tc = C / S;
+  return static_cast<size_t>(im.tile_base + 1 + tr * im.grid_w + tc) * T + (R - tr * S) * S + (C - tc * S);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_splice_kernel(const MergeSpliceArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < a.total_rows; row += nwarps) {
+    // warp-uniform binary search: last segment with dst_row <= row
+    int lo = 0, hi = a.n_segments - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&a.segments[mid].dst_row) <= row) lo = mid; else hi = mid - 1;
+    }
+    const radvlm_splice_segment seg = a.segments[lo];
+    const int off = static_cast<int>(row - seg.dst_row);
+    uint4* dst = a.out + static_cast<size_t>(row) * a.nvec;
+    int64_t label = a.ignore_index;
+    uint8_t mask = 1;
+    int64_t pos = seg.pos0 + off;
+
+    if (seg.kind == RADVLM_SEG_PAD || off >= seg.length) {
+      for (int i = lane; i < a.nvec; i += 32) st_stream(dst + i, make_uint4(0, 0, 0, 0));
+      mask = 0;
+      pos = 0;
+    } else if (seg.kind == RADVLM_SEG_TEXT) {
+      const int32_t sp = __ldg(a.text_src + seg.src_off + off);
+      const int64_t tok = __ldg(a.input_ids + sp);
+      if (a.labels_in != nullptr) label = __ldg(a.labels_in + sp);
+      copy_row(a.embed + static_cast<size_t>(tok) * a.nvec, dst, a.nvec, lane);
+    } else {
+      const radvlm_merge_image im = a.images[seg.image];
+      const int t = seg.src_off + off;
+      if (im.mode == RADVLM_MERGE_FLAT) {
+        copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
+      } else if (t < a.T) {  // base tile
+        copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
+      } else if (im.mode == RADVLM_MERGE_SINGLE) {
+        copy_row(a.newline, dst, a.nvec, lane);
+      } else {
+        const int u = t - a.T;
+        const int r = u / (im.out_w + 1);
+        const int c = u - r * (im.out_w + 1);
+        if (c == im.out_w) {
+          copy_row(a.newline, dst, a.nvec, lane);
+        } else if (!im.pool) {
+          const size_t srow = grid_src_row(im, r + im.crop_r0, c + im.crop_c0, a.S, a.T);
+          copy_row(a.features + srow * a.nvec, dst, a.nvec, lane);
+        } else {
+          const float sh = static_cast<float>(im.crop_h) / static_cast<float>(im.out_h);
+          const float sw = static_cast<float>(im.crop_w) / static_cast<float>(im.out_w);
+          float sy = sh * (static_cast<float>(r) + 0.5f) - 0.5f;
+          float sx = sw * (static_cast<float>(c) + 0.5f) - 0.5f;
+          sy = sy < 0.f ? 0.f : sy;
+          sx = sx < 0.f ? 0.f : sx;
+          const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+          const int y1 = y0 + (y0 < im.crop_h - 1 ? 1 : 0), x1 = x0 + (x0 < im.crop_w - 1 ? 1 : 0);
+          const float ly1 = sy - static_cast<float>(y0), lx1 = sx - static_cast<float>(x0);
+          const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+          const uint4* p00 = a.features + grid_src_row(im, y0 + im.crop_r0, x0 + im.crop_c0, a.S, a.T) * a.nvec;
+          const uint4* p01 = a.features + grid_src_row(im, y0 + im.crop_r0, x1 + im.crop_c0, a.S, a.T) * a.nvec;
+          const uint4* p10 = a.features + grid_src_row(im, y1 + im.crop_r0, x0 + im.crop_c0, a.S, a.T) * a.nvec;
+          const uint4* p11 = a.features + grid_src_row(im, y1 + im.crop_r0, x1 + im.crop_c0, a.S, a.T) * a.nvec;
+          for (int i = lane; i < a.nvec; i += 32) {
+            float f00[Vec16<T>::N], f01[Vec16<T>::N], f10[Vec16<T>::N], f11[Vec16<T>::N], o[Vec16<T>::N];
+            Vec16<T>::unpack(ld_stream(p00 + i), f00);
+            Vec16<T>::unpack(ld_stream(p01 + i), f01);
+            Vec16<T>::unpack(ld_stream(p10 + i), f10);
+            Vec16<T>::unpack(ld_stream(p11 + i), f11);
+#pragma unroll
+            for (int e = 0; e < Vec16<T>::N; ++e)
+              o[e] = ly0 * (lx0 * f00[e] + lx1 * f01[e]) + ly1 * (lx0 * f10[e] + lx1 * f11[e]);
+            st_stream(dst + i, Vec16<T>::pack(o));
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      if (a.out_labels) a.out_labels[row] = label;
+      if (a.out_mask) a.out_mask[row] = mask;
+      if (a.out_pos) a.out_pos[row] = pos;
+    }
+  }
+}
+
+}  // namespace rv
+
+extern "C" int radvlm_merge_splice(const void* features, const void* newline, const void* embed_table,
+                                   int dtype, int hidden, int tokens_per_tile, int patches_per_side,
+                                   const int64_t* input_ids, const int64_t* labels_in,
+                                   const int32_t* text_src, const radvlm_splice_segment* segments,
+                                   int n_segments, const radvlm_merge_image* images, int n_images,
+                                   int64_t total_rows, void* out_embeds, int64_t* out_labels,
+                                   uint8_t* out_mask, int64_t* out_pos, int64_t ignore_index,
+                                   void* stream) {
+  using namespace rv;
+  int st = require_sm100();
+  if (st) return st;
+  RV_CHECK_ARG(segments && n_segments > 0 && out_embeds && total_rows > 0, "merge_splice: bad arguments");
+  RV_CHECK_ARG(n_images == 0 || (images && features), "merge_splice: image table without features");
+  const int esize = (dtype == RADVLM_DT_F32) ? 4 : 2;
+  RV_CHECK_ARG((static_cast<long long>(hidden) * esize) % 16 == 0, "merge_splice: row bytes must be a multiple of 16");
+  MergeSpliceArgs a;
+  a.features = static_cast<const uint4*>(features);
+  a.newline = static_cast<const uint4*>(newline);
+  a.embed = static_cast<const uint4*>(embed_table);
+  a.nvec = hidden * esize / 16;
+  a.T = tokens_per_tile;
+  a.S = patches_per_side;
+  a.input_ids = input_ids;
+  a.labels_in = labels_in;
+  a.text_src = text_src;
+  a.segments = segments;
+  a.n_segments = n_segments;
+  a.images = images;
+  a.total_rows = total_rows;
+  a.out = static_cast<uint4*>(out_embeds);
+  a.out_labels = out_labels;
+  a.out_mask = out_mask;
+  a.out_pos = out_pos;
+  a.ignore_index = ignore_index;
+  const int threads = 256;
+  const int64_t want = (total_rows * 32 + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;  // 8 resident CTAs per SM
+  const int blocks = static_cast<int>(want < cap ? want : cap);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case RADVLM_DT_F32: merge_splice_kernel<float><<<blocks, threads, 0, s>>>(a); break;
+    case RADVLM_DT_BF16: merge_splice_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(a); break;
+    case RADVLM_DT_F16: merge_splice_kernel<__half><<<blocks, threads, 0, s>>>(a); break;
+    default: set_error("merge_splice: unknown dtype %d", dtype); return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}

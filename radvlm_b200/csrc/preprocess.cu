@@ -1,0 +1,368 @@
+// Fused anyres preprocessing on the GPU (HBM-bound, integer arithmetic, bit-exact with Pillow):
+//   uint8 HWC image -> aspect-preserving BICUBIC resize -> centred paste on a black canvas ->
+//   384x384 crops (row-major) + the aspect-distorting 384x384 base tile -> rescale(1/255) ->
+//   normalize((x-0.5)/0.5) -> CHW tiles [1+gw*gh, 3, 384, 384] in fp32 / bf16 / fp16.
+//
+// Replaces (reference, all on CPU in DataLoader workers):
+//   process_anyres_image / resize_and_pad_image / divide_to_patches   mm_utils.py:152-210,243-293
+//   SigLipImageProcessor.preprocess                                   siglip_encoder.py:47-67
+// Third-party arithmetic restated: Pillow's 8bpc ImagingResample (pinned 10.3.0, verified against the
+// 12.2.0 in this image): separable, horizontal pass first into a uint8 intermediate, 22-bit fixed-point
+// coefficients from a float64 bicubic (a=-0.5) kernel of support 2*max(1, in/out), accumulator seeded
+// with 1<<21, arithmetic >>22, clip to [0,255].  transformers.image_transforms.rescale/normalize:
+// float32(float64(u8) * (1/255)), then (x - 0.5f) / 0.5f in fp32.
+//
+// Kernels (all batched over images through a device-resident descriptor table):
+//   1. resample_coeffs_kernel : per image, 4 coefficient tables (x/y for the canvas resize, x/y for the base tile)
+//   2. resample_h_kernel      : horizontal pass -> uint8 intermediates (canvas and base)
+//   3. resample_v_tiles_kernel: vertical pass + paste + crop + normalise + CHW scatter
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace rv {
+
+constexpr int kPrecisionBits = 22;
+constexpr int kMaxKsize = 129;  // supports down-scales up to 32x
+
+struct AxisLayout {
+  int ksize;
+  size_t bounds_off;  // int32 [2*out]
+  size_t kk_off;      // int32 [out*ksize]
+};
+
+struct PreLayout {
+  AxisLayout xm, ym, xb, yb;  // main (canvas) x / y, base tile x / y
+  size_t tmp_main_off;        // uint8 [H, nw, C]
+  size_t tmp_base_off;        // uint8 [H, S, C]
+  size_t total;
+};
+
+__host__ __device__ inline int resample_ksize(int in, int out) {
+  double fs = static_cast<double>(in) / static_cast<double>(out);
+  if (fs < 1.0) fs = 1.0;
+  const double support = 2.0 * fs;
+  return static_cast<int>(ceil(support)) * 2 + 1;
+}
+
+__host__ __device__ inline size_t al16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+
+__host__ __device__ inline PreLayout make_pre_layout(int W, int H, int C, int nw, int nh, int S) {
+  PreLayout L;
+  size_t off = 0;
+  auto axis = [&](AxisLayout& a, int in, int out) {
+    a.ksize = resample_ksize(in, out);
+    a.bounds_off = off;
+    off = al16(off + static_cast<size_t>(out) * 2 * 4);
+    a.kk_off = off;
+    off = al16(off + static_cast<size_t>(out) * a.ksize * 4);
+  };
+  axis(L.xm, W, nw);
+  axis(L.ym, H, nh);
+  axis(L.xb, W, S);
+  axis(L.yb, H, S);
+  L.tmp_main_off = off;
+  off = al16(off + static_cast<size_t>(H) * nw * C);
+  L.tmp_base_off = off;
+  off = al16(off + static_cast<size_t>(H) * S * C);
+  L.total = off;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. coefficient tables (Pillow precompute_coeffs + normalize_coeffs_8bpc), fp64 without contraction
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bicubic_filter(double x) {
+  if (x < 0.0) x = -x;
+  if (x < 1.0) {
+    // ((a + 2.0) * x - (a + 3.0)) * x * x + 1, a = -0.5
+    double t = __dsub_rn(__dmul_rn(1.5, x), 2.5);
+    t = __dmul_rn(t, x);
+    t = __dmul_rn(t, x);
+    return __dadd_rn(t, 1.0);
+  }
+  if (x < 2.0) {
+    // (((x - 5) * x + 8) * x - 4) * a
+    double t = __dsub_rn(x, 5.0);
+    t = __dadd_rn(__dmul_rn(t, x), 8.0);
+    t = __dsub_rn(__dmul_rn(t, x), 4.0);
+    return __dmul_rn(t, -0.5);
+  }
+  return 0.0;
+}
+
+__device__ void compute_axis_coeffs(int in, int out, int ksize, int xx, int32_t* bounds, int32_t* kk) {
+  const double scale = __ddiv_rn(static_cast<double>(in), static_cast<double>(out));
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = __dmul_rn(2.0, filterscale);
+  const double center = __dmul_rn(__dadd_rn(static_cast<double>(xx), 0.5), scale);
+  const double ss = __ddiv_rn(1.0, filterscale);
+  int xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+  if (xmax > in) xmax = in;
+  xmax -= xmin;
+  double w[kMaxKsize];
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    const double arg = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+    w[x] = bicubic_filter(arg);
+    ww = __dadd_rn(ww, w[x]);
+  }
+  int32_t* k = kk + static_cast<size_t>(xx) * ksize;
+  for (int x = 0; x < ksize; ++x) {
+    int32_t c = 0;
+    if (x < xmax) {
+      double v = w[x];
+      if (ww != 0.0) v = __ddiv_rn(v, ww);
+      const double s = __dmul_rn(v, static_cast<double>(1 << kPrecisionBits));
+      c = (v < 0.0) ? static_cast<int32_t>(__dadd_rn(-0.5, s)) : static_cast<int32_t>(__dadd_rn(0.5, s));
+    }
+    k[x] = c;
+  }
+  bounds[2 * xx] = xmin;
+  bounds[2 * xx + 1] = xmax;
+}
+
+__global__ void __launch_bounds__(64)
+resample_coeffs_kernel(const radvlm_preprocess_image* __restrict__ imgs, uint8_t* __restrict__ scratch,
+                       int S) {
+  const radvlm_preprocess_image im = imgs[blockIdx.z];
+  const PreLayout L = make_pre_layout(im.width, im.height, im.channels, im.resized_w, im.resized_h, S);
+  const int axis = blockIdx.y;
+  int in, out;
+  AxisLayout A;
+  switch (axis) {
+    case 0: in = im.width; out = im.resized_w; A = L.xm; break;
+    case 1: in = im.height; out = im.resized_h; A = L.ym; break;
+    case 2: in = im.width; out = S; A = L.xb; break;
+    default: in = im.height; out = S; A = L.yb; break;
+  }
+  uint8_t* base = scratch + im.scratch_offset;
+  for (int xx = blockIdx.x * blockDim.x + threadIdx.x; xx < out; xx += gridDim.x * blockDim.x)
+    compute_axis_coeffs(in, out, A.ksize, xx, reinterpret_cast<int32_t*>(base + A.bounds_off),
+                        reinterpret_cast<int32_t*>(base + A.kk_off));
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= kPrecisionBits;
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. horizontal pass: src [H, W, C] -> tmp [H, out_w, C]   (z = image*2 + target; target 0 canvas, 1 base)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+resample_h_kernel(const radvlm_preprocess_image* __restrict__ imgs, const uint8_t* __restrict__ src,
+                  uint8_t* __restrict__ scratch, int S) {
+  const radvlm_preprocess_image im = imgs[blockIdx.z >> 1];
+  const int target = blockIdx.z & 1;
+  const int out_w = target ? S : im.resized_w;
+  const int y = blockIdx.y;
+  if (y >= im.height) return;
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xx >= out_w) return;
+  if (out_w == im.width) return;  // pass skipped (Pillow copies); the vertical pass reads the source
+  const PreLayout L = make_pre_layout(im.width, im.height, im.channels, im.resized_w, im.resized_h, S);
+  const AxisLayout A = target ? L.xb : L.xm;
+  uint8_t* base = scratch + im.scratch_offset;
+  const int32_t* bounds = reinterpret_cast<const int32_t*>(base + A.bounds_off);
+  const int32_t* k = reinterpret_cast<const int32_t*>(base + A.kk_off) + static_cast<size_t>(xx) * A.ksize;
+  const int xmin = bounds[2 * xx], xmax = bounds[2 * xx + 1];
+  const int C = im.channels;
+  const uint8_t* row = src + im.src_offset + static_cast<size_t>(y) * im.width * C;
+  uint8_t* out = base + (target ? L.tmp_base_off : L.tmp_main_off) +
+                 (static_cast<size_t>(y) * out_w + xx) * C;
+  if (C == 1) {
+    int s0 = 1 << (kPrecisionBits - 1);
+    for (int x = 0; x < xmax; ++x) s0 += static_cast<int>(row[x + xmin]) * k[x];
+    out[0] = clip8(s0);
+  } else {
+    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < xmax; ++x) {
+      const uint8_t* p = row + static_cast<size_t>(x + xmin) * 3;
+      const int kv = k[x];
+      s0 += static_cast<int>(p[0]) * kv;
+      s1 += static_cast<int>(p[1]) * kv;
+      s2 += static_cast<int>(p[2]) * kv;
+    }
+    out[0] = clip8(s0);
+    out[1] = clip8(s1);
+    out[2] = clip8(s2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. vertical pass + paste + crop + normalise + CHW tile scatter
+//    grid: x = 128-pixel column chunks, y = canvas row (rows >= gh*S address the base tile), z = image
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+resample_v_tiles_kernel(const radvlm_preprocess_image* __restrict__ imgs, const uint8_t* __restrict__ src,
+                        const uint8_t* __restrict__ scratch, T* __restrict__ tiles, int S) {
+  __shared__ float lut[256];
+  {
+    // rescale: float32(float64(u8) * (1/255));  normalize: (x - 0.5f) / 0.5f
+    for (int u = threadIdx.x; u < 256; u += blockDim.x) {
+      const float r = __double2float_rn(__dmul_rn(static_cast<double>(u), 1.0 / 255.0));
+      lut[u] = __fdiv_rn(__fsub_rn(r, 0.5f), 0.5f);
+    }
+  }
+  __syncthreads();
+  const radvlm_preprocess_image im = imgs[blockIdx.z];
+  const int canvas_w = im.grid_w * S, canvas_h = im.grid_h * S;
+  const int Y = blockIdx.y;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool is_base = (Y >= canvas_h);
+  if (Y >= canvas_h + S) return;
+  if (X >= (is_base ? S : canvas_w)) return;
+
+  const PreLayout L = make_pre_layout(im.width, im.height, im.channels, im.resized_w, im.resized_h, S);
+  const uint8_t* base = scratch + im.scratch_offset;
+  const int C = im.channels;
+
+  int tile, ty, tx;      // destination tile and in-tile coordinates
+  int oy, ox;            // coordinates inside the resized image
+  int out_w, out_h;      // resized image size of this target
+  AxisLayout A;
+  const uint8_t* hsrc;   // horizontally resampled intermediate (or the source when that pass is skipped)
+  bool inside = true;
+  if (is_base) {
+    tile = im.tile_base;
+    ty = Y - canvas_h;
+    tx = X;
+    oy = ty;
+    ox = tx;
+    out_w = S;
+    out_h = S;
+    A = L.yb;
+    hsrc = (S == im.width) ? (src + im.src_offset) : (base + L.tmp_base_off);
+  } else {
+    const int gy = Y / S, gx = X / S;
+    tile = im.tile_base + 1 + gy * im.grid_w + gx;
+    ty = Y - gy * S;
+    tx = X - gx * S;
+    oy = Y - im.paste_y;
+    ox = X - im.paste_x;
+    out_w = im.resized_w;
+    out_h = im.resized_h;
+    inside = (oy >= 0 && oy < out_h && ox >= 0 && ox < out_w);
+    A = L.ym;
+    hsrc = (im.resized_w == im.width) ? (src + im.src_offset) : (base + L.tmp_main_off);
+  }
+
+  int v0 = 0, v1 = 0, v2 = 0;  // black canvas outside the pasted image
+  if (inside) {
+    if (out_h == im.height) {  // vertical pass skipped
+      const uint8_t* p = hsrc + (static_cast<size_t>(oy) * out_w + ox) * C;
+      v0 = p[0];
+      if (C == 3) { v1 = p[1]; v2 = p[2]; }
+    } else {
+      const int32_t* bounds = reinterpret_cast<const int32_t*>(base + A.bounds_off);
+      const int32_t* k = reinterpret_cast<const int32_t*>(base + A.kk_off) + static_cast<size_t>(oy) * A.ksize;
+      const int ymin = bounds[2 * oy], ymax = bounds[2 * oy + 1];
+      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+      const size_t pitch = static_cast<size_t>(out_w) * C;
+      const uint8_t* p = hsrc + static_cast<size_t>(ymin) * pitch + static_cast<size_t>(ox) * C;
+      if (C == 1) {
+        for (int y = 0; y < ymax; ++y) s0 += static_cast<int>(p[y * pitch]) * k[y];
+        v0 = clip8(s0);
+      } else {
+        for (int y = 0; y < ymax; ++y) {
+          const uint8_t* q = p + y * pitch;
+          const int kv = k[y];
+          s0 += static_cast<int>(q[0]) * kv;
+          s1 += static_cast<int>(q[1]) * kv;
+          s2 += static_cast<int>(q[2]) * kv;
+        }
+        v0 = clip8(s0);
+        v1 = clip8(s1);
+        v2 = clip8(s2);
+      }
+    }
+    if (C == 1) { v1 = v0; v2 = v0; }
+  }
+  const size_t plane = static_cast<size_t>(S) * S;
+  T* o = tiles + static_cast<size_t>(tile) * 3 * plane + static_cast<size_t>(ty) * S + tx;
+  o[0] = cvt_out<T>(lut[v0]);
+  o[plane] = cvt_out<T>(lut[v1]);
+  o[2 * plane] = cvt_out<T>(lut[v2]);
+}
+
+}  // namespace rv
+
+extern "C" size_t radvlm_preprocess_scratch_bytes(int width, int height, int channels, int resized_w,
+                                                  int resized_h, int tile_size) {
+  if (width <= 0 || height <= 0 || resized_w <= 0 || resized_h <= 0 || tile_size <= 0) return 0;
+  return rv::make_pre_layout(width, height, channels, resized_w, resized_h, tile_size).total;
+}
+
+extern "C" int radvlm_preprocess_anyres(const uint8_t* src, const radvlm_preprocess_image* images_dev,
+                                        const radvlm_preprocess_image* images_host, int n_images,
+                                        int tile_size, void* tiles_out, int out_dtype, void* scratch,
+                                        size_t scratch_bytes, void* stream) {
+  using namespace rv;
+  int st = require_sm100();
+  if (st) return st;
+  RV_CHECK_ARG(src && images_dev && images_host && n_images > 0 && tiles_out && scratch,
+               "preprocess: bad arguments");
+  int max_out = tile_size, max_h = 0, max_cw = tile_size, max_rows = 0;
+  size_t need = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const radvlm_preprocess_image& im = images_host[i];
+    RV_CHECK_ARG(im.channels == 1 || im.channels == 3, "preprocess: image %d has %d channels (1 or 3)", i,
+                 im.channels);
+    RV_CHECK_ARG(im.width > 0 && im.height > 0 && im.grid_w > 0 && im.grid_h > 0 && im.resized_w > 0 &&
+                     im.resized_h > 0,
+                 "preprocess: image %d has a bad plan", i);
+    const PreLayout L = make_pre_layout(im.width, im.height, im.channels, im.resized_w, im.resized_h, tile_size);
+    if (L.xm.ksize > kMaxKsize || L.ym.ksize > kMaxKsize || L.xb.ksize > kMaxKsize || L.yb.ksize > kMaxKsize) {
+      set_error("preprocess: image %d (%dx%d) needs a down-scale beyond the supported 32x", i, im.width, im.height);
+      return RADVLM_ERR_UNSUPPORTED_SHAPE;
+    }
+    if (im.scratch_offset + L.total > need) need = im.scratch_offset + L.total;
+    if (im.resized_w > max_out) max_out = im.resized_w;
+    if (im.resized_h > max_out) max_out = im.resized_h;
+    if (im.height > max_h) max_h = im.height;
+    if (im.grid_w * tile_size > max_cw) max_cw = im.grid_w * tile_size;
+    if ((im.grid_h + 1) * tile_size > max_rows) max_rows = (im.grid_h + 1) * tile_size;
+  }
+  if (need > scratch_bytes) {
+    set_error("preprocess: scratch too small (%zu < %zu)", scratch_bytes, need);
+    return RADVLM_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* scr = static_cast<uint8_t*>(scratch);
+  resample_coeffs_kernel<<<dim3((max_out + 63) / 64, 4, n_images), 64, 0, s>>>(images_dev, scr, tile_size);
+  RV_CUDA(cudaGetLastError());
+  resample_h_kernel<<<dim3((max_out + 127) / 128, max_h, n_images * 2), 128, 0, s>>>(images_dev, src, scr,
+                                                                                   tile_size);
+  RV_CUDA(cudaGetLastError());
+  dim3 grid((max_cw + 127) / 128, max_rows, n_images);
+  switch (out_dtype) {
+    case RADVLM_DT_F32:
+      resample_v_tiles_kernel<float><<<grid, 128, 0, s>>>(images_dev, src, scr, static_cast<float*>(tiles_out), tile_size);
+      break;
+    case RADVLM_DT_BF16:
+      resample_v_tiles_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(images_dev, src, scr, static_cast<__nv_bfloat16*>(tiles_out), tile_size);
+      break;
+    case RADVLM_DT_F16:
+      resample_v_tiles_kernel<__half><<<grid, 128, 0, s>>>(images_dev, src, scr, static_cast<__half*>(tiles_out), tile_size);
+      break;
+    default:
+      set_error("preprocess: unknown out_dtype %d", out_dtype);
+      return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}

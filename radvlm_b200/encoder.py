@@ -1,0 +1,214 @@
+"""Host side of the B200 encode path: weight packing and the ``encode_images`` runner.
+
+Mirrors ``SigLipVisionTower.forward`` (siglip_encoder.py:576-589) followed by ``mm_projector``
+(llava_arch.py:192-196).  PyTorch is used only for device memory, streams and parameter storage; all
+compute is done by the sm_100a kernels behind the C ABI (``libradvlm_b200.so``).
+
+Weights are consumed from the reference's own Parameters (state-dict names).  The
+bf16 matrices the tensor-core kernels read are *caches* keyed on ``(data_ptr, _version)`` of every
+source tensor, so optimizer steps / checkpoint loads are picked up and the Parameters stay in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class PackedWeights:
+    """bf16 / fp32 device copies of tower + projector weights and the C structs pointing at them."""
+
+    def __init__(self, tower_sd: Mapping[str, torch.Tensor], proj_sd: Mapping[str, torch.Tensor], device,
+                 num_heads: int = 16, image_size: int = 384, ln_eps: float = 1e-6,
+                 num_layers: Optional[int] = None):
+        dev = torch.device(device)
+        keep = []  # every device tensor referenced by the structs
+
+        def w(t):  # matrix -> bf16 [out, in] contiguous
+            x = t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            keep.append(x)
+            return x
+
+        def v(t):  # vector / table -> fp32 contiguous
+            x = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(x)
+            return x
+
+        pre = "vision_model."
+        pw = tower_sd[pre + "embeddings.patch_embedding.weight"]  # [hidden, C, ps, ps]
+        hidden, channels, ps, _ = pw.shape
+        k = channels * ps * ps
+        k_pad = (k + 63) // 64 * 64
+        patch_w = torch.zeros(hidden, k_pad, dtype=torch.bfloat16, device=dev)
+        patch_w[:, :k] = pw.detach().reshape(hidden, k).to(device=dev, dtype=torch.bfloat16)
+        keep.append(patch_w)
+        pos = v(tower_sd[pre + "embeddings.position_embedding.weight"])
+        if num_layers is None:
+            num_layers = 0
+            while (pre + "encoder.layers.%d.layer_norm1.weight" % num_layers) in tower_sd:
+                num_layers += 1
+        layers = (_lib.VitLayerWeights * num_layers)()
+        inter = None
+        for i in range(num_layers):
+            lp = pre + "encoder.layers.%d." % i
+            g = lambda n: tower_sd[lp + n]
+            qkv_w = torch.cat([g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"),
+                               g("self_attn.v_proj.weight")], dim=0)
+            qkv_b = torch.cat([g("self_attn.q_proj.bias"), g("self_attn.k_proj.bias"),
+                               g("self_attn.v_proj.bias")], dim=0)
+            L = layers[i]
+            L.ln1_gamma = v(g("layer_norm1.weight")).data_ptr()
+            L.ln1_beta = v(g("layer_norm1.bias")).data_ptr()
+            L.qkv_w = w(qkv_w).data_ptr()
+            L.qkv_b = v(qkv_b).data_ptr()
+            L.out_w = w(g("self_attn.out_proj.weight")).data_ptr()
+            L.out_b = v(g("self_attn.out_proj.bias")).data_ptr()
+            L.ln2_gamma = v(g("layer_norm2.weight")).data_ptr()
+            L.ln2_beta = v(g("layer_norm2.bias")).data_ptr()
+            L.fc1_w = w(g("mlp.fc1.weight")).data_ptr()
+            L.fc1_b = v(g("mlp.fc1.bias")).data_ptr()
+            L.fc2_w = w(g("mlp.fc2.weight")).data_ptr()
+            L.fc2_b = v(g("mlp.fc2.bias")).data_ptr()
+            inter = g("mlp.fc1.weight").shape[0]
+        tw = _lib.SiglipWeights()
+        tw.hidden, tw.intermediate, tw.heads, tw.num_layers = hidden, int(inter or 0), num_heads, num_layers
+        tw.image_size, tw.patch_size, tw.channels, tw.patch_k_pad = image_size, ps, channels, k_pad
+        tw.ln_eps = ln_eps
+        tw.patch_w = patch_w.data_ptr()
+        tw.patch_b = v(tower_sd[pre + "embeddings.patch_embedding.bias"]).data_ptr()
+        tw.pos_embed = pos.data_ptr()
+        tw.layers = C.cast(layers, C.POINTER(_lib.VitLayerWeights))
+        pj = _lib.ProjectorWeights()
+        w1, w2 = proj_sd["0.weight"], proj_sd["2.weight"]
+        pj.in_dim, pj.hidden = w1.shape[1], w1.shape[0]
+        assert tuple(w2.shape) == (pj.hidden, pj.hidden), "mlp2x_gelu projector expected (builder.py:41-48)"
+        pj.w1 = w(w1).data_ptr()
+        pj.b1 = v(proj_sd["0.bias"]).data_ptr()
+        pj.w2 = w(w2).data_ptr()
+        pj.b2 = v(proj_sd["2.bias"]).data_ptr()
+        self.tower, self.projector = tw, pj
+        self._layers, self._keep = layers, keep
+        self.device = dev
+        self.tokens_per_tile = (image_size // ps) ** 2
+        self.patches_per_side = image_size // ps
+        self.hidden, self.proj_hidden = hidden, pj.hidden
+
+
+def _version_key(tensors) -> tuple:
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+class B200VisionEncoder:
+    """``encode_images`` for a (vision tower, projector) pair, executed by the sm_100a library."""
+
+    def __init__(self, tower_module: torch.nn.Module, projector_module: torch.nn.Module, num_heads: int = 16,
+                 image_size: int = 384, ln_eps: float = 1e-6, max_tiles_per_call: int = 80):
+        self.tower_module = tower_module          # SigLipVisionModel (state-dict prefix "vision_model.")
+        self.projector_module = projector_module  # nn.Sequential(Linear, GELU, Linear)
+        self.num_heads, self.image_size, self.ln_eps = num_heads, image_size, ln_eps
+        self.max_tiles_per_call = max_tiles_per_call
+        self._packed: Optional[PackedWeights] = None
+        self._key = None
+        self._frozen = False
+        self._ws: Dict[torch.device, torch.Tensor] = {}
+        _lib.load()  # fail loudly at construction time if the extension is missing
+
+    # ---- weights -------------------------------------------------------------------------------
+    def _source_tensors(self):
+        return list(self.tower_module.parameters()) + list(self.projector_module.parameters())
+
+    def freeze(self, flag: bool = True):
+        """Skip the per-call version check (inference: weights never change)."""
+        self._frozen = flag
+        return self
+
+    def packed(self, device) -> PackedWeights:
+        if self._packed is not None and self._frozen and self._packed.device == torch.device(device):
+            return self._packed
+        key = (torch.device(device), _version_key(self._source_tensors()))
+        if self._packed is None or key != self._key:
+            n_layers = len(self.tower_module.vision_model.encoder.layers)
+            self._packed = PackedWeights(self.tower_module.state_dict(), self.projector_module.state_dict(),
+                                         device, num_heads=self.num_heads, image_size=self.image_size,
+                                         ln_eps=self.ln_eps, num_layers=n_layers)
+            self._key = key
+        return self._packed
+
+    def _workspace(self, device, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[device] = ws
+        return ws
+
+    # ---- forward -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_images(self, images: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """images [n, 3, S, S] -> features [n, T, projector_hidden] (dtype = images.dtype, siglip_encoder.py:586)."""
+        if images.dim() != 4:
+            raise ValueError("encode_images expects [n, C, S, S], got %s" % (tuple(images.shape),))
+        if not torch.cuda.is_available():
+            raise RuntimeError("radvlm_b200: no CUDA device; the encode path has no CPU fallback")
+        dev = next(self.projector_module.parameters()).device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        out_dtype = out_dtype or images.dtype
+        if images.dtype not in _DT:
+            images = images.float()
+        images = images.to(dev).contiguous()
+        pk = self.packed(dev)
+        lib = _lib.load()
+        n = images.shape[0]
+        T, Hp = pk.tokens_per_tile, pk.proj_hidden
+        kernel_out = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        out = torch.empty(n, T, Hp, dtype=kernel_out, device=dev)
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(dev)
+            step = max(1, self.max_tiles_per_call)
+            for s in range(0, n, step):
+                m = min(step, n - s)
+                need = lib.radvlm_encode_workspace_bytes(C.byref(pk.tower), C.byref(pk.projector), m)
+                if need == 0:
+                    raise _lib.RadvlmError(_lib.ERR_BAD_ARGUMENT, _lib.last_error())
+                ws = self._workspace(dev, need)
+                _lib.check(lib.radvlm_encode_images(
+                    C.byref(pk.tower), C.byref(pk.projector), images[s:s + m].data_ptr(), _DT[images.dtype], m,
+                    out[s:s + m].data_ptr(), _DT[kernel_out], ws.data_ptr(), ws.numel(), stream))
+        return out if out.dtype == out_dtype else out.to(out_dtype)
+
+    @torch.no_grad()
+    def tower_forward(self, images: torch.Tensor) -> torch.Tensor:
+        """SigLipVisionTower.forward only: [n,3,S,S] -> fp32 hidden_states[-1] [n, T, hidden]."""
+        dev = next(self.projector_module.parameters()).device
+        if images.dtype not in _DT:
+            images = images.float()
+        images = images.to(dev).contiguous()
+        pk = self.packed(dev)
+        lib = _lib.load()
+        n = images.shape[0]
+        out = torch.empty(n, pk.tokens_per_tile, pk.hidden, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            need = lib.radvlm_encode_workspace_bytes(C.byref(pk.tower), C.byref(pk.projector), n)
+            ws = self._workspace(dev, need)
+            _lib.check(lib.radvlm_siglip_tower_forward(C.byref(pk.tower), images.data_ptr(), _DT[images.dtype], n,
+                                                       out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+        return out
+
+
+def flops_per_tile(hidden=1152, inter=4304, layers=26, seq=729, patch_k=588, proj=3584) -> float:
+    """Algorithmic forward FLOPs per tile (2*M*N*K, unpadded)."""
+    per_layer = 2 * seq * (3 * hidden * hidden + hidden * hidden + 2 * hidden * inter) + 4 * seq * seq * hidden
+    return 2.0 * seq * patch_k * hidden + layers * per_layer + 2.0 * seq * (hidden * proj + proj * proj)
+
+
+assert math.isclose(flops_per_tile() / 1e9, 666.55, rel_tol=1e-3)

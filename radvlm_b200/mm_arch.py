@@ -1,0 +1,235 @@
+"""Drop-in replacements for ``LlavaMetaForCausalLM.encode_images`` and
+``LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal`` (finetuning/llava/model/llava_arch.py:192-196,
+251-555) backed by the sm_100a library.
+
+Same signatures, argument meaning, return tuple and error behaviour as the reference for the RadVLM
+configuration (SigLIP tower, ``mlp2x_gelu`` projector, ``mm_patch_merge_type="spatial_unpad"``,
+``image_aspect_ratio="anyres_max_9"``); see ``INTEGRATION.md`` for how to attach it to the reference's
+``LlavaQwenForCausalLM`` without touching its callers (llava_qwen.py:83,131).
+
+Differences by design: one host sync per batch (the ids are read once to plan the splice) instead of two
+per sample; visual tokens are written exactly once, directly into the padded ``[B, max_len, H]`` tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+import re
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, planner
+from .encoder import B200VisionEncoder
+from .planner import IGNORE_INDEX, IMAGE_TOKEN_INDEX
+
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
+
+
+def _encoder_for(self) -> B200VisionEncoder:
+    enc = getattr(self, "_radvlm_b200_encoder", None)
+    tower = self.get_vision_tower()
+    proj = self.get_model().mm_projector
+    if enc is None or enc.tower_module is not tower.vision_tower or enc.projector_module is not proj:
+        cfg = getattr(tower, "config", None)
+        enc = B200VisionEncoder(
+            tower.vision_tower, proj,
+            num_heads=getattr(cfg, "num_attention_heads", 16),
+            image_size=getattr(cfg, "image_size", 384),
+            ln_eps=getattr(cfg, "layer_norm_eps", 1e-6))
+        object.__setattr__(self, "_radvlm_b200_encoder", enc)
+    return enc
+
+
+def _check_forward_only(self):
+    if torch.is_grad_enabled() and not getattr(self, "radvlm_b200_allow_no_grad", False):
+        params = list(self.get_vision_tower().parameters()) + list(self.get_model().mm_projector.parameters())
+        if any(p.requires_grad for p in params):
+            raise NotImplementedError(
+                "radvlm_b200: the encode path is forward-only in this round (backward = SURVEY.md section 8(f) "
+                "row 1).  Call under torch.no_grad(), freeze the tower/projector, or set "
+                "model.radvlm_b200_allow_no_grad = True to run the forward without gradients.")
+
+
+def encode_images(self, images: torch.Tensor) -> torch.Tensor:
+    """llava_arch.py:192-196: tower -> mm_projector.  [n,3,S,S] -> [n, 729, hidden_size], dtype = images.dtype."""
+    _check_forward_only(self)
+    return _encoder_for(self).encode_images(images)
+
+
+def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool):
+    """Per-image merge descriptors + visual-token counts (llava_arch.py:294-413)."""
+    cfg = self.config
+    tower = self.get_vision_tower()
+    S = tower.num_patches_per_side
+    T = S * S
+    merge_type = getattr(cfg, "mm_patch_merge_type", "flat")
+    aspect = getattr(cfg, "image_aspect_ratio", "square")
+    table = (_lib.MergeImage * max(len(tile_counts), 1))()
+    tokens = []
+    base = 0
+    for i, tiles in enumerate(tile_counts):
+        m = table[i]
+        m.tile_base = base
+        if flat_batch or merge_type == "flat":
+            m.mode, m.n_tokens = _lib.MERGE_FLAT, tiles * T
+        elif merge_type.startswith("spatial"):
+            if tiles > 1:
+                if "maxpool2x2" in merge_type or "nobase" in merge_type or "unpad" not in merge_type:
+                    raise NotImplementedError("radvlm_b200 implements mm_patch_merge_type='spatial_unpad' "
+                                              "(RadVLM); got %r" % merge_type)
+                if not (aspect == "anyres" or "anyres_max" in aspect):
+                    raise NotImplementedError("radvlm_b200 implements the anyres / anyres_max_N aspect modes; got %r" % aspect)
+                max_num_patches = 0
+                mt = re.match(r"anyres_max_(\d+)", aspect)
+                if mt:
+                    max_num_patches = int(mt.group(1))
+                if not hasattr(tower, "image_size"):
+                    raise ValueError("vision_tower_image_size is not found in the vision tower.")
+                try:
+                    plan = planner.plan_image(image_sizes[i], cfg.image_grid_pinpoints, tower.image_size, S,
+                                              max_num_patches)
+                except Exception as e:
+                    # reference: grid-shape failure falls back to a 2x2 grid (llava_arch.py:367-371); the unpad
+                    # window is still computed from image_sizes[i] and raises if that is unusable.
+                    print("Error: %s" % e)
+                    ts = tower.image_size
+                    plan = planner.plan_image(image_sizes[i], [[2 * ts, 2 * ts]], ts, S, max_num_patches)
+                if plan.grid_w * plan.grid_h != tiles - 1:
+                    raise RuntimeError("shape '[%d, %d, %d, %d, -1]' is invalid for input of %d tiles (image %d)"
+                                       % (plan.grid_h, plan.grid_w, S, S, tiles - 1, i))
+                m.mode = _lib.MERGE_ANYRES
+                m.grid_w = plan.grid_w
+                m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = plan.crop_r0, plan.crop_c0, plan.crop_h, plan.crop_w
+                m.pool, m.out_h, m.out_w, m.n_tokens = plan.pool, plan.out_h, plan.out_w, plan.n_tokens
+            else:
+                if "unpad" in merge_type:
+                    m.mode, m.n_tokens = _lib.MERGE_SINGLE, T + 1
+                else:
+                    m.mode, m.n_tokens = _lib.MERGE_FLAT, T
+        else:
+            raise ValueError("Unexpected mm_patch_merge_type: %s" % merge_type)
+        tokens.append(int(m.n_tokens))
+        base += tiles
+    return table, tokens
+
+
+def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
+                                         images, modalities=["image"], image_sizes=None):
+    """llava_arch.py:251-555.  Returns (None, position_ids, attention_mask, past_key_values, inputs_embeds, labels)."""
+    vision_tower = self.get_vision_tower()
+    if vision_tower is None or images is None or input_ids.shape[1] == 1:
+        return input_ids, position_ids, attention_mask, past_key_values, None, labels
+    if isinstance(modalities, str):
+        modalities = [modalities]
+    if any(m == "video" for m in modalities):
+        raise NotImplementedError("radvlm_b200: the video / get_2dPool branch is out of scope (SURVEY.md section 8(f) row 4)")
+    _check_forward_only(self)
+    enc = _encoder_for(self)
+    lib = _lib.load()
+
+    # ---- encode all tiles of all images in one call (llava_arch.py:261-279)
+    if type(images) is list or images.ndim == 5:
+        if type(images) is list:
+            images = [x.unsqueeze(0) if x.ndim == 3 else x for x in images]
+        images_list = [im if im.ndim == 4 else im.unsqueeze(0) for im in images]
+        concat_images = torch.cat([im for im in images_list], dim=0)
+        tile_counts = [int(im.shape[0]) for im in images_list]
+        flat_batch = False
+    else:
+        concat_images = images
+        tile_counts = [1] * int(images.shape[0])
+        flat_batch = True
+    features = enc.encode_images(concat_images)            # [tiles, T, H]
+    dev = features.device
+    if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
+        raise NotImplementedError
+    merge_table, image_tokens = _merge_table(self, tile_counts, image_sizes, flat_batch)
+
+    # ---- splice plan on the host: one D2H of the ids instead of 2 syncs per sample (llava_arch.py:428-493)
+    _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask
+    B, L = input_ids.shape
+    B_eff = min(B, len(modalities))  # the reference's zip(new_input_embeds, modalities) truncates (llava_arch.py:499-500)
+    ids_host = input_ids.detach().to("cpu", torch.int64).numpy()
+    mask_host = None if attention_mask is None else attention_mask.detach().to("cpu").bool().numpy().astype(np.uint8)
+    max_length = getattr(self.config, "tokenizer_model_max_length", None)
+    left_pad = getattr(self.config, "tokenizer_padding_side", "right") == "left"
+    plan = planner.plan_splice(ids_host, mask_host, image_tokens, max_length, left_pad)
+    if B_eff < B:
+        plan = planner.plan_splice(ids_host[:B_eff], None if mask_host is None else mask_host[:B_eff],
+                                   image_tokens, max_length, left_pad)
+    max_len = plan.max_len
+    embed = self.get_model().embed_tokens.weight
+    if features.dtype != embed.dtype:
+        features = features.to(embed.dtype)
+    newline = getattr(self.get_model(), "image_newline", None)
+    if newline is None:
+        newline = torch.zeros(embed.shape[1], dtype=embed.dtype, device=dev)
+    newline = newline.detach().to(device=dev, dtype=embed.dtype).contiguous()
+    H = embed.shape[1]
+    total_rows = B_eff * max_len
+
+    # ---- tables -> device (one pinned staging buffer)
+    seg_bytes = plan.n_segments * C.sizeof(_lib.SpliceSegment)
+    img_bytes = len(tile_counts) * C.sizeof(_lib.MergeImage)
+    txt_bytes = plan.n_text * 4
+    off_img = (seg_bytes + 15) // 16 * 16
+    off_txt = off_img + (img_bytes + 15) // 16 * 16
+    tot = off_txt + (txt_bytes + 15) // 16 * 16 + 16
+    host = torch.zeros(tot, dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    hv[:seg_bytes] = np.frombuffer(bytes(plan.segments)[:seg_bytes], dtype=np.uint8)
+    hv[off_img:off_img + img_bytes] = np.frombuffer(bytes(merge_table)[:img_bytes], dtype=np.uint8)
+    if txt_bytes:
+        hv[off_txt:off_txt + txt_bytes] = plan.text_src.view(np.uint8)
+    with torch.cuda.device(dev):
+        tables = host.to(dev, non_blocking=True)
+        ids_dev = input_ids.detach().to(dev, torch.int64).contiguous()
+        labels_dev = None if labels is None else labels.detach().to(dev, torch.int64).contiguous()
+        out = torch.empty(B_eff, max_len, H, dtype=embed.dtype, device=dev)
+        out_labels = torch.empty(B_eff, max_len, dtype=torch.int64, device=dev)
+        out_mask = torch.empty(B_eff, max_len, dtype=torch.uint8, device=dev)
+        out_pos = torch.empty(B_eff, max_len, dtype=torch.int64, device=dev)
+        if total_rows > 0:
+            _lib.check(lib.radvlm_merge_splice(
+                features.data_ptr(), newline.data_ptr(), embed.detach().data_ptr(), _DT[embed.dtype], H,
+                enc.packed(dev).tokens_per_tile, enc.packed(dev).patches_per_side,
+                ids_dev.data_ptr(), None if labels_dev is None else labels_dev.data_ptr(),
+                tables.data_ptr() + off_txt, tables.data_ptr(), plan.n_segments,
+                tables.data_ptr() + off_img, len(tile_counts), total_rows,
+                out.data_ptr(), out_labels.data_ptr(), out_mask.data_ptr(), out_pos.data_ptr(), IGNORE_INDEX,
+                torch.cuda.current_stream(dev).cuda_stream))
+
+    # ---- return contract (llava_arch.py:533-555)
+    new_labels = None if _labels is None else out_labels.to(_labels.dtype)
+    if _attention_mask is None:
+        new_mask = None
+    else:
+        new_mask = out_mask.bool().to(dtype=_attention_mask.dtype)
+    new_pos = None if _position_ids is None else out_pos.to(_position_ids.dtype)
+    if getattr(self.config, "use_pos_skipping", False) and self.training:
+        new_pos = torch.arange(out.size(1), device=out.device).unsqueeze(0).to(out.device)
+        split_position = random.randint(0, out.size(1))
+        left_add = random.randint(0, self.config.pos_skipping_range)
+        right_add = random.randint(left_add, self.config.pos_skipping_range)
+        new_pos[:, :split_position] += left_add
+        new_pos[:, split_position:] += right_add
+    return None, new_pos, new_mask, past_key_values, out, new_labels
+
+
+class B200LlavaMetaForCausalLM:
+    """Mixin with the reference's method names; put it BEFORE ``LlavaMetaForCausalLM`` in the MRO."""
+
+    encode_images = encode_images
+    prepare_inputs_labels_for_multimodal = prepare_inputs_labels_for_multimodal
+
+
+def attach(model):
+    """Monkey-patch one model instance (any class built on LlavaMetaForCausalLM) to use the B200 path."""
+    import types
+
+    model.encode_images = types.MethodType(encode_images, model)
+    model.prepare_inputs_labels_for_multimodal = types.MethodType(prepare_inputs_labels_for_multimodal, model)
+    return model
