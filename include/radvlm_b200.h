@@ -38,6 +38,14 @@ extern "C" {
 const char* radvlm_last_error(void);
 int radvlm_abi_version(void);
 
+/* Optional device timing per kernel class (CUDA events on the launch stream; off by default).
+ * classes: 0 gemm, 1 attention, 2 layernorm, 3 misc (im2col/cast/memset), 4 preprocess, 5 merge_splice.
+ * radvlm_profile_read waits for the recorded events, returns summed milliseconds and kernel-launch
+ * counts per class, and clears the record list. */
+#define RADVLM_PROF_NUM_CLASSES 6
+int radvlm_profile_enable(int on);
+int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_classes);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM building block:  out[M,N] = A[M,K](bf16) * W[N,K]^T(bf16)  (+ fused epilogue), fp32 accumulate
  * in TMEM (tcgen05.mma, TMA-fed).  Replaces nn.Linear.forward at

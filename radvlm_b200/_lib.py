@@ -105,6 +105,8 @@ _pi = C.POINTER(C.c_int)
 SIGNATURES = {
     "radvlm_last_error": (C.c_char_p, []),
     "radvlm_abi_version": (_i, []),
+    "radvlm_profile_enable": (_i, [_i]),
+    "radvlm_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int64), _i]),
     "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
@@ -145,6 +147,22 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+PROF_CLASSES = ("gemm", "attention", "layernorm", "misc", "preprocess", "merge_splice")
+
+
+def profile_enable(on: bool):
+    load().radvlm_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> ({class: milliseconds}, {class: kernel launches}) since the previous read."""
+    n = len(PROF_CLASSES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int64 * n)()
+    check(load().radvlm_profile_read(ms, cnt, n))
+    return dict(zip(PROF_CLASSES, [float(v) for v in ms])), dict(zip(PROF_CLASSES, [int(v) for v in cnt]))
 
 
 def last_error() -> str:

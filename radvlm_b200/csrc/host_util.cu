@@ -2,6 +2,9 @@
 
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 namespace rv {
 
 static thread_local char g_err[512] = "";
@@ -96,7 +99,68 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return RADVLM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// profiling
+// ---------------------------------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t beg, end;
+  int cls;
+  int launches;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;      // recorded scopes since the last reset
+static std::vector<ProfRec> g_prof_pool; // reusable event pairs
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(int cls, cudaStream_t stream, int launches) : idx_(-1), stream_(stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (!g_prof_pool.empty()) {
+    r = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&r.beg) != cudaSuccess || cudaEventCreate(&r.end) != cudaSuccess) return;
+  }
+  r.cls = cls;
+  r.launches = launches;
+  cudaEventRecord(r.beg, stream);
+  g_prof.push_back(r);
+  idx_ = static_cast<int>(g_prof.size()) - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[idx_].end, stream_);
+}
+
 }  // namespace rv
+
+extern "C" int radvlm_profile_enable(int on) {
+  rv::g_prof_on = (on != 0);
+  return RADVLM_OK;
+}
+
+// Sums the recorded scopes per class (waits for their completion), then clears the record list.
+extern "C" int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_classes) {
+  std::lock_guard<std::mutex> lk(rv::g_prof_mu);
+  for (int i = 0; i < n_classes; ++i) {
+    if (ms_per_class) ms_per_class[i] = 0.f;
+    if (launches_per_class) launches_per_class[i] = 0;
+  }
+  for (auto& r : rv::g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.end) == cudaSuccess) cudaEventElapsedTime(&ms, r.beg, r.end);
+    if (r.cls >= 0 && r.cls < n_classes) {
+      if (ms_per_class) ms_per_class[r.cls] += ms;
+      if (launches_per_class) launches_per_class[r.cls] += r.launches;
+    }
+    rv::g_prof_pool.push_back(r);
+  }
+  rv::g_prof.clear();
+  return RADVLM_OK;
+}
 
 extern "C" const char* radvlm_last_error(void) { return rv::last_error(); }
 extern "C" int radvlm_abi_version(void) { return 1; }

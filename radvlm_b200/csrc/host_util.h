@@ -42,4 +42,22 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
                       uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                       CUtensorMapSwizzle swizzle);
 
+// Optional per-kernel-class device timing (CUDA events recorded on the launch stream).  Off by default;
+// bench.py turns it on to report the live duration / launch count of each kernel class.
+enum ProfClass : int {
+  PROF_GEMM = 0,
+  PROF_ATTENTION = 1,
+  PROF_LAYERNORM = 2,
+  PROF_MISC = 3,        // im2col, cast, padding memsets
+  PROF_PREPROCESS = 4,
+  PROF_MERGE_SPLICE = 5,
+  PROF_NUM_CLASSES = 6
+};
+struct ProfScope {
+  ProfScope(int cls, cudaStream_t stream, int launches = 1);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t stream_;
+};
+
 }  // namespace rv

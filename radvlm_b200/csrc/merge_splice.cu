@@ -248,6 +248,7 @@ extern "C" int radvlm_merge_splice(const void* features, const void* newline, co
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;  // 8 resident CTAs per SM
   const int blocks = static_cast<int>(want < cap ? want : cap);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_MERGE_SPLICE, s);
   switch (dtype) {
     case RADVLM_DT_F32: merge_splice_kernel<float><<<blocks, threads, 0, s>>>(a); break;
     case RADVLM_DT_BF16: merge_splice_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(a); break;

@@ -343,6 +343,7 @@ extern "C" int radvlm_preprocess_anyres(const uint8_t* src, const radvlm_preproc
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* scr = static_cast<uint8_t*>(scratch);
+  ProfScope ps(PROF_PREPROCESS, s, 3);
   resample_coeffs_kernel<<<dim3((max_out + 63) / 64, 4, n_images), 64, 0, s>>>(images_dev, scr, tile_size);
   RV_CUDA(cudaGetLastError());
   resample_h_kernel<<<dim3((max_out + 127) / 128, max_h, n_images * 2), 128, 0, s>>>(images_dev, src, scr,

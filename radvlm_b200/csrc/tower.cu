@@ -65,13 +65,17 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   int st;
 
   // padding of q/k/vt must be zero (never written by the QKV epilogue)
-  RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
-  RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
-  RV_CUDA(cudaMemsetAsync(vt, 0, L.qkv_bytes, stream));
+  {
+    ProfScope ps(PROF_MISC, stream, 0);
+    RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
+    RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
+    RV_CUDA(cudaMemsetAsync(vt, 0, L.qkv_bytes, stream));
+  }
 
   // --- embeddings: patch GEMM + bias + position embedding (siglip_encoder.py:169-174)
+  { ProfScope ps(PROF_MISC, stream);
   st = im2col_launch(pixels, pixel_dtype, xn, n_tiles, tw->channels, tw->image_size, tw->patch_size,
-                     tw->patch_k_pad, stream);
+                     tw->patch_k_pad, stream); }
   if (st) return st;
   {
     GemmArgs a{};
@@ -79,7 +83,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     a.bias = tw->patch_b;
     a.out = hidden; a.ldo = D;
     a.aux = tw->pos_embed; a.aux_period = L.T;
-    st = gemm_dispatch(xn, tw->patch_k_pad, tw->patch_w, tw->patch_k_pad, a, EPI_POS_F32, 0, stream);
+    { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, tw->patch_k_pad, tw->patch_w, tw->patch_k_pad, a, EPI_POS_F32, 0, stream); }
     if (st) return st;
   }
 
@@ -87,7 +91,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   for (int l = 0; l < tw->num_layers; ++l) {
     const radvlm_vit_layer_weights& w = tw->layers[l];
     // x = x + out_proj(attn(LN1(x)))
-    st = layernorm_launch(hidden, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream);
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(hidden, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
@@ -97,28 +101,28 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.k = static_cast<__nv_bfloat16*>(k);
       a.vt = static_cast<__nv_bfloat16*>(vt);
       a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
-      st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream);
+      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
-    st = attention_launch(q, k, vt, xn, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream);
+    { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, xn, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
     if (st) return st;
     {
       GemmArgs a{};
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
       a.out = hidden; a.ldo = D; a.aux = hidden;
-      st = gemm_dispatch(xn, D, w.out_w, D, a, EPI_RESID_F32, 0, stream);
+      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
-    st = layernorm_launch(hidden, w.ln2_gamma, w.ln2_beta, xn, M, D, tw->ln_eps, stream);
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(hidden, w.ln2_gamma, w.ln2_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
       a.M = M; a.N = I; a.K = D;
       a.bias = w.fc1_b;
       a.out = h1; a.ldo = I;
-      st = gemm_dispatch(xn, D, w.fc1_w, D, a, EPI_GELU_TANH_BF16, 0, stream);
+      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
     {
@@ -126,7 +130,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
       a.out = hidden; a.ldo = D; a.aux = hidden;
-      st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream);
+      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
   }
@@ -138,14 +142,15 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
   RV_CHECK_ARG(out_dtype == RADVLM_DT_BF16 || out_dtype == RADVLM_DT_F32,
                "projector: out_dtype must be bf16 or f32");
   RV_CHECK_ARG((pw->in_dim % 8) == 0 && (pw->hidden % 8) == 0, "projector: dims must be multiples of 8");
-  int st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream);
+  int st;
+  { ProfScope ps(PROF_MISC, stream); st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream); }
   if (st) return st;
   {
     GemmArgs a{};
     a.M = rows; a.N = pw->hidden; a.K = pw->in_dim;
     a.bias = pw->b1;
     a.out = h1; a.ldo = pw->hidden;
-    st = gemm_dispatch(xn, pw->in_dim, pw->w1, pw->in_dim, a, EPI_GELU_ERF_BF16, 0, stream);
+    { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, pw->in_dim, pw->w1, pw->in_dim, a, EPI_GELU_ERF_BF16, 0, stream); }
     if (st) return st;
   }
   {
@@ -153,8 +158,8 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
     a.M = rows; a.N = pw->hidden; a.K = pw->hidden;
     a.bias = pw->b2;
     a.out = out; a.ldo = pw->hidden;
-    st = gemm_dispatch(h1, pw->hidden, pw->w2, pw->hidden, a,
-                       out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32, 0, stream);
+    { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(h1, pw->hidden, pw->w2, pw->hidden, a,
+                       out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32, 0, stream); }
     if (st) return st;
   }
   return RADVLM_OK;

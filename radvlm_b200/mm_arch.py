@@ -126,8 +126,6 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         modalities = [modalities]
     if any(m == "video" for m in modalities):
         raise NotImplementedError("radvlm_b200: the video / get_2dPool branch is out of scope (SURVEY.md section 8(f) row 4)")
-    _check_forward_only(self)
-    enc = _encoder_for(self)
     lib = _lib.load()
 
     # ---- encode all tiles of all images in one call (llava_arch.py:261-279)
@@ -142,8 +140,12 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         concat_images = images
         tile_counts = [1] * int(images.shape[0])
         flat_batch = True
-    features = enc.encode_images(concat_images)            # [tiles, T, H]
-    dev = features.device
+    features = self.encode_images(concat_images)            # [tiles, T, H]  (llava_arch.py:279)
+    embed = self.get_model().embed_tokens.weight
+    dev = embed.device
+    if dev.type != "cuda":
+        raise RuntimeError("radvlm_b200: embed_tokens lives on %s; the merge/splice kernel has no CPU fallback" % dev)
+    features = features.to(device=dev, dtype=embed.dtype).contiguous()
     if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
         raise NotImplementedError
     merge_table, image_tokens = _merge_table(self, tile_counts, image_sizes, flat_batch)
@@ -161,9 +163,6 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         plan = planner.plan_splice(ids_host[:B_eff], None if mask_host is None else mask_host[:B_eff],
                                    image_tokens, max_length, left_pad)
     max_len = plan.max_len
-    embed = self.get_model().embed_tokens.weight
-    if features.dtype != embed.dtype:
-        features = features.to(embed.dtype)
     newline = getattr(self.get_model(), "image_newline", None)
     if newline is None:
         newline = torch.zeros(embed.shape[1], dtype=embed.dtype, device=dev)
@@ -195,7 +194,7 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         if total_rows > 0:
             _lib.check(lib.radvlm_merge_splice(
                 features.data_ptr(), newline.data_ptr(), embed.detach().data_ptr(), _DT[embed.dtype], H,
-                enc.packed(dev).tokens_per_tile, enc.packed(dev).patches_per_side,
+                vision_tower.num_patches_per_side ** 2, vision_tower.num_patches_per_side,
                 ids_dev.data_ptr(), None if labels_dev is None else labels_dev.data_ptr(),
                 tables.data_ptr() + off_txt, tables.data_ptr(), plan.n_segments,
                 tables.data_ptr() + off_img, len(tile_counts), total_rows,
