@@ -64,6 +64,10 @@ int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int
                      const float* bias, int epilogue, void* out, int64_t ldo, const float* aux,
                      int aux_period, int block_n /* 0 = auto, else 128|192|256 */, void* stream);
 
+/* Tile-shape policy of the GEMM: 0 = auto (CTA pairs, tcgen05 cta_group::2, 256 x BN tiles when M >= 512),
+ * 1 = force single-CTA 128 x BN tiles, 2 = force CTA-pair tiles.  Process-wide; meant for tests / tuning. */
+int radvlm_gemm_set_mode(int mode);
+
 /* QKV projection with the head-split scatter fused into the epilogue
  * (siglip_encoder.py:207-213: three Linear + view/transpose).  W is the row-concatenation
  * [q_proj; k_proj; v_proj] = [3*heads*hd, K]; bias likewise.  Outputs (bf16):

@@ -1,4 +1,5 @@
 // C-ABI launchers for the tcgen05 GEMM (see gemm_sm100.cuh).
+#include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -22,6 +23,36 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return RADVLM_OK;
 }
 
+template <int BN, int EPI>
+static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                             cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    RV_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EPI>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_tiles = ((args.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((args.N + BN - 1) / BN);
+  const int pairs = device_sm_count() / 2;
+  const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
+  gemm_bf16_tn_2cta_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+template <int EPI>
+static int launch_gemm2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                           cudaStream_t stream) {
+  switch (bn) {
+    case 128: return launch_gemm2_inst<128, EPI>(ta, tb, args, stream);
+    case 192: return launch_gemm2_inst<192, EPI>(ta, tb, args, stream);
+    case 256: return launch_gemm2_inst<256, EPI>(ta, tb, args, stream);
+  }
+  set_error("block_n must be 128, 192 or 256 (got %d)", bn);
+  return RADVLM_ERR_BAD_ARGUMENT;
+}
+
 template <int EPI>
 static int launch_gemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
                           cudaStream_t stream) {
@@ -35,9 +66,11 @@ static int launch_gemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, 
 }
 
 // Wave-quantisation aware tile-width choice: cost = waves * BN (MMA cycles per K step scale with BN).
-int gemm_pick_block_n(int M, int N) {
-  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-  const int num_m = (M + kGemmBM - 1) / kGemmBM;
+static int g_gemm_mode = 0;  // 0 auto, 1 force single-CTA tiles, 2 force CTA-pair tiles
+
+int gemm_pick_block_n(int M, int N, int cta_group) {
+  const int sms = (device_sm_count() > 0 ? device_sm_count() : 148) / cta_group;
+  const int num_m = (M + cta_group * kGemmBM - 1) / (cta_group * kGemmBM);
   int best = 256;
   long best_cost = -1;
   const int cands[3] = {256, 192, 128};
@@ -45,7 +78,8 @@ int gemm_pick_block_n(int M, int N) {
     const int bn = cands[i];
     const long tiles = static_cast<long>(num_m) * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * bn;
+    // per-tile cost ~ BN, penalised for narrow tiles (more L2->SMEM bytes per FLOP, the binding limit)
+    const long cost = waves * bn * (bn == 256 ? 100 : (bn == 192 ? 108 : 135));
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = bn;
@@ -62,15 +96,30 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   RV_CHECK_ARG(args.M > 0 && args.N > 0 && args.K > 0, "gemm: bad shape M=%d N=%d K=%d", args.M,
                args.N, args.K);
   RV_CHECK_ARG(lda >= args.K && ldw >= args.K, "gemm: row pitch smaller than K");
-  const int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N);
+  // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs
+  const bool pair = g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
+  const int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N, pair ? 2 : 1);
   CUtensorMap ta, tb;
   st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M),
                          static_cast<uint64_t>(lda) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
-                         static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(bn),
+                         static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(pair ? bn / 2 : bn),
                          CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
+  if (pair) {
+    switch (epilogue) {
+      case EPI_BIAS_BF16: return launch_gemm2_bn<EPI_BIAS_BF16>(bn, ta, tb, args, stream);
+      case EPI_GELU_TANH_BF16: return launch_gemm2_bn<EPI_GELU_TANH_BF16>(bn, ta, tb, args, stream);
+      case EPI_GELU_ERF_BF16: return launch_gemm2_bn<EPI_GELU_ERF_BF16>(bn, ta, tb, args, stream);
+      case EPI_RESID_F32: return launch_gemm2_bn<EPI_RESID_F32>(bn, ta, tb, args, stream);
+      case EPI_POS_F32: return launch_gemm2_bn<EPI_POS_F32>(bn, ta, tb, args, stream);
+      case EPI_QKV_SPLIT: return launch_gemm2_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
+      case EPI_BIAS_F32: return launch_gemm2_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
+    }
+    set_error("gemm: unknown epilogue %d", epilogue);
+    return RADVLM_ERR_BAD_ARGUMENT;
+  }
   switch (epilogue) {
     case EPI_BIAS_BF16: return launch_gemm_bn<EPI_BIAS_BF16>(bn, ta, tb, args, stream);
     case EPI_GELU_TANH_BF16: return launch_gemm_bn<EPI_GELU_TANH_BF16>(bn, ta, tb, args, stream);
@@ -85,6 +134,15 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 }
 
 }  // namespace rv
+
+extern "C" int radvlm_gemm_set_mode(int mode) {
+  if (mode < 0 || mode > 2) {
+    rv::set_error("gemm mode must be 0 (auto), 1 (single-CTA tiles) or 2 (CTA-pair tiles)");
+    return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  rv::g_gemm_mode = mode;
+  return RADVLM_OK;
+}
 
 extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N,
                                 int K, const float* bias, int epilogue, void* out, int64_t ldo,

@@ -20,7 +20,8 @@ namespace rv {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kGemmEpiWarps = 8;   // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 
 template <int BN>
 struct GemmCfg {
@@ -149,6 +150,21 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
   }
 }
 
+// Drain NCOLS accumulator columns of this thread's row: two tcgen05.ld in flight per wait.
+template <int EPI, int NCOLS>
+__device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row) {
+  static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
+#pragma unroll 1
+  for (int c = 0; c < NCOLS; c += 64) {
+    uint32_t r0[32], r1[32];
+    tmem_ld_x32(t_row + c, r0);
+    if (c + 32 < NCOLS) tmem_ld_x32(t_row + c + 32, r1);
+    tmem_wait_ld();
+    gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
+    if (c + 32 < NCOLS) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -183,7 +199,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), kGemmEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -259,6 +275,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else {
     // ===================== epilogue (4 warps) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -268,14 +285,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const int row = m_blk * kGemmBM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c, r);
-        tmem_wait_ld();
-        gemm_epilogue_chunk<EPI>(args, row, n_blk * BN + c, r);
-      }
+                             static_cast<uint32_t>(acc * BN + half * (BN / 2));
+      const int col_base = n_blk * BN + half * (BN / 2);
+      gemm_epilogue_drain<EPI, BN / 2>(args, row, col_base, t_row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

@@ -10,7 +10,7 @@ namespace rv {
 
 int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
                   int epilogue, int block_n, cudaStream_t stream);
-int gemm_pick_block_n(int M, int N);
+int gemm_pick_block_n(int M, int N, int cta_group);
 int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,

@@ -45,44 +45,42 @@ def preprocess_anyres_batch(images: Sequence, grid_pinpoints, device=None, dtype
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("radvlm_b200: preprocessing runs on a CUDA device only (got %s); no CPU fallback" % device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     srcs = [_to_uint8_hwc(im) for im in images]
     n = len(srcs)
     plans, descs = [], (_lib.PreprocessImage * n)()
-    src_off = scratch_off = tile_base = 0
+    scratch_off = tile_base = 0
     sizes, splits = [], []
-    for i, t in enumerate(srcs):
-        H, W = int(t.shape[0]), int(t.shape[1])
-        ch = 1 if t.dim() == 2 else 3
-        p = planner.plan_image((W, H), grid_pinpoints, tile_size, patches_per_side, max_num_patches or 0)
-        plans.append(p)
-        d = descs[i]
-        d.src_offset, d.scratch_offset = src_off, scratch_off
-        d.width, d.height, d.channels = W, H, ch
-        d.grid_w, d.grid_h = p.grid_w, p.grid_h
-        d.resized_w, d.resized_h, d.paste_x, d.paste_y = p.resized_w, p.resized_h, p.paste_x, p.paste_y
-        d.tile_base = tile_base
-        src_off += (H * W * ch + 15) // 16 * 16
-        scratch_off += lib.radvlm_preprocess_scratch_bytes(W, H, ch, p.resized_w, p.resized_h, tile_size)
-        tile_base += p.n_tiles
-        sizes.append((W, H))
-        splits.append(p.n_tiles)
-    # one staged host buffer: [image bytes | descriptor table]
-    desc_bytes = C.sizeof(descs)
-    host = torch.empty(src_off + desc_bytes, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else \
-        torch.empty(src_off + desc_bytes, dtype=torch.uint8)
-    for d, t in zip(descs, srcs):
-        if t.device.type == "cpu":
-            host[d.src_offset: d.src_offset + t.numel()] = t.reshape(-1)
-    host[src_off:] = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
     with torch.cuda.device(device):
-        dev_buf = host.to(device, non_blocking=True)
-        for d, t in zip(descs, srcs):  # images that already live on the device
-            if t.device.type == "cuda":
-                dev_buf[d.src_offset: d.src_offset + t.numel()] = t.reshape(-1).to(device)
+        # host images go H2D straight from their own (ideally pinned) storage; device images are used in place
+        dev_srcs = [t if t.device == device else t.to(device, non_blocking=True) for t in srcs]
+        base_ptr = min(t.data_ptr() for t in dev_srcs)
+        for i, t in enumerate(dev_srcs):
+            H, W = int(t.shape[0]), int(t.shape[1])
+            ch = 1 if t.dim() == 2 else 3
+            p = planner.plan_image((W, H), grid_pinpoints, tile_size, patches_per_side, max_num_patches or 0)
+            plans.append(p)
+            d = descs[i]
+            d.src_offset, d.scratch_offset = t.data_ptr() - base_ptr, scratch_off
+            d.width, d.height, d.channels = W, H, ch
+            d.grid_w, d.grid_h = p.grid_w, p.grid_h
+            d.resized_w, d.resized_h, d.paste_x, d.paste_y = p.resized_w, p.resized_h, p.paste_x, p.paste_y
+            d.tile_base = tile_base
+            scratch_off += lib.radvlm_preprocess_scratch_bytes(W, H, ch, p.resized_w, p.resized_h, tile_size)
+            tile_base += p.n_tiles
+            sizes.append((W, H))
+            splits.append(p.n_tiles)
+        desc_host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            desc_host = desc_host.pin_memory()
+        desc_dev = desc_host.to(device, non_blocking=True)
         scratch = torch.empty(max(scratch_off, 16), dtype=torch.uint8, device=device)
         tiles = torch.empty(tile_base, 3, tile_size, tile_size, dtype=dtype, device=device)
         _lib.check(lib.radvlm_preprocess_anyres(
-            dev_buf.data_ptr(), dev_buf.data_ptr() + src_off, descs, n, tile_size, tiles.data_ptr(), _DT[dtype],
+            base_ptr, desc_dev.data_ptr(), descs, n, tile_size, tiles.data_ptr(), _DT[dtype],
             scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream(device).cuda_stream))
     return tiles, sizes, splits, plans
 

@@ -174,8 +174,20 @@ int main(int argc, char** argv) {
     cases.push_back({29160, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 256});
     cases.push_back({29160, 1152, 4304, RADVLM_EPI_RESID_F32, 0});
   }
+  if (argc > 2 && !strcmp(argv[1], "perf")) {  // ./test_gemm perf <mode> : the three big shapes only (ncu target)
+    radvlm_gemm_set_mode(atoi(argv[2]));
+    int f = 0;
+    f += run_case({29160, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 256});
+    f += run_case({29160, 1152, 4304, RADVLM_EPI_RESID_F32, 0});
+    f += run_case({29160, 3456, 1152, RADVLM_EPI_BIAS_BF16, 256});
+    return f;
+  }
   int fails = 0;
-  for (const auto& c : cases) fails += run_case(c);
+  for (int mode = 1; mode <= 2; ++mode) {
+    radvlm_gemm_set_mode(mode);
+    printf("---- GEMM mode %d (%s) ----\n", mode, mode == 1 ? "single-CTA 128xBN tiles" : "CTA-pair 256xBN tiles");
+    for (const auto& c : cases) fails += run_case(c);
+  }
   printf("%s (%d failing cases)\n", fails ? "GEMM TEST FAILED" : "GEMM TEST PASSED", fails);
   return fails ? 1 : 0;
 }
