@@ -39,10 +39,11 @@ const char* radvlm_last_error(void);
 int radvlm_abi_version(void);
 
 /* Optional device timing per kernel class (CUDA events on the launch stream; off by default).
- * classes: 0 gemm, 1 attention, 2 layernorm, 3 misc (im2col/cast/memset), 4 preprocess, 5 merge_splice.
+ * classes: 0 gemm (patch embed + projector), 1 attention, 2 layernorm, 3 misc (im2col/cast/memset),
+ * 4 preprocess, 5 merge_splice, 6 gemm qkv, 7 gemm out_proj, 8 gemm fc1, 9 gemm fc2.
  * radvlm_profile_read waits for the recorded events, returns summed milliseconds and kernel-launch
  * counts per class, and clears the record list. */
-#define RADVLM_PROF_NUM_CLASSES 6
+#define RADVLM_PROF_NUM_CLASSES 10
 int radvlm_profile_enable(int on);
 int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_classes);
 

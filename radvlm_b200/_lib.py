@@ -150,7 +150,8 @@ def load():
     return lib
 
 
-PROF_CLASSES = ("gemm", "attention", "layernorm", "misc", "preprocess", "merge_splice")
+PROF_CLASSES = ("gemm_patch_proj", "attention", "layernorm", "misc", "preprocess", "merge_splice",
+                "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2")
 
 
 def profile_enable(on: bool):

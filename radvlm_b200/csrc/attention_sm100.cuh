@@ -11,7 +11,7 @@
 // One CTA = 128 query rows of one (tile, head).  Warp roles: warp0 TMA producer, warp1 tcgen05.mma
 // issuer, warps 2..5 softmax (one query row per thread).  S = Q K_j^T (128x128 fp32) and the running
 // O (128x80 fp32) live in TMEM; P_j is written to shared memory as bf16 in the 128B-swizzled K-major
-// layout and fed back as the A operand of O += P_j V_j.  Online softmax with lazy rescale: the
+// layout and fed back as the A operand of O += P_j V_j.  Online softmax with lazy, deferred rescale: the
 // reference maximum only moves when the row maximum grows by more than 2^8, so the TMEM O rescale
 // (tcgen05.ld -> mul -> tcgen05.st) is rare.  Two CTAs are resident per SM (256 TMEM columns and
 // ~93 KB shared memory each) so one CTA's softmax overlaps the other's MMAs.
@@ -158,8 +158,14 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // row within the query block
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m_ref = -INFINITY;  // reference maximum (scaled, log2 domain) used for the exponentials
+    // Online softmax, single pass over each S block in 32-column chunks with the next tcgen05.ld in flight:
+    // exponentials use the RUNNING reference m_ref (log2 domain); when a block's maximum exceeds it by more than
+    // 2^8 the reference moves and the O / l rescale is deferred to the start of the next block (after that
+    // block's PV has drained).  The result is exact: O and l always share one reference.
+    float m_ref = 0.f;
     float l_sum = 0.f;
+    float pend_alpha = 1.f;
+    bool pend = false;
     const float sc = args.scale_log2e;
     const uint32_t p_row = sP + static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
@@ -168,52 +174,12 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const uint32_t par = static_cast<uint32_t>(j & 1);
       mbar_wait(bar_s, par);
       tc_fence_after();
-      uint32_t s[128];
-      tmem_ld_x32(tS + lane_off + 0, s + 0);
-      tmem_ld_x32(tS + lane_off + 32, s + 32);
-      tmem_ld_x32(tS + lane_off + 64, s + 64);
-      tmem_ld_x32(tS + lane_off + 96, s + 96);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(bar_sfree);
-
-      const int valid = args.seq - j * kAttnBKV;  // keys with index >= valid are padding
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) {
-        float v = __uint_as_float(s[i]) * sc;
-        if (i >= valid) v = -INFINITY;
-        s[i] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
-      }
-      float alpha = 1.f;
-      bool need = false;
-      if (mx > m_ref + kAttnRescaleThreshold) {
-        alpha = exp2f(m_ref - mx);  // 0 on the first block (m_ref = -inf)
-        m_ref = mx;
-        need = (j > 0);
-      }
-      float sum = 0.f;
-      // previous PV must be complete before P is overwritten / O is rescaled
-      if (j > 0) mbar_wait(bar_o, par ^ 1u);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = exp2f(__uint_as_float(s[c * 8 + i]) - m_ref);
-          sum += p[i];
-        }
-        const uint32_t atom = static_cast<uint32_t>(c >> 3);
-        const uint32_t chunk = static_cast<uint32_t>(c & 7) ^ sw;
-        const uint32_t addr = p_row + atom * 16384u + chunk * 16u;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                     "r"(pack_bf16x2(p[0], p[1])), "r"(pack_bf16x2(p[2], p[3])),
-                     "r"(pack_bf16x2(p[4], p[5])), "r"(pack_bf16x2(p[6], p[7]))
-                     : "memory");
-      }
-      l_sum = l_sum * alpha + sum;
-      if (__any_sync(0xffffffffu, need)) {
+      uint32_t sbuf[2][32];
+      tmem_ld_x32(tS + lane_off, sbuf[0]);
+      bool waited_o = (j == 0);
+      if (__any_sync(0xffffffffu, pend)) {  // deferred rescale (rare): needs PV_{j-1} complete
+        mbar_wait(bar_o, par ^ 1u);
+        waited_o = true;
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < kAttnHdPad / 16; ++c) {
@@ -221,10 +187,70 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tmem_ld_x16(tO + lane_off + c * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * pend_alpha);
           tmem_st_x16(tO + lane_off + c * 16, o);
         }
         tmem_wait_st();
+        l_sum *= pend_alpha;
+        pend_alpha = 1.f;
+        pend = false;
+      }
+      const int valid = args.seq - j * kAttnBKV;  // keys >= valid are padding (last block only)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t* cur = sbuf[c & 1];
+        tmem_wait_ld();
+        if (c < 3) {
+          tmem_ld_x32(tS + lane_off + 32 * (c + 1), sbuf[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          mbar_arrive(bar_sfree);  // S_j is entirely in registers: the MMA warp may overwrite it
+        }
+        if (valid < kAttnBKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) cur[i] = 0xFF800000u;  // -inf
+        }
+        if (j == 0 && c == 0) {  // initial reference: maximum of the first 32 keys
+          float m0[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m0[i] = __uint_as_float(cur[i]);
+#pragma unroll
+          for (int i = 4; i < 32; ++i) m0[i & 3] = fmaxf(m0[i & 3], __uint_as_float(cur[i]));
+          m_ref = fmaxf(fmaxf(m0[0], m0[1]), fmaxf(m0[2], m0[3])) * sc;
+        }
+        const float neg_m = -m_ref;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float v0 = __uint_as_float(cur[i]), v1 = __uint_as_float(cur[i + 1]);
+          mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(v0, v1));
+          // p = 2^(s * scale*log2e - m_ref): one FFMA + one MUFU.EX2 (argument clamped against overflow)
+          const float a0 = fminf(fmaf(v0, sc, neg_m), 100.f), a1 = fminf(fmaf(v1, sc, neg_m), 100.f);
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(a0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(a1));
+          sum4[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        if (c == 0 && !waited_o) mbar_wait(bar_o, par ^ 1u);  // PV_{j-1} done: the P buffer may be overwritten
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ sw;
+          const uint32_t addr = p_row + static_cast<uint32_t>(c >> 1) * 16384u + unit * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u + 0]),
+                       "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                       : "memory");
+        }
+      }
+      l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;
+      if (mx > m_ref + kAttnRescaleThreshold) {
+        pend_alpha = exp2f(m_ref - mx);
+        m_ref = mx;
+        pend = true;
       }
       fence_proxy_async_smem();
       tc_fence_before();

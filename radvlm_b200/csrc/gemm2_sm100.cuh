@@ -82,9 +82,9 @@ struct Gemm2Cfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;   // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;  // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 8 : (BN <= 192 ? 7 : 6);
+  static constexpr int kStages = (BN <= 128) ? 8 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kGemmStagingBytes + 1024 + 256;
 };
 
 template <int BN, int EPI>
@@ -97,7 +97,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t stage_base = smem_base + kStages * Cfg::kStageBytes;  // epilogue transpose buffers
+  const uint32_t bar_base = stage_base + kGemmStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -215,7 +216,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
-      gemm_epilogue_drain<EPI, BN / 2>(args, row, n_blk * BN + half * (BN / 2), t_row);
+      gemm_epilogue_drain<EPI, BN / 2>(args, row, n_blk * BN + half * (BN / 2), t_row,
+                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -23,14 +23,18 @@ constexpr int kGemmBK = 64;
 constexpr int kGemmEpiWarps = 8;   // two warps per TMEM lane quadrant, each takes half of the columns
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 
+constexpr int kGemmStageWarpBytes = 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
+constexpr int kGemmStagingBytes = kGemmEpiWarps * kGemmStageWarpBytes;
+
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kGemmStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int EPI>
@@ -150,18 +154,141 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coalesced epilogues.  tcgen05.ld hands each thread one accumulator ROW; writing that straight to global
+// memory makes every 16-byte access of a warp hit 32 different rows (32 LSU wavefronts per instruction),
+// which made the fp32 residual epilogue slower than the K=1152 main loop.  Instead each epilogue warp
+// transposes its 32 x 128 B block through a private XOR-swizzled shared-memory buffer and then touches
+// global memory with 8 lanes per row (4 full 128-byte lines per instruction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_store_row(uint32_t stage, int lane, const uint32_t* w /*32 words*/) {
+  const uint32_t my = stage + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = my + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * j]), "r"(w[4 * j + 1]),
+                 "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                 : "memory");
+  }
+}
+__device__ __forceinline__ uint4 stage_load_vec(uint32_t stage, int rr, int v) {
+  uint4 x;
+  const uint32_t addr = stage + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(v ^ (rr & 7)) << 4);
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(addr));
+  return x;
+}
+
+// fp32 outputs (EPI_RESID_F32 / EPI_POS_F32 / EPI_BIAS_F32): one 32-column chunk, requires N % 4 == 0
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc,
+                                                         uint32_t stage, int lane) {
+  stage_store_row(stage, lane, acc);
+  __syncwarp();
+  const int v = lane & 7;
+  const int gcol = col0 + 4 * v;
+  if (gcol < a.N) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(a.bias + gcol));
+    float4 xr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grow = row0 + i * 4 + (lane >> 3);
+      xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < a.M) {
+        if constexpr (EPI == EPI_RESID_F32)
+          xr[i] = *reinterpret_cast<const float4*>(a.aux + static_cast<size_t>(grow) * a.ldo + gcol);
+        if constexpr (EPI == EPI_POS_F32)
+          xr[i] = __ldg(reinterpret_cast<const float4*>(a.aux + static_cast<size_t>(grow % a.aux_period) * a.N + gcol));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      const int grow = row0 + rr;
+      if (grow < a.M) {
+        const uint4 t = stage_load_vec(stage, rr, v);
+        float4 o;
+        o.x = __uint_as_float(t.x) + b.x + xr[i].x;
+        o.y = __uint_as_float(t.y) + b.y + xr[i].y;
+        o.z = __uint_as_float(t.z) + b.z + xr[i].z;
+        o.w = __uint_as_float(t.w) + b.w + xr[i].w;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol) = o;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// bf16 outputs (EPI_BIAS_BF16 / EPI_GELU_*): two 32-column chunks = 64 columns = 128 B per row, requires N % 8 == 0
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
+                                                          const uint32_t* acc1, uint32_t stage, int lane) {
+  uint32_t pk[32];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t* acc = h ? acc1 : acc0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + 32 * h + 4 * j;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
+      float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
+      if constexpr (EPI == EPI_GELU_TANH_BF16) {
+        v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
+      }
+      if constexpr (EPI == EPI_GELU_ERF_BF16) {
+        v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
+      }
+      pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
+      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
+    }
+  }
+  stage_store_row(stage, lane, pk);
+  __syncwarp();
+  const int v = lane & 7;
+  const int gcol = col0 + 8 * v;
+  if (gcol < a.N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      const int grow = row0 + rr;
+      if (grow < a.M) {
+        const uint4 t = stage_load_vec(stage, rr, v);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol) = t;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // Drain NCOLS accumulator columns of this thread's row: two tcgen05.ld in flight per wait.
 template <int EPI, int NCOLS>
-__device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row) {
+__device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row,
+                                                    uint32_t stage, int lane) {
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
+  constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32);
+  constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16);
+  const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
+  const int row0 = row - lane;
 #pragma unroll 1
   for (int c = 0; c < NCOLS; c += 64) {
     uint32_t r0[32], r1[32];
+    const bool two = (c + 32 < NCOLS);
     tmem_ld_x32(t_row + c, r0);
-    if (c + 32 < NCOLS) tmem_ld_x32(t_row + c + 32, r1);
+    if (two) tmem_ld_x32(t_row + c + 32, r1);
     tmem_wait_ld();
-    gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
-    if (c + 32 < NCOLS) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);
+    if (kF32 && staged) {
+      if constexpr (kF32) {
+        gemm_epilogue_f32_staged<EPI>(args, row0, col_base + c, r0, stage, lane);
+        if (two) gemm_epilogue_f32_staged<EPI>(args, row0, col_base + c + 32, r1, stage, lane);
+      }
+    } else if (kBf16 && staged && two) {
+      if constexpr (kBf16) gemm_epilogue_bf16_staged<EPI>(args, row0, col_base + c, r0, r1, stage, lane);
+    } else {
+      gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
+      if (two) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);
+    }
   }
 }
 
@@ -174,7 +301,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t stage_base = smem_base + kStages * Cfg::kStageBytes;  // epilogue transpose buffers
+  const uint32_t bar_base = stage_base + kGemmStagingBytes;
   // barrier map (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -287,7 +415,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
       const int col_base = n_blk * BN + half * (BN / 2);
-      gemm_epilogue_drain<EPI, BN / 2>(args, row, col_base, t_row);
+      gemm_epilogue_drain<EPI, BN / 2>(args, row, col_base, t_row,
+                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

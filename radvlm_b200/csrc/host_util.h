@@ -45,13 +45,17 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 // Optional per-kernel-class device timing (CUDA events recorded on the launch stream).  Off by default;
 // bench.py turns it on to report the live duration / launch count of each kernel class.
 enum ProfClass : int {
-  PROF_GEMM = 0,
+  PROF_GEMM = 0,        // patch embed + projector GEMMs
   PROF_ATTENTION = 1,
   PROF_LAYERNORM = 2,
   PROF_MISC = 3,        // im2col, cast, padding memsets
   PROF_PREPROCESS = 4,
   PROF_MERGE_SPLICE = 5,
-  PROF_NUM_CLASSES = 6
+  PROF_GEMM_QKV = 6,
+  PROF_GEMM_OUT = 7,
+  PROF_GEMM_FC1 = 8,
+  PROF_GEMM_FC2 = 9,
+  PROF_NUM_CLASSES = 10
 };
 struct ProfScope {
   ProfScope(int cls, cudaStream_t stream, int launches = 1);

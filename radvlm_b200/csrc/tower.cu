@@ -101,7 +101,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.k = static_cast<__nv_bfloat16*>(k);
       a.vt = static_cast<__nv_bfloat16*>(vt);
       a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
-      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
+      { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
     { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, xn, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
@@ -111,7 +111,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
       a.out = hidden; a.ldo = D; a.aux = hidden;
-      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
+      { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(xn, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
@@ -122,7 +122,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = I; a.K = D;
       a.bias = w.fc1_b;
       a.out = h1; a.ldo = I;
-      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, EPI_GELU_TANH_BF16, 0, stream); }
+      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
     {
@@ -130,7 +130,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
       a.out = hidden; a.ldo = D; a.aux = hidden;
-      { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
+      { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
   }
