@@ -218,6 +218,46 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     return None, new_pos, new_mask, past_key_values, out, new_labels
 
 
+def merge_images(self, features: torch.Tensor, tile_counts: List[int], image_sizes) -> torch.Tensor:
+    """Per-image spatial merge only (llava_arch.py:350-412): features [tiles, T, H] -> merged visual tokens
+    of all images concatenated, [sum N_i, H].  Used by the data-parallel encode (radvlm_b200.dist), where the
+    token blocks are all-gathered before the splice."""
+    lib = _lib.load()
+    tower = self.get_vision_tower()
+    table, tokens = _merge_table(self, tile_counts, image_sizes, False)
+    total = int(sum(tokens))
+    dev = features.device
+    features = features.contiguous()
+    H = features.shape[-1]
+    newline = getattr(self.get_model(), "image_newline", None)
+    if newline is None:
+        newline = torch.zeros(H, dtype=features.dtype, device=dev)
+    newline = newline.detach().to(device=dev, dtype=features.dtype).contiguous()
+    segs = (_lib.SpliceSegment * max(len(tokens), 1))()
+    row = 0
+    for i, n in enumerate(tokens):
+        segs[i].dst_row, segs[i].length, segs[i].kind, segs[i].image = row, n, _lib.SEG_IMAGE, i
+        row += n
+    seg_bytes = len(tokens) * C.sizeof(_lib.SpliceSegment)
+    img_bytes = len(tokens) * C.sizeof(_lib.MergeImage)
+    off_img = (seg_bytes + 15) // 16 * 16
+    host = torch.zeros(off_img + img_bytes + 16, dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    hv[:seg_bytes] = np.frombuffer(bytes(segs)[:seg_bytes], dtype=np.uint8)
+    hv[off_img:off_img + img_bytes] = np.frombuffer(bytes(table)[:img_bytes], dtype=np.uint8)
+    out = torch.empty(total, H, dtype=features.dtype, device=dev)
+    if total == 0:
+        return out
+    with torch.cuda.device(dev):
+        tables = host.to(dev, non_blocking=True)
+        _lib.check(lib.radvlm_merge_splice(
+            features.data_ptr(), newline.data_ptr(), None, _DT[features.dtype], H,
+            tower.num_patches_per_side ** 2, tower.num_patches_per_side, None, None, None,
+            tables.data_ptr(), len(tokens), tables.data_ptr() + off_img, len(tokens), total,
+            out.data_ptr(), None, None, None, IGNORE_INDEX, torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
 class B200LlavaMetaForCausalLM:
     """Mixin with the reference's method names; put it BEFORE ``LlavaMetaForCausalLM`` in the MRO."""
 

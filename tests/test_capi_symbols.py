@@ -1,0 +1,49 @@
+"""The C-ABI library loads and exports every symbol include/radvlm_b200.h declares (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+
+from radvlm_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "radvlm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(radvlm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export: %s" % n
+        assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_struct_sizes_match_header():
+    assert ctypes.sizeof(_lib.ImagePlan) == 19 * 4
+    assert ctypes.sizeof(_lib.SpliceSegment) == 32
+    assert ctypes.sizeof(_lib.MergeImage) == 12 * 4
+    assert ctypes.sizeof(_lib.PreprocessImage) == 16 + 10 * 4
+    assert ctypes.sizeof(_lib.VitLayerWeights) == 12 * 8
+
+
+def test_gpu_entry_points_fail_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = _lib.load()
+    st = lib.radvlm_layernorm_f32_bf16(None, None, None, None, 1, 1152, 1e-6, None)
+    assert st == _lib.ERR_UNSUPPORTED_DEVICE
+    assert "no CPU fallback" in _lib.last_error() or "sm_" in _lib.last_error()
+    from radvlm_b200 import synthetic, mm_arch
+    import pytest
+    host = synthetic.build_host(hidden_size=64, vocab=16, dtype=torch.float32, device="cpu",
+                                vision_cfg=synthetic.siglip_config(hidden_size=144, intermediate_size=272,
+                                                                   num_hidden_layers=1, num_attention_heads=2))
+    with pytest.raises(RuntimeError):
+        host.encode_images(torch.zeros(1, 3, 384, 384))

@@ -1,0 +1,65 @@
+"""Host-side logic of the data-parallel encode (radvlm_b200.dist) on CPU: world_size-2 gloo processes.
+Covers the LPT sharding and the all-gather-v reassembly; the per-rank encode is faked by a deterministic
+function of the image index (the GPU kernels are covered by the -m gpu tests)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from radvlm_b200 import dist as rdist
+
+
+def test_lpt_sharding_balanced_and_deterministic():
+    tiles = [10, 2, 37, 13, 13, 31, 3, 10, 17, 5]
+    for world in (1, 2, 4, 8):
+        owned = rdist.shard_images_lpt(tiles, world)
+        assert sorted(i for o in owned for i in o) == list(range(len(tiles)))   # a partition
+        loads = [sum(tiles[i] for i in o) for o in owned]
+        assert max(loads) - min(loads) <= max(tiles)                              # LPT bound
+        assert owned == rdist.shard_images_lpt(tiles, world)
+    assert rdist.shard_images_lpt([10] * 8, 8) == [[i] for i in range(8)]
+    assert rdist.shard_images_lpt([], 2) == [[], []]
+
+
+def _fake_tokens(i, n, H):
+    g = torch.Generator().manual_seed(100 + i)
+    return torch.randn(n, H, generator=g)
+
+
+def _worker(rank, world, port, tiles, counts, H, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def encode_and_merge(indices):
+            if not indices:
+                return torch.zeros(0, H)
+            return torch.cat([_fake_tokens(i, counts[i], H) for i in indices], dim=0)
+
+        out = rdist.encode_images_sharded([None] * len(tiles), [None] * len(tiles), tiles, counts, encode_and_merge)
+        ok = all(torch.equal(out[i], _fake_tokens(i, counts[i], H)) for i in range(len(tiles)))
+        ret[rank] = bool(ok and len(out) == len(tiles))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tiles", [[10, 2, 13, 31, 3], [10, 10], [2]])
+def test_all_gather_v_world2_gloo(tiles):
+    counts = [729 + 7 * t for t in tiles]   # ragged token counts
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, tiles, counts, 16, ret), nprocs=2, join=True)
+    assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_single_process_passthrough():
+    counts = [5, 9, 3]
+    toks = torch.cat([_fake_tokens(i, n, 8) for i, n in enumerate(counts)])
+    out = rdist.gather_visual_tokens(toks, [[0, 1, 2]], counts)
+    assert all(torch.equal(out[i], _fake_tokens(i, counts[i], 8)) for i in range(3))
