@@ -72,8 +72,9 @@ int radvlm_gemm_set_mode(int mode);
 /* QKV projection with the head-split scatter fused into the epilogue
  * (siglip_encoder.py:207-213: three Linear + view/transpose).  W is the row-concatenation
  * [q_proj; k_proj; v_proj] = [3*heads*hd, K]; bias likewise.  Outputs (bf16):
- *   q, k : [tiles, heads, seq_pad, hd_pad]       vt : [tiles, heads, hd_pad, seq_pad]  (V transposed)
- * Padding regions are never written: the caller zero-fills the buffers once. */
+ *   q, k : bf16 [tiles, heads, seq_pad, hd_pad]       vt : bf16 [tiles, heads, hd_pad, seq_pad]  (V transposed)
+ * Padding regions are never written: the caller zero-fills q / k once and prepares vt with
+ * radvlm_attention_prepare_vt (zero padding + the ones row the attention kernel sums P with). */
 int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K,
                           const float* bias, void* q, void* k, void* vt, int seq, int seq_pad,
                           int heads, int hd, int hd_pad, int block_n, void* stream);
@@ -81,9 +82,16 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
 /* ------------------------------------------------------------------------------------------------
  * Fused non-causal attention for one ViT block (siglip_encoder.py:216-235: q k^T * scale ->
  * softmax(fp32) -> p v -> transpose/reshape).  Inputs in the layout radvlm_gemm_qkv_split writes;
- * out: bf16 [tiles*seq, heads*hd] token-major (A operand of out_proj).
- * Supported geometry: hd_pad == 80, hd % 8 == 0, seq_pad % 128 == 0, seq_pad - 128 < seq <= seq_pad.
+ * out: bf16 [tiles*seq, heads*hd] token-major (A operand of out_proj).  vt must have been prepared with
+ * radvlm_attention_prepare_vt before the QKV epilogue filled it.
+ * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 128 == 0, seq_pad - 128 < seq <= seq_pad.
  * ---------------------------------------------------------------------------------------------- */
+/* Zero the padded V^T buffer (bf16 [tiles, heads, hd_pad, seq_pad]) and write ones into row `hd` of every head
+ * for the valid keys: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */
+int radvlm_attention_prepare_vt(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
+                                void* stream);
+/* tools only: device buffer [ctas][3 roles][64] of clock64 stamps written by the attention kernel (NULL = off) */
+int radvlm_attention_set_debug_buffer(void* dev_buffer);
 int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                          int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradvlm_b200.so")
+# RADVLM_B200_LIB: tuning builds only (tools/build_variant.sh); the shipped library is the in-tree one.
+LIB_PATH = os.environ.get("RADVLM_B200_LIB") or os.path.join(_HERE, "libradvlm_b200.so")
 
 OK = 0
 ERR_BAD_ARGUMENT = 1
@@ -110,6 +111,8 @@ SIGNATURES = {
     "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_set_mode": (_i, [_i]),
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "radvlm_attention_prepare_vt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "radvlm_attention_set_debug_buffer": (_i, [_vp]),
     "radvlm_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "radvlm_layernorm_f32_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "radvlm_patch_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),

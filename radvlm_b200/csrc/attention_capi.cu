@@ -4,6 +4,8 @@
 
 namespace rv {
 
+static long long* g_attn_dbg = nullptr;  // tools only: timeline buffer (see RV_ATTN_STAMP)
+
 int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream) {
   int st = require_sm100();
@@ -20,15 +22,20 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   if (!configured) {
     RV_CUDA(cudaFuncSetAttribute(siglip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kAttnSmemBytes));
+    // two CTAs per SM need the full 228 KB shared-memory carveout
+    RV_CUDA(cudaFuncSetAttribute(siglip_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   const uint64_t th = static_cast<uint64_t>(tiles) * heads;
-  CUtensorMap tq, tk, tv;
-  st = make_tmap_bf16_2d(&tq, q, hd_pad, th * seq_pad, static_cast<uint64_t>(hd_pad) * 2, 16, kAttnBQ,
-                         CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tq, tq2, tk, tk2, tv;
+  const uint64_t pitch = static_cast<uint64_t>(hd_pad) * 2;
+  st = make_tmap_bf16_2d(&tq, q, hd_pad, th * seq_pad, pitch, 64, kAttnBQ, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tk, k, hd_pad, th * seq_pad, static_cast<uint64_t>(hd_pad) * 2, 16, kAttnBKV,
-                         CU_TENSOR_MAP_SWIZZLE_32B);
+  st = make_tmap_bf16_2d(&tq2, q, hd_pad, th * seq_pad, pitch, 16, kAttnBQ, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tk, k, hd_pad, th * seq_pad, pitch, 64, kAttnBKV, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tk2, k, hd_pad, th * seq_pad, pitch, 16, kAttnBKV, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64,
                          kAttnHdPad, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -40,13 +47,19 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   a.heads = heads;
   a.hd = hd;
   a.scale_log2e = scale * 1.4426950408889634f;
+  a.dbg = g_attn_dbg;
   dim3 grid((seq + kAttnBQ - 1) / kAttnBQ, heads, tiles);
-  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tk, tv, a);
+  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }
 
 }  // namespace rv
+
+extern "C" int radvlm_attention_set_debug_buffer(void* dev_buffer) {
+  rv::g_attn_dbg = static_cast<long long*>(dev_buffer);
+  return RADVLM_OK;
+}
 
 extern "C" int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles,
                                     int heads, int seq, int seq_pad, int hd, int hd_pad, float scale,

@@ -5,16 +5,28 @@
 //    matmul(q,k^T)*scale -> softmax(fp32) -> cast -> matmul(p,v) -> transpose/reshape)
 // with one fused kernel.  Layout contract (produced by the QKV GEMM epilogue, gemm_sm100.cuh):
 //    Q, K : [tiles*heads, seq_pad, hd_pad] bf16, zero padded (hd 72 -> 80, seq 729 -> 768)
-//    Vt   : [tiles*heads, hd_pad, seq_pad] bf16  (V transposed so the PV B-operand is K-major)
+//    Vt   : [tiles*heads, hd_pad, seq_pad] bf16  (V transposed so the PV B-operand is K-major); row `hd` of
+//           every head holds ones for the valid keys, so the tensor core accumulates the softmax row sum
+//           (O[:, hd] = sum_j P_j 1) from exactly the bf16 P values the numerator uses
 //    out  : [tiles*seq, heads*hd] bf16 token-major (the A operand of out_proj)
 //
-// One CTA = 128 query rows of one (tile, head).  Warp roles: warp0 TMA producer, warp1 tcgen05.mma
-// issuer, warps 2..5 softmax (one query row per thread).  S = Q K_j^T (128x128 fp32) and the running
-// O (128x80 fp32) live in TMEM; P_j is written to shared memory as bf16 in the 128B-swizzled K-major
-// layout and fed back as the A operand of O += P_j V_j.  Online softmax with lazy, deferred rescale: the
-// reference maximum only moves when the row maximum grows by more than 2^8, so the TMEM O rescale
-// (tcgen05.ld -> mul -> tcgen05.st) is rare.  Two CTAs are resident per SM (256 TMEM columns and
-// ~93 KB shared memory each) so one CTA's softmax overlaps the other's MMAs.
+// One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM (256 TMEM columns and ~100 KB
+// shared memory each).  Warp roles: warp0 TMA producer, warp1 tcgen05.mma issuer, warps 2..9 softmax.
+// S = Q K_j^T (128x128 fp32) and the running O (128x80 fp32) live in TMEM.  P_j never touches shared memory:
+// it is written back into TMEM over S_j (bf16 pairs, 64 columns) and read from there as the A operand of
+// O += P_j V_j.  ncu showed the earlier smem-P version bound by shared-memory bandwidth (both CTAs together
+// moved ~113 B/clk of the 128 B/clk an SM has: Q/K/P/V operand reads of N<=128 MMAs + P stores + TMA writes);
+// P in TMEM removes 64 of the 164 KB a key block moved.
+//
+// What is left is bound by the MUFU unit (16 ex2 / clk / SM, measured: tools/bench_mufu.cu), so the softmax is
+// organised to keep that pipe fed: TWO threads per query row (each owns 64 of the 128 key columns of a block),
+// ~3 issue slots per element (FFMA + EX2 + half a pack + half a 3-input max), no row-sum adds (ones row above).
+// A thread pulls its 64 columns into registers with one TMEM round trip; the block maximum is exchanged between
+// the two half-row threads through shared memory, so every exponential uses an exact, current reference: no
+// clamps, nothing stale.  Within a CTA the chain softmax_j -> PV_j -> S_{j+1} is serial (P aliases S); the
+// second resident CTA fills the tensor pipe / MUFU while the first is in the other phase.
+// Online softmax with lazy rescale: the reference maximum only moves when the row maximum grows by more than
+// 2^8, so the TMEM O rescale (tcgen05.ld -> mul -> tcgen05.st) is rare.
 #pragma once
 
 #include "common.cuh"
@@ -28,40 +40,83 @@ struct AttnArgs {
   int heads;           // 16
   int hd;              // 72
   float scale_log2e;   // hd^-0.5 * log2(e)
+  long long* dbg;      // optional timeline buffer (tools only): [cta][role 0..2][64] clock64 stamps
 };
 
 constexpr int kAttnBQ = 128;       // query rows per CTA
 constexpr int kAttnBKV = 128;      // keys per inner step
 constexpr int kAttnHdPad = 80;     // padded head dim (5 x UMMA_K)
-constexpr int kAttnThreads = 192;
-constexpr int kAttnQBytes = kAttnBQ * kAttnHdPad * 2;    // 20480 : 5 chunks of [128 x 32 B] (SW32)
+constexpr int kAttnSoftmaxWarps = 8;
+constexpr int kAttnSoftmaxThreads = kAttnSoftmaxWarps * 32;
+constexpr int kAttnThreads = 64 + kAttnSoftmaxThreads;   // 320
+constexpr int kAttnQBytes = kAttnBQ * kAttnHdPad * 2;    // 20480 : [128 x 128 B] (SW128) + [128 x 32 B] (SW32)
 constexpr int kAttnKBytes = kAttnBKV * kAttnHdPad * 2;   // 20480
 constexpr int kAttnVBytes = kAttnHdPad * kAttnBKV * 2;   // 20480 : 2 atoms of [80 x 128 B] (SW128)
-constexpr int kAttnPBytes = kAttnBQ * kAttnBKV * 2;      // 32768 : 2 atoms of [128 x 128 B] (SW128)
-constexpr int kAttnSmemBytes = kAttnQBytes + kAttnKBytes + kAttnVBytes + kAttnPBytes + 1024 + 128;
-constexpr int kAttnTmemCols = 256;  // S: [0,128)  O: [128,208)
+constexpr int kAttnXchBytes = 2 * kAttnBQ * 2;           // 512 : block maxima of the two column halves (bf16)
+// K and V are double buffered (loads run two key blocks ahead).  No alignment slack: the dynamic shared window of
+// a kernel without static shared memory starts 1024-byte aligned (checked at run time).
+constexpr int kAttnSmemBytes = kAttnQBytes + 2 * kAttnKBytes + 2 * kAttnVBytes + kAttnXchBytes + 128;
+static_assert(2 * (kAttnSmemBytes + 1024) <= 228 * 1024, "two attention CTAs must fit one SM");
+constexpr int kAttnTmemCols = 256;  // S: [0,128) (P_j: bf16 pairs over [0,64))  O: [128,208)
 constexpr float kAttnRescaleThreshold = 8.0f;
+// Exponentials per 16 computed on the FMA pipe (degree-3 polynomial) instead of MUFU.EX2.
+#ifndef RV_ATTN_POLY_PER_16
+#define RV_ATTN_POLY_PER_16 2
+#endif
+
+// 2^x on the FMA pipe: round-to-nearest split x = n + f (magic-number add), degree-3 minimax of 2^f on
+// [-0.5, 0.5] (max relative error 1.1e-4, far below half a bf16 ulp), exponent inserted with an integer add.
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23
+  const float n = t - 12582912.f;
+  const float f = x - n;
+  float p = fmaf(f, 0.05459282547f, 0.24221783876f);
+  p = fmaf(p, f, 0.69336861372f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+#define RV_ATTN_STAMP(role, idx)                                                                  \
+  do {                                                                                             \
+    if (args.dbg != nullptr && (idx) < 64)                                                         \
+      args.dbg[((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 192 + (role) * 64 + (idx)] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
-                        const __grid_constant__ CUtensorMap tmap_k,
+siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  columns [0,64)  : SW128 box {64, 128}
+                        const __grid_constant__ CUtensorMap tmap_q2,  // Q  columns [64,80) : SW32  box {16, 128}
+                        const __grid_constant__ CUtensorMap tmap_k,   // K  columns [0,64)
+                        const __grid_constant__ CUtensorMap tmap_k2,  // K  columns [64,80)
                         const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 60);  // kernel entry
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();  // swizzled operand tiles need 1024-byte alignment
   const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + kAttnQBytes;
-  const uint32_t sV = sK + kAttnKBytes;
-  const uint32_t sP = sV + kAttnVBytes;
-  const uint32_t bar_base = sP + kAttnPBytes;
-  const uint32_t bar_k = bar_base + 0;       // K_j (+Q for j == 0) landed
-  const uint32_t bar_v = bar_base + 8;       // Vt_j landed
-  const uint32_t bar_s = bar_base + 16;      // S_j complete in TMEM (also: K buffer free)
-  const uint32_t bar_sfree = bar_base + 24;  // softmax has read S_j out of TMEM
-  const uint32_t bar_p = bar_base + 32;      // P_j in smem, O rescaled
-  const uint32_t bar_o = bar_base + 40;      // O += P_j V_j complete (P and V buffers free)
-  const uint32_t tmem_ptr_smem = bar_base + 48;
+  const uint32_t sK = sQ + kAttnQBytes;      // two buffers: K_j lives in sK + (j & 1) * kAttnKBytes
+  const uint32_t sV = sK + 2 * kAttnKBytes;  // two buffers: Vt_j lives in sV + (j & 1) * kAttnVBytes
+  const uint32_t sX = sV + 2 * kAttnVBytes;  // [2 halves][128 rows] bf16 block maxima
+  const uint32_t bar_base = sX + kAttnXchBytes;
+  const uint32_t bar_k = bar_base + 0;       // [2] K_j (+Q for j == 0) landed in buffer j & 1
+  const uint32_t bar_v = bar_base + 16;      // [2] Vt_j landed in buffer j & 1
+  const uint32_t bar_kfree = bar_base + 32;  // [2] S_j complete: K buffer j & 1 may be refilled
+  const uint32_t bar_vfree = bar_base + 48;  // [2] PV_j complete: V buffer j & 1 may be refilled
+  const uint32_t bar_s = bar_base + 64;      // S_j complete in TMEM
+  const uint32_t bar_p = bar_base + 72;      // P_j in TMEM, O rescaled
+  const uint32_t bar_o = bar_base + 80;      // O += P_j V_j complete (P / S region free)
+  const uint32_t tmem_ptr_smem = bar_base + 88;
 
   const int warp = threadIdx.x >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform copy (role dispatch)
   const int lane = threadIdx.x & 31;
   const int qblk = blockIdx.x;
   const int head = blockIdx.y;
@@ -71,13 +126,18 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_q2);
     tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_k2);
     tma_prefetch_desc(&tmap_vt);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
+    for (uint32_t i = 0; i < 2; ++i) {
+      mbar_init(bar_k + 8 * i, 1);
+      mbar_init(bar_v + 8 * i, 1);
+      mbar_init(bar_kfree + 8 * i, 1);
+      mbar_init(bar_vfree + 8 * i, 1);
+    }
     mbar_init(bar_s, 1);
-    mbar_init(bar_sfree, 128);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, kAttnSoftmaxThreads);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
@@ -90,190 +150,200 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 61);  // set-up done (barriers, TMEM allocation)
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + 128;
 
-  if (warp == 0) {
+  if (warp_u == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int q_row0 = th * args.seq_pad + qblk * kAttnBQ;
-      for (int j = 0; j < num_kv; ++j) {
-        const uint32_t par = static_cast<uint32_t>(j & 1);
-        // K buffer is free once S_{j-1} has been computed
-        if (j > 0) mbar_wait(bar_s, par ^ 1u);
-        mbar_arrive_expect_tx(bar_k, j == 0 ? (kAttnQBytes + kAttnKBytes) : kAttnKBytes);
+      for (int j = 0; j < num_kv; ++j) {  // K_j and Vt_j -> buffers j & 1; a buffer's reuse waits for its consumer
+        const uint32_t b = static_cast<uint32_t>(j & 1);
+        const uint32_t prev = static_cast<uint32_t>(((j >> 1) - 1) & 1);
+        if (j >= 2) mbar_wait(bar_kfree + 8 * b, prev);  // S_{j-2} complete
+        RV_ATTN_STAMP(0, 2 * j);  // K_j issue
+        mbar_arrive_expect_tx(bar_k + 8 * b, j == 0 ? (kAttnQBytes + kAttnKBytes) : kAttnKBytes);
         if (j == 0) {
-#pragma unroll
-          for (int c = 0; c < 5; ++c) tma_load_2d(sQ + c * 4096, &tmap_q, bar_k, c * 16, q_row0);
+          tma_load_2d(sQ, &tmap_q, bar_k, 0, q_row0);
+          tma_load_2d(sQ + 16384, &tmap_q2, bar_k, 64, q_row0);
         }
         const int k_row0 = th * args.seq_pad + j * kAttnBKV;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) tma_load_2d(sK + c * 4096, &tmap_k, bar_k, c * 16, k_row0);
-        // V buffer is free once PV_{j-1} has completed
-        if (j > 0) mbar_wait(bar_o, par ^ 1u);
-        mbar_arrive_expect_tx(bar_v, kAttnVBytes);
-        tma_load_2d(sV, &tmap_vt, bar_v, j * kAttnBKV, th * kAttnHdPad);
-        tma_load_2d(sV + 10240, &tmap_vt, bar_v, j * kAttnBKV + 64, th * kAttnHdPad);
+        tma_load_2d(sK + b * kAttnKBytes, &tmap_k, bar_k + 8 * b, 0, k_row0);
+        tma_load_2d(sK + b * kAttnKBytes + 16384, &tmap_k2, bar_k + 8 * b, 64, k_row0);
+        if (j >= 2) mbar_wait(bar_vfree + 8 * b, prev);  // PV_{j-2} complete
+        RV_ATTN_STAMP(0, 2 * j + 1);  // V_j issue
+        mbar_arrive_expect_tx(bar_v + 8 * b, kAttnVBytes);
+        tma_load_2d(sV + b * kAttnVBytes, &tmap_vt, bar_v + 8 * b, j * kAttnBKV, th * kAttnHdPad);
+        tma_load_2d(sV + b * kAttnVBytes + 10240, &tmap_vt, bar_v + 8 * b, j * kAttnBKV + 64, th * kAttnHdPad);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp_u == 1) {
+    // ===================== MMA issuer: the whole warp runs this code converged, elect.sync picks the issuing lane
+    // inside each asm block (see umma_bf16_ss_elect) =====================
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad);
-      auto issue_s = [&]() {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const uint64_t ad = make_smem_desc(sQ + c * 4096, 256, kLayoutSw32);
-          const uint64_t bd = make_smem_desc(sK + c * 4096, 256, kLayoutSw32);
-          umma_bf16_ss(tS, ad, bd, idesc_s, c != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_s);
-      };
-      mbar_wait(bar_k, 0);
-      tc_fence_after();
-      issue_s();
-      for (int j = 0; j < num_kv; ++j) {
-        const uint32_t par = static_cast<uint32_t>(j & 1);
-        if (j + 1 < num_kv) {
-          mbar_wait(bar_k, par ^ 1u);   // K_{j+1} landed
-          mbar_wait(bar_sfree, par);    // softmax drained S_j
-          tc_fence_after();
-          issue_s();
-        }
-        mbar_wait(bar_p, par);  // P_j written, O rescaled
-        mbar_wait(bar_v, par);  // Vt_j landed
+      const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0), tO_u = __shfl_sync(0xffffffffu, tO, 0);
+      const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);          // head dims [0,64): 32 B per K step
+      const uint64_t qd32 = make_smem_desc(sQ + 16384, 256, kLayoutSw32);     // head dims [64,80)
+      const uint64_t kd128 = make_smem_desc(sK, 1024, kLayoutSw128);
+      const uint64_t kd32 = make_smem_desc(sK + 16384, 256, kLayoutSw32);
+      const uint64_t vd = make_smem_desc(sV, 1024, kLayoutSw128);
+      auto issue_s = [&](int j) {
+        const uint32_t b = static_cast<uint32_t>(j & 1);
+        mbar_wait(bar_k + 8 * b, static_cast<uint32_t>((j >> 1) & 1));  // K_j landed
         tc_fence_after();
+        const uint64_t koff = static_cast<uint64_t>(b * (kAttnKBytes >> 4));  // buffer 1 = buffer 0 + constant
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const uint64_t ad = make_smem_desc(sP + (s >> 2) * 16384 + (s & 3) * 32, 1024, kLayoutSw128);
-          const uint64_t bd = make_smem_desc(sV + (s >> 2) * 10240 + (s & 3) * 32, 1024, kLayoutSw128);
-          umma_bf16_ss(tO, ad, bd, idesc_o, (j | s) != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_o);
+        for (int c = 0; c < 4; ++c) umma_bf16_ss_elect(tS_u, qd128 + 2 * c, kd128 + koff + 2 * c, idesc_s, c != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tS_u, qd32, kd32 + koff, idesc_s, 1u);
+        umma_commit_elect(bar_s);
+        umma_commit_elect(bar_kfree + 8 * b);
+        if (lane == 0) RV_ATTN_STAMP(1, 2 * j);  // S_j issued
+      };
+      issue_s(0);
+      for (int j = 0; j < num_kv; ++j) {
+        const uint32_t b = static_cast<uint32_t>(j & 1);
+        mbar_wait(bar_p, b);                                            // P_j in TMEM, O rescaled
+        mbar_wait(bar_v + 8 * b, static_cast<uint32_t>((j >> 1) & 1));  // Vt_j landed
+        tc_fence_after();
+        const uint64_t voff = static_cast<uint64_t>(b * (kAttnVBytes >> 4));
+#pragma unroll
+        for (int s = 0; s < 8; ++s)  // A = P_j from TMEM (8 columns = 16 bf16 per K step)
+          umma_bf16_ts_elect(tO_u, tS_u + static_cast<uint32_t>(s * 8),
+                             vd + voff + static_cast<uint64_t>((s >> 2) * (10240 >> 4) + (s & 3) * 2), idesc_o,
+                             (j | s) != 0 ? 1u : 0u);
+        umma_commit_elect(bar_o);
+        umma_commit_elect(bar_vfree + 8 * b);
+        if (lane == 0) RV_ATTN_STAMP(1, 2 * j + 1);  // PV_j issued
+        // S_{j+1} overwrites the region P_j is read from: tcgen05.mma executes in issue order, so it cannot pass PV_j
+        if (j + 1 < num_kv) issue_s(j + 1);
       }
     }
   } else {
-    // ===================== softmax / correction / output (4 warps, one row per thread) ==========
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row within the query block
+    // ===================== softmax / correction / output (8 warps, two threads per query row) ==========
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // which 64 of the 128 key columns of a block
+    const int r = quad * 32 + lane;          // row within the query block
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    // Online softmax, single pass over each S block in 32-column chunks with the next tcgen05.ld in flight:
-    // exponentials use the RUNNING reference m_ref (log2 domain); when a block's maximum exceeds it by more than
-    // 2^8 the reference moves and the O / l rescale is deferred to the start of the next block (after that
-    // block's PV has drained).  The result is exact: O and l always share one reference.
-    float m_ref = 0.f;
-    float l_sum = 0.f;
-    float pend_alpha = 1.f;
-    bool pend = false;
+    const uint32_t tSh = tS + lane_off + static_cast<uint32_t>(half * 64);
+    const uint32_t tOh = tO + lane_off + static_cast<uint32_t>(half * 40);  // this thread's 40 O columns
+    float m_ref = -INFINITY;  // reference maximum (scaled, log2 domain), identical in both threads of a row
     const float sc = args.scale_log2e;
-    const uint32_t p_row = sP + static_cast<uint32_t>(r) * 128u;
-    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t tPh = tS + lane_off + static_cast<uint32_t>(half * 32);  // this thread's 32 packed P columns
+    const uint32_t x_own = sX + static_cast<uint32_t>(half * kAttnBQ + r) * 2u;
+    const uint32_t x_other = sX + static_cast<uint32_t>((half ^ 1) * kAttnBQ + r) * 2u;
+    const bool stamp = (warp == 2 && lane == 0);
 
     for (int j = 0; j < num_kv; ++j) {
       const uint32_t par = static_cast<uint32_t>(j & 1);
       mbar_wait(bar_s, par);
       tc_fence_after();
-      uint32_t sbuf[2][32];
-      tmem_ld_x32(tS + lane_off, sbuf[0]);
-      bool waited_o = (j == 0);
-      if (__any_sync(0xffffffffu, pend)) {  // deferred rescale (rare): needs PV_{j-1} complete
-        mbar_wait(bar_o, par ^ 1u);
-        waited_o = true;
-        tc_fence_after();
+      if (stamp) RV_ATTN_STAMP(1, 32 + 2 * j);  // S_j seen ready by softmax warp 2
+      // keys >= nvalid (relative to this thread's first column) are padding: last block only
+      const int nvalid = args.seq - j * kAttnBKV - half * 64;
+
+      // ---- S_j (this thread's 64 columns) -> registers with one TMEM round trip
+      uint32_t s[64];
+      tmem_ld_x32(tSh + 0, s + 0);
+      tmem_ld_x32(tSh + 32, s + 32);
+      tmem_wait_ld();
+      if (nvalid < 64) {
 #pragma unroll
-        for (int c = 0; c < kAttnHdPad / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld_x16(tO + lane_off + c * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * pend_alpha);
-          tmem_st_x16(tO + lane_off + c * 16, o);
-        }
-        tmem_wait_st();
-        l_sum *= pend_alpha;
-        pend_alpha = 1.f;
-        pend = false;
+        for (int i = 0; i < 64; ++i)
+          if (i >= nvalid) s[i] = 0xFF800000u;  // -inf -> P = 0
       }
-      const int valid = args.seq - j * kAttnBKV;  // keys >= valid are padding (last block only)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t* cur = sbuf[c & 1];
-        tmem_wait_ld();
-        if (c < 3) {
-          tmem_ld_x32(tS + lane_off + 32 * (c + 1), sbuf[(c + 1) & 1]);
-        } else {
-          tc_fence_before();
-          mbar_arrive(bar_sfree);  // S_j is entirely in registers: the MMA warp may overwrite it
+      for (int i = 0; i < 64; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+      }
+      // exchange the block maximum with the thread that owns the other 64 columns of this row (both use the
+      // bf16-rounded values, so both compute the same reference).  The barrier also tells each thread that its
+      // partner has S_j in registers: P_j (below) overwrites columns the partner read.  The slot is reused every
+      // block: the partner's read of block j-1 precedes its bar_p arrival, hence PV_{j-1}, hence S_j (bar_s).
+      {
+        const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx0, mx1) * sc);
+        const uint16_t own_bits = *reinterpret_cast<const uint16_t*>(&own);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own), "h"(own_bits) : "memory");
+        switch (quad) {  // compile-time barrier ids (a register id would reserve all 16 hardware barriers)
+          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
         }
-        if (valid < kAttnBKV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) cur[i] = 0xFF800000u;  // -inf
+        uint16_t other_bits;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other_bits) : "r"(x_other) : "memory");
+        const float mo = __uint_as_float(static_cast<uint32_t>(other_bits) << 16);
+        const float mb = fmaxf(__uint_as_float(static_cast<uint32_t>(own_bits) << 16), mo);
+        float alpha = 1.f;
+        bool need = false;
+        if (mb > m_ref + kAttnRescaleThreshold) {
+          alpha = exp2f(m_ref - mb);  // 0 on the first block (m_ref = -inf)
+          m_ref = mb;
+          need = (j > 0);
         }
-        if (j == 0 && c == 0) {  // initial reference: maximum of the first 32 keys
-          float m0[4];
+        if (stamp) RV_ATTN_STAMP(1, 33 + 2 * j);  // reference decided (softmax warp 2)
+        // rare: the reference moved, rescale this thread's 40 O columns (PV_{j-1} completed before S_j was issued)
+        if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) m0[i] = __uint_as_float(cur[i]);
+          for (int c = 0; c < 5; ++c) {
+            uint32_t o[8];
+            tmem_ld_x8(tOh + c * 8, o);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 4; i < 32; ++i) m0[i & 3] = fmaxf(m0[i & 3], __uint_as_float(cur[i]));
-          m_ref = fmaxf(fmaxf(m0[0], m0[1]), fmaxf(m0[2], m0[3])) * sc;
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x8(tOh + c * 8, o);
+          }
         }
-        const float neg_m = -m_ref;
+      }
+      const float neg_m = -m_ref;
+
+      // ---- P = 2^(s * scale * log2e - m_ref) -> bf16 pairs -> TMEM columns [32 * half, +32) of the S region
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float v0 = __uint_as_float(cur[i]), v1 = __uint_as_float(cur[i + 1]);
-          mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(v0, v1));
-          // p = 2^(s * scale*log2e - m_ref): one FFMA + one MUFU.EX2 (argument clamped against overflow)
-          const float a0 = fminf(fmaf(v0, sc, neg_m), 100.f), a1 = fminf(fmaf(v1, sc, neg_m), 100.f);
+          const float a0 = fmaf(__uint_as_float(s[c * 32 + i]), sc, neg_m);
+          const float a1 = fmaf(__uint_as_float(s[c * 32 + i + 1]), sc, neg_m);
           float p0, p1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(a0));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(a1));
-          sum4[(i >> 1) & 3] += p0 + p1;
+          if ((i & 15) >= 16 - RV_ATTN_POLY_PER_16) {
+            p0 = exp2_poly3(a0);
+            p1 = exp2_poly3(a1);
+          } else {
+            p0 = ex2_approx(a0);
+            p1 = ex2_approx(a1);
+          }
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        if (c == 0 && !waited_o) mbar_wait(bar_o, par ^ 1u);  // PV_{j-1} done: the P buffer may be overwritten
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ sw;
-          const uint32_t addr = p_row + static_cast<uint32_t>(c >> 1) * 16384u + unit * 16u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u + 0]),
-                       "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
-                       : "memory");
-        }
+        tmem_st_x16(tPh + static_cast<uint32_t>(c * 16), pk);
       }
-      l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;
-      if (mx > m_ref + kAttnRescaleThreshold) {
-        pend_alpha = exp2f(m_ref - mx);
-        m_ref = mx;
-        pend = true;
-      }
-      fence_proxy_async_smem();
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (lane == 0) RV_ATTN_STAMP(2, 8 * j + (warp - 2));  // P_j published by this softmax warp
     }
 
-    // ---- final: O / l -> bf16 -> out[(tile*seq + t), head*hd + d]
+    // ---- final: O / l -> bf16 -> out[(tile*seq + t), head*hd + d]; this thread writes columns [40*half, +40) < hd
     mbar_wait(bar_o, static_cast<uint32_t>((num_kv - 1) & 1));
     tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
     const int t = qblk * kAttnBQ + r;
-    uint32_t o[kAttnHdPad];
+    uint32_t o[40];
 #pragma unroll
-    for (int c = 0; c < kAttnHdPad / 16; ++c) tmem_ld_x16(tO + lane_off + c * 16, o + c * 16);
+    for (int c = 0; c < 5; ++c) tmem_ld_x8(tOh + c * 8, o + c * 8);
+    const uint32_t l_bits = tmem_ld_x1(tO + lane_off + static_cast<uint32_t>(args.hd));  // ones row of V^T
     tmem_wait_ld();
+    const float inv_l = 1.0f / __uint_as_float(l_bits);
     if (t < args.seq) {
       __nv_bfloat16* dst = args.out +
                            (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +
-                           head * args.hd;
-      const int nvec = args.hd / 8;
+                           head * args.hd + half * 40;
 #pragma unroll
-      for (int c = 0; c < kAttnHdPad / 8; ++c) {
-        if (c < nvec) {
+      for (int c = 0; c < 5; ++c) {
+        if (half * 40 + c * 8 < args.hd) {
           uint4 pk;
           pk.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
           pk.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
@@ -287,6 +357,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 62);  // all roles done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kAttnTmemCols);

@@ -40,7 +40,7 @@ int device_sm_count();
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows, row pitch in bytes.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
-                      CUtensorMapSwizzle swizzle);
+                      CUtensorMapSwizzle swizzle);  // (any 16-bit element type: the copy is bit-exact)
 
 // Optional per-kernel-class device timing (CUDA events recorded on the launch stream).  Off by default;
 // bench.py turns it on to report the live duration / launch count of each kernel class.

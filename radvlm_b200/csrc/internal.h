@@ -13,6 +13,8 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 int gemm_pick_block_n(int M, int N, int cta_group);
 int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
+int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
+                                cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
                      float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream);

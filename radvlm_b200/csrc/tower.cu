@@ -69,7 +69,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     ProfScope ps(PROF_MISC, stream, 0);
     RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
     RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
-    RV_CUDA(cudaMemsetAsync(vt, 0, L.qkv_bytes, stream));
+    int pst = attention_prepare_vt_launch(vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, stream);
+    if (pst) return pst;
   }
 
   // --- embeddings: patch GEMM + bias + position embedding (siglip_encoder.py:169-174)

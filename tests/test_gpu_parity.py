@@ -101,14 +101,16 @@ def test_qkv_split_and_attention_vs_torch(lib):
     b = torch.randn(3 * D, device="cuda", generator=g) * 0.1
     q = torch.zeros(tiles, heads, Tp, hp, device="cuda", dtype=torch.bfloat16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(tiles, heads, hp, Tp, device="cuda", dtype=torch.bfloat16)
+    vt = torch.empty(tiles, heads, hp, Tp, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.radvlm_attention_prepare_vt(vt.data_ptr(), tiles, heads, T, Tp, hd, hp, _stream()))
     _lib.check(lib.radvlm_gemm_qkv_split(X.data_ptr(), D, W.data_ptr(), D, tiles * T, D, b.data_ptr(), q.data_ptr(),
                                          k.data_ptr(), vt.data_ptr(), T, Tp, heads, hd, hp, 0, _stream()))
     qkv = (X.float() @ W.float().t() + b).view(tiles, T, 3, heads, hd).permute(2, 0, 3, 1, 4)  # [3,tiles,heads,T,hd]
     torch.testing.assert_close(q[:, :, :T, :hd].float(), qkv[0], rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(k[:, :, :T, :hd].float(), qkv[1], rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(vt[:, :, :hd, :T].float(), qkv[2].transpose(-1, -2), rtol=1e-2, atol=1e-2)
-    assert q[:, :, T:, :].abs().max() == 0 and q[:, :, :, hd:].abs().max() == 0 and vt[:, :, hd:, :].abs().max() == 0
+    assert q[:, :, T:, :].abs().max() == 0 and q[:, :, :, hd:].abs().max() == 0 and vt[:, :, hd + 1:, :].abs().max() == 0
+    assert bool((vt[:, :, hd, :T] == 1).all()) and vt[:, :, hd, T:].abs().max() == 0   # ones row: P row sums
     out = torch.empty(tiles * T, D, device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.radvlm_attention_fwd(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), tiles, heads, T, Tp,
                                         hd, hp, hd ** -0.5, _stream()))

@@ -1,10 +1,12 @@
 // Stand-alone bring-up test: QKV head-split GEMM epilogue + fused attention, through the C ABI.
 // Reference = naive fp32 CUDA-core kernels on the same bf16 inputs.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -72,8 +74,8 @@ static int test_attention(int tiles, int heads, float amp) {
   const int seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
   const int th = tiles * heads;
   const size_t nq = (size_t)th * seq_pad * hd_pad;
-  std::vector<__nv_bfloat16> hq(nq, __float2bfloat16(0.f)), hk(nq, __float2bfloat16(0.f)),
-      hv(nq, __float2bfloat16(0.f));
+  std::vector<__nv_bfloat16> hq(nq, __float2bfloat16(0.f)), hk(nq, __float2bfloat16(0.f));
+  std::vector<__nv_bfloat16> hv(nq, __float2bfloat16(0.f));
   for (int a = 0; a < th; ++a)
     for (int t = 0; t < seq; ++t)
       for (int d = 0; d < hd; ++d) {
@@ -81,13 +83,16 @@ static int test_attention(int tiles, int heads, float amp) {
         hk[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
         hv[((size_t)a * hd_pad + d) * seq_pad + t] = __float2bfloat16(frand() * 2.f);
       }
-  __nv_bfloat16 *dq, *dk, *dv, *dout;
+  __nv_bfloat16 *dq, *dk, *dout;
+  __nv_bfloat16* dv;
   float* dref;
   const size_t nout = (size_t)tiles * seq * heads * hd;
   CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2));
   CK(cudaMalloc(&dout, nout * 2)); CK(cudaMalloc(&dref, nout * 4));
   CK(cudaMemcpy(dq, hq.data(), nq * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dk, hk.data(), nq * 2, cudaMemcpyHostToDevice));
+  for (int a = 0; a < th; ++a)
+    for (int t = 0; t < seq; ++t) hv[((size_t)a * hd_pad + hd) * seq_pad + t] = __float2bfloat16(1.0f);  // ones row
   CK(cudaMemcpy(dv, hv.data(), nq * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xFF, nout * 2));
   const float scale = 1.0f / sqrtf((float)hd);
@@ -141,12 +146,13 @@ static int test_qkv_split(int tiles) {
   for (auto& v : hA) v = __float2bfloat16(frand());
   for (auto& v : hW) v = __float2bfloat16(frand() * 0.2f);
   for (auto& v : hb) v = frand();
-  __nv_bfloat16 *dA, *dW, *dq, *dk, *dv; float *db, *dref;
+  __nv_bfloat16 *dA, *dW, *dq, *dk; __nv_bfloat16* dv; float *db, *dref;
   const size_t nq = (size_t)tiles * heads * seq_pad * hd_pad;
   CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dW, hW.size() * 2)); CK(cudaMalloc(&db, N * 4));
   CK(cudaMalloc(&dref, (size_t)M * N * 4));
   CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2));
-  CK(cudaMemset(dq, 0, nq * 2)); CK(cudaMemset(dk, 0, nq * 2)); CK(cudaMemset(dv, 0, nq * 2));
+  CK(cudaMemset(dq, 0, nq * 2)); CK(cudaMemset(dk, 0, nq * 2));
+  if (radvlm_attention_prepare_vt(dv, tiles, heads, seq, seq_pad, hd, hd_pad, nullptr)) { printf("prepare_vt: %s\n", radvlm_last_error()); return 1; }
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db, hb.data(), N * 4, cudaMemcpyHostToDevice));
@@ -157,7 +163,8 @@ static int test_qkv_split(int tiles) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("qkv kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
   std::vector<float> hr((size_t)M * N);
-  std::vector<__nv_bfloat16> hq(nq), hk(nq), hv(nq);
+  std::vector<__nv_bfloat16> hq(nq), hk(nq);
+  std::vector<__nv_bfloat16> hv(nq);
   CK(cudaMemcpy(hr.data(), dref, hr.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(hq.data(), dq, nq * 2, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(hk.data(), dk, nq * 2, cudaMemcpyDeviceToHost));
@@ -172,7 +179,8 @@ static int test_qkv_split(int tiles) {
           float gk = __bfloat162float(hk[(th * seq_pad + t) * hd_pad + d]);
           float gv = __bfloat162float(hv[(th * hd_pad + d) * seq_pad + t]);
           if (t >= seq || d >= hd) {
-            if (gq != 0.f || gk != 0.f || gv != 0.f) ++nonzero_pad;
+            const float want_v = (d == hd && t < seq) ? 1.f : 0.f;  // ones row
+            if (gq != 0.f || gk != 0.f || gv != want_v) ++nonzero_pad;
             continue;
           }
           const size_t row = (size_t)tile * seq + t;
@@ -190,12 +198,48 @@ static int test_qkv_split(int tiles) {
   return (bad || nonzero_pad) ? 1 : 0;
 }
 
-int main() {
+static void timeline() {
+  const int tiles = 10, heads = 16, seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
+  const size_t nq = (size_t)tiles * heads * seq_pad * hd_pad;
+  __nv_bfloat16 *dq, *dk, *dout;
+  __nv_bfloat16* dv;
+  long long* dbg;
+  const size_t nctas = 6 * heads * tiles;
+  CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2));
+  CK(cudaMemset(dq, 0, nq * 2)); CK(cudaMemset(dk, 0, nq * 2)); CK(cudaMemset(dv, 0, nq * 2));
+  CK(cudaMalloc(&dout, (size_t)tiles * seq * heads * hd * 2));
+  CK(cudaMalloc(&dbg, nctas * 192 * 8)); CK(cudaMemset(dbg, 0, nctas * 192 * 8));
+  radvlm_attention_fwd(dq, dk, dv, dout, tiles, heads, seq, seq_pad, hd, hd_pad, 0.1f, nullptr);  // warm
+  radvlm_attention_set_debug_buffer(dbg);
+  radvlm_attention_fwd(dq, dk, dv, dout, tiles, heads, seq, seq_pad, hd, hd_pad, 0.1f, nullptr);
+  CK(cudaDeviceSynchronize());
+  radvlm_attention_set_debug_buffer(nullptr);
+  std::vector<long long> h(nctas * 192);
+  CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+  const size_t pick[3] = {0, 300, 700};
+  for (size_t c : pick) {
+    const long long* e = &h[c * 192];
+    const long long t0 = e[0];
+    printf("CTA %zu (cycles rel. to first K issue): entry %lld, set-up done %lld, all roles done %lld\n", c, e[60] - t0,
+           e[61] - t0, e[62] - t0);
+    for (int j = 0; j < 6; ++j) {
+      printf("  j=%d  K_iss %6lld V_iss %6lld | S_iss %6lld PV_iss %6lld | S_rdy %6lld ref %6lld | P_pub by warp:", j,
+             e[2 * j] - t0, e[2 * j + 1] - t0, e[64 + 2 * j] - t0, e[64 + 2 * j + 1] - t0, e[64 + 32 + 2 * j] - t0,
+             e[64 + 33 + 2 * j] - t0);
+      for (int w = 0; w < 8; ++w) printf(" %6lld", e[128 + 8 * j + w] - t0);
+      printf("\n");
+    }
+  }
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "timeline")) { timeline(); return 0; }
   int fails = 0;
   fails += test_qkv_split(2);
   fails += test_attention(1, 2, 2.0f);
   fails += test_attention(2, 16, 6.0f);   // larger logits: exercises the lazy rescale path
-  fails += test_attention(10, 16, 2.0f);  // one 1024^2 image worth of tiles
+  fails += test_attention(10, 16, 2.0f);
+  fails += test_attention(37, 16, 2.0f);  // 12 full waves of CTAs: steady-state throughput  // one 1024^2 image worth of tiles
   printf("%s (%d failing)\n", fails ? "ATTENTION TEST FAILED" : "ATTENTION TEST PASSED", fails);
   return fails ? 1 : 0;
 }
