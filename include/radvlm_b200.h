@@ -90,8 +90,6 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
  * for the valid keys: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */
 int radvlm_attention_prepare_vt(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 void* stream);
-/* tools only: device buffer [ctas][3 roles][64] of clock64 stamps written by the attention kernel (NULL = off) */
-int radvlm_attention_set_debug_buffer(void* dev_buffer);
 int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                          int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
 

@@ -112,7 +112,6 @@ SIGNATURES = {
     "radvlm_gemm_set_mode": (_i, [_i]),
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_prepare_vt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "radvlm_attention_set_debug_buffer": (_i, [_vp]),
     "radvlm_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "radvlm_layernorm_f32_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "radvlm_patch_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),

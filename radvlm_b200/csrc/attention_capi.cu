@@ -1,10 +1,10 @@
 // C-ABI launcher for the fused SigLIP attention kernel (attention_sm100.cuh).
+#include <algorithm>
+
 #include "attention_sm100.cuh"
 #include "host_util.h"
 
 namespace rv {
-
-static long long* g_attn_dbg = nullptr;  // tools only: timeline buffer (see RV_ATTN_STAMP)
 
 int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream) {
@@ -47,19 +47,15 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   a.heads = heads;
   a.hd = hd;
   a.scale_log2e = scale * 1.4426950408889634f;
-  a.dbg = g_attn_dbg;
-  dim3 grid((seq + kAttnBQ - 1) / kAttnBQ, heads, tiles);
+  a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
+  a.total_items = tiles * heads * a.num_qblk;
+  const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
   siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }
 
 }  // namespace rv
-
-extern "C" int radvlm_attention_set_debug_buffer(void* dev_buffer) {
-  rv::g_attn_dbg = static_cast<long long*>(dev_buffer);
-  return RADVLM_OK;
-}
 
 extern "C" int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles,
                                     int heads, int seq, int seq_pad, int hd, int hd_pad, float scale,

@@ -10,8 +10,9 @@
 //           (O[:, hd] = sum_j P_j 1) from exactly the bf16 P values the numerator uses
 //    out  : [tiles*seq, heads*hd] bf16 token-major (the A operand of out_proj)
 //
-// One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM (256 TMEM columns and ~100 KB
-// shared memory each).  Warp roles: warp0 TMA producer, warp1 tcgen05.mma issuer, warps 2..9 softmax.
+// A work item = 128 query rows of one (tile, head).  The kernel is persistent: two CTAs are resident per SM (256
+// TMEM columns and ~100 KB shared memory each) and each walks a strided list of items, so barrier set-up, the
+// TMEM allocation and above all the first Q / K / V load latency are paid once per CTA, not once per item.  Warp roles: warp0 TMA producer, warp1 tcgen05.mma issuer, warps 2..9 softmax.
 // S = Q K_j^T (128x128 fp32) and the running O (128x80 fp32) live in TMEM.  P_j never touches shared memory:
 // it is written back into TMEM over S_j (bf16 pairs, 64 columns) and read from there as the A operand of
 // O += P_j V_j.  ncu showed the earlier smem-P version bound by shared-memory bandwidth (both CTAs together
@@ -40,7 +41,8 @@ struct AttnArgs {
   int heads;           // 16
   int hd;              // 72
   float scale_log2e;   // hd^-0.5 * log2(e)
-  long long* dbg;      // optional timeline buffer (tools only): [cta][role 0..2][64] clock64 stamps
+  int num_qblk;        // ceil(seq / 128) query blocks per (tile, head)
+  int total_items;     // tiles * heads * num_qblk
 };
 
 constexpr int kAttnBQ = 128;       // query rows per CTA
@@ -85,12 +87,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-#define RV_ATTN_STAMP(role, idx)                                                                  \
-  do {                                                                                             \
-    if (args.dbg != nullptr && (idx) < 64)                                                         \
-      args.dbg[((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 192 + (role) * 64 + (idx)] = clock64(); \
-  } while (0)
-
+// Work item w = (tile * heads + head) * num_qblk + qblk; CTA c processes w = c, c + gridDim.x, ...  (consecutive
+// CTAs share a head's K / V through L2).  `g` counts key blocks over all of a CTA's items: the K / V rings, S / P / O
+// barriers keep running across items, so the producer prefetches the next item's Q, K_0, K_1, V_0, V_1 while the
+// current item finishes and the per-item cost is only the O read-out.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  columns [0,64)  : SW128 box {64, 128}
                         const __grid_constant__ CUtensorMap tmap_q2,  // Q  columns [64,80) : SW32  box {16, 128}
@@ -98,31 +98,31 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
                         const __grid_constant__ CUtensorMap tmap_k2,  // K  columns [64,80)
                         const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
-  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 60);  // kernel entry
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // swizzled operand tiles need 1024-byte alignment
   const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + kAttnQBytes;      // two buffers: K_j lives in sK + (j & 1) * kAttnKBytes
-  const uint32_t sV = sK + 2 * kAttnKBytes;  // two buffers: Vt_j lives in sV + (j & 1) * kAttnVBytes
+  const uint32_t sK = sQ + kAttnQBytes;      // two buffers: K_g lives in sK + (g & 1) * kAttnKBytes
+  const uint32_t sV = sK + 2 * kAttnKBytes;  // two buffers: Vt_g lives in sV + (g & 1) * kAttnVBytes
   const uint32_t sX = sV + 2 * kAttnVBytes;  // [2 halves][128 rows] bf16 block maxima
   const uint32_t bar_base = sX + kAttnXchBytes;
-  const uint32_t bar_k = bar_base + 0;       // [2] K_j (+Q for j == 0) landed in buffer j & 1
-  const uint32_t bar_v = bar_base + 16;      // [2] Vt_j landed in buffer j & 1
-  const uint32_t bar_kfree = bar_base + 32;  // [2] S_j complete: K buffer j & 1 may be refilled
-  const uint32_t bar_vfree = bar_base + 48;  // [2] PV_j complete: V buffer j & 1 may be refilled
-  const uint32_t bar_s = bar_base + 64;      // S_j complete in TMEM
-  const uint32_t bar_p = bar_base + 72;      // P_j in TMEM, O rescaled
-  const uint32_t bar_o = bar_base + 80;      // O += P_j V_j complete (P / S region free)
-  const uint32_t tmem_ptr_smem = bar_base + 88;
+  const uint32_t bar_k = bar_base + 0;       // [2] K_g landed in buffer g & 1
+  const uint32_t bar_v = bar_base + 16;      // [2] Vt_g landed in buffer g & 1
+  const uint32_t bar_kfree = bar_base + 32;  // [2] S_g complete: K buffer g & 1 may be refilled
+  const uint32_t bar_vfree = bar_base + 48;  // [2] PV_g complete: V buffer g & 1 may be refilled
+  const uint32_t bar_s = bar_base + 64;      // S_g complete in TMEM
+  const uint32_t bar_p = bar_base + 72;      // P_g in TMEM, O rescaled
+  const uint32_t bar_o = bar_base + 80;      // O += P_g V_g complete
+  const uint32_t bar_q = bar_base + 88;      // Q of item `it` landed
+  const uint32_t bar_qfree = bar_base + 96;  // last S of the item complete: Q may be overwritten
+  const uint32_t bar_ofree = bar_base + 104; // the item's O is in registers: the next item's PV_0 may overwrite it
+  const uint32_t tmem_ptr_smem = bar_base + 112;
 
   const int warp = threadIdx.x >> 5;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform copy (role dispatch)
   const int lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x;
-  const int head = blockIdx.y;
-  const int tile = blockIdx.z;
-  const int th = tile * args.heads + head;
   const int num_kv = args.seq_pad / kAttnBKV;
+  const int num_items = (args.total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                        static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -139,6 +139,9 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
     mbar_init(bar_s, 1);
     mbar_init(bar_p, kAttnSoftmaxThreads);
     mbar_init(bar_o, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_qfree, 1);
+    mbar_init(bar_ofree, kAttnSoftmaxThreads);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -150,75 +153,83 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
-  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 61);  // set-up done (barriers, TMEM allocation)
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + 128;
 
   if (warp_u == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int q_row0 = th * args.seq_pad + qblk * kAttnBQ;
-      for (int j = 0; j < num_kv; ++j) {  // K_j and Vt_j -> buffers j & 1; a buffer's reuse waits for its consumer
-        const uint32_t b = static_cast<uint32_t>(j & 1);
-        const uint32_t prev = static_cast<uint32_t>(((j >> 1) - 1) & 1);
-        if (j >= 2) mbar_wait(bar_kfree + 8 * b, prev);  // S_{j-2} complete
-        RV_ATTN_STAMP(0, 2 * j);  // K_j issue
-        mbar_arrive_expect_tx(bar_k + 8 * b, j == 0 ? (kAttnQBytes + kAttnKBytes) : kAttnKBytes);
-        if (j == 0) {
-          tma_load_2d(sQ, &tmap_q, bar_k, 0, q_row0);
-          tma_load_2d(sQ + 16384, &tmap_q2, bar_k, 64, q_row0);
+      int g = 0;
+      for (int it = 0; it < num_items; ++it) {
+        const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+        const int th = w / args.num_qblk, qblk = w - th * args.num_qblk;
+        if (it > 0) mbar_wait(bar_qfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's last S complete
+        mbar_arrive_expect_tx(bar_q, kAttnQBytes);
+        const int q_row0 = th * args.seq_pad + qblk * kAttnBQ;
+        tma_load_2d(sQ, &tmap_q, bar_q, 0, q_row0);
+        tma_load_2d(sQ + 16384, &tmap_q2, bar_q, 64, q_row0);
+        for (int j = 0; j < num_kv; ++j, ++g) {  // K_g and Vt_g -> buffers g & 1; reuse waits for the consumer
+          const uint32_t b = static_cast<uint32_t>(g & 1);
+          const uint32_t prev = static_cast<uint32_t>(((g >> 1) - 1) & 1);
+          if (g >= 2) mbar_wait(bar_kfree + 8 * b, prev);  // S_{g-2} complete
+          mbar_arrive_expect_tx(bar_k + 8 * b, kAttnKBytes);
+          const int k_row0 = th * args.seq_pad + j * kAttnBKV;
+          tma_load_2d(sK + b * kAttnKBytes, &tmap_k, bar_k + 8 * b, 0, k_row0);
+          tma_load_2d(sK + b * kAttnKBytes + 16384, &tmap_k2, bar_k + 8 * b, 64, k_row0);
+          if (g >= 2) mbar_wait(bar_vfree + 8 * b, prev);  // PV_{g-2} complete
+          mbar_arrive_expect_tx(bar_v + 8 * b, kAttnVBytes);
+          tma_load_2d(sV + b * kAttnVBytes, &tmap_vt, bar_v + 8 * b, j * kAttnBKV, th * kAttnHdPad);
+          tma_load_2d(sV + b * kAttnVBytes + 10240, &tmap_vt, bar_v + 8 * b, j * kAttnBKV + 64, th * kAttnHdPad);
         }
-        const int k_row0 = th * args.seq_pad + j * kAttnBKV;
-        tma_load_2d(sK + b * kAttnKBytes, &tmap_k, bar_k + 8 * b, 0, k_row0);
-        tma_load_2d(sK + b * kAttnKBytes + 16384, &tmap_k2, bar_k + 8 * b, 64, k_row0);
-        if (j >= 2) mbar_wait(bar_vfree + 8 * b, prev);  // PV_{j-2} complete
-        RV_ATTN_STAMP(0, 2 * j + 1);  // V_j issue
-        mbar_arrive_expect_tx(bar_v + 8 * b, kAttnVBytes);
-        tma_load_2d(sV + b * kAttnVBytes, &tmap_vt, bar_v + 8 * b, j * kAttnBKV, th * kAttnHdPad);
-        tma_load_2d(sV + b * kAttnVBytes + 10240, &tmap_vt, bar_v + 8 * b, j * kAttnBKV + 64, th * kAttnHdPad);
       }
     }
   } else if (warp_u == 1) {
     // ===================== MMA issuer: the whole warp runs this code converged, elect.sync picks the issuing lane
     // inside each asm block (see umma_bf16_ss_elect) =====================
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad);
-      const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0), tO_u = __shfl_sync(0xffffffffu, tO, 0);
-      const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);          // head dims [0,64): 32 B per K step
-      const uint64_t qd32 = make_smem_desc(sQ + 16384, 256, kLayoutSw32);     // head dims [64,80)
-      const uint64_t kd128 = make_smem_desc(sK, 1024, kLayoutSw128);
-      const uint64_t kd32 = make_smem_desc(sK + 16384, 256, kLayoutSw32);
-      const uint64_t vd = make_smem_desc(sV, 1024, kLayoutSw128);
-      auto issue_s = [&](int j) {
-        const uint32_t b = static_cast<uint32_t>(j & 1);
-        mbar_wait(bar_k + 8 * b, static_cast<uint32_t>((j >> 1) & 1));  // K_j landed
-        tc_fence_after();
-        const uint64_t koff = static_cast<uint64_t>(b * (kAttnKBytes >> 4));  // buffer 1 = buffer 0 + constant
+    constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
+    constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad);
+    const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0), tO_u = __shfl_sync(0xffffffffu, tO, 0);
+    const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);       // head dims [0,64): 32 B per K step
+    const uint64_t qd32 = make_smem_desc(sQ + 16384, 256, kLayoutSw32);  // head dims [64,80)
+    const uint64_t kd128 = make_smem_desc(sK, 1024, kLayoutSw128);
+    const uint64_t kd32 = make_smem_desc(sK + 16384, 256, kLayoutSw32);
+    const uint64_t vd = make_smem_desc(sV, 1024, kLayoutSw128);
+    const int total_blocks = num_items * num_kv;
+    auto issue_s = [&](int g, int it, int j) {  // S_g = Q_it K_g^T
+      const uint32_t b = static_cast<uint32_t>(g & 1);
+      if (j == 0) mbar_wait(bar_q, static_cast<uint32_t>(it & 1));    // Q of this item landed
+      mbar_wait(bar_k + 8 * b, static_cast<uint32_t>((g >> 1) & 1));  // K_g landed
+      tc_fence_after();
+      const uint64_t koff = static_cast<uint64_t>(b * (kAttnKBytes >> 4));  // buffer 1 = buffer 0 + constant
 #pragma unroll
-        for (int c = 0; c < 4; ++c) umma_bf16_ss_elect(tS_u, qd128 + 2 * c, kd128 + koff + 2 * c, idesc_s, c != 0 ? 1u : 0u);
-        umma_bf16_ss_elect(tS_u, qd32, kd32 + koff, idesc_s, 1u);
-        umma_commit_elect(bar_s);
-        umma_commit_elect(bar_kfree + 8 * b);
-        if (lane == 0) RV_ATTN_STAMP(1, 2 * j);  // S_j issued
-      };
-      issue_s(0);
-      for (int j = 0; j < num_kv; ++j) {
-        const uint32_t b = static_cast<uint32_t>(j & 1);
-        mbar_wait(bar_p, b);                                            // P_j in TMEM, O rescaled
-        mbar_wait(bar_v + 8 * b, static_cast<uint32_t>((j >> 1) & 1));  // Vt_j landed
+      for (int c = 0; c < 4; ++c) umma_bf16_ss_elect(tS_u, qd128 + 2 * c, kd128 + koff + 2 * c, idesc_s, c != 0 ? 1u : 0u);
+      umma_bf16_ss_elect(tS_u, qd32, kd32 + koff, idesc_s, 1u);
+      umma_commit_elect(bar_s);
+      umma_commit_elect(bar_kfree + 8 * b);
+      if (j == num_kv - 1) umma_commit_elect(bar_qfree);
+    };
+    if (total_blocks > 0) issue_s(0, 0, 0);
+    int g = 0;
+    for (int it = 0; it < num_items; ++it) {
+      for (int j = 0; j < num_kv; ++j, ++g) {
+        const uint32_t b = static_cast<uint32_t>(g & 1);
+        mbar_wait(bar_p, b);                                            // P_g in TMEM, O rescaled
+        mbar_wait(bar_v + 8 * b, static_cast<uint32_t>((g >> 1) & 1));  // Vt_g landed
+        if (j == 0 && it > 0) mbar_wait(bar_ofree, static_cast<uint32_t>((it - 1) & 1));  // previous O read out
         tc_fence_after();
         const uint64_t voff = static_cast<uint64_t>(b * (kAttnVBytes >> 4));
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // A = P_j from TMEM (8 columns = 16 bf16 per K step)
+        for (int s = 0; s < 8; ++s)  // A = P_g from TMEM (8 columns = 16 bf16 per K step)
           umma_bf16_ts_elect(tO_u, tS_u + static_cast<uint32_t>(s * 8),
                              vd + voff + static_cast<uint64_t>((s >> 2) * (10240 >> 4) + (s & 3) * 2), idesc_o,
                              (j | s) != 0 ? 1u : 0u);
         umma_commit_elect(bar_o);
         umma_commit_elect(bar_vfree + 8 * b);
-        if (lane == 0) RV_ATTN_STAMP(1, 2 * j + 1);  // PV_j issued
-        // S_{j+1} overwrites the region P_j is read from: tcgen05.mma executes in issue order, so it cannot pass PV_j
-        if (j + 1 < num_kv) issue_s(j + 1);
+        // S_{g+1} overwrites the region P_g is read from: tcgen05.mma executes in issue order, so it cannot pass PV_g
+        if (g + 1 < total_blocks) {
+          const bool wrap = (j + 1 == num_kv);
+          issue_s(g + 1, wrap ? it + 1 : it, wrap ? 0 : j + 1);
+        }
       }
     }
   } else {
@@ -229,127 +240,131 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tSh = tS + lane_off + static_cast<uint32_t>(half * 64);
     const uint32_t tOh = tO + lane_off + static_cast<uint32_t>(half * 40);  // this thread's 40 O columns
-    float m_ref = -INFINITY;  // reference maximum (scaled, log2 domain), identical in both threads of a row
-    const float sc = args.scale_log2e;
     const uint32_t tPh = tS + lane_off + static_cast<uint32_t>(half * 32);  // this thread's 32 packed P columns
+    const float sc = args.scale_log2e;
     const uint32_t x_own = sX + static_cast<uint32_t>(half * kAttnBQ + r) * 2u;
     const uint32_t x_other = sX + static_cast<uint32_t>((half ^ 1) * kAttnBQ + r) * 2u;
-    const bool stamp = (warp == 2 && lane == 0);
 
-    for (int j = 0; j < num_kv; ++j) {
-      const uint32_t par = static_cast<uint32_t>(j & 1);
-      mbar_wait(bar_s, par);
+    int g = 0;
+    for (int it = 0; it < num_items; ++it) {
+      float m_ref = -INFINITY;  // reference maximum (scaled, log2 domain), identical in both threads of a row
+      for (int j = 0; j < num_kv; ++j, ++g) {
+        mbar_wait(bar_s, static_cast<uint32_t>(g & 1));
+        tc_fence_after();
+        // keys >= nvalid (relative to this thread's first column) are padding: last block only
+        const int nvalid = args.seq - j * kAttnBKV - half * 64;
+
+        // ---- S_g (this thread's 64 columns) -> registers with one TMEM round trip
+        uint32_t s[64];
+        tmem_ld_x32(tSh + 0, s + 0);
+        tmem_ld_x32(tSh + 32, s + 32);
+        tmem_wait_ld();
+        if (nvalid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= nvalid) s[i] = 0xFF800000u;  // -inf -> P = 0
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        }
+        // exchange the block maximum with the thread that owns the other 64 columns of this row (both use the
+        // bf16-rounded values, so both compute the same reference).  The barrier also tells each thread that its
+        // partner has S_g in registers: P_g (below) overwrites columns the partner read.  The slot is reused every
+        // block: the partner's read of block g-1 precedes its bar_p arrival, hence PV_{g-1}, hence S_g (bar_s).
+        {
+          const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx0, mx1) * sc);
+          const uint16_t own_bits = *reinterpret_cast<const uint16_t*>(&own);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own), "h"(own_bits) : "memory");
+          switch (quad) {  // compile-time barrier ids (a register id would reserve all 16 hardware barriers)
+            case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+            case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+            case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+            default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+          }
+          uint16_t other_bits;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other_bits) : "r"(x_other) : "memory");
+          const float mo = __uint_as_float(static_cast<uint32_t>(other_bits) << 16);
+          const float mb = fmaxf(__uint_as_float(static_cast<uint32_t>(own_bits) << 16), mo);
+          float alpha = 1.f;
+          bool need = false;
+          if (mb > m_ref + kAttnRescaleThreshold) {
+            alpha = exp2f(m_ref - mb);  // 0 on the first block (m_ref = -inf)
+            m_ref = mb;
+            need = (j > 0);
+          }
+          // rare: the reference moved, rescale this thread's 40 O columns (PV_{g-1} completed before S_g was issued)
+          if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              uint32_t o[8];
+              tmem_ld_x8(tOh + c * 8, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x8(tOh + c * 8, o);
+            }
+          }
+        }
+        const float neg_m = -m_ref;
+
+        // ---- P = 2^(s * scale * log2e - m_ref) -> bf16 pairs -> TMEM columns [32 * half, +32) of the S region
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a0 = fmaf(__uint_as_float(s[c * 32 + i]), sc, neg_m);
+            const float a1 = fmaf(__uint_as_float(s[c * 32 + i + 1]), sc, neg_m);
+            float p0, p1;
+            if ((i & 15) >= 16 - RV_ATTN_POLY_PER_16) {
+              p0 = exp2_poly3(a0);
+              p1 = exp2_poly3(a1);
+            } else {
+              p0 = ex2_approx(a0);
+              p1 = ex2_approx(a1);
+            }
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(tPh + static_cast<uint32_t>(c * 16), pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
+
+      // ---- item done: O / l -> registers (then the next item's PV_0 may overwrite O) -> bf16 ->
+      //      out[(tile*seq + t), head*hd + d]; this thread writes columns [40*half, +40) < hd
+      mbar_wait(bar_o, static_cast<uint32_t>((g - 1) & 1));  // PV of the item's last key block complete
       tc_fence_after();
-      if (stamp) RV_ATTN_STAMP(1, 32 + 2 * j);  // S_j seen ready by softmax warp 2
-      // keys >= nvalid (relative to this thread's first column) are padding: last block only
-      const int nvalid = args.seq - j * kAttnBKV - half * 64;
-
-      // ---- S_j (this thread's 64 columns) -> registers with one TMEM round trip
-      uint32_t s[64];
-      tmem_ld_x32(tSh + 0, s + 0);
-      tmem_ld_x32(tSh + 32, s + 32);
+      uint32_t o[40];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tmem_ld_x8(tOh + c * 8, o + c * 8);
+      const uint32_t l_bits = tmem_ld_x1(tO + lane_off + static_cast<uint32_t>(args.hd));  // ones row of V^T
       tmem_wait_ld();
-      if (nvalid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= nvalid) s[i] = 0xFF800000u;  // -inf -> P = 0
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-      }
-      // exchange the block maximum with the thread that owns the other 64 columns of this row (both use the
-      // bf16-rounded values, so both compute the same reference).  The barrier also tells each thread that its
-      // partner has S_j in registers: P_j (below) overwrites columns the partner read.  The slot is reused every
-      // block: the partner's read of block j-1 precedes its bar_p arrival, hence PV_{j-1}, hence S_j (bar_s).
-      {
-        const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx0, mx1) * sc);
-        const uint16_t own_bits = *reinterpret_cast<const uint16_t*>(&own);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own), "h"(own_bits) : "memory");
-        switch (quad) {  // compile-time barrier ids (a register id would reserve all 16 hardware barriers)
-          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-        }
-        uint16_t other_bits;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other_bits) : "r"(x_other) : "memory");
-        const float mo = __uint_as_float(static_cast<uint32_t>(other_bits) << 16);
-        const float mb = fmaxf(__uint_as_float(static_cast<uint32_t>(own_bits) << 16), mo);
-        float alpha = 1.f;
-        bool need = false;
-        if (mb > m_ref + kAttnRescaleThreshold) {
-          alpha = exp2f(m_ref - mb);  // 0 on the first block (m_ref = -inf)
-          m_ref = mb;
-          need = (j > 0);
-        }
-        if (stamp) RV_ATTN_STAMP(1, 33 + 2 * j);  // reference decided (softmax warp 2)
-        // rare: the reference moved, rescale this thread's 40 O columns (PV_{j-1} completed before S_j was issued)
-        if (__any_sync(0xffffffffu, need)) {
-#pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            uint32_t o[8];
-            tmem_ld_x8(tOh + c * 8, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x8(tOh + c * 8, o);
-          }
-        }
-      }
-      const float neg_m = -m_ref;
-
-      // ---- P = 2^(s * scale * log2e - m_ref) -> bf16 pairs -> TMEM columns [32 * half, +32) of the S region
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float a0 = fmaf(__uint_as_float(s[c * 32 + i]), sc, neg_m);
-          const float a1 = fmaf(__uint_as_float(s[c * 32 + i + 1]), sc, neg_m);
-          float p0, p1;
-          if ((i & 15) >= 16 - RV_ATTN_POLY_PER_16) {
-            p0 = exp2_poly3(a0);
-            p1 = exp2_poly3(a1);
-          } else {
-            p0 = ex2_approx(a0);
-            p1 = ex2_approx(a1);
-          }
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_x16(tPh + static_cast<uint32_t>(c * 16), pk);
-      }
-      tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(bar_p);
-      if (lane == 0) RV_ATTN_STAMP(2, 8 * j + (warp - 2));  // P_j published by this softmax warp
-    }
-
-    // ---- final: O / l -> bf16 -> out[(tile*seq + t), head*hd + d]; this thread writes columns [40*half, +40) < hd
-    mbar_wait(bar_o, static_cast<uint32_t>((num_kv - 1) & 1));
-    tc_fence_after();
-    const int t = qblk * kAttnBQ + r;
-    uint32_t o[40];
+      mbar_arrive(bar_ofree);
+      const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      const int th = w / args.num_qblk, qblk = w - th * args.num_qblk;
+      const int tile = th / args.heads, head = th - tile * args.heads;
+      const int t = qblk * kAttnBQ + r;
+      const float inv_l = 1.0f / __uint_as_float(l_bits);
+      if (t < args.seq) {
+        __nv_bfloat16* dst = args.out +
+                             (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +
+                             head * args.hd + half * 40;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) tmem_ld_x8(tOh + c * 8, o + c * 8);
-    const uint32_t l_bits = tmem_ld_x1(tO + lane_off + static_cast<uint32_t>(args.hd));  // ones row of V^T
-    tmem_wait_ld();
-    const float inv_l = 1.0f / __uint_as_float(l_bits);
-    if (t < args.seq) {
-      __nv_bfloat16* dst = args.out +
-                           (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +
-                           head * args.hd + half * 40;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        if (half * 40 + c * 8 < args.hd) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
-          pk.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
-          pk.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
-          pk.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
-          reinterpret_cast<uint4*>(dst)[c] = pk;
+        for (int c = 0; c < 5; ++c) {
+          if (half * 40 + c * 8 < args.hd) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
+            pk.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
+            pk.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
+            pk.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
+            reinterpret_cast<uint4*>(dst)[c] = pk;
+          }
         }
       }
     }
@@ -357,7 +372,6 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) RV_ATTN_STAMP(0, 62);  // all roles done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kAttnTmemCols);

@@ -198,42 +198,7 @@ static int test_qkv_split(int tiles) {
   return (bad || nonzero_pad) ? 1 : 0;
 }
 
-static void timeline() {
-  const int tiles = 10, heads = 16, seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
-  const size_t nq = (size_t)tiles * heads * seq_pad * hd_pad;
-  __nv_bfloat16 *dq, *dk, *dout;
-  __nv_bfloat16* dv;
-  long long* dbg;
-  const size_t nctas = 6 * heads * tiles;
-  CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2));
-  CK(cudaMemset(dq, 0, nq * 2)); CK(cudaMemset(dk, 0, nq * 2)); CK(cudaMemset(dv, 0, nq * 2));
-  CK(cudaMalloc(&dout, (size_t)tiles * seq * heads * hd * 2));
-  CK(cudaMalloc(&dbg, nctas * 192 * 8)); CK(cudaMemset(dbg, 0, nctas * 192 * 8));
-  radvlm_attention_fwd(dq, dk, dv, dout, tiles, heads, seq, seq_pad, hd, hd_pad, 0.1f, nullptr);  // warm
-  radvlm_attention_set_debug_buffer(dbg);
-  radvlm_attention_fwd(dq, dk, dv, dout, tiles, heads, seq, seq_pad, hd, hd_pad, 0.1f, nullptr);
-  CK(cudaDeviceSynchronize());
-  radvlm_attention_set_debug_buffer(nullptr);
-  std::vector<long long> h(nctas * 192);
-  CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
-  const size_t pick[3] = {0, 300, 700};
-  for (size_t c : pick) {
-    const long long* e = &h[c * 192];
-    const long long t0 = e[0];
-    printf("CTA %zu (cycles rel. to first K issue): entry %lld, set-up done %lld, all roles done %lld\n", c, e[60] - t0,
-           e[61] - t0, e[62] - t0);
-    for (int j = 0; j < 6; ++j) {
-      printf("  j=%d  K_iss %6lld V_iss %6lld | S_iss %6lld PV_iss %6lld | S_rdy %6lld ref %6lld | P_pub by warp:", j,
-             e[2 * j] - t0, e[2 * j + 1] - t0, e[64 + 2 * j] - t0, e[64 + 2 * j + 1] - t0, e[64 + 32 + 2 * j] - t0,
-             e[64 + 33 + 2 * j] - t0);
-      for (int w = 0; w < 8; ++w) printf(" %6lld", e[128 + 8 * j + w] - t0);
-      printf("\n");
-    }
-  }
-}
-
 int main(int argc, char** argv) {
-  if (argc > 1 && !strcmp(argv[1], "timeline")) { timeline(); return 0; }
   int fails = 0;
   fails += test_qkv_split(2);
   fails += test_attention(1, 2, 2.0f);
