@@ -84,7 +84,8 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
  * softmax(fp32) -> p v -> transpose/reshape).  Inputs in the layout radvlm_gemm_qkv_split writes;
  * out: bf16 [tiles*seq, heads*hd] token-major (A operand of out_proj).  vt must have been prepared with
  * radvlm_attention_prepare_vt before the QKV epilogue filled it.
- * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 128 == 0, seq_pad - 128 < seq <= seq_pad.
+ * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 384 == 0 (query blocks of 128, key blocks
+ * of 96), 1 <= seq <= seq_pad.
  * ---------------------------------------------------------------------------------------------- */
 /* Zero the padded V^T buffer (bf16 [tiles, heads, hd_pad, seq_pad]) and write ones into row `hd` of every head
  * for the valid keys: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */

@@ -12,10 +12,10 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   if (st != RADVLM_OK) return st;
   RV_CHECK_ARG(q && k && vt && out, "attention: null pointer");
   RV_CHECK_ARG(tiles > 0 && heads > 0, "attention: bad batch (tiles=%d heads=%d)", tiles, heads);
-  if (hd_pad != kAttnHdPad || hd > hd_pad || (hd % 8) != 0 || (seq_pad % kAttnBKV) != 0 ||
-      seq > seq_pad || seq <= seq_pad - kAttnBKV) {
-    set_error("attention: unsupported geometry seq=%d seq_pad=%d hd=%d hd_pad=%d (need hd_pad=80, "
-              "hd%%8==0, seq_pad%%128==0, seq_pad-128 < seq <= seq_pad)", seq, seq_pad, hd, hd_pad);
+  if (hd_pad != kAttnHdPad || hd >= hd_pad || (hd % 8) != 0 || (seq_pad % kAttnBKV) != 0 ||
+      (seq_pad % kAttnBQ) != 0 || seq > seq_pad || seq < 1) {
+    set_error("attention: unsupported geometry seq=%d seq_pad=%d hd=%d hd_pad=%d (need hd_pad=80, hd<80, "
+              "hd%%8==0, seq_pad%%384==0, 1 <= seq <= seq_pad)", seq, seq_pad, hd, hd_pad);
     return RADVLM_ERR_UNSUPPORTED_SHAPE;
   }
   static thread_local bool configured = false;
@@ -27,7 +27,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
     configured = true;
   }
   const uint64_t th = static_cast<uint64_t>(tiles) * heads;
-  CUtensorMap tq, tq2, tk, tk2, tv;
+  CUtensorMap tq, tq2, tk, tk2, tv, tv2;
   const uint64_t pitch = static_cast<uint64_t>(hd_pad) * 2;
   st = make_tmap_bf16_2d(&tq, q, hd_pad, th * seq_pad, pitch, 64, kAttnBQ, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
@@ -37,8 +37,11 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tk2, k, hd_pad, th * seq_pad, pitch, 16, kAttnBKV, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64,
-                         kAttnHdPad, CU_TENSOR_MAP_SWIZZLE_128B);
+  st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64, kAttnHdPad,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+  if (st != RADVLM_OK) return st;
+  st = make_tmap_bf16_2d(&tv2, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 32, kAttnHdPad,
+                         CU_TENSOR_MAP_SWIZZLE_64B);
   if (st != RADVLM_OK) return st;
   AttnArgs a;
   a.out = static_cast<__nv_bfloat16*>(out);
@@ -50,7 +53,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
   a.total_items = tiles * heads * a.num_qblk;
   const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
-  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
+  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, tv2, a);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

@@ -45,21 +45,29 @@ struct AttnArgs {
   int total_items;     // tiles * heads * num_qblk
 };
 
-constexpr int kAttnBQ = 128;       // query rows per CTA
-constexpr int kAttnBKV = 128;      // keys per inner step
+constexpr int kAttnBQ = 128;       // query rows per work item
+constexpr int kAttnBKV = 96;       // keys per inner step (S 96 + O 80 + P 48 TMEM columns <= 256: P does not alias S)
 constexpr int kAttnHdPad = 80;     // padded head dim (5 x UMMA_K)
 constexpr int kAttnSoftmaxWarps = 8;
 constexpr int kAttnSoftmaxThreads = kAttnSoftmaxWarps * 32;
 constexpr int kAttnThreads = 64 + kAttnSoftmaxThreads;   // 320
+constexpr int kAttnHalf = kAttnBKV / 2;                  // key columns per softmax thread
 constexpr int kAttnQBytes = kAttnBQ * kAttnHdPad * 2;    // 20480 : [128 x 128 B] (SW128) + [128 x 32 B] (SW32)
-constexpr int kAttnKBytes = kAttnBKV * kAttnHdPad * 2;   // 20480
-constexpr int kAttnVBytes = kAttnHdPad * kAttnBKV * 2;   // 20480 : 2 atoms of [80 x 128 B] (SW128)
-constexpr int kAttnXchBytes = 2 * kAttnBQ * 2;           // 512 : block maxima of the two column halves (bf16)
-// K and V are double buffered (loads run two key blocks ahead).  No alignment slack: the dynamic shared window of
-// a kernel without static shared memory starts 1024-byte aligned (checked at run time).
-constexpr int kAttnSmemBytes = kAttnQBytes + 2 * kAttnKBytes + 2 * kAttnVBytes + kAttnXchBytes + 128;
+constexpr int kAttnQ2Off = kAttnBQ * 128;                // offset of the SW32 slab (head dims [64,80))
+constexpr int kAttnKBytes = kAttnBKV * kAttnHdPad * 2;   // 15360 : [96 x 128 B] (SW128) + [96 x 32 B] (SW32)
+constexpr int kAttnK2Off = kAttnBKV * 128;
+constexpr int kAttnVBytes = kAttnHdPad * kAttnBKV * 2;   // 15360 : [80 x 128 B] (SW128, keys 0-63) + [80 x 64 B] (SW64, keys 64-95)
+constexpr int kAttnV2Off = kAttnHdPad * 128;
+constexpr int kAttnStages = 3;                           // K / V ring depth
+constexpr int kAttnXchBytes = 2 * 2 * kAttnBQ * 2;       // 1024 : [block parity][column half][row] bf16 block maxima
+// No alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte aligned
+// (checked at run time).
+constexpr int kAttnSmemBytes = kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes) + kAttnXchBytes + 256;
 static_assert(2 * (kAttnSmemBytes + 1024) <= 228 * 1024, "two attention CTAs must fit one SM");
-constexpr int kAttnTmemCols = 256;  // S: [0,128) (P_j: bf16 pairs over [0,64))  O: [128,208)
+static_assert(kAttnKBytes % 1024 == 0 && kAttnVBytes % 1024 == 0, "operand buffers must stay 1024-byte aligned");
+constexpr int kAttnTmemCols = 256;  // S: [0,96)  O: [96,176)  P (bf16 pairs): [176,224)
+constexpr int kAttnTmemO = kAttnBKV, kAttnTmemP = kAttnBKV + kAttnHdPad;
+static_assert(kAttnTmemP + kAttnBKV / 2 <= kAttnTmemCols, "TMEM budget");
 constexpr float kAttnRescaleThreshold = 8.0f;
 // Exponentials per 16 computed on the FMA pipe (degree-3 polynomial) instead of MUFU.EX2.
 #ifndef RV_ATTN_POLY_PER_16
@@ -88,34 +96,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // Work item w = (tile * heads + head) * num_qblk + qblk; CTA c processes w = c, c + gridDim.x, ...  (consecutive
-// CTAs share a head's K / V through L2).  `g` counts key blocks over all of a CTA's items: the K / V rings, S / P / O
-// barriers keep running across items, so the producer prefetches the next item's Q, K_0, K_1, V_0, V_1 while the
+// CTAs share a head's K / V through L2).  `g` counts key blocks over all of a CTA's items: the K / V rings and the
+// S / P / O barriers keep running across items, so the producer prefetches the next item's Q / K / V while the
 // current item finishes and the per-item cost is only the O read-out.
 __global__ void __launch_bounds__(kAttnThreads, 2)
-siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  columns [0,64)  : SW128 box {64, 128}
-                        const __grid_constant__ CUtensorMap tmap_q2,  // Q  columns [64,80) : SW32  box {16, 128}
-                        const __grid_constant__ CUtensorMap tmap_k,   // K  columns [0,64)
-                        const __grid_constant__ CUtensorMap tmap_k2,  // K  columns [64,80)
-                        const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
+siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  columns [0,64)  : SW128 box {64, 128}
+                        const __grid_constant__ CUtensorMap tmap_q2,   // Q  columns [64,80) : SW32  box {16, 128}
+                        const __grid_constant__ CUtensorMap tmap_k,    // K  columns [0,64)  : SW128 box {64, 96}
+                        const __grid_constant__ CUtensorMap tmap_k2,   // K  columns [64,80) : SW32  box {16, 96}
+                        const __grid_constant__ CUtensorMap tmap_vt,   // Vt keys [0,64) of a block  : SW128 box {64, 80}
+                        const __grid_constant__ CUtensorMap tmap_vt2,  // Vt keys [64,96) of a block : SW64  box {32, 80}
+                        const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // swizzled operand tiles need 1024-byte alignment
   const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + kAttnQBytes;      // two buffers: K_g lives in sK + (g & 1) * kAttnKBytes
-  const uint32_t sV = sK + 2 * kAttnKBytes;  // two buffers: Vt_g lives in sV + (g & 1) * kAttnVBytes
-  const uint32_t sX = sV + 2 * kAttnVBytes;  // [2 halves][128 rows] bf16 block maxima
+  const uint32_t sK = sQ + kAttnQBytes;               // ring: K_g lives in sK + (g % stages) * kAttnKBytes
+  const uint32_t sV = sK + kAttnStages * kAttnKBytes; // ring: Vt_g lives in sV + (g % stages) * kAttnVBytes
+  const uint32_t sX = sV + kAttnStages * kAttnVBytes; // [2 parities][2 halves][128 rows] bf16 block maxima
   const uint32_t bar_base = sX + kAttnXchBytes;
-  const uint32_t bar_k = bar_base + 0;       // [2] K_g landed in buffer g & 1
-  const uint32_t bar_v = bar_base + 16;      // [2] Vt_g landed in buffer g & 1
-  const uint32_t bar_kfree = bar_base + 32;  // [2] S_g complete: K buffer g & 1 may be refilled
-  const uint32_t bar_vfree = bar_base + 48;  // [2] PV_g complete: V buffer g & 1 may be refilled
-  const uint32_t bar_s = bar_base + 64;      // S_g complete in TMEM
-  const uint32_t bar_p = bar_base + 72;      // P_g in TMEM, O rescaled
-  const uint32_t bar_o = bar_base + 80;      // O += P_g V_g complete
-  const uint32_t bar_q = bar_base + 88;      // Q of item `it` landed
-  const uint32_t bar_qfree = bar_base + 96;  // last S of the item complete: Q may be overwritten
-  const uint32_t bar_ofree = bar_base + 104; // the item's O is in registers: the next item's PV_0 may overwrite it
-  const uint32_t tmem_ptr_smem = bar_base + 112;
+  const uint32_t bar_k = bar_base + 0;        // [stages] K_g landed
+  const uint32_t bar_v = bar_base + 32;       // [stages] Vt_g landed
+  const uint32_t bar_kfree = bar_base + 64;   // [stages] S_g complete: its K buffer may be refilled
+  const uint32_t bar_vfree = bar_base + 96;   // [stages] PV_g complete: its V buffer may be refilled
+  const uint32_t bar_s = bar_base + 128;      // S_g complete in TMEM
+  const uint32_t bar_sfree = bar_base + 136;  // S_g is in registers: S_{g+1} may overwrite it
+  const uint32_t bar_p = bar_base + 144;      // P_g in TMEM, O rescaled
+  const uint32_t bar_o = bar_base + 152;      // O += P_g V_g complete (P region free again)
+  const uint32_t bar_q = bar_base + 160;      // Q of item `it` landed
+  const uint32_t bar_qfree = bar_base + 168;  // last S of the item complete: Q may be overwritten
+  const uint32_t bar_ofree = bar_base + 176;  // the item's O is in registers: the next item's PV_0 may overwrite it
+  const uint32_t tmem_ptr_smem = bar_base + 184;
+  static_assert(kAttnStages <= 4, "barrier layout");
 
   const int warp = threadIdx.x >> 5;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform copy (role dispatch)
@@ -130,13 +142,15 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_k2);
     tma_prefetch_desc(&tmap_vt);
-    for (uint32_t i = 0; i < 2; ++i) {
+    tma_prefetch_desc(&tmap_vt2);
+    for (uint32_t i = 0; i < kAttnStages; ++i) {
       mbar_init(bar_k + 8 * i, 1);
       mbar_init(bar_v + 8 * i, 1);
       mbar_init(bar_kfree + 8 * i, 1);
       mbar_init(bar_vfree + 8 * i, 1);
     }
     mbar_init(bar_s, 1);
+    mbar_init(bar_sfree, kAttnSoftmaxThreads);
     mbar_init(bar_p, kAttnSoftmaxThreads);
     mbar_init(bar_o, 1);
     mbar_init(bar_q, 1);
@@ -154,12 +168,14 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   const uint32_t tS = tmem_base;
-  const uint32_t tO = tmem_base + 128;
+  const uint32_t tO = tmem_base + kAttnTmemO;
+  const uint32_t tP = tmem_base + kAttnTmemP;
 
   if (warp_u == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int g = 0;
+      uint32_t slot = 0, ring_par = 0;  // slot = g % stages, ring_par = (g / stages) & 1
       for (int it = 0; it < num_items; ++it) {
         const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
         const int th = w / args.num_qblk, qblk = w - th * args.num_qblk;
@@ -167,19 +183,19 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
         mbar_arrive_expect_tx(bar_q, kAttnQBytes);
         const int q_row0 = th * args.seq_pad + qblk * kAttnBQ;
         tma_load_2d(sQ, &tmap_q, bar_q, 0, q_row0);
-        tma_load_2d(sQ + 16384, &tmap_q2, bar_q, 64, q_row0);
-        for (int j = 0; j < num_kv; ++j, ++g) {  // K_g and Vt_g -> buffers g & 1; reuse waits for the consumer
-          const uint32_t b = static_cast<uint32_t>(g & 1);
-          const uint32_t prev = static_cast<uint32_t>(((g >> 1) - 1) & 1);
-          if (g >= 2) mbar_wait(bar_kfree + 8 * b, prev);  // S_{g-2} complete
-          mbar_arrive_expect_tx(bar_k + 8 * b, kAttnKBytes);
+        tma_load_2d(sQ + kAttnQ2Off, &tmap_q2, bar_q, 64, q_row0);
+        for (int j = 0; j < num_kv; ++j, ++g) {
+          if (g >= kAttnStages) mbar_wait(bar_kfree + 8 * slot, ring_par ^ 1u);  // S_{g-stages} complete
+          mbar_arrive_expect_tx(bar_k + 8 * slot, kAttnKBytes);
           const int k_row0 = th * args.seq_pad + j * kAttnBKV;
-          tma_load_2d(sK + b * kAttnKBytes, &tmap_k, bar_k + 8 * b, 0, k_row0);
-          tma_load_2d(sK + b * kAttnKBytes + 16384, &tmap_k2, bar_k + 8 * b, 64, k_row0);
-          if (g >= 2) mbar_wait(bar_vfree + 8 * b, prev);  // PV_{g-2} complete
-          mbar_arrive_expect_tx(bar_v + 8 * b, kAttnVBytes);
-          tma_load_2d(sV + b * kAttnVBytes, &tmap_vt, bar_v + 8 * b, j * kAttnBKV, th * kAttnHdPad);
-          tma_load_2d(sV + b * kAttnVBytes + 10240, &tmap_vt, bar_v + 8 * b, j * kAttnBKV + 64, th * kAttnHdPad);
+          tma_load_2d(sK + slot * kAttnKBytes, &tmap_k, bar_k + 8 * slot, 0, k_row0);
+          tma_load_2d(sK + slot * kAttnKBytes + kAttnK2Off, &tmap_k2, bar_k + 8 * slot, 64, k_row0);
+          if (g >= kAttnStages) mbar_wait(bar_vfree + 8 * slot, ring_par ^ 1u);  // PV_{g-stages} complete
+          mbar_arrive_expect_tx(bar_v + 8 * slot, kAttnVBytes);
+          tma_load_2d(sV + slot * kAttnVBytes, &tmap_vt, bar_v + 8 * slot, j * kAttnBKV, th * kAttnHdPad);
+          tma_load_2d(sV + slot * kAttnVBytes + kAttnV2Off, &tmap_vt2, bar_v + 8 * slot, j * kAttnBKV + 64,
+                      th * kAttnHdPad);
+          if (++slot == kAttnStages) { slot = 0; ring_par ^= 1u; }
         }
       }
     }
@@ -189,58 +205,65 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
     constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
     constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad);
     const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0), tO_u = __shfl_sync(0xffffffffu, tO, 0);
-    const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);       // head dims [0,64): 32 B per K step
-    const uint64_t qd32 = make_smem_desc(sQ + 16384, 256, kLayoutSw32);  // head dims [64,80)
+    const uint32_t tP_u = __shfl_sync(0xffffffffu, tP, 0);
+    const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);             // head dims [0,64): 32 B per K step
+    const uint64_t qd32 = make_smem_desc(sQ + kAttnQ2Off, 256, kLayoutSw32);   // head dims [64,80)
     const uint64_t kd128 = make_smem_desc(sK, 1024, kLayoutSw128);
-    const uint64_t kd32 = make_smem_desc(sK + 16384, 256, kLayoutSw32);
-    const uint64_t vd = make_smem_desc(sV, 1024, kLayoutSw128);
+    const uint64_t kd32 = make_smem_desc(sK + kAttnK2Off, 256, kLayoutSw32);
+    const uint64_t vd128 = make_smem_desc(sV, 1024, kLayoutSw128);             // keys [0,64) of the block
+    const uint64_t vd64 = make_smem_desc(sV + kAttnV2Off, 512, kLayoutSw64);   // keys [64,96)
     const int total_blocks = num_items * num_kv;
+    // ring bookkeeping for S issue (runs one block ahead of the PV issue)
+    uint32_t s_slot = 0, s_par = 0;
     auto issue_s = [&](int g, int it, int j) {  // S_g = Q_it K_g^T
-      const uint32_t b = static_cast<uint32_t>(g & 1);
-      if (j == 0) mbar_wait(bar_q, static_cast<uint32_t>(it & 1));    // Q of this item landed
-      mbar_wait(bar_k + 8 * b, static_cast<uint32_t>((g >> 1) & 1));  // K_g landed
+      if (j == 0) mbar_wait(bar_q, static_cast<uint32_t>(it & 1));  // Q of this item landed
+      mbar_wait(bar_k + 8 * s_slot, s_par);                          // K_g landed
+      if (g > 0) mbar_wait(bar_sfree, static_cast<uint32_t>((g - 1) & 1));  // S_{g-1} is in registers
       tc_fence_after();
-      const uint64_t koff = static_cast<uint64_t>(b * (kAttnKBytes >> 4));  // buffer 1 = buffer 0 + constant
+      const uint64_t koff = static_cast<uint64_t>(s_slot * (kAttnKBytes >> 4));
 #pragma unroll
       for (int c = 0; c < 4; ++c) umma_bf16_ss_elect(tS_u, qd128 + 2 * c, kd128 + koff + 2 * c, idesc_s, c != 0 ? 1u : 0u);
       umma_bf16_ss_elect(tS_u, qd32, kd32 + koff, idesc_s, 1u);
       umma_commit_elect(bar_s);
-      umma_commit_elect(bar_kfree + 8 * b);
+      umma_commit_elect(bar_kfree + 8 * s_slot);
       if (j == num_kv - 1) umma_commit_elect(bar_qfree);
+      if (++s_slot == kAttnStages) { s_slot = 0; s_par ^= 1u; }
     };
     if (total_blocks > 0) issue_s(0, 0, 0);
     int g = 0;
+    uint32_t slot = 0, ring_par = 0;
     for (int it = 0; it < num_items; ++it) {
       for (int j = 0; j < num_kv; ++j, ++g) {
-        const uint32_t b = static_cast<uint32_t>(g & 1);
-        mbar_wait(bar_p, b);                                            // P_g in TMEM, O rescaled
-        mbar_wait(bar_v + 8 * b, static_cast<uint32_t>((g >> 1) & 1));  // Vt_g landed
-        if (j == 0 && it > 0) mbar_wait(bar_ofree, static_cast<uint32_t>((it - 1) & 1));  // previous O read out
-        tc_fence_after();
-        const uint64_t voff = static_cast<uint64_t>(b * (kAttnVBytes >> 4));
-#pragma unroll
-        for (int s = 0; s < 8; ++s)  // A = P_g from TMEM (8 columns = 16 bf16 per K step)
-          umma_bf16_ts_elect(tO_u, tS_u + static_cast<uint32_t>(s * 8),
-                             vd + voff + static_cast<uint64_t>((s >> 2) * (10240 >> 4) + (s & 3) * 2), idesc_o,
-                             (j | s) != 0 ? 1u : 0u);
-        umma_commit_elect(bar_o);
-        umma_commit_elect(bar_vfree + 8 * b);
-        // S_{g+1} overwrites the region P_g is read from: tcgen05.mma executes in issue order, so it cannot pass PV_g
+        // S_{g+1} first: it only needs S_g to have been read out, and runs while the softmax of block g computes
         if (g + 1 < total_blocks) {
           const bool wrap = (j + 1 == num_kv);
           issue_s(g + 1, wrap ? it + 1 : it, wrap ? 0 : j + 1);
         }
+        mbar_wait(bar_p, static_cast<uint32_t>(g & 1));  // P_g in TMEM, O rescaled
+        mbar_wait(bar_v + 8 * slot, ring_par);            // Vt_g landed
+        if (j == 0 && it > 0) mbar_wait(bar_ofree, static_cast<uint32_t>((it - 1) & 1));  // previous O read out
+        tc_fence_after();
+        const uint64_t voff = static_cast<uint64_t>(slot * (kAttnVBytes >> 4));
+#pragma unroll
+        for (int s = 0; s < 4; ++s)  // A = P_g from TMEM (8 columns = 16 bf16 per K step), keys [0,64)
+          umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(s * 8), vd128 + voff + 2 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 2; ++s)  // keys [64,96)
+          umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(32 + s * 8), vd64 + voff + 2 * s, idesc_o, 1u);
+        umma_commit_elect(bar_o);
+        umma_commit_elect(bar_vfree + 8 * slot);
+        if (++slot == kAttnStages) { slot = 0; ring_par ^= 1u; }
       }
     }
   } else {
     // ===================== softmax / correction / output (8 warps, two threads per query row) ==========
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;        // which 64 of the 128 key columns of a block
+    const int half = (warp - 2) >> 2;        // which half of the key columns of a block
     const int r = quad * 32 + lane;          // row within the query block
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tSh = tS + lane_off + static_cast<uint32_t>(half * 64);
-    const uint32_t tOh = tO + lane_off + static_cast<uint32_t>(half * 40);  // this thread's 40 O columns
-    const uint32_t tPh = tS + lane_off + static_cast<uint32_t>(half * 32);  // this thread's 32 packed P columns
+    const uint32_t tSh = tS + lane_off + static_cast<uint32_t>(half * kAttnHalf);
+    const uint32_t tOh = tO + lane_off + static_cast<uint32_t>(half * 40);           // this thread's 40 O columns
+    const uint32_t tPh = tP + lane_off + static_cast<uint32_t>(half * (kAttnHalf / 2));  // its packed P columns
     const float sc = args.scale_log2e;
     const uint32_t x_own = sX + static_cast<uint32_t>(half * kAttnBQ + r) * 2u;
     const uint32_t x_other = sX + static_cast<uint32_t>((half ^ 1) * kAttnBQ + r) * 2u;
@@ -252,84 +275,86 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  colu
         mbar_wait(bar_s, static_cast<uint32_t>(g & 1));
         tc_fence_after();
         // keys >= nvalid (relative to this thread's first column) are padding: last block only
-        const int nvalid = args.seq - j * kAttnBKV - half * 64;
+        const int nvalid = args.seq - j * kAttnBKV - half * kAttnHalf;
 
-        // ---- S_g (this thread's 64 columns) -> registers with one TMEM round trip
-        uint32_t s[64];
+        // ---- S_g (this thread's 48 columns) -> registers with one TMEM round trip, then S is released: the MMA
+        //      warp computes S_{g+1} while the exponentials below run
+        uint32_t s[kAttnHalf];
         tmem_ld_x32(tSh + 0, s + 0);
-        tmem_ld_x32(tSh + 32, s + 32);
+        tmem_ld_x16(tSh + 32, s + 32);
         tmem_wait_ld();
-        if (nvalid < 64) {
+        tc_fence_before();
+        mbar_arrive(bar_sfree);
+        if (nvalid < kAttnHalf) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
+          for (int i = 0; i < kAttnHalf; ++i)
             if (i >= nvalid) s[i] = 0xFF800000u;  // -inf -> P = 0
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < kAttnHalf; i += 4) {
           mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
           mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         }
-        // exchange the block maximum with the thread that owns the other 64 columns of this row (both use the
-        // bf16-rounded values, so both compute the same reference).  The barrier also tells each thread that its
-        // partner has S_g in registers: P_g (below) overwrites columns the partner read.  The slot is reused every
-        // block: the partner's read of block g-1 precedes its bar_p arrival, hence PV_{g-1}, hence S_g (bar_s).
-        {
-          const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx0, mx1) * sc);
-          const uint16_t own_bits = *reinterpret_cast<const uint16_t*>(&own);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own), "h"(own_bits) : "memory");
-          switch (quad) {  // compile-time barrier ids (a register id would reserve all 16 hardware barriers)
-            case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-            case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-            case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-            default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-          }
-          uint16_t other_bits;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other_bits) : "r"(x_other) : "memory");
-          const float mo = __uint_as_float(static_cast<uint32_t>(other_bits) << 16);
-          const float mb = fmaxf(__uint_as_float(static_cast<uint32_t>(own_bits) << 16), mo);
-          float alpha = 1.f;
-          bool need = false;
-          if (mb > m_ref + kAttnRescaleThreshold) {
-            alpha = exp2f(m_ref - mb);  // 0 on the first block (m_ref = -inf)
-            m_ref = mb;
-            need = (j > 0);
-          }
-          // rare: the reference moved, rescale this thread's 40 O columns (PV_{g-1} completed before S_g was issued)
-          if (__any_sync(0xffffffffu, need)) {
+        // exchange the block maximum with the thread that owns the other half of this row's columns (both use the
+        // bf16-rounded values, so both compute the same reference).  The slot alternates with the block parity: a
+        // slot is rewritten two blocks later, after another bar.sync that the partner only reaches past its read.
+        const uint32_t xpar = static_cast<uint32_t>(g & 1) * (2u * kAttnBQ * 2u);
+        const __nv_bfloat16 own = __float2bfloat16_rn(fmaxf(mx0, mx1) * sc);
+        const uint16_t own_bits = *reinterpret_cast<const uint16_t*>(&own);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own + xpar), "h"(own_bits) : "memory");
+        switch (quad) {  // compile-time barrier ids (a register id would reserve all 16 hardware barriers)
+          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+        }
+        uint16_t other_bits;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other_bits) : "r"(x_other + xpar) : "memory");
+        const float mo = __uint_as_float(static_cast<uint32_t>(other_bits) << 16);
+        const float mb = fmaxf(__uint_as_float(static_cast<uint32_t>(own_bits) << 16), mo);
+        float alpha = 1.f;
+        bool need = false;
+        if (mb > m_ref + kAttnRescaleThreshold) {
+          alpha = exp2f(m_ref - mb);  // 0 on the first block (m_ref = -inf)
+          m_ref = mb;
+          need = (j > 0);
+        }
+        // PV_{g-1} must be complete before the P region is overwritten or O is rescaled (it normally is: it was
+        // issued a whole softmax block ago)
+        if (g > 0) mbar_wait(bar_o, static_cast<uint32_t>((g - 1) & 1));
+        if (__any_sync(0xffffffffu, need)) {  // rare: the reference moved, rescale this thread's 40 O columns
+          tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              uint32_t o[8];
-              tmem_ld_x8(tOh + c * 8, o);
-              tmem_wait_ld();
+          for (int c = 0; c < 5; ++c) {
+            uint32_t o[8];
+            tmem_ld_x8(tOh + c * 8, o);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_x8(tOh + c * 8, o);
-            }
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x8(tOh + c * 8, o);
           }
         }
         const float neg_m = -m_ref;
 
-        // ---- P = 2^(s * scale * log2e - m_ref) -> bf16 pairs -> TMEM columns [32 * half, +32) of the S region
+        // ---- P = 2^(s * scale * log2e - m_ref) -> bf16 pairs -> this thread's 24 packed columns of the P region
+        uint32_t pk[kAttnHalf / 2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a0 = fmaf(__uint_as_float(s[c * 32 + i]), sc, neg_m);
-            const float a1 = fmaf(__uint_as_float(s[c * 32 + i + 1]), sc, neg_m);
-            float p0, p1;
-            if ((i & 15) >= 16 - RV_ATTN_POLY_PER_16) {
-              p0 = exp2_poly3(a0);
-              p1 = exp2_poly3(a1);
-            } else {
-              p0 = ex2_approx(a0);
-              p1 = ex2_approx(a1);
-            }
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < kAttnHalf; i += 2) {
+          const float a0 = fmaf(__uint_as_float(s[i]), sc, neg_m);
+          const float a1 = fmaf(__uint_as_float(s[i + 1]), sc, neg_m);
+          float p0, p1;
+          if ((i & 15) >= 16 - RV_ATTN_POLY_PER_16) {
+            p0 = exp2_poly3(a0);
+            p1 = exp2_poly3(a1);
+          } else {
+            p0 = ex2_approx(a0);
+            p1 = ex2_approx(a1);
           }
-          tmem_st_x16(tPh + static_cast<uint32_t>(c * 16), pk);
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
+        tmem_st_x16(tPh, pk);
+        tmem_st_x8(tPh + 16, pk + 16);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar_p);

@@ -70,6 +70,31 @@ __device__ __forceinline__ void umma_bf16_ss_cta2(uint32_t d_tmem, uint64_t ades
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Whole-warp issue variants (see umma_bf16_ss_elect in common.cuh): the converged warp executes the block, elect.sync
+// picks the issuing lane, ptxas emits back-to-back UTCHMMA on uniform registers (no ELECT / R2UR loop per MMA).
+__device__ __forceinline__ void umma_bf16_ss_cta2_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1, p;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@P1 tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cta2_mc_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "@P1 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_cta2_mc(uint32_t bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -168,8 +193,12 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // The whole warp runs the loop converged (all operands are warp-uniform); elect.sync inside the asm blocks picks
+    // the lane that issues.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t desc0 = make_smem_desc(smem_base, 1024, kLayoutSw128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -177,20 +206,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = desc0 + static_cast<uint64_t>((stage * Cfg::kStageBytes) >> 4);
+          const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * 32, 1024, kLayoutSw128);
-            const uint64_t bdesc = make_smem_desc(sb + k * 32, 1024, kLayoutSw128);
-            umma_bf16_ss_cta2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_cta2_mc(empty_bar(stage), 3);
-          if (kb == num_k - 1) umma_commit_cta2_mc(tfull_bar(acc), 3);
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            umma_bf16_ss_cta2_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cta2_mc_elect(empty_bar(stage), 3);
+          if (kb == num_k - 1) umma_commit_cta2_mc_elect(tfull_bar(acc), 3);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;

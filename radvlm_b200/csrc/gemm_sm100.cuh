@@ -366,8 +366,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (all operands are warp-uniform); elect.sync inside the asm blocks picks
+    // the lane that issues (umma_bf16_ss_elect, common.cuh).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t desc0 = make_smem_desc(smem_base, 1024, kLayoutSw128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -375,20 +379,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = desc0 + static_cast<uint64_t>((stage * Cfg::kStageBytes) >> 4);
+          const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * 32, 1024, kLayoutSw128);
-            const uint64_t bdesc = make_smem_desc(sb + k * 32, 1024, kLayoutSw128);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
-          if (kb == num_k - 1) umma_commit(tfull_bar(acc));
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            umma_bf16_ss_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_elect(empty_bar(stage));
+          if (kb == num_k - 1) umma_commit_elect(tfull_bar(acc));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;

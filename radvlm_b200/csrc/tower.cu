@@ -25,7 +25,7 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
   RV_CHECK_ARG(tw->patch_size > 0 && tw->heads > 0 && tw->hidden > 0, "encode: bad tower config");
   L->P = tw->image_size / tw->patch_size;
   L->T = L->P * L->P;
-  L->seq_pad = (L->T + 127) / 128 * 128;
+  L->seq_pad = (L->T + 383) / 384 * 384;  // multiple of the attention query (128) and key (96) block sizes
   L->hd = tw->hidden / tw->heads;
   L->hd_pad = 80;
   if (L->hd * tw->heads != tw->hidden || L->hd > L->hd_pad || (L->hd % 8) != 0 || (tw->hidden % 8) != 0 ||

@@ -1,4 +1,4 @@
-for v in poly2 poly4 poly6; do
+for v in poly0 poly4 poly6; do
   RADVLM_B200_LIB=$PWD/build/var_$v/libradvlm_b200.so python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2>/dev/null
   python - <<P
 import json
