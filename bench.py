@@ -328,14 +328,39 @@ def run_b200_arm(args):
         tokens_step = B * world * TOKENS_PER_IMAGE
         value = tokens_step / (ms / args.steps / 1e3)
         e2e = tokens_step / (ms_e2e / args.steps / 1e3)
-        # roofline of the dominant kernel class: all tcgen05 GEMM launches of a step (patch, qkv, out, fc1, fc2, projector)
+        # ---- rooflines.  Algorithmic work per launch / average launch duration measured live
+        # (CUDA events on the launch stream, radvlm_profile_*).  `roofline` is the dominant single kernel by time:
+        # the fc2 GEMM ([tiles*729, 4304] x [1152, 4304]^T with the fp32 residual epilogue).
         attn_flops = 26 * 4.0 * 729 * 729 * 1152
         gemm_flops_step = (flops_per_tile() - attn_flops) * TILES_PER_IMAGE * B
         gemm_total_ms = sum(v for k, v in prof_ms.items() if k.startswith("gemm"))
         gemm_ms_step = gemm_total_ms / args.steps
-        achieved = gemm_flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
+        achieved_all = gemm_flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        hbm_peak = float(peaks.get("hbm_gbs", 6545.0))
         total_ms = sum(prof_ms.values()) or 1.0
+        rows_step = B * TILES_PER_IMAGE * 729
+        traffic = _ncu_traffic()
+
+        def per_launch(cls, work_step):
+            n = max(prof_n.get(cls, 0), 1)
+            return work_step * args.steps / n, prof_ms.get(cls, 0.0) / n, n / args.steps
+
+        def traffic_of(cls, launches_per_step):
+            """DRAM bytes of one launch from the ncu capture, if it was taken at this run's tiles-per-launch."""
+            t = traffic.get(cls)
+            tower_calls = launches_per_step / (52.0 if cls == "layernorm" else 26.0)
+            if not t or tower_calls <= 0:
+                return None
+            if abs(B * TILES_PER_IMAGE / tower_calls - traffic.get("tiles_per_launch", -1)) > 1e-6:
+                return None
+            return (t["dram_read_mb"] + t["dram_write_mb"]) * 1e6
+
+        fc2_flops, fc2_ms, fc2_lps = per_launch("gemm_fc2", 26 * 2.0 * rows_step * 1152 * 4304)
+        fc2_ach = fc2_flops / (fc2_ms * 1e-3) / 1e12 if fc2_ms > 0 else 0.0
+        ln_bytes, ln_ms, ln_lps = per_launch("layernorm", 52 * 6.0 * rows_step * 1152)
+        ln_ach = ln_bytes / (ln_ms * 1e-3) / 1e9 if ln_ms > 0 else 0.0
+        at_flops, at_ms, at_lps = per_launch("attention", attn_flops * TILES_PER_IMAGE * B)
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -345,12 +370,29 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": B * Lp * 8 + 4},
             "gpu_launches": int(sum(prof_n.values())),
             "clocks": clk,
-            "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05, all instantiations of a step)", "bound": "tensor",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "roofline": {"kernel": "gemm_bf16_tn_2cta_kernel<192,3> as the fc2 GEMM (tcgen05 cta_group::2, fp32 residual "
+                                   "epilogue)", "bound": "tensor",
+                         "achieved": fc2_ach, "peak": peak, "unit": "TFLOP/s", "frac": fc2_ach / peak,
                          "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
-                         "traffic": None,
-                         "algorithmic_flops_per_step": gemm_flops_step, "kernel_ms_per_step": gemm_ms_step,
-                         "share_of_step": gemm_total_ms / total_ms},
+                         "traffic": traffic_of("gemm_fc2", fc2_lps),
+                         "algorithmic_flops_per_launch": fc2_flops, "ms_per_launch": fc2_ms,
+                         "launches_per_step": fc2_lps,
+                         "share_of_step": prof_ms.get("gemm_fc2", 0.0) / total_ms},
+            "roofline_all_gemms": {"kernel": "all tcgen05 GEMM launches of a step (patch, qkv, out, fc1, fc2, projector)",
+                                   "bound": "tensor", "achieved": achieved_all, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": achieved_all / peak, "traffic": None,
+                                   "algorithmic_flops_per_step": gemm_flops_step, "kernel_ms_per_step": gemm_ms_step,
+                                   "share_of_step": gemm_total_ms / total_ms},
+            "roofline_attention": {"kernel": "siglip_attention_kernel", "bound": "tensor (MUFU co-limited, DESIGN.md)",
+                                   "achieved": at_flops / (at_ms * 1e-3) / 1e12 if at_ms > 0 else 0.0, "peak": peak,
+                                   "unit": "TFLOP/s", "frac": (at_flops / (at_ms * 1e-3) / 1e12 / peak) if at_ms > 0 else 0.0,
+                                   "traffic": traffic_of("attention", at_lps),
+                                   "share_of_step": prof_ms.get("attention", 0.0) / total_ms},
+            "roofline_layernorm": {"kernel": "layernorm_f32_to_bf16_kernel", "bound": "hbm", "achieved": ln_ach,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": ln_ach / hbm_peak,
+                                   "traffic": traffic_of("layernorm", ln_lps),
+                                   "algorithmic_bytes_per_launch": ln_bytes, "ms_per_launch": ln_ms,
+                                   "share_of_step": prof_ms.get("layernorm", 0.0) / total_ms},
             "kernel_ms_per_step": {k: v / args.steps for k, v in prof_ms.items()},
             "kernel_launches_per_step": {k: v / args.steps for k, v in prof_n.items()},
             "path_tflops": flops_per_tile() * TILES_PER_IMAGE * B * world / (ms / args.steps / 1e3) / 1e12,
@@ -365,6 +407,16 @@ def run_b200_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json); {} if absent."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 def main():
