@@ -60,10 +60,24 @@ int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_
 #define RADVLM_EPI_RESID_F32 3      /* out f32  = acc + bias + aux[M,ldo]    siglip_encoder.py:293,298 */
 #define RADVLM_EPI_POS_F32 4        /* out f32  = acc + bias + aux[row % aux_period, N]  siglip_encoder.py:173 */
 #define RADVLM_EPI_BIAS_F32 6       /* out f32  = acc + bias */
+#define RADVLM_EPI_ATOMIC_F32 7     /* out f32 += acc (atomic; split-K partial sums, gradient accumulation) */
 
 int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                      const float* bias, int epilogue, void* out, int64_t ldo, const float* aux,
                      int aux_period, int block_n /* 0 = auto, else 128|192|256 */, void* stream);
+
+/* Backward-pass form of the same GEMM: the operands are read as autograd leaves them, without transposes.
+ *   a_layout 0: A is [M, K] row-major            1: A is stored as [K, M] row-major (e.g. dY for a weight gradient)
+ *   b_layout 0: W is [N, K] row-major            1: W is stored as [K, N] row-major (e.g. the Linear weight [out, in]
+ *                                                   when the contraction runs over `out`: dX = dY W)
+ *   k_splits > 1 cuts the K range into partial products that are summed with atomics (RADVLM_EPI_ATOMIC_F32 only:
+ *   out must hold the running sum, e.g. zeros or the gradient accumulated so far).
+ * nn.Linear backward (torch/nn/functional.linear autograd, used by every Linear of siglip_encoder.py / builder.py):
+ *   dX[M, in]    = dY[M, out] W[out, in]       -> a_layout 0, b_layout 1, K = out
+ *   dW[out, in] += dY^T[out, M] X[M, in]       -> a_layout 1, b_layout 1, K = M, RADVLM_EPI_ATOMIC_F32 */
+int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, const void* W, int64_t ldw, int b_layout, int M, int N,
+                        int K, const float* bias, int epilogue, void* out, int64_t ldo, const float* aux,
+                        int aux_period, int k_splits, void* stream);
 
 /* Tile-shape policy of the GEMM: 0 = auto (CTA pairs, tcgen05 cta_group::2, 256 x BN tiles when M >= 512),
  * 1 = force single-CTA 128 x BN tiles, 2 = force CTA-pair tiles.  Process-wide; meant for tests / tuning. */

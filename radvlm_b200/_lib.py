@@ -109,6 +109,7 @@ SIGNATURES = {
     "radvlm_profile_enable": (_i, [_i]),
     "radvlm_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int64), _i]),
     "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
+    "radvlm_gemm_bf16_ex": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_set_mode": (_i, [_i]),
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_prepare_vt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),

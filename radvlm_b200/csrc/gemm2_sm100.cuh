@@ -139,8 +139,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int num_m = (args.M + kTileM - 1) / kTileM;
   const int num_n = (args.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_k = (args.K + kGemmBK - 1) / kGemmBK;
+  const int num_mn = num_m * num_n;
+  const int num_k_all = (args.K + kGemmBK - 1) / kGemmBK;
+  // split-K: work item t = split * num_mn + tile; split s covers K slabs [s * k_per, min(num_k_all, (s+1) * k_per))
+  const int k_splits = args.k_splits > 1 ? args.k_splits : 1;
+  const int k_per = (num_k_all + k_splits - 1) / k_splits;
+  const int num_tiles = num_mn * k_splits;
+  auto k_range = [&](int t, int& kb0, int& kb1) {
+    const int split = t / num_mn;
+    kb0 = split * k_per;
+    kb1 = min(num_k_all, kb0 + k_per);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -171,19 +180,34 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int tile = t % num_mn;
         const int m_blk = tile / num_n;
         const int n_blk = tile - m_blk * num_n;
         const int row_a = m_blk * kTileM + static_cast<int>(rank) * kGemmBM;
         const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = 0; kb < num_k; ++kb) {
+        int kb0, kb1;
+        k_range(t, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
           else mbar_arrive_remote(full_bar(stage), 0);
-          tma_load_2d_cta2(sa, &tmap_a, full_bar(stage), kb * kGemmBK, row_a);
-          tma_load_2d_cta2(sb, &tmap_b, full_bar(stage), kb * kGemmBK, row_b);
+          if (!args.a_mn) {
+            tma_load_2d_cta2(sa, &tmap_a, full_bar(stage), kb * kGemmBK, row_a);
+          } else {  // A stored [K, M]: boxes of {64 M-elements, 64 K-rows}, one per 64 rows of the tile
+#pragma unroll
+            for (int i = 0; i < kGemmBM / 64; ++i)
+              tma_load_2d_cta2(sa + i * 8192, &tmap_a, full_bar(stage), row_a + 64 * i, kb * kGemmBK);
+          }
+          if (!args.b_mn) {
+            tma_load_2d_cta2(sb, &tmap_b, full_bar(stage), kb * kGemmBK, row_b);
+          } else {  // W stored [K, N]: boxes of {64 N-elements, 64 K-rows}
+#pragma unroll
+            for (int i = 0; i < BN / 2 / 64; ++i)
+              tma_load_2d_cta2(sb + i * 8192, &tmap_b, full_bar(stage), row_b + 64 * i, kb * kGemmBK);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -196,27 +220,37 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // The whole warp runs the loop converged (all operands are warp-uniform); elect.sync inside the asm blocks picks
     // the lane that issues.
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
+      // instruction descriptor: bits 15 / 16 select MN-major A / B
+      const uint32_t idesc = make_idesc_bf16(kTileM, BN) | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint64_t desc0 = make_smem_desc(smem_base, 1024, kLayoutSw128);
+      // K-major operand: 8-row groups 1024 B apart, 32 B per 16-element K step inside the 128B swizzle atom.
+      // MN-major operand (TMA boxes of 64 MN-elements x 64 K-rows, 8 KB each): 8 K-rows per 1024 B atom (SBO),
+      // 64-element MN groups 8192 B apart (LBO), 2048 B per 16-row K step.
+      const uint64_t desc_k = make_smem_desc(smem_base, 1024, kLayoutSw128);
+      const uint64_t desc_mn = (desc_k & ~(static_cast<uint64_t>(0x3FFF) << 16)) | (static_cast<uint64_t>(8192 >> 4) << 16);
+      const uint64_t a0 = args.a_mn ? desc_mn : desc_k, b0 = args.b_mn ? desc_mn : desc_k;
+      const uint64_t a_step = args.a_mn ? (2048 >> 4) : 2, b_step = args.b_mn ? (2048 >> 4) : 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int kb0, kb1;
+        k_range(t, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = desc0 + static_cast<uint64_t>((stage * Cfg::kStageBytes) >> 4);
-          const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kABytes >> 4);
+          const uint64_t soff = static_cast<uint64_t>((stage * Cfg::kStageBytes) >> 4);
+          const uint64_t adesc = a0 + soff;
+          const uint64_t bdesc = b0 + soff + static_cast<uint64_t>(Cfg::kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k)
-            umma_bf16_ss_cta2_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_cta2_elect(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           umma_commit_cta2_mc_elect(empty_bar(stage), 3);
-          if (kb == num_k - 1) umma_commit_cta2_mc_elect(tfull_bar(acc), 3);
+          if (kb == kb1 - 1) umma_commit_cta2_mc_elect(tfull_bar(acc), 3);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -234,7 +268,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int tile = t % num_mn;
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
       mbar_wait(tfull_bar(acc), acc_phase);

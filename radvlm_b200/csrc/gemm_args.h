@@ -12,6 +12,7 @@ enum GemmEpilogue : int {
   EPI_POS_F32 = 4,         // out_f32  = acc + bias + pos[row % period]  (siglip_encoder.py:170-173)
   EPI_QKV_SPLIT = 5,       // head split scatter of q/k/v                (siglip_encoder.py:207-213)
   EPI_BIAS_F32 = 6,        // out_f32  = acc + bias
+  EPI_ATOMIC_F32 = 7,      // out_f32 += acc (red.global.add; split-K partial sums, weight-gradient accumulation)
 };
 
 struct GemmArgs {
@@ -26,6 +27,11 @@ struct GemmArgs {
   __nv_bfloat16* k;   // [tiles, heads, seq_pad, hd_pad]
   __nv_bfloat16* vt;  // [tiles, heads, hd_pad, seq_pad]
   int seq, seq_pad, heads, hd, hd_pad;
+  // Operand layouts (backward GEMMs read activations / weights as they are stored, no transposes):
+  //   a_mn = 0: A is [M, K] row-major (K-major operand);  a_mn = 1: A is stored as [K, M] row-major (MN-major)
+  //   b_mn = 0: W is [N, K] row-major;                    b_mn = 1: W is stored as [K, N] row-major
+  int a_mn, b_mn;
+  int k_splits;  // >= 1: the K range is cut into k_splits partial products (EPI_ATOMIC_F32 only)
 };
 
 }  // namespace rv

@@ -33,7 +33,8 @@ static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int num_tiles = ((args.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((args.N + BN - 1) / BN);
+  const int num_tiles = ((args.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((args.N + BN - 1) / BN) *
+                        (args.k_splits > 1 ? args.k_splits : 1);
   const int pairs = device_sm_count() / 2;
   const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
   gemm_bf16_tn_2cta_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
@@ -88,24 +89,45 @@ int gemm_pick_block_n(int M, int N, int cta_group) {
   return best;
 }
 
-int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
+int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args_in,
                   int epilogue, int block_n, cudaStream_t stream) {
   int st = require_sm100();
   if (st != RADVLM_OK) return st;
+  GemmArgs args = args_in;
   RV_CHECK_ARG(A != nullptr && W != nullptr, "gemm: null operand");
   RV_CHECK_ARG(args.M > 0 && args.N > 0 && args.K > 0, "gemm: bad shape M=%d N=%d K=%d", args.M,
                args.N, args.K);
-  RV_CHECK_ARG(lda >= args.K && ldw >= args.K, "gemm: row pitch smaller than K");
-  // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs
-  const bool pair = g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
-  const int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N, pair ? 2 : 1);
+  RV_CHECK_ARG(lda >= (args.a_mn ? args.M : args.K) && ldw >= (args.b_mn ? args.N : args.K),
+               "gemm: row pitch smaller than the stored row length");
+  RV_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: operand pitches must be multiples of 8 elements");
+  const bool general = args.a_mn || args.b_mn || args.k_splits > 1;
+  RV_CHECK_ARG(args.k_splits <= 1 || epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the atomic fp32 epilogue");
+  // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs; the MN-major / split-K paths
+  // exist in the pair kernel only
+  const bool pair = general || g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
+  int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N, pair ? 2 : 1);
+  if (args.b_mn && bn == 192) bn = 256;  // MN-major B is fetched in 64-column boxes per CTA: BN/2 % 64 == 0
+  if (args.k_splits > 1) {  // no empty split: (splits - 1) * ceil(slabs / splits) < slabs
+    const int slabs = (args.K + kGemmBK - 1) / kGemmBK;
+    int sp = args.k_splits < slabs ? args.k_splits : slabs;
+    while (sp > 1 && (sp - 1) * ((slabs + sp - 1) / sp) >= slabs) --sp;
+    args.k_splits = sp;
+  }
   CUtensorMap ta, tb;
-  st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M),
-                         static_cast<uint64_t>(lda) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!args.a_mn)
+    st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M),
+                           static_cast<uint64_t>(lda) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.M), static_cast<uint64_t>(args.K),
+                           static_cast<uint64_t>(lda) * 2, 64, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
-                         static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(pair ? bn / 2 : bn),
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!args.b_mn)
+    st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
+                           static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(pair ? bn / 2 : bn),
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.N), static_cast<uint64_t>(args.K),
+                           static_cast<uint64_t>(ldw) * 2, 64, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
   if (pair) {
     switch (epilogue) {
@@ -116,6 +138,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_POS_F32: return launch_gemm2_bn<EPI_POS_F32>(bn, ta, tb, args, stream);
       case EPI_QKV_SPLIT: return launch_gemm2_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
       case EPI_BIAS_F32: return launch_gemm2_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
+      case EPI_ATOMIC_F32: return launch_gemm2_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -128,6 +151,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     case EPI_POS_F32: return launch_gemm_bn<EPI_POS_F32>(bn, ta, tb, args, stream);
     case EPI_QKV_SPLIT: return launch_gemm_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
     case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
+    case EPI_ATOMIC_F32: return launch_gemm_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
   return RADVLM_ERR_BAD_ARGUMENT;
@@ -162,6 +186,28 @@ extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64
   a.aux = aux;
   a.aux_period = aux_period;
   return gemm_dispatch(A, lda, W, ldw, a, epilogue, block_n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, const void* W, int64_t ldw, int b_layout,
+                                   int M, int N, int K, const float* bias, int epilogue, void* out, int64_t ldo,
+                                   const float* aux, int aux_period, int k_splits, void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
+  RV_CHECK_ARG(out != nullptr && ldo >= N && (ldo % 8) == 0, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
+  RV_CHECK_ARG((a_layout | b_layout) >= 0 && a_layout <= 1 && b_layout <= 1, "gemm: layouts are 0 or 1");
+  RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");
+  RV_CHECK_ARG(epilogue != EPI_POS_F32 || (aux != nullptr && aux_period > 0 && (N % 4) == 0),
+               "gemm: position epilogue needs aux/aux_period and N % 4 == 0");
+  RV_CHECK_ARG(epilogue != EPI_ATOMIC_F32 || ((N % 4) == 0 && bias == nullptr), "gemm: atomic epilogue: N % 4 == 0, no bias");
+  GemmArgs a{};
+  a.M = M; a.N = N; a.K = K;
+  a.bias = bias;
+  a.out = out;
+  a.ldo = static_cast<int>(ldo);
+  a.aux = aux;
+  a.aux_period = aux_period;
+  a.a_mn = a_layout; a.b_mn = b_layout; a.k_splits = k_splits;
+  return gemm_dispatch(A, lda, W, ldw, a, epilogue, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw, int M,

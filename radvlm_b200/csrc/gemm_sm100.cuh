@@ -92,6 +92,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
       for (int j = 0; j < 32; ++j)
         if (col0 + j < a.N) o[j] = __float2bfloat16_rn(v[j]);
     }
+  } else if constexpr (EPI == EPI_ATOMIC_F32) {
+    float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) atomicAdd(o + j, v[j]);
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32) {
     float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
     const float* x = nullptr;
@@ -212,7 +217,15 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
         o.y = __uint_as_float(t.y) + b.y + xr[i].y;
         o.z = __uint_as_float(t.z) + b.z + xr[i].z;
         o.w = __uint_as_float(t.w) + b.w + xr[i].w;
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol) = o;
+        float* dst = reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol;
+        if constexpr (EPI == EPI_ATOMIC_F32) {
+          atomicAdd(dst + 0, o.x);
+          atomicAdd(dst + 1, o.y);
+          atomicAdd(dst + 2, o.z);
+          atomicAdd(dst + 3, o.w);
+        } else {
+          *reinterpret_cast<float4*>(dst) = o;
+        }
       }
     }
   }
@@ -267,7 +280,7 @@ template <int EPI, int NCOLS>
 __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row,
                                                     uint32_t stage, int lane) {
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
-  constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32);
+  constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
   constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16);
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;

@@ -150,6 +150,65 @@ static int run_case(const Case& c) {
   return bad ? 1 : 0;
 }
 
+// Backward-form GEMM: operands stored transposed (MN-major tcgen05 operands), optional split-K with the atomic epilogue.
+static int run_case_ex(int M, int N, int K, int a_layout, int b_layout, int k_splits, int epi) {
+  std::vector<__nv_bfloat16> hA((size_t)M * K), hW((size_t)N * K);   // logical row-major [M,K], [N,K]
+  for (auto& v : hA) v = __float2bfloat16(frand());
+  for (auto& v : hW) v = __float2bfloat16(frand());
+  const int lda = a_layout ? (M + 7) / 8 * 8 : K, ldw = b_layout ? (N + 7) / 8 * 8 : K;
+  std::vector<__nv_bfloat16> sA(a_layout ? (size_t)K * lda : (size_t)M * K, __float2bfloat16(0.f));
+  std::vector<__nv_bfloat16> sW(b_layout ? (size_t)K * ldw : (size_t)N * K, __float2bfloat16(0.f));
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) sA[a_layout ? (size_t)k * lda + m : (size_t)m * K + k] = hA[(size_t)m * K + k];
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) sW[b_layout ? (size_t)k * ldw + n : (size_t)n * K + k] = hW[(size_t)n * K + k];
+  __nv_bfloat16 *dA, *dW, *dAs, *dWs;
+  float *dref, *dout;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dW, hW.size() * 2));
+  CK(cudaMalloc(&dAs, sA.size() * 2)); CK(cudaMalloc(&dWs, sW.size() * 2));
+  CK(cudaMalloc(&dref, (size_t)M * N * 4)); CK(cudaMalloc(&dout, (size_t)M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dAs, sA.data(), sA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dWs, sW.data(), sW.size() * 2, cudaMemcpyHostToDevice));
+  ref_gemm<<<dim3((N + 127) / 128, M), 128>>>(dA, dW, nullptr, dref, M, N, K);
+  CK(cudaGetLastError());
+  const bool atomic = (epi == RADVLM_EPI_ATOMIC_F32);
+  const float init = atomic ? 1.5f : -7.f;
+  std::vector<float> hinit((size_t)M * N, init);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 3;
+  int st = 0;
+  for (int i = 0; i < reps; ++i) {
+    CK(cudaMemcpy(dout, hinit.data(), hinit.size() * 4, cudaMemcpyHostToDevice));
+    if (i == reps - 1) cudaEventRecord(e0);
+    st = radvlm_gemm_bf16_ex(dAs, lda, a_layout, dWs, ldw, b_layout, M, N, K, nullptr, epi, dout, N, nullptr, 0, k_splits, nullptr);
+    if (st) break;
+  }
+  cudaEventRecord(e1);
+  if (st) { printf("ex case: API error %d: %s\n", st, radvlm_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("ex case kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<float> href((size_t)M * N), hout((size_t)M * N);
+  CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hout.data(), dout, hout.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0; size_t bad = 0;
+  for (size_t i = 0; i < href.size(); ++i) {
+    const double want = href[i] + (atomic ? init : 0.f);
+    const double err = fabs(hout[i] - want);
+    if (!(err <= 2e-3 + 2e-4 * fabs(want))) ++bad;
+    if (err > max_err) max_err = err;
+    if (fabs(want) > max_ref) max_ref = fabs(want);
+  }
+  printf("ex   M=%5d N=%5d K=%6d a_layout=%d b_layout=%d splits=%d epi=%d : max_err=%.3e max_ref=%.3e bad=%zu/%zu  %.3f ms %.1f TFLOP/s %s\n",
+         M, N, K, a_layout, b_layout, k_splits, epi, max_err, max_ref, bad, href.size(), ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12,
+         bad ? "FAIL" : "ok");
+  cudaFree(dA); cudaFree(dW); cudaFree(dAs); cudaFree(dWs); cudaFree(dref); cudaFree(dout);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   std::vector<Case> cases = {
@@ -187,6 +246,20 @@ int main(int argc, char** argv) {
     radvlm_gemm_set_mode(mode);
     printf("---- GEMM mode %d (%s) ----\n", mode, mode == 1 ? "single-CTA 128xBN tiles" : "CTA-pair 256xBN tiles");
     for (const auto& c : cases) fails += run_case(c);
+  }
+  radvlm_gemm_set_mode(0);
+  // backward forms: dgrad (W read as stored, contraction over its rows) and wgrad (both operands transposed, split-K)
+  fails += run_case_ex(512, 256, 128, 0, 1, 1, RADVLM_EPI_BIAS_F32);
+  fails += run_case_ex(512, 256, 128, 1, 0, 1, RADVLM_EPI_BIAS_F32);
+  fails += run_case_ex(512, 256, 256, 1, 1, 1, RADVLM_EPI_BIAS_F32);
+  fails += run_case_ex(1458, 1152, 4304, 0, 1, 1, RADVLM_EPI_BIAS_F32);     // dX = dY W   (fc1: out 4304 -> in 1152)
+  fails += run_case_ex(1152, 4304, 1458, 1, 1, 1, RADVLM_EPI_ATOMIC_F32);   // dW2 += dY^T A
+  fails += run_case_ex(4304, 1152, 1458, 1, 1, 3, RADVLM_EPI_ATOMIC_F32);   // dW1 += dU^T X, split-K 3
+  fails += run_case_ex(300, 200, 1000, 1, 1, 4, RADVLM_EPI_ATOMIC_F32);     // ragged everything
+  if (!quick) {
+    fails += run_case_ex(29160, 1152, 4304, 0, 1, 1, RADVLM_EPI_BIAS_F32);
+    fails += run_case_ex(4304, 1152, 29160, 1, 1, 4, RADVLM_EPI_ATOMIC_F32);
+    fails += run_case_ex(1152, 4304, 29160, 1, 1, 4, RADVLM_EPI_ATOMIC_F32);
   }
   printf("%s (%d failing cases)\n", fails ? "GEMM TEST FAILED" : "GEMM TEST PASSED", fails);
   return fails ? 1 : 0;
