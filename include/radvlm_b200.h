@@ -107,6 +107,20 @@ int radvlm_attention_prepare_vt(void* vt, int tiles, int heads, int seq, int seq
                                 void* stream);
 int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
                          int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
+/* Same, also writing lse fp32 [tiles*heads, seq_pad]: the base-2 log-sum-exp of the scaled scores of every valid
+ * query row (softmax = 2^(s * scale * log2(e) - lse)), which the backward kernel recomputes P from. */
+int radvlm_attention_fwd_lse(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles, int heads,
+                             int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
+
+/* Backward of the attention (autograd of siglip_encoder.py:216-235).  q, k: the padded head-major buffers of the
+ * forward; vt: V^T prepared with plain ZEROS in its padding rows (no ones row); dout / out: gradient and value of the
+ * attention output, bf16 token-major [tiles*seq, heads*hd]; lse from radvlm_attention_fwd_lse.
+ * dqkv: bf16 [tiles*seq, 3*heads*hd] = [dQ | dK | dV] in the column order of the concatenated QKV projection, i.e.
+ * the dY of that Linear.  workspace: radvlm_attention_bwd_workspace_bytes (row dots + fp32 dQ accumulator). */
+size_t radvlm_attention_bwd_workspace_bytes(int tiles, int heads, int seq_pad);
+int radvlm_attention_bwd(const void* q, const void* k, const void* vt, const void* dout, const void* out,
+                         const float* lse, void* dqkv, void* workspace, size_t workspace_bytes, int tiles, int heads,
+                         int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound tower helpers.

@@ -114,6 +114,9 @@ SIGNATURES = {
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_prepare_vt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "radvlm_attention_bwd_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "radvlm_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "radvlm_attention_fwd_lse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "radvlm_layernorm_f32_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "radvlm_patch_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "radvlm_cast_f32_bf16": (_i, [_vp, _vp, _sz, _vp]),

@@ -1,0 +1,341 @@
+// Backward of the SigLIP attention (siglip_encoder.py:216-235 under autograd) on sm_100a tensor cores.
+//
+//   P  = softmax(Q K^T * scale)            recomputed from the forward's log-sum-exp:  P = 2^(S * scale * log2e - lse)
+//   dV = P^T dO        dP = dO V^T         dS = P o (dP - delta) * scale,  delta = rowsum(dO o O)
+//   dQ = dS K          dK = dS^T Q
+//
+// One CTA owns one 128-key block j of one (tile, head): dK_j and dV_j accumulate in TMEM over the query blocks
+// i = 0..5, dQ_i partial products are added to an fp32 buffer with atomics (every key block contributes to every
+// query block).  All five products run on tcgen05; the operands are read in place, without transposed copies:
+//   * Q_i, K_j, dO_i sit in shared memory as five [128 rows x 32 B] 32B-swizzled chunks (dO_i is fetched by TMA
+//     straight out of the token-major [tokens, heads*hd] gradient of the attention output).  The same bytes are a
+//     K-major operand when the contraction runs over head_dim (S, dP) and an MN-major operand when it runs over
+//     the rows (dV = P^T dO, dK = dS^T Q, dQ = dS K).
+//   * V_j is the forward's V^T tile ([80 x 128 keys], 128B swizzle) used as an MN-major B operand.
+//   * P and dS are written by the softmax warps as bf16 [q][key] tiles (128B swizzle): K-major A for dQ = dS K,
+//     MN-major A for P^T dO and dS^T Q.
+// Warp roles: warp0 TMA, warp1 MMA issue (whole warp, elect.sync), warps 2..9 two threads per query row.
+// TMEM: S [0,128)  dP [128,256)  dV [256,336)  dK [336,416)  dQ [416,496).
+//
+// Padding contract: Q / K pad rows and head-dim pad columns are zero; V^T rows >= hd are zero (NO ones row: use a
+// buffer prepared with plain zeros); rows of dO beyond this tile (the next tile's tokens) are neutralised by zeroing
+// the P / dS rows of invalid queries.
+#pragma once
+
+#include "common.cuh"
+
+namespace rv {
+
+struct AttnBwdArgs {
+  const float* lse;      // [tiles*heads, seq_pad] base-2 log-sum-exp from the forward
+  const float* delta;    // [tiles*heads, seq_pad] rowsum(dO o O)
+  float* dq_acc;         // [tiles*heads, seq_pad, 80] fp32, zero-initialised
+  __nv_bfloat16* dqkv;   // [tiles*seq, 3*heads*hd]: this kernel writes the dK and dV column blocks
+  int seq, seq_pad, heads, hd;
+  float scale, scale_log2e;
+};
+
+constexpr int kAbThreads = 320;
+constexpr int kAbTile = 128 * 80 * 2;   // 20480: Q / K / dO tiles (5 SW32 chunks) and the V^T tile (2 SW128 atoms)
+constexpr int kAbPTile = 128 * 128 * 2; // 32768: P and dS
+constexpr int kAbSmemBytes = 4 * kAbTile + 2 * kAbPTile + 128;
+constexpr int kAbTmemCols = 512;
+
+__device__ __forceinline__ float ex2_approx_bwd(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// shared-memory descriptor with an explicit leading-dimension byte offset (MN-major operands need it)
+__device__ __forceinline__ uint64_t make_smem_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kAbThreads, 1)
+siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  [th*seq_pad, 80]   box {16, 128} SW32
+                            const __grid_constant__ CUtensorMap tmap_k,   // K  same
+                            const __grid_constant__ CUtensorMap tmap_vt,  // Vt [th*80, seq_pad]   box {64, 80} SW128
+                            const __grid_constant__ CUtensorMap tmap_do,  // dO [tiles*seq, heads*hd] box {16, 128} SW32
+                            const AttnBwdArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t sK = smem_base;
+  const uint32_t sV = sK + kAbTile;
+  const uint32_t sQ = sV + kAbTile;
+  const uint32_t sdO = sQ + kAbTile;
+  const uint32_t sP = sdO + kAbTile;
+  const uint32_t sdS = sP + kAbPTile;
+  const uint32_t bar_base = sdS + kAbPTile;
+  const uint32_t bar_kv = bar_base + 0;       // K_j, Vt_j landed
+  const uint32_t bar_qdo = bar_base + 8;      // Q_i, dO_i landed
+  const uint32_t bar_sdp = bar_base + 16;     // S, dP complete in TMEM
+  const uint32_t bar_pds = bar_base + 24;     // P, dS written to shared memory (256 arrivals)
+  const uint32_t bar_mma2 = bar_base + 32;    // dV, dK, dQ products of this query block complete
+  const uint32_t bar_dqfree = bar_base + 40;  // dQ read out of TMEM (256 arrivals)
+  const uint32_t tmem_ptr_smem = bar_base + 48;
+
+  const int warp = threadIdx.x >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int lane = threadIdx.x & 31;
+  const int jblk = blockIdx.x;
+  const int head = blockIdx.y;
+  const int tile = blockIdx.z;
+  const int th = tile * args.heads + head;
+  const int num_q = (args.seq + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_vt);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_qdo, 1);
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, 256);
+    mbar_init(bar_mma2, 1);
+    mbar_init(bar_dqfree, 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, kAbTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 336,
+                 tdQ = tmem_base + 416;
+
+  if (warp_u == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int k_row0 = th * args.seq_pad + jblk * 128;
+      mbar_arrive_expect_tx(bar_kv, 2 * kAbTile);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tma_load_2d(sK + c * 4096, &tmap_k, bar_kv, c * 16, k_row0);
+      tma_load_2d(sV, &tmap_vt, bar_kv, jblk * 128, th * 80);
+      tma_load_2d(sV + 10240, &tmap_vt, bar_kv, jblk * 128 + 64, th * 80);
+      for (int i = 0; i < num_q; ++i) {
+        if (i > 0) mbar_wait(bar_mma2, static_cast<uint32_t>((i - 1) & 1));  // Q / dO consumed
+        mbar_arrive_expect_tx(bar_qdo, 2 * kAbTile);
+        const int q_row0 = th * args.seq_pad + i * 128;
+        const int do_row0 = tile * args.seq + i * 128;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          tma_load_2d(sQ + c * 4096, &tmap_q, bar_qdo, c * 16, q_row0);
+          tma_load_2d(sdO + c * 4096, &tmap_do, bar_qdo, head * args.hd + c * 16, do_row0);
+        }
+      }
+    }
+  } else if (warp_u == 1) {
+    // ===================== MMA issue (whole warp, elect.sync inside the asm blocks) =====================
+    constexpr uint32_t kAMn = 1u << 15, kBMn = 1u << 16;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);                  // S  = Q K^T      (K-major, K-major)
+    constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128) | kBMn;          // dP = dO V^T     (K-major, MN-major V^T)
+    constexpr uint32_t idesc_kv = make_idesc_bf16(128, 80) | kAMn | kBMn;    // dV = P^T dO, dK = dS^T Q
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, 80) | kBMn;           // dQ = dS K
+    const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0);
+    const uint32_t tdP_u = tS_u + 128, tdV_u = tS_u + 256, tdK_u = tS_u + 336, tdQ_u = tS_u + 416;
+    // K-major views (contraction over head_dim): chunk c = K step c
+    const uint64_t q_k = make_smem_desc(sQ, 256, kLayoutSw32), k_k = make_smem_desc(sK, 256, kLayoutSw32);
+    const uint64_t do_k = make_smem_desc(sdO, 256, kLayoutSw32);
+    // MN-major views (contraction over the 128 rows): 16-element head-dim groups 4096 B apart, 8 rows per 256 B atom
+    const uint64_t q_mn = make_smem_desc_lbo(sQ, 4096, 256, kLayoutSw32);
+    const uint64_t k_mn = make_smem_desc_lbo(sK, 4096, 256, kLayoutSw32);
+    const uint64_t do_mn = make_smem_desc_lbo(sdO, 4096, 256, kLayoutSw32);
+    // V^T tile [80 x 128 keys] as MN-major B (N = keys): 64-key groups 10240 B apart, 8 head-dim rows per 1024 B atom
+    const uint64_t v_mn = make_smem_desc_lbo(sV, 10240, 1024, kLayoutSw128);
+    // P / dS tiles [128 q x 128 keys]: K-major A (contraction over keys) and MN-major A (contraction over queries)
+    const uint64_t ds_k = make_smem_desc(sdS, 1024, kLayoutSw128);
+    const uint64_t p_mn = make_smem_desc_lbo(sP, 16384, 1024, kLayoutSw128);
+    const uint64_t ds_mn = make_smem_desc_lbo(sdS, 16384, 1024, kLayoutSw128);
+
+    mbar_wait(bar_kv, 0);
+    for (int i = 0; i < num_q; ++i) {
+      const uint32_t par = static_cast<uint32_t>(i & 1);
+      mbar_wait(bar_qdo, par);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 5; ++c)   // S: K step c = chunk c (4096 B)
+        umma_bf16_ss_elect(tS_u, q_k + c * 256, k_k + c * 256, idesc_s, c != 0 ? 1u : 0u);
+#pragma unroll
+      for (int c = 0; c < 5; ++c)   // dP: K step c = 16 head-dim rows of V^T (2048 B)
+        umma_bf16_ss_elect(tdP_u, do_k + c * 256, v_mn + c * 128, idesc_dp, c != 0 ? 1u : 0u);
+      umma_commit_elect(bar_sdp);
+
+      mbar_wait(bar_pds, par);                                  // P, dS in shared memory
+      if (i > 0) mbar_wait(bar_dqfree, par ^ 1u);               // previous dQ read out
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 8; ++s)   // dV += P^T dO: K step s = 16 query rows (P: 2048 B, dO chunks: 512 B)
+        umma_bf16_ss_elect(tdV_u, p_mn + s * 128, do_mn + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
+#pragma unroll
+      for (int s = 0; s < 8; ++s)   // dK += dS^T Q
+        umma_bf16_ss_elect(tdK_u, ds_mn + s * 128, q_mn + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
+#pragma unroll
+      for (int s = 0; s < 8; ++s)   // dQ = dS K: K step s = 16 keys (dS: 32 B inside its 64-key atom, K chunks: 512 B)
+        umma_bf16_ss_elect(tdQ_u, ds_k + (s >> 2) * 1024 + (s & 3) * 2, k_mn + s * 32, idesc_dq, s != 0 ? 1u : 0u);
+      umma_commit_elect(bar_mma2);
+    }
+  } else {
+    // ===================== softmax-gradient warps: two threads per query row =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t row_off = static_cast<uint32_t>(half) * 16384u + static_cast<uint32_t>(r) * 128u;
+    const int D = args.heads * args.hd;
+
+    for (int i = 0; i < num_q; ++i) {
+      const uint32_t par = static_cast<uint32_t>(i & 1);
+      const int qrow = i * 128 + r;
+      const bool q_ok = qrow < args.seq;
+      float lse = 0.f, delta = 0.f;
+      if (q_ok) {
+        lse = __ldg(args.lse + static_cast<size_t>(th) * args.seq_pad + qrow);
+        delta = __ldg(args.delta + static_cast<size_t>(th) * args.seq_pad + qrow);
+      }
+      mbar_wait(bar_sdp, par);
+      tc_fence_after();
+      if (i > 0) mbar_wait(bar_mma2, par ^ 1u);  // the products that read the previous P / dS are complete
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld_x32(tS + lane_off + static_cast<uint32_t>(half * 64 + c * 32), s);
+        tmem_ld_x32(tdP + lane_off + static_cast<uint32_t>(half * 64 + c * 32), dp);
+        tmem_wait_ld();
+        const int key0 = jblk * 128 + half * 64 + c * 32;
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ex2_approx_bwd(fmaf(__uint_as_float(s[e]), args.scale_log2e, -lse));
+          float p1 = ex2_approx_bwd(fmaf(__uint_as_float(s[e + 1]), args.scale_log2e, -lse));
+          if (!q_ok || key0 + e >= args.seq) p0 = 0.f;
+          if (!q_ok || key0 + e + 1 >= args.seq) p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[e]) - delta) * args.scale;
+          const float d1 = p1 * (__uint_as_float(dp[e + 1]) - delta) * args.scale;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dk[e >> 1] = pack_bf16x2(d0, d1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t chunk = static_cast<uint32_t>(4 * c + u) ^ sw;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + row_off + chunk * 16u), "r"(pk[4 * u]),
+                       "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + row_off + chunk * 16u), "r"(dk[4 * u]),
+                       "r"(dk[4 * u + 1]), "r"(dk[4 * u + 2]), "r"(dk[4 * u + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+
+      // ---- dQ_i partial product of this key block -> fp32 atomics (columns [40*half, +40) < hd)
+      mbar_wait(bar_mma2, par);
+      tc_fence_after();
+      uint32_t dq[40];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tmem_ld_x8(tdQ + lane_off + static_cast<uint32_t>(half * 40 + c * 8), dq + c * 8);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_dqfree);
+      if (q_ok) {
+        float* dst = args.dq_acc + (static_cast<size_t>(th) * args.seq_pad + qrow) * 80 + half * 40;
+#pragma unroll
+        for (int e = 0; e < 40; ++e)
+          if (half * 40 + e < args.hd) atomicAdd(dst + e, __uint_as_float(dq[e]));
+      }
+    }
+
+    // ---- dK_j, dV_j -> bf16 -> dqkv[(tile*seq + key), D + head*hd + d] and [.., 2D + head*hd + d]
+    //      (lanes are keys now; the last bar_mma2 wait above covers the final products)
+    const int key = jblk * 128 + r;
+    uint32_t kk[40], vv[40];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      tmem_ld_x8(tdK + lane_off + static_cast<uint32_t>(half * 40 + c * 8), kk + c * 8);
+      tmem_ld_x8(tdV + lane_off + static_cast<uint32_t>(half * 40 + c * 8), vv + c * 8);
+    }
+    tmem_wait_ld();
+    if (key < args.seq) {
+      __nv_bfloat16* base = args.dqkv + (static_cast<size_t>(tile) * args.seq + key) * (3 * D) + head * args.hd + half * 40;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (half * 40 + c * 8 < args.hd) {
+          uint4 a, b;
+          a.x = pack_bf16x2(__uint_as_float(kk[8 * c + 0]), __uint_as_float(kk[8 * c + 1]));
+          a.y = pack_bf16x2(__uint_as_float(kk[8 * c + 2]), __uint_as_float(kk[8 * c + 3]));
+          a.z = pack_bf16x2(__uint_as_float(kk[8 * c + 4]), __uint_as_float(kk[8 * c + 5]));
+          a.w = pack_bf16x2(__uint_as_float(kk[8 * c + 6]), __uint_as_float(kk[8 * c + 7]));
+          b.x = pack_bf16x2(__uint_as_float(vv[8 * c + 0]), __uint_as_float(vv[8 * c + 1]));
+          b.y = pack_bf16x2(__uint_as_float(vv[8 * c + 2]), __uint_as_float(vv[8 * c + 3]));
+          b.z = pack_bf16x2(__uint_as_float(vv[8 * c + 4]), __uint_as_float(vv[8 * c + 5]));
+          b.w = pack_bf16x2(__uint_as_float(vv[8 * c + 6]), __uint_as_float(vv[8 * c + 7]));
+          reinterpret_cast<uint4*>(base + D)[c] = a;
+          reinterpret_cast<uint4*>(base + 2 * D)[c] = b;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAbTmemCols);
+  }
+}
+
+// delta[th, q] = sum_d dO[token, head*hd + d] * O[token, head*hd + d]: one warp per (token, head)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, float* __restrict__ delta,
+                  int tokens, int seq, int seq_pad, int heads, int hd) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= tokens * heads) return;
+  const int token = w / heads, head = w - token * heads;
+  const size_t off = static_cast<size_t>(token) * heads * hd + head * hd;
+  float acc = 0.f;
+  for (int d = lane; d < hd; d += 32) acc += __bfloat162float(dO[off + d]) * __bfloat162float(O[off + d]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int tile = token / seq, t = token - tile * seq;
+    delta[(static_cast<size_t>(tile) * heads + head) * seq_pad + t] = acc;
+  }
+}
+
+// dq_acc fp32 [th, seq_pad, 80] -> bf16 dqkv[(tile*seq + q), head*hd + d]
+__global__ void __launch_bounds__(256)
+attn_dq_store_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int tokens, int seq,
+                     int seq_pad, int heads, int hd) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per (token, head, d/8)
+  const int per_head = hd / 8;
+  const size_t total = static_cast<size_t>(tokens) * heads * per_head;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % per_head);
+  const int head = static_cast<int>((idx / per_head) % heads);
+  const int token = static_cast<int>(idx / (static_cast<size_t>(per_head) * heads));
+  const int tile = token / seq, t = token - tile * seq;
+  const float* src = dq_acc + ((static_cast<size_t>(tile) * heads + head) * seq_pad + t) * 80 + v * 8;
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+  *reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(token) * (3 * heads * hd) + head * hd + v * 8) = o;
+}
+
+}  // namespace rv

@@ -6,7 +6,7 @@
 
 namespace rv {
 
-int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
+int attention_launch(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream) {
   int st = require_sm100();
   if (st != RADVLM_OK) return st;
@@ -50,6 +50,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
   a.heads = heads;
   a.hd = hd;
   a.scale_log2e = scale * 1.4426950408889634f;
+  a.lse = lse;
   a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
   a.total_items = tiles * heads * a.num_qblk;
   const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
@@ -63,6 +64,13 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, in
 extern "C" int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles,
                                     int heads, int seq, int seq_pad, int hd, int hd_pad, float scale,
                                     void* stream) {
-  return rv::attention_launch(q, k, vt, out, tiles, heads, seq, seq_pad, hd, hd_pad, scale,
+  return rv::attention_launch(q, k, vt, out, nullptr, tiles, heads, seq, seq_pad, hd, hd_pad, scale,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_attention_fwd_lse(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles,
+                                        int heads, int seq, int seq_pad, int hd, int hd_pad, float scale,
+                                        void* stream) {
+  return rv::attention_launch(q, k, vt, out, lse, tiles, heads, seq, seq_pad, hd, hd_pad, scale,
                               static_cast<cudaStream_t>(stream));
 }

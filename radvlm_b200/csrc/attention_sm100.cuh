@@ -41,6 +41,7 @@ struct AttnArgs {
   int heads;           // 16
   int hd;              // 72
   float scale_log2e;   // hd^-0.5 * log2(e)
+  float* lse;          // optional [tiles*heads, seq_pad]: log2-domain log-sum-exp of the scaled scores (for backward)
   int num_qblk;        // ceil(seq / 128) query blocks per (tile, head)
   int total_items;     // tiles * heads * num_qblk
 };
@@ -376,6 +377,8 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
       const int tile = th / args.heads, head = th - tile * args.heads;
       const int t = qblk * kAttnBQ + r;
       const float inv_l = 1.0f / __uint_as_float(l_bits);
+      if (args.lse != nullptr && half == 0 && t < args.seq)  // softmax = 2^(s * scale * log2e - lse)
+        args.lse[static_cast<size_t>(th) * args.seq_pad + t] = m_ref + log2f(__uint_as_float(l_bits));
       if (t < args.seq) {
         __nv_bfloat16* dst = args.out +
                              (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +

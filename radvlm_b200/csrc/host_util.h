@@ -36,6 +36,7 @@ const char* last_error();
 // Returns 0 when the current device is sm_100 (B200); otherwise sets the error and returns a status.
 int require_sm100();
 int device_sm_count();
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows, row pitch in bytes.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,

@@ -11,8 +11,12 @@ namespace rv {
 int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
                   int epilogue, int block_n, cudaStream_t stream);
 int gemm_pick_block_n(int M, int N, int cta_group);
-int attention_launch(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
+int attention_launch(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
+size_t attention_bwd_workspace_bytes(int tiles, int heads, int seq_pad);
+int attention_bwd_launch(const void* q, const void* k, const void* vt, const void* dout, const void* out,
+                         const float* lse, void* dqkv, void* workspace, size_t workspace_bytes, int tiles, int heads,
+                         int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
 int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,

@@ -10,7 +10,6 @@
 
 namespace rv {
 
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct EncodeLayout {
   int P, T, seq_pad, hd, hd_pad;
@@ -105,7 +104,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
-    { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, xn, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
+    { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, xn, nullptr, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
     if (st) return st;
     {
       GemmArgs a{};

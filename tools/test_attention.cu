@@ -198,6 +198,135 @@ static int test_qkv_split(int tiles) {
   return (bad || nonzero_pad) ? 1 : 0;
 }
 
+// ---- attention backward: reference = one thread per (th, query row), fp32, atomics for dK / dV
+__global__ void ref_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
+                                  const __nv_bfloat16* dout, float* dq, float* dk, float* dv, int th_count, int heads,
+                                  int seq, int seq_pad, int hd, int hd_pad, float scale) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int th = blockIdx.y;
+  if (t >= seq || th >= th_count) return;
+  const int tile = th / heads, head = th % heads;
+  const __nv_bfloat16* qr = q + ((size_t)th * seq_pad + t) * hd_pad;
+  const __nv_bfloat16* dor = dout + ((size_t)tile * seq + t) * (heads * hd) + head * hd;
+  float mx = -1e30f;
+  for (int j = 0; j < seq; ++j) {
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s += __bfloat162float(qr[d]) * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
+    mx = fmaxf(mx, s * scale);
+  }
+  float l = 0.f, o[72], dqa[72];
+  for (int d = 0; d < hd; ++d) { o[d] = 0.f; dqa[d] = 0.f; }
+  for (int j = 0; j < seq; ++j) {
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s += __bfloat162float(qr[d]) * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
+    float p = expf(s * scale - mx);
+    l += p;
+    for (int d = 0; d < hd; ++d) o[d] += p * __bfloat162float(vt[((size_t)th * hd_pad + d) * seq_pad + j]);
+  }
+  float delta = 0.f;
+  for (int d = 0; d < hd; ++d) delta += (o[d] / l) * __bfloat162float(dor[d]);
+  for (int j = 0; j < seq; ++j) {
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < hd; ++d) {
+      s += __bfloat162float(qr[d]) * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
+      dp += __bfloat162float(dor[d]) * __bfloat162float(vt[((size_t)th * hd_pad + d) * seq_pad + j]);
+    }
+    const float p = expf(s * scale - mx) / l;
+    const float ds = p * (dp - delta) * scale;
+    for (int d = 0; d < hd; ++d) {
+      dqa[d] += ds * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
+      atomicAdd(&dk[((size_t)th * seq + j) * hd + d], ds * __bfloat162float(qr[d]));
+      atomicAdd(&dv[((size_t)th * seq + j) * hd + d], p * __bfloat162float(dor[d]));
+    }
+  }
+  for (int d = 0; d < hd; ++d) dq[((size_t)th * seq + t) * hd + d] = dqa[d];
+}
+
+static int test_attention_bwd(int tiles, int heads, float amp) {
+  const int seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
+  const int th = tiles * heads, D = heads * hd;
+  const size_t nq = (size_t)th * seq_pad * hd_pad, ntok = (size_t)tiles * seq;
+  std::vector<__nv_bfloat16> hq(nq, __float2bfloat16(0.f)), hk(nq, __float2bfloat16(0.f)), hv(nq, __float2bfloat16(0.f));
+  std::vector<__nv_bfloat16> hdo(ntok * D);
+  for (int a = 0; a < th; ++a)
+    for (int t = 0; t < seq; ++t)
+      for (int d = 0; d < hd; ++d) {
+        hq[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
+        hk[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
+        hv[((size_t)a * hd_pad + d) * seq_pad + t] = __float2bfloat16(frand() * 2.f);
+      }
+  for (auto& v : hdo) v = __float2bfloat16(frand());
+  std::vector<__nv_bfloat16> hv1 = hv;  // forward copy with the ones row
+  for (int a = 0; a < th; ++a)
+    for (int t = 0; t < seq; ++t) hv1[((size_t)a * hd_pad + hd) * seq_pad + t] = __float2bfloat16(1.0f);
+  __nv_bfloat16 *dq, *dk, *dv, *dv1, *ddo, *dout, *dqkv;
+  float *dlse, *rdq, *rdk, *rdv;
+  void* ws;
+  const size_t wsb = radvlm_attention_bwd_workspace_bytes(tiles, heads, seq_pad);
+  CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2)); CK(cudaMalloc(&dv1, nq * 2));
+  CK(cudaMalloc(&ddo, ntok * D * 2)); CK(cudaMalloc(&dout, ntok * D * 2)); CK(cudaMalloc(&dqkv, ntok * 3 * D * 2));
+  CK(cudaMalloc(&dlse, (size_t)th * seq_pad * 4)); CK(cudaMalloc(&ws, wsb));
+  CK(cudaMalloc(&rdq, (size_t)th * seq * hd * 4)); CK(cudaMalloc(&rdk, (size_t)th * seq * hd * 4));
+  CK(cudaMalloc(&rdv, (size_t)th * seq * hd * 4));
+  CK(cudaMemset(rdq, 0, (size_t)th * seq * hd * 4)); CK(cudaMemset(rdk, 0, (size_t)th * seq * hd * 4));
+  CK(cudaMemset(rdv, 0, (size_t)th * seq * hd * 4));
+  CK(cudaMemcpy(dq, hq.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dk, hk.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dv, hv.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dv1, hv1.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ddo, hdo.data(), ntok * D * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dqkv, 0xFF, ntok * 3 * D * 2));
+  const float scale = 1.0f / sqrtf((float)hd);
+  int st = radvlm_attention_fwd_lse(dq, dk, dv1, dout, dlse, tiles, heads, seq, seq_pad, hd, hd_pad, scale, nullptr);
+  if (st) { printf("fwd_lse API error %d: %s\n", st, radvlm_last_error()); return 1; }
+  ref_attention_bwd<<<dim3((seq + 63) / 64, th), 64>>>(dq, dk, dv, ddo, rdq, rdk, rdv, th, heads, seq, seq_pad, hd, hd_pad, scale);
+  CK(cudaGetLastError());
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 3;
+  for (int i = 0; i < reps + 1; ++i) {
+    if (i == 1) cudaEventRecord(e0);
+    st = radvlm_attention_bwd(dq, dk, dv, ddo, dout, dlse, dqkv, ws, wsb, tiles, heads, seq, seq_pad, hd, hd_pad, scale, nullptr);
+    if (st) break;
+  }
+  cudaEventRecord(e1);
+  if (st) { printf("attention_bwd API error %d: %s\n", st, radvlm_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("attention_bwd kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+  std::vector<__nv_bfloat16> hg(ntok * 3 * D);
+  std::vector<float> hr[3];
+  CK(cudaMemcpy(hg.data(), dqkv, hg.size() * 2, cudaMemcpyDeviceToHost));
+  float* rp[3] = {rdq, rdk, rdv};
+  int fails = 0;
+  const char* names[3] = {"dQ", "dK", "dV"};
+  for (int w = 0; w < 3; ++w) {
+    hr[w].resize((size_t)th * seq * hd);
+    CK(cudaMemcpy(hr[w].data(), rp[w], hr[w].size() * 4, cudaMemcpyDeviceToHost));
+    double max_ref = 0, max_err = 0, dot = 0, n1 = 0, n2 = 0;
+    for (int a = 0; a < th; ++a)
+      for (int t = 0; t < seq; ++t)
+        for (int d = 0; d < hd; ++d) {
+          const int tile = a / heads, head = a % heads;
+          const double g = __bfloat162float(hg[((size_t)tile * seq + t) * 3 * D + w * D + head * hd + d]);
+          const double r = hr[w][((size_t)a * seq + t) * hd + d];
+          max_ref = fmax(max_ref, fabs(r));
+          if (!(fabs(g - r) <= max_err)) max_err = fabs(g - r);
+          dot += g * r; n1 += g * g; n2 += r * r;
+        }
+    const double cosv = dot / (sqrt(n1) * sqrt(n2) + 1e-30);
+    const bool ok = cosv > 0.999 && max_err <= 3e-2 * max_ref;
+    printf("attention_bwd tiles=%d heads=%d %s: cos=%.6f max_err=%.3e max_ref=%.3e %s\n", tiles, heads, names[w], cosv,
+           max_err, max_ref, ok ? "ok" : "FAIL");
+    fails += ok ? 0 : 1;
+  }
+  const double flops = 2.5 * 4.0 * th * (double)seq * seq * hd;
+  printf("attention_bwd tiles=%d heads=%d: %.3f ms  %.1f TFLOP/s(alg)\n", tiles, heads, ms, flops / (ms * 1e-3) / 1e12);
+  cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dv1); cudaFree(ddo); cudaFree(dout); cudaFree(dqkv); cudaFree(dlse);
+  cudaFree(ws); cudaFree(rdq); cudaFree(rdk); cudaFree(rdv);
+  return fails;
+}
+
 int main(int argc, char** argv) {
   int fails = 0;
   fails += test_qkv_split(2);
@@ -205,6 +334,9 @@ int main(int argc, char** argv) {
   fails += test_attention(2, 16, 6.0f);   // larger logits: exercises the lazy rescale path
   fails += test_attention(10, 16, 2.0f);
   fails += test_attention(37, 16, 2.0f);  // 12 full waves of CTAs: steady-state throughput  // one 1024^2 image worth of tiles
+  fails += test_attention_bwd(1, 2, 2.0f);
+  fails += test_attention_bwd(2, 16, 4.0f);
+  fails += test_attention_bwd(10, 16, 2.0f);
   printf("%s (%d failing)\n", fails ? "ATTENTION TEST FAILED" : "ATTENTION TEST PASSED", fails);
   return fails ? 1 : 0;
 }
