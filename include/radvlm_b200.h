@@ -205,6 +205,58 @@ int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvlm_projector
                          int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training mode (BASELINE config 5; mm_tunable_parts = mm_vision_tower, mm_mlp_adapter: train.py:1642-1665).
+ * The forward keeps, per layer, the fp32 residual stream entering it, the attention output and the attention
+ * log-sum-exp (`saved`, radvlm_tower_saved_bytes); the backward recomputes the rest layer by layer (the reference
+ * checkpoints whole encoder layers: siglip_encoder.py:381-387).  Gradient pointers are fp32, same shapes as the
+ * packed weights, ACCUMULATED (+=); a null pointer freezes that parameter.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct radvlm_vit_layer_grads {
+  float* ln1_gamma; float* ln1_beta;
+  float* qkv_w;  /* [3*hidden, hidden] */
+  float* qkv_b;
+  float* out_w;  float* out_b;
+  float* ln2_gamma; float* ln2_beta;
+  float* fc1_w;  float* fc1_b;
+  float* fc2_w;  float* fc2_b;
+} radvlm_vit_layer_grads;
+
+typedef struct radvlm_siglip_grads {
+  float* patch_w;   /* [hidden, patch_k_pad] */
+  float* patch_b;
+  float* pos_embed; /* [P*P, hidden] */
+  const radvlm_vit_layer_grads* layers; /* host array [num_layers] or NULL */
+} radvlm_siglip_grads;
+
+typedef struct radvlm_projector_grads {
+  float* w1; float* b1; float* w2; float* b2;
+} radvlm_projector_grads;
+
+size_t radvlm_tower_saved_bytes(const radvlm_siglip_weights* tw, int n_tiles);
+/* byte offset, inside `saved`, of the tower output: fp32 [n_tiles*P*P, hidden] */
+size_t radvlm_tower_saved_hidden_offset(const radvlm_siglip_weights* tw, int n_tiles);
+/* workspace: radvlm_encode_workspace_bytes(tw, NULL, n_tiles) */
+int radvlm_siglip_tower_forward_train(const radvlm_siglip_weights* tw, const void* pixels, int pixel_dtype,
+                                      int n_tiles, void* saved, size_t saved_bytes, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+size_t radvlm_tower_backward_workspace_bytes(const radvlm_siglip_weights* tw, int n_tiles);
+/* d_hidden: fp32 [n_tiles*P*P, hidden], dL/d(tower output) on entry; used as the running residual gradient. */
+int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads, const void* pixels,
+                                 int pixel_dtype, int n_tiles, const void* saved, size_t saved_bytes, float* d_hidden,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+size_t radvlm_projector_backward_workspace_bytes(const radvlm_projector_weights* pw, int rows);
+/* hidden: fp32 [rows, in_dim] (the projector input); d_features: bf16 [rows, hidden];
+ * d_hidden: fp32 [rows, in_dim] written (may be NULL when the tower is frozen). */
+int radvlm_projector_backward(const radvlm_projector_weights* pw, const radvlm_projector_grads* grads,
+                              const float* hidden, const void* d_features, int rows, float* d_hidden, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* helpers exposed for tests */
+int radvlm_colsum_bf16(const void* x, int rows, int cols, int ld, float* out, void* stream);
+int radvlm_gelu_fwd_bwd_bf16(const void* u, void* da_du, void* a, int64_t n, int erf_form, void* stream);
+int radvlm_layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dres, float* dgamma, float* dbeta,
+                         int rows, int D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Planner (CPU only, no CUDA): every integer decision of the path with the reference's Python
  * float64/int semantics, bit-exact.
  *   radvlm_plan_select_best_resolution : mm_utils.py:119-149 (candidates are (width,height) pairs)
@@ -285,6 +337,14 @@ int radvlm_merge_splice(const void* features, const void* newline, const void* e
                         const radvlm_merge_image* images, int n_images, int64_t total_rows,
                         void* out_embeds, int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
                         int64_t ignore_index, void* stream);
+
+/* Backward of radvlm_merge_splice (autograd of llava_arch.py:350-531).  d_out_embeds: [B*max_len, H] of `dtype`.
+ *   d_features fp32 [tiles*T, H] and d_newline fp32 [H]: accumulated with atomics (zero or running sums on entry);
+ *   d_text [n_text, H] of `dtype` (or NULL): gradient rows of the text tokens in text_src order. */
+int radvlm_merge_splice_backward(const void* d_out_embeds, int dtype, int hidden, int tokens_per_tile,
+                                 int patches_per_side, const radvlm_splice_segment* segments, int n_segments,
+                                 const radvlm_merge_image* images, int n_images, int64_t total_rows,
+                                 float* d_features, float* d_newline, void* d_text, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused anyres preprocessing (uint8 -> resize -> pad -> tile -> normalise), bit-exact with

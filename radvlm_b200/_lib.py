@@ -28,6 +28,7 @@ EPI_GELU_ERF_BF16 = 2
 EPI_RESID_F32 = 3
 EPI_POS_F32 = 4
 EPI_BIAS_F32 = 6
+EPI_ATOMIC_F32 = 7
 
 SEG_PAD, SEG_TEXT, SEG_IMAGE = 0, 1, 2
 MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT = 0, 1, 2
@@ -66,6 +67,21 @@ class ProjectorWeights(C.Structure):
         ("in_dim", C.c_int), ("hidden", C.c_int),
         ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
     ]
+
+
+class VitLayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_gamma", "ln1_beta", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_gamma", "ln2_beta", "fc1_w", "fc1_b",
+        "fc2_w", "fc2_b")]
+
+
+class SiglipGrads(C.Structure):
+    _fields_ = [("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("pos_embed", C.c_void_p),
+                ("layers", C.POINTER(VitLayerGrads))]
+
+
+class ProjectorGrads(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p)]
 
 
 class ImagePlan(C.Structure):
@@ -124,6 +140,19 @@ SIGNATURES = {
     "radvlm_siglip_tower_forward": (_i, [C.POINTER(SiglipWeights), _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "radvlm_projector_forward": (_i, [C.POINTER(ProjectorWeights), _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "radvlm_encode_images": (_i, [C.POINTER(SiglipWeights), C.POINTER(ProjectorWeights), _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "radvlm_tower_saved_bytes": (_sz, [C.POINTER(SiglipWeights), _i]),
+    "radvlm_tower_saved_hidden_offset": (_sz, [C.POINTER(SiglipWeights), _i]),
+    "radvlm_siglip_tower_forward_train": (_i, [C.POINTER(SiglipWeights), _vp, _i, _i, _vp, _sz, _vp, _sz, _vp]),
+    "radvlm_tower_backward_workspace_bytes": (_sz, [C.POINTER(SiglipWeights), _i]),
+    "radvlm_siglip_tower_backward": (_i, [C.POINTER(SiglipWeights), C.POINTER(SiglipGrads), _vp, _i, _i, _vp, _sz, _vp,
+                                          _vp, _sz, _vp]),
+    "radvlm_projector_backward_workspace_bytes": (_sz, [C.POINTER(ProjectorWeights), _i]),
+    "radvlm_projector_backward": (_i, [C.POINTER(ProjectorWeights), C.POINTER(ProjectorGrads), _vp, _vp, _i, _vp, _vp,
+                                       _sz, _vp]),
+    "radvlm_colsum_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "radvlm_gelu_fwd_bwd_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "radvlm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "radvlm_merge_splice_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "radvlm_plan_select_best_resolution": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _pi, _pi]),
     "radvlm_plan_image": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _i, _i, _i, C.POINTER(ImagePlan)]),
     "radvlm_plan_splice": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _i64, _i,

@@ -19,6 +19,11 @@ int attention_bwd_launch(const void* q, const void* k, const void* vt, const voi
                          int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
 int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 cudaStream_t stream);
+int colsum_bf16_launch(const void* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
+int gelu_fwd_bwd_launch(const void* u, void* da_du, void* a, size_t n, int erf_form, cudaStream_t stream);
+int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, float* dres, float* dgamma, float* dbeta,
+                         int rows, int D, float eps, cudaStream_t stream);
+int pos_embed_grad_launch(const float* dh, float* dpos, int tiles, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
                      float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream);

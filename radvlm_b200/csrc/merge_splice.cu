@@ -207,6 +207,91 @@ merge_splice_kernel(const MergeSpliceArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the gather above (autograd of llava_arch.py:350-531): one warp per output row scatters its gradient
+// to where the forward read it from.  Feature / newline gradients are fp32 and accumulated with atomics (a pooled
+// row feeds four sources, the newline feeds many rows); text rows are copied to a compact [n_text, H] buffer in
+// text_src order (the caller index_adds them into the embedding gradient).
+// ---------------------------------------------------------------------------------------------
+struct MergeSpliceBwdArgs {
+  const uint4* dout;
+  int nvec, T, S;
+  const radvlm_splice_segment* segments;
+  int n_segments;
+  const radvlm_merge_image* images;
+  int64_t total_rows;
+  float* dfeat;     // [tiles*T, H] fp32
+  float* dnewline;  // [H] fp32
+  uint4* dtext;     // [n_text, H] (dtype of dout) or nullptr
+};
+
+template <typename T>
+__device__ __forceinline__ void scatter_row(const uint4* __restrict__ src, float* __restrict__ dst, float wgt, int nvec,
+                                            int lane) {
+  for (int i = lane; i < nvec; i += 32) {
+    float f[Vec16<T>::N];
+    Vec16<T>::unpack(ld_stream(src + i), f);
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) atomicAdd(dst + static_cast<size_t>(i) * Vec16<T>::N + e, wgt * f[e]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_splice_bwd_kernel(const MergeSpliceBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const size_t H = static_cast<size_t>(a.nvec) * Vec16<T>::N;
+  for (int64_t row = warp0; row < a.total_rows; row += nwarps) {
+    int lo = 0, hi = a.n_segments - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&a.segments[mid].dst_row) <= row) lo = mid; else hi = mid - 1;
+    }
+    const radvlm_splice_segment seg = a.segments[lo];
+    const int off = static_cast<int>(row - seg.dst_row);
+    const uint4* src = a.dout + static_cast<size_t>(row) * a.nvec;
+    if (seg.kind == RADVLM_SEG_PAD || off >= seg.length) continue;
+    if (seg.kind == RADVLM_SEG_TEXT) {
+      if (a.dtext != nullptr) copy_row(src, a.dtext + static_cast<size_t>(seg.src_off + off) * a.nvec, a.nvec, lane);
+      continue;
+    }
+    const radvlm_merge_image im = a.images[seg.image];
+    const int t = seg.src_off + off;
+    if (im.mode == RADVLM_MERGE_FLAT || t < a.T) {
+      scatter_row<T>(src, a.dfeat + (static_cast<size_t>(im.tile_base) * a.T + t) * H, 1.f, a.nvec, lane);
+    } else if (im.mode == RADVLM_MERGE_SINGLE) {
+      scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+    } else {
+      const int u = t - a.T;
+      const int r = u / (im.out_w + 1);
+      const int c = u - r * (im.out_w + 1);
+      if (c == im.out_w) {
+        scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+      } else if (!im.pool) {
+        scatter_row<T>(src, a.dfeat + grid_src_row(im, r + im.crop_r0, c + im.crop_c0, a.S, a.T) * H, 1.f, a.nvec, lane);
+      } else {
+        const float sh = static_cast<float>(im.crop_h) / static_cast<float>(im.out_h);
+        const float sw = static_cast<float>(im.crop_w) / static_cast<float>(im.out_w);
+        float sy = sh * (static_cast<float>(r) + 0.5f) - 0.5f;
+        float sx = sw * (static_cast<float>(c) + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+        const int y1 = y0 + (y0 < im.crop_h - 1 ? 1 : 0), x1 = x0 + (x0 < im.crop_w - 1 ? 1 : 0);
+        const float ly1 = sy - static_cast<float>(y0), lx1 = sx - static_cast<float>(x0);
+        const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        scatter_row<T>(src, a.dfeat + grid_src_row(im, y0 + im.crop_r0, x0 + im.crop_c0, a.S, a.T) * H, ly0 * lx0, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + grid_src_row(im, y0 + im.crop_r0, x1 + im.crop_c0, a.S, a.T) * H, ly0 * lx1, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + grid_src_row(im, y1 + im.crop_r0, x0 + im.crop_c0, a.S, a.T) * H, ly1 * lx0, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + grid_src_row(im, y1 + im.crop_r0, x1 + im.crop_c0, a.S, a.T) * H, ly1 * lx1, a.nvec, lane);
+      }
+    }
+  }
+}
+
 }  // namespace rv
 
 extern "C" int radvlm_merge_splice(const void* features, const void* newline, const void* embed_table,
@@ -254,6 +339,44 @@ extern "C" int radvlm_merge_splice(const void* features, const void* newline, co
     case RADVLM_DT_BF16: merge_splice_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(a); break;
     case RADVLM_DT_F16: merge_splice_kernel<__half><<<blocks, threads, 0, s>>>(a); break;
     default: set_error("merge_splice: unknown dtype %d", dtype); return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+extern "C" int radvlm_merge_splice_backward(const void* d_out_embeds, int dtype, int hidden, int tokens_per_tile,
+                                            int patches_per_side, const radvlm_splice_segment* segments, int n_segments,
+                                            const radvlm_merge_image* images, int n_images, int64_t total_rows,
+                                            float* d_features, float* d_newline, void* d_text, void* stream) {
+  using namespace rv;
+  int st = require_sm100();
+  if (st) return st;
+  RV_CHECK_ARG(d_out_embeds && segments && n_segments > 0 && total_rows > 0, "merge_splice_backward: bad arguments");
+  RV_CHECK_ARG(n_images == 0 || (images && d_features && d_newline), "merge_splice_backward: image table without gradients");
+  const int esize = (dtype == RADVLM_DT_F32) ? 4 : 2;
+  RV_CHECK_ARG((static_cast<long long>(hidden) * esize) % 16 == 0, "merge_splice_backward: row bytes must be a multiple of 16");
+  MergeSpliceBwdArgs a;
+  a.dout = static_cast<const uint4*>(d_out_embeds);
+  a.nvec = hidden * esize / 16;
+  a.T = tokens_per_tile;
+  a.S = patches_per_side;
+  a.segments = segments;
+  a.n_segments = n_segments;
+  a.images = images;
+  a.total_rows = total_rows;
+  a.dfeat = d_features;
+  a.dnewline = d_newline;
+  a.dtext = static_cast<uint4*>(d_text);
+  const int threads = 256;
+  const int64_t want = (total_rows * 32 + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;
+  const int blocks = static_cast<int>(want < cap ? want : cap);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case RADVLM_DT_F32: merge_splice_bwd_kernel<float><<<blocks, threads, 0, s>>>(a); break;
+    case RADVLM_DT_BF16: merge_splice_bwd_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(a); break;
+    case RADVLM_DT_F16: merge_splice_bwd_kernel<__half><<<blocks, threads, 0, s>>>(a); break;
+    default: set_error("merge_splice_backward: unknown dtype %d", dtype); return RADVLM_ERR_BAD_ARGUMENT;
   }
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;

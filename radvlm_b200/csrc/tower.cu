@@ -51,11 +51,39 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
   return RADVLM_OK;
 }
 
+// Activations kept for the backward pass (training mode): the fp32 residual stream at the input of every layer
+// (+ the tower output), the attention output (A operand of out_proj) and the attention log-sum-exp of every layer.
+// Everything else is recomputed layer by layer in tower_backward_impl (the reference checkpoints whole encoder
+// layers too: siglip_encoder.py:381-387).
+struct TowerSaved {
+  size_t h_bytes, ao_bytes, lse_bytes, total;
+  uint8_t* base;
+  float* h(int l) const { return reinterpret_cast<float*>(base + static_cast<size_t>(l) * h_bytes); }
+  void* ao(int l, int L) const { return base + static_cast<size_t>(L + 1) * h_bytes + static_cast<size_t>(l) * ao_bytes; }
+  float* lse(int l, int L) const {
+    return reinterpret_cast<float*>(base + static_cast<size_t>(L + 1) * h_bytes + static_cast<size_t>(L) * ao_bytes +
+                                    static_cast<size_t>(l) * lse_bytes);
+  }
+};
+
+static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, void* base) {
+  TowerSaved s;
+  s.h_bytes = align_up(L.M * tw->hidden * 4, 1024);
+  s.ao_bytes = align_up(L.M * tw->hidden * 2, 1024);
+  s.lse_bytes = align_up(static_cast<size_t>(n_tiles) * tw->heads * L.seq_pad * 4, 1024);
+  s.total = (tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes);
+  s.base = static_cast<uint8_t*>(base);
+  return s;
+}
+
+// `hidden`: inference: the in-place residual stream (= output).  Training (save != nullptr): scratch for the
+// mid-layer residual; layer l reads save->h(l) and writes save->h(l + 1), the output is save->h(num_layers).
 static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixels, int pixel_dtype,
                               int n_tiles, float* hidden, const EncodeLayout& L, uint8_t* ws,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, const TowerSaved* save = nullptr) {
   const int D = tw->hidden, I = tw->intermediate;
   const int M = static_cast<int>(L.M);
+  const int NL = tw->num_layers;
   void* xn = ws + L.off_xn;
   void* q = ws + L.off_q;
   void* k = ws + L.off_k;
@@ -81,7 +109,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     GemmArgs a{};
     a.M = M; a.N = D; a.K = tw->patch_k_pad;
     a.bias = tw->patch_b;
-    a.out = hidden; a.ldo = D;
+    a.out = save ? save->h(0) : hidden; a.ldo = D;
     a.aux = tw->pos_embed; a.aux_period = L.T;
     { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, tw->patch_k_pad, tw->patch_w, tw->patch_k_pad, a, EPI_POS_F32, 0, stream); }
     if (st) return st;
@@ -90,8 +118,11 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   const float scale = 1.0f / sqrtf(static_cast<float>(L.hd));
   for (int l = 0; l < tw->num_layers; ++l) {
     const radvlm_vit_layer_weights& w = tw->layers[l];
+    const float* h_in = save ? save->h(l) : hidden;     // residual stream entering the layer
+    float* h_out = save ? save->h(l + 1) : hidden;      // ... leaving it
+    void* ao = save ? save->ao(l, NL) : xn;             // attention output (bf16)
     // x = x + out_proj(attn(LN1(x)))
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(hidden, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
@@ -104,14 +135,14 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
-    { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, xn, nullptr, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
+    { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, ao, save ? save->lse(l, NL) : nullptr, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
     if (st) return st;
     {
       GemmArgs a{};
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
-      a.out = hidden; a.ldo = D; a.aux = hidden;
-      { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(xn, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
+      a.out = hidden; a.ldo = D; a.aux = h_in;
+      { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
@@ -129,7 +160,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       GemmArgs a{};
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
-      a.out = hidden; a.ldo = D; a.aux = hidden;
+      a.out = h_out; a.ldo = D; a.aux = hidden;
       { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
@@ -162,6 +193,201 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
                        out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32, 0, stream); }
     if (st) return st;
   }
+  return RADVLM_OK;
+}
+
+
+// =================================================================================================
+// Backward (training mode): gradients of the tower / projector parameters.  Weight gradients are fp32 and are
+// ACCUMULATED (+=) with atomics, so micro-batches and tile chunks add up; a null gradient pointer skips that
+// parameter (frozen, train.py:1642-1665 mm_tunable_parts).
+// =================================================================================================
+struct BackwardLayout {
+  size_t off_xn1, off_xn2, off_g, off_dx, off_h1, off_u, off_da, off_a, off_dqkv, off_q, off_k, off_vt, off_attn, total;
+  size_t attn_bytes;
+};
+
+static void make_bwd_layout(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, BackwardLayout* B) {
+  const size_t M = L.M, D = tw->hidden, I = tw->intermediate;
+  const size_t xn_cols = D > static_cast<size_t>(tw->patch_k_pad) ? D : tw->patch_k_pad;
+  size_t off = 0;
+  B->off_xn1 = off;  off = align_up(off + M * xn_cols * 2, 1024);  // LN1 output / im2col rows
+  B->off_xn2 = off;  off = align_up(off + M * D * 2, 1024);        // LN2 output
+  B->off_g = off;    off = align_up(off + M * D * 2, 1024);        // bf16 copy of the residual gradient
+  B->off_dx = off;   off = align_up(off + M * D * 2, 1024);        // dgrad outputs of width D
+  B->off_h1 = off;   off = align_up(off + M * D * 4, 1024);        // recomputed mid-layer residual (fp32)
+  B->off_u = off;    off = align_up(off + M * I * 2, 1024);        // fc1 pre-activation
+  B->off_da = off;   off = align_up(off + M * I * 2, 1024);        // dL/da -> dL/du
+  B->off_a = off;    off = align_up(off + M * I * 2, 1024);        // gelu(u)
+  B->off_dqkv = off; off = align_up(off + M * 3 * D * 2, 1024);    // [dQ | dK | dV]
+  B->off_q = off;    off = align_up(off + L.qkv_bytes, 1024);
+  B->off_k = off;    off = align_up(off + L.qkv_bytes, 1024);
+  B->off_vt = off;   off = align_up(off + L.qkv_bytes, 1024);
+  B->attn_bytes = attention_bwd_workspace_bytes(n_tiles, tw->heads, L.seq_pad);
+  B->off_attn = off; off = align_up(off + B->attn_bytes, 1024);
+  B->total = off;
+}
+
+static int pick_splits(int M, int N) {  // wgrad tiles are few (weights are small): cut K so ~3 waves of CTA pairs run
+  const int pairs = (device_sm_count() > 0 ? device_sm_count() : 148) / 2;
+  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int sp = (3 * pairs + tiles - 1) / tiles;
+  return sp < 1 ? 1 : (sp > 16 ? 16 : sp);
+}
+
+// dW[out, in] += dY^T[out, rows] X[rows, in];  db[out] += colsum(dY)
+static int linear_wgrad(const void* dY, int ldy, const void* X, int ldx, int rows, int out_dim, int in_dim, float* dW,
+                        int ldw, float* db, cudaStream_t stream) {
+  int st = RADVLM_OK;
+  if (dW != nullptr) {
+    GemmArgs a{};
+    a.M = out_dim; a.N = in_dim; a.K = rows;
+    a.out = dW; a.ldo = ldw;
+    a.a_mn = 1; a.b_mn = 1; a.k_splits = pick_splits(out_dim, in_dim);
+    st = gemm_dispatch(dY, ldy, X, ldx, a, EPI_ATOMIC_F32, 0, stream);
+    if (st) return st;
+  }
+  if (db != nullptr) st = colsum_bf16_launch(dY, rows, out_dim, ldy, db, stream);
+  return st;
+}
+
+// dX[rows, in] = dY[rows, out] W[out, in]   (W read as stored)
+static int linear_dgrad(const void* dY, int ldy, const void* W, int ldw, int rows, int out_dim, int in_dim, void* dX,
+                        int ldx, bool f32_out, cudaStream_t stream) {
+  GemmArgs a{};
+  a.M = rows; a.N = in_dim; a.K = out_dim;
+  a.out = dX; a.ldo = ldx;
+  a.b_mn = 1;
+  return gemm_dispatch(dY, ldy, W, ldw, a, f32_out ? EPI_BIAS_F32 : EPI_BIAS_BF16, 0, stream);
+}
+
+static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* gr, const void* pixels,
+                               int pixel_dtype, int n_tiles, const TowerSaved& sv, float* dh, const EncodeLayout& L,
+                               const BackwardLayout& B, uint8_t* ws, cudaStream_t stream) {
+  const int D = tw->hidden, I = tw->intermediate, NL = tw->num_layers;
+  const int M = static_cast<int>(L.M);
+  void* xn1 = ws + B.off_xn1;
+  void* xn2 = ws + B.off_xn2;
+  void* g = ws + B.off_g;
+  void* dx = ws + B.off_dx;
+  float* h1 = reinterpret_cast<float*>(ws + B.off_h1);
+  void* u = ws + B.off_u;
+  void* da = ws + B.off_da;
+  void* act = ws + B.off_a;
+  void* dqkv = ws + B.off_dqkv;
+  void* q = ws + B.off_q;
+  void* k = ws + B.off_k;
+  void* vt = ws + B.off_vt;
+  void* attn_ws = ws + B.off_attn;
+  int st;
+  // q / k / vt padding must be zero; the backward attention wants plain zeros in the V^T padding rows (no ones row)
+  RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
+  RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
+  RV_CUDA(cudaMemsetAsync(vt, 0, L.qkv_bytes, stream));
+  const float scale = 1.0f / sqrtf(static_cast<float>(L.hd));
+  const size_t MD = static_cast<size_t>(M) * D;
+
+  for (int l = NL - 1; l >= 0; --l) {
+    const radvlm_vit_layer_weights& w = tw->layers[l];
+    const radvlm_vit_layer_grads* lg = (gr != nullptr && gr->layers != nullptr) ? &gr->layers[l] : nullptr;
+    auto G = [&](float* radvlm_vit_layer_grads::*m) -> float* { return lg ? lg->*m : nullptr; };
+    const float* h0 = sv.h(l);
+    const void* ao = sv.ao(l, NL);
+    // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
+    if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
+    {
+      GemmArgs a{};
+      a.M = M; a.N = 3 * D; a.K = D;
+      a.bias = w.qkv_b;
+      a.q = static_cast<__nv_bfloat16*>(q);
+      a.k = static_cast<__nv_bfloat16*>(k);
+      a.vt = static_cast<__nv_bfloat16*>(vt);
+      a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
+      if ((st = gemm_dispatch(xn1, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream))) return st;
+    }
+    {
+      GemmArgs a{};
+      a.M = M; a.N = D; a.K = D;
+      a.bias = w.out_b;
+      a.out = h1; a.ldo = D; a.aux = h0;
+      if ((st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream))) return st;
+    }
+    if ((st = layernorm_launch(h1, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream))) return st;
+    {
+      GemmArgs a{};
+      a.M = M; a.N = I; a.K = D;
+      a.bias = w.fc1_b;
+      a.out = u; a.ldo = I;
+      if ((st = gemm_dispatch(xn2, D, w.fc1_w, D, a, EPI_BIAS_BF16, 0, stream))) return st;
+    }
+    // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
+    if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+    if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream))) return st;           // dL/da
+    if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(M) * I, 0, stream))) return st;   // a, dL/du
+    if ((st = linear_wgrad(g, D, act, I, M, D, I, G(&radvlm_vit_layer_grads::fc2_w), I, G(&radvlm_vit_layer_grads::fc2_b), stream))) return st;
+    if ((st = linear_wgrad(da, I, xn2, D, M, I, D, G(&radvlm_vit_layer_grads::fc1_w), D, G(&radvlm_vit_layer_grads::fc1_b), stream))) return st;
+    if ((st = linear_dgrad(da, I, w.fc1_w, D, M, I, D, dx, D, false, stream))) return st;           // dL/dLN2
+    {
+      float* dg = G(&radvlm_vit_layer_grads::ln2_gamma);
+      float* db = G(&radvlm_vit_layer_grads::ln2_beta);
+      float* scratch = reinterpret_cast<float*>(attn_ws);  // frozen LN: the parameter sums go to scratch
+      if (!dg || !db) RV_CUDA(cudaMemsetAsync(scratch, 0, 2 * D * sizeof(float), stream));
+      if ((st = layernorm_bwd_launch(h1, w.ln2_gamma, dx, dh, dg ? dg : scratch, db ? db : scratch + D, M, D, tw->ln_eps, stream))) return st;
+    }
+    // ---- attention branch: h1 = h0 + out_proj(attn(LN1(h0)))
+    if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+    if ((st = linear_wgrad(g, D, ao, D, M, D, D, G(&radvlm_vit_layer_grads::out_w), D, G(&radvlm_vit_layer_grads::out_b), stream))) return st;
+    if ((st = linear_dgrad(g, D, w.out_w, D, M, D, D, dx, D, false, stream))) return st;            // dL/d(attn out)
+    if ((st = attention_bwd_launch(q, k, vt, dx, ao, sv.lse(l, NL), dqkv, attn_ws, B.attn_bytes, n_tiles, tw->heads,
+                                   L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream))) return st;
+    if ((st = linear_wgrad(dqkv, 3 * D, xn1, D, M, 3 * D, D, G(&radvlm_vit_layer_grads::qkv_w), D, G(&radvlm_vit_layer_grads::qkv_b), stream))) return st;
+    if ((st = linear_dgrad(dqkv, 3 * D, w.qkv_w, D, M, 3 * D, D, dx, D, false, stream))) return st;  // dL/dLN1
+    {
+      float* dg = G(&radvlm_vit_layer_grads::ln1_gamma);
+      float* db = G(&radvlm_vit_layer_grads::ln1_beta);
+      float* scratch = reinterpret_cast<float*>(attn_ws);
+      if (!dg || !db) RV_CUDA(cudaMemsetAsync(scratch, 0, 2 * D * sizeof(float), stream));
+      if ((st = layernorm_bwd_launch(h0, w.ln1_gamma, dx, dh, dg ? dg : scratch, db ? db : scratch + D, M, D, tw->ln_eps, stream))) return st;
+    }
+  }
+  // ---- embeddings: hidden0 = im2col(pixels) Wp^T + bp + pos  (siglip_encoder.py:169-174)
+  if (gr != nullptr && (gr->patch_w || gr->patch_b || gr->pos_embed)) {
+    if (gr->pos_embed && (st = pos_embed_grad_launch(dh, gr->pos_embed, n_tiles, L.T, D, stream))) return st;
+    if (gr->patch_w || gr->patch_b) {
+      if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+      if (gr->patch_w && (st = im2col_launch(pixels, pixel_dtype, xn1, n_tiles, tw->channels, tw->image_size,
+                                             tw->patch_size, tw->patch_k_pad, stream))) return st;
+      if ((st = linear_wgrad(g, D, xn1, tw->patch_k_pad, M, D, tw->patch_k_pad, gr->patch_w, tw->patch_k_pad, gr->patch_b, stream))) return st;
+    }
+  }
+  return RADVLM_OK;
+}
+
+// projector: y = W2 gelu_erf(W1 x + b1) + b2  (builder.py:41-48); x = bf16(hidden)
+static int projector_backward_impl(const radvlm_projector_weights* pw, const radvlm_projector_grads* gr,
+                                   const float* hidden, const void* dfeat /* bf16 [rows, P] */, int rows, float* d_hidden,
+                                   uint8_t* ws, cudaStream_t stream) {
+  const int Din = pw->in_dim, P = pw->hidden;
+  const size_t x_bytes = align_up(static_cast<size_t>(rows) * Din * 2, 1024);
+  const size_t p_bytes = align_up(static_cast<size_t>(rows) * P * 2, 1024);
+  void* x = ws;
+  void* u = ws + x_bytes;
+  void* da = ws + x_bytes + p_bytes;
+  void* act = ws + x_bytes + 2 * p_bytes;
+  int st;
+  if ((st = cast_f32_bf16_launch(hidden, x, static_cast<size_t>(rows) * Din, stream))) return st;
+  {
+    GemmArgs a{};
+    a.M = rows; a.N = P; a.K = Din;
+    a.bias = pw->b1;
+    a.out = u; a.ldo = P;
+    if ((st = gemm_dispatch(x, Din, pw->w1, Din, a, EPI_BIAS_BF16, 0, stream))) return st;
+  }
+  if ((st = linear_dgrad(dfeat, P, pw->w2, P, rows, P, P, da, P, false, stream))) return st;
+  if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(rows) * P, 1, stream))) return st;
+  if ((st = linear_wgrad(dfeat, P, act, P, rows, P, P, gr ? gr->w2 : nullptr, P, gr ? gr->b2 : nullptr, stream))) return st;
+  if ((st = linear_wgrad(da, P, x, Din, rows, P, Din, gr ? gr->w1 : nullptr, Din, gr ? gr->b1 : nullptr, stream))) return st;
+  if (d_hidden != nullptr && (st = linear_dgrad(da, P, pw->w1, Din, rows, P, Din, d_hidden, Din, true, stream))) return st;
   return RADVLM_OK;
 }
 
@@ -233,4 +459,87 @@ extern "C" int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvl
   if (st) return st;
   return projector_forward_impl(pw, hidden, static_cast<int>(L.M), features_out, out_dtype,
                                 ws + L.off_xn, ws + L.off_h1, s);
+}
+
+// ------------------------------------------------------------------------------------------------ training mode
+extern "C" size_t radvlm_tower_saved_bytes(const radvlm_siglip_weights* tw, int n_tiles) {
+  EncodeLayout L;
+  if (make_layout(tw, nullptr, n_tiles, &L) != RADVLM_OK) return 0;
+  return make_saved(tw, L, n_tiles, nullptr).total;
+}
+
+extern "C" size_t radvlm_tower_saved_hidden_offset(const radvlm_siglip_weights* tw, int n_tiles) {
+  EncodeLayout L;
+  if (make_layout(tw, nullptr, n_tiles, &L) != RADVLM_OK) return 0;
+  return make_saved(tw, L, n_tiles, nullptr).h_bytes * static_cast<size_t>(tw->num_layers);
+}
+
+extern "C" int radvlm_siglip_tower_forward_train(const radvlm_siglip_weights* tw, const void* pixels, int pixel_dtype,
+                                                 int n_tiles, void* saved, size_t saved_bytes, void* workspace,
+                                                 size_t workspace_bytes, void* stream) {
+  int st = require_sm100();
+  if (st) return st;
+  EncodeLayout L;
+  st = make_layout(tw, nullptr, n_tiles, &L);
+  if (st) return st;
+  RV_CHECK_ARG(pixels && saved && workspace, "tower_train: null pointer");
+  const TowerSaved sv = make_saved(tw, L, n_tiles, saved);
+  if (workspace_bytes < L.total || saved_bytes < sv.total) {
+    set_error("tower_train: buffers too small (workspace %zu < %zu or saved %zu < %zu)", workspace_bytes, L.total,
+              saved_bytes, sv.total);
+    return RADVLM_ERR_WORKSPACE_TOO_SMALL;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  return tower_forward_impl(tw, pixels, pixel_dtype, n_tiles, reinterpret_cast<float*>(ws + L.off_hidden), L, ws,
+                            static_cast<cudaStream_t>(stream), &sv);
+}
+
+extern "C" size_t radvlm_tower_backward_workspace_bytes(const radvlm_siglip_weights* tw, int n_tiles) {
+  EncodeLayout L;
+  if (make_layout(tw, nullptr, n_tiles, &L) != RADVLM_OK) return 0;
+  BackwardLayout B;
+  make_bwd_layout(tw, L, n_tiles, &B);
+  return B.total;
+}
+
+extern "C" int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads,
+                                            const void* pixels, int pixel_dtype, int n_tiles, const void* saved,
+                                            size_t saved_bytes, float* d_hidden, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  int st = require_sm100();
+  if (st) return st;
+  EncodeLayout L;
+  st = make_layout(tw, nullptr, n_tiles, &L);
+  if (st) return st;
+  RV_CHECK_ARG(pixels && saved && d_hidden && workspace, "tower_backward: null pointer");
+  const TowerSaved sv = make_saved(tw, L, n_tiles, const_cast<void*>(saved));
+  BackwardLayout B;
+  make_bwd_layout(tw, L, n_tiles, &B);
+  if (workspace_bytes < B.total || saved_bytes < sv.total) {
+    set_error("tower_backward: buffers too small (workspace %zu < %zu or saved %zu < %zu)", workspace_bytes, B.total,
+              saved_bytes, sv.total);
+    return RADVLM_ERR_WORKSPACE_TOO_SMALL;
+  }
+  return tower_backward_impl(tw, grads, pixels, pixel_dtype, n_tiles, sv, d_hidden, L, B,
+                             static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t radvlm_projector_backward_workspace_bytes(const radvlm_projector_weights* pw, int rows) {
+  if (pw == nullptr || rows <= 0) return 0;
+  return align_up(static_cast<size_t>(rows) * pw->in_dim * 2, 1024) + 3 * align_up(static_cast<size_t>(rows) * pw->hidden * 2, 1024);
+}
+
+extern "C" int radvlm_projector_backward(const radvlm_projector_weights* pw, const radvlm_projector_grads* grads,
+                                         const float* hidden, const void* d_features, int rows, float* d_hidden,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  int st = require_sm100();
+  if (st) return st;
+  RV_CHECK_ARG(pw && hidden && d_features && workspace && rows > 0, "projector_backward: bad arguments");
+  RV_CHECK_ARG((pw->in_dim % 8) == 0 && (pw->hidden % 8) == 0, "projector_backward: dims must be multiples of 8");
+  if (workspace_bytes < radvlm_projector_backward_workspace_bytes(pw, rows)) {
+    set_error("projector_backward: workspace too small");
+    return RADVLM_ERR_WORKSPACE_TOO_SMALL;
+  }
+  return projector_backward_impl(pw, grads, hidden, d_features, rows, d_hidden, static_cast<uint8_t*>(workspace),
+                                 static_cast<cudaStream_t>(stream));
 }

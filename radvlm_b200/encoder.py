@@ -205,6 +205,189 @@ class B200VisionEncoder:
         return out
 
 
+# =================================================================================================
+# Training mode: encode_images under autograd (BASELINE config 5; mm_tunable_parts = vision tower + projector,
+# train.py:1642-1665).  The forward keeps what radvlm_siglip_tower_forward_train saves; the backward runs
+# radvlm_projector_backward + radvlm_siglip_tower_backward and hands the fp32 gradient buffers back to autograd as
+# the gradients of the module Parameters (so accumulation, DDP hooks and optimizers see ordinary .grad tensors).
+# =================================================================================================
+class _GradBuffers:
+    """fp32 accumulators with the packed-weight shapes + the C structs pointing at them (NULL = frozen)."""
+
+    def __init__(self, enc: "B200VisionEncoder", pk: PackedWeights, dev):
+        tw = pk.tower
+        D, I, NL = tw.hidden, tw.intermediate, tw.num_layers
+        tsd = dict(enc.tower_module.named_parameters())
+        psd = dict(enc.projector_module.named_parameters())
+        pre = "vision_model."
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+        def alloc(key, shape, *src_names, table=tsd):
+            if not any(table[n].requires_grad for n in src_names):
+                return None
+            t = torch.zeros(shape, dtype=torch.float32, device=dev)
+            self.bufs[key] = t
+            return t.data_ptr()
+
+        self.layers = (_lib.VitLayerGrads * NL)()
+        for i in range(NL):
+            lp = pre + "encoder.layers.%d." % i
+            L = self.layers[i]
+            L.ln1_gamma = alloc("l%d.ln1_g" % i, (D,), lp + "layer_norm1.weight")
+            L.ln1_beta = alloc("l%d.ln1_b" % i, (D,), lp + "layer_norm1.bias")
+            L.qkv_w = alloc("l%d.qkv_w" % i, (3 * D, D), lp + "self_attn.q_proj.weight", lp + "self_attn.k_proj.weight",
+                            lp + "self_attn.v_proj.weight")
+            L.qkv_b = alloc("l%d.qkv_b" % i, (3 * D,), lp + "self_attn.q_proj.bias", lp + "self_attn.k_proj.bias",
+                            lp + "self_attn.v_proj.bias")
+            L.out_w = alloc("l%d.out_w" % i, (D, D), lp + "self_attn.out_proj.weight")
+            L.out_b = alloc("l%d.out_b" % i, (D,), lp + "self_attn.out_proj.bias")
+            L.ln2_gamma = alloc("l%d.ln2_g" % i, (D,), lp + "layer_norm2.weight")
+            L.ln2_beta = alloc("l%d.ln2_b" % i, (D,), lp + "layer_norm2.bias")
+            L.fc1_w = alloc("l%d.fc1_w" % i, (I, D), lp + "mlp.fc1.weight")
+            L.fc1_b = alloc("l%d.fc1_b" % i, (I,), lp + "mlp.fc1.bias")
+            L.fc2_w = alloc("l%d.fc2_w" % i, (D, I), lp + "mlp.fc2.weight")
+            L.fc2_b = alloc("l%d.fc2_b" % i, (D,), lp + "mlp.fc2.bias")
+        self.tower = _lib.SiglipGrads()
+        self.tower.patch_w = alloc("patch_w", (D, tw.patch_k_pad), pre + "embeddings.patch_embedding.weight")
+        self.tower.patch_b = alloc("patch_b", (D,), pre + "embeddings.patch_embedding.bias")
+        self.tower.pos_embed = alloc("pos", (pk.tokens_per_tile, D), pre + "embeddings.position_embedding.weight")
+        self.tower.layers = C.cast(self.layers, C.POINTER(_lib.VitLayerGrads))
+        self.tower_trainable = bool(self.bufs)
+        P = pk.proj_hidden
+        self.proj = _lib.ProjectorGrads()
+        self.proj.w1 = alloc("p.w1", (P, D), "0.weight", table=psd)
+        self.proj.b1 = alloc("p.b1", (P,), "0.bias", table=psd)
+        self.proj.w2 = alloc("p.w2", (P, P), "2.weight", table=psd)
+        self.proj.b2 = alloc("p.b2", (P,), "2.bias", table=psd)
+        self._D, self._NL, self._pre = D, NL, pre
+
+    def for_parameter(self, name: str, p: torch.Tensor, is_tower: bool) -> Optional[torch.Tensor]:
+        """Gradient of one module Parameter (its shape / dtype), or None when frozen."""
+        if not p.requires_grad:
+            return None
+        D, b = self._D, self.bufs
+        g = None
+        if not is_tower:
+            g = b.get({"0.weight": "p.w1", "0.bias": "p.b1", "2.weight": "p.w2", "2.bias": "p.b2"}.get(name, ""))
+        elif name == self._pre + "embeddings.patch_embedding.weight":
+            g = b["patch_w"][:, :p[0].numel()].reshape(p.shape)
+        elif name == self._pre + "embeddings.patch_embedding.bias":
+            g = b["patch_b"]
+        elif name == self._pre + "embeddings.position_embedding.weight":
+            g = b["pos"]
+        elif name.startswith(self._pre + "encoder.layers."):
+            rest = name[len(self._pre + "encoder.layers."):]
+            i, leaf = rest.split(".", 1)
+            i = int(i)
+            if i < self._NL:
+                k = "l%d." % i
+                simple = {"layer_norm1.weight": "ln1_g", "layer_norm1.bias": "ln1_b", "layer_norm2.weight": "ln2_g",
+                          "layer_norm2.bias": "ln2_b", "self_attn.out_proj.weight": "out_w",
+                          "self_attn.out_proj.bias": "out_b", "mlp.fc1.weight": "fc1_w", "mlp.fc1.bias": "fc1_b",
+                          "mlp.fc2.weight": "fc2_w", "mlp.fc2.bias": "fc2_b"}
+                if leaf in simple:
+                    g = b[k + simple[leaf]]
+                else:
+                    for j, proj in enumerate(("q_proj", "k_proj", "v_proj")):
+                        if leaf == "self_attn.%s.weight" % proj:
+                            g = b[k + "qkv_w"][j * D:(j + 1) * D]
+                        elif leaf == "self_attn.%s.bias" % proj:
+                            g = b[k + "qkv_b"][j * D:(j + 1) * D]
+        if g is None:   # a parameter the path does not use (post_layernorm, head, the dropped 27th layer)
+            return torch.zeros_like(p)
+        return g.to(p.dtype).reshape(p.shape)
+
+
+class _EncodeImagesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, images, out_dtype, n_tower, *params):
+        dev = images.device
+        pk = enc.packed(dev)
+        lib = _lib.load()
+        n = images.shape[0]
+        T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
+        kernel_out = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        out = torch.empty(n, T, Hp, dtype=kernel_out, device=dev)
+        chunks = []
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(dev)
+            step = max(1, enc.max_tiles_per_call)
+            for s in range(0, n, step):
+                m = min(step, n - s)
+                need = lib.radvlm_encode_workspace_bytes(C.byref(pk.tower), C.byref(pk.projector), m)
+                sbytes = lib.radvlm_tower_saved_bytes(C.byref(pk.tower), m)
+                if need == 0 or sbytes == 0:
+                    raise _lib.RadvlmError(_lib.ERR_BAD_ARGUMENT, _lib.last_error())
+                ws = enc._workspace(dev, need)
+                saved = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+                _lib.check(lib.radvlm_siglip_tower_forward_train(
+                    C.byref(pk.tower), images[s:s + m].data_ptr(), _DT[images.dtype], m, saved.data_ptr(), sbytes,
+                    ws.data_ptr(), ws.numel(), stream))
+                hid_ptr = saved.data_ptr() + lib.radvlm_tower_saved_hidden_offset(C.byref(pk.tower), m)
+                _lib.check(lib.radvlm_projector_forward(
+                    C.byref(pk.projector), hid_ptr, m * T, out[s:s + m].data_ptr(), _DT[kernel_out], ws.data_ptr(),
+                    ws.numel(), stream))
+                chunks.append((s, m, saved))
+        ctx.enc, ctx.pk, ctx.images, ctx.chunks, ctx.n_tower = enc, pk, images, chunks, n_tower
+        ctx.param_names = enc._param_names()
+        ctx.params = params
+        return out if out.dtype == out_dtype else out.to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        enc, pk, images = ctx.enc, ctx.pk, ctx.images
+        dev = images.device
+        lib = _lib.load()
+        T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
+        d_out = d_out.to(device=dev, dtype=torch.bfloat16).contiguous()
+        gb = _GradBuffers(enc, pk, dev)
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(dev)
+            for s, m, saved in ctx.chunks:
+                rows = m * T
+                pws = lib.radvlm_projector_backward_workspace_bytes(C.byref(pk.projector), rows)
+                tws = lib.radvlm_tower_backward_workspace_bytes(C.byref(pk.tower), m) if gb.tower_trainable else 0
+                ws = enc._workspace(dev, max(pws, tws))
+                hid_ptr = saved.data_ptr() + lib.radvlm_tower_saved_hidden_offset(C.byref(pk.tower), m)
+                d_hidden = torch.empty(rows, D, dtype=torch.float32, device=dev) if gb.tower_trainable else None
+                _lib.check(lib.radvlm_projector_backward(
+                    C.byref(pk.projector), C.byref(gb.proj), hid_ptr, d_out[s:s + m].data_ptr(), rows,
+                    None if d_hidden is None else d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                if gb.tower_trainable:
+                    _lib.check(lib.radvlm_siglip_tower_backward(
+                        C.byref(pk.tower), C.byref(gb.tower), images[s:s + m].data_ptr(), _DT[images.dtype], m,
+                        saved.data_ptr(), saved.numel(), d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        grads = []
+        for idx, ((name, is_tower), p) in enumerate(zip(ctx.param_names, ctx.params)):
+            grads.append(gb.for_parameter(name, p, is_tower) if ctx.needs_input_grad[4 + idx] else None)
+        ctx.chunks = None
+        return (None, None, None, None, *grads)
+
+
+def _encode_images_train(self: "B200VisionEncoder", images: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    if images.dim() != 4:
+        raise ValueError("encode_images expects [n, C, S, S], got %s" % (tuple(images.shape),))
+    if not torch.cuda.is_available():
+        raise RuntimeError("radvlm_b200: no CUDA device; the encode path has no CPU fallback")
+    dev = next(self.projector_module.parameters()).device
+    out_dtype = out_dtype or images.dtype
+    if images.dtype not in _DT:
+        images = images.float()
+    images = images.detach().to(dev).contiguous()
+    tparams = [p for _, p in self.tower_module.named_parameters()]
+    pparams = [p for _, p in self.projector_module.named_parameters()]
+    return _EncodeImagesFn.apply(self, images, out_dtype, len(tparams), *tparams, *pparams)
+
+
+def _param_names(self: "B200VisionEncoder"):
+    return [(n, True) for n, _ in self.tower_module.named_parameters()] + \
+           [(n, False) for n, _ in self.projector_module.named_parameters()]
+
+
+B200VisionEncoder.encode_images_train = _encode_images_train
+B200VisionEncoder._param_names = _param_names
+
+
 def flops_per_tile(hidden=1152, inter=4304, layers=26, seq=729, patch_k=588, proj=3584) -> float:
     """Algorithmic forward FLOPs per tile (2*M*N*K, unpadded)."""
     per_layer = 2 * seq * (3 * hidden * hidden + hidden * hidden + 2 * hidden * inter) + 4 * seq * seq * hidden

@@ -43,20 +43,14 @@ def _encoder_for(self) -> B200VisionEncoder:
     return enc
 
 
-def _check_forward_only(self):
-    if torch.is_grad_enabled() and not getattr(self, "radvlm_b200_allow_no_grad", False):
-        params = list(self.get_vision_tower().parameters()) + list(self.get_model().mm_projector.parameters())
-        if any(p.requires_grad for p in params):
-            raise NotImplementedError(
-                "radvlm_b200: the encode path is forward-only in this round (backward = SURVEY.md section 8(f) "
-                "row 1).  Call under torch.no_grad(), freeze the tower/projector, or set "
-                "model.radvlm_b200_allow_no_grad = True to run the forward without gradients.")
-
-
 def encode_images(self, images: torch.Tensor) -> torch.Tensor:
-    """llava_arch.py:192-196: tower -> mm_projector.  [n,3,S,S] -> [n, 729, hidden_size], dtype = images.dtype."""
-    _check_forward_only(self)
-    return _encoder_for(self).encode_images(images)
+    """llava_arch.py:192-196: tower -> mm_projector.  [n,3,S,S] -> [n, 729, hidden_size], dtype = images.dtype.
+    With autograd enabled and trainable tower / projector parameters the result carries a grad_fn whose backward
+    runs the sm_100a backward kernels (radvlm_projector_backward, radvlm_siglip_tower_backward)."""
+    enc = _encoder_for(self)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in enc._source_tensors()):
+        return enc.encode_images_train(images)
+    return enc.encode_images(images)
 
 
 def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool):
@@ -116,6 +110,74 @@ def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool):
     return table, tokens
 
 
+class _NullCtx:
+    """stand-in autograd context for calling a Function's forward directly (inference)"""
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+class _MergeSpliceFn(torch.autograd.Function):
+    """radvlm_merge_splice under autograd: gradients flow to the visual features, image_newline and embed_tokens
+    (llava_arch.py:350-531 are all differentiable gathers / lerps in the reference)."""
+
+    @staticmethod
+    def forward(ctx, features, newline, embed, m):
+        lib = _lib.load()
+        dev = embed.device
+        H = embed.shape[1]
+        with torch.cuda.device(dev):
+            out = torch.empty(m["B"], m["max_len"], H, dtype=embed.dtype, device=dev)
+            out_labels = torch.empty(m["B"], m["max_len"], dtype=torch.int64, device=dev)
+            out_mask = torch.empty(m["B"], m["max_len"], dtype=torch.uint8, device=dev)
+            out_pos = torch.empty(m["B"], m["max_len"], dtype=torch.int64, device=dev)
+            if m["total_rows"] > 0:
+                tables = m["tables"]
+                _lib.check(lib.radvlm_merge_splice(
+                    features.data_ptr(), newline.data_ptr(), embed.data_ptr(), _DT[embed.dtype], H, m["T"], m["S"],
+                    m["ids_dev"].data_ptr(), None if m["labels_dev"] is None else m["labels_dev"].data_ptr(),
+                    tables.data_ptr() + m["off_txt"], tables.data_ptr(), m["n_segments"],
+                    tables.data_ptr() + m["off_img"], m["n_images"], m["total_rows"],
+                    out.data_ptr(), out_labels.data_ptr(), out_mask.data_ptr(), out_pos.data_ptr(), IGNORE_INDEX,
+                    torch.cuda.current_stream(dev).cuda_stream))
+        ctx.m = m
+        ctx.feat_shape, ctx.feat_dtype = tuple(features.shape), features.dtype
+        ctx.newline_dtype, ctx.embed_shape, ctx.embed_dtype = newline.dtype, tuple(embed.shape), embed.dtype
+        ctx.mark_non_differentiable(out_labels, out_mask, out_pos)
+        return out, out_labels, out_mask, out_pos
+
+    @staticmethod
+    def backward(ctx, d_out, *_unused):
+        m = ctx.m
+        lib = _lib.load()
+        dev = d_out.device
+        H = ctx.embed_shape[1]
+        need_f, need_n, need_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_out = d_out.to(ctx.embed_dtype).contiguous()
+        with torch.cuda.device(dev):
+            n_rows = ctx.feat_shape[0] * ctx.feat_shape[1] if len(ctx.feat_shape) == 3 else ctx.feat_shape[0]
+            d_feat = torch.zeros(max(n_rows, 1), H, dtype=torch.float32, device=dev)
+            d_newline = torch.zeros(H, dtype=torch.float32, device=dev)
+            d_text = torch.empty(max(m["n_text"], 1), H, dtype=ctx.embed_dtype, device=dev) if need_e else None
+            if m["total_rows"] > 0:
+                tables = m["tables"]
+                _lib.check(lib.radvlm_merge_splice_backward(
+                    d_out.data_ptr(), _DT[ctx.embed_dtype], H, m["T"], m["S"], tables.data_ptr(), m["n_segments"],
+                    tables.data_ptr() + m["off_img"], m["n_images"], m["total_rows"], d_feat.data_ptr(),
+                    d_newline.data_ptr(), None if d_text is None else d_text.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream))
+            g_feat = d_feat.to(ctx.feat_dtype).reshape(ctx.feat_shape) if need_f else None
+            g_newline = d_newline.to(ctx.newline_dtype) if need_n else None
+            g_embed = None
+            if need_e:
+                g_embed = torch.zeros(ctx.embed_shape, dtype=ctx.embed_dtype, device=dev)
+                if m["n_text"] > 0:
+                    src = tables[m["off_txt"]:m["off_txt"] + 4 * m["n_text"]].view(torch.int32).long()
+                    tok = m["ids_dev"].reshape(-1)[src]
+                    g_embed.index_add_(0, tok, d_text[:m["n_text"]])
+        return g_feat, g_newline, g_embed, None
+
+
 def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
                                          images, modalities=["image"], image_sizes=None):
     """llava_arch.py:251-555.  Returns (None, position_ids, attention_mask, past_key_values, inputs_embeds, labels)."""
@@ -166,7 +228,7 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     newline = getattr(self.get_model(), "image_newline", None)
     if newline is None:
         newline = torch.zeros(embed.shape[1], dtype=embed.dtype, device=dev)
-    newline = newline.detach().to(device=dev, dtype=embed.dtype).contiguous()
+    newline = newline.to(device=dev, dtype=embed.dtype).contiguous()
     H = embed.shape[1]
     total_rows = B_eff * max_len
 
@@ -184,22 +246,18 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     if txt_bytes:
         hv[off_txt:off_txt + txt_bytes] = plan.text_src.view(np.uint8)
     with torch.cuda.device(dev):
-        tables = host.to(dev, non_blocking=True)
-        ids_dev = input_ids.detach().to(dev, torch.int64).contiguous()
-        labels_dev = None if labels is None else labels.detach().to(dev, torch.int64).contiguous()
-        out = torch.empty(B_eff, max_len, H, dtype=embed.dtype, device=dev)
-        out_labels = torch.empty(B_eff, max_len, dtype=torch.int64, device=dev)
-        out_mask = torch.empty(B_eff, max_len, dtype=torch.uint8, device=dev)
-        out_pos = torch.empty(B_eff, max_len, dtype=torch.int64, device=dev)
-        if total_rows > 0:
-            _lib.check(lib.radvlm_merge_splice(
-                features.data_ptr(), newline.data_ptr(), embed.detach().data_ptr(), _DT[embed.dtype], H,
-                vision_tower.num_patches_per_side ** 2, vision_tower.num_patches_per_side,
-                ids_dev.data_ptr(), None if labels_dev is None else labels_dev.data_ptr(),
-                tables.data_ptr() + off_txt, tables.data_ptr(), plan.n_segments,
-                tables.data_ptr() + off_img, len(tile_counts), total_rows,
-                out.data_ptr(), out_labels.data_ptr(), out_mask.data_ptr(), out_pos.data_ptr(), IGNORE_INDEX,
-                torch.cuda.current_stream(dev).cuda_stream))
+        meta = dict(
+            tables=host.to(dev, non_blocking=True), off_img=off_img, off_txt=off_txt, n_segments=plan.n_segments,
+            n_images=len(tile_counts), n_text=plan.n_text, total_rows=total_rows, B=B_eff, max_len=max_len,
+            T=vision_tower.num_patches_per_side ** 2, S=vision_tower.num_patches_per_side,
+            ids_dev=input_ids.detach().to(dev, torch.int64).contiguous(),
+            labels_dev=None if labels is None else labels.detach().to(dev, torch.int64).contiguous())
+    if torch.is_grad_enabled() and (features.requires_grad or newline.requires_grad or embed.requires_grad):
+        out, out_labels, out_mask, out_pos = _MergeSpliceFn.apply(features, newline, embed, meta)
+    else:
+        with torch.no_grad():
+            out, out_labels, out_mask, out_pos = _MergeSpliceFn.forward(_NullCtx(), features.detach(), newline.detach(),
+                                                                        embed.detach(), meta)
 
     # ---- return contract (llava_arch.py:533-555)
     new_labels = None if _labels is None else out_labels.to(_labels.dtype)

@@ -142,8 +142,51 @@ def encoder_golden():
     return res
 
 
+def grad_golden(ref):
+    """Gradients of the REAL reference path (fp32, CPU): process_anyres_image -> prepare_inputs_labels_for_multimodal
+    (tower, projector, unpad / bilinear pool / newline, splice) -> L = sum(inputs_embeds * R) -> autograd."""
+    from PIL import Image
+    from radvlm_b200.synthetic import seeded_init_
+    host, _ = build_reference_host(vocab=64, hidden_size=gi.SMALL_PROJ, seed=0, vision_kwargs=gi.SMALL_VISION)
+    seeded_init_(host, gi.GRAD_SEED)
+    host.requires_grad_(True)
+    host.train()
+    proc = host.get_vision_tower().image_processor
+    tiles, sizes = [], []
+    for name in gi.GRAD_IMAGES:
+        arr = gi.grad_image(name)
+        if arr.ndim == 2:
+            arr = np.repeat(arr[:, :, None], 3, axis=2)
+        img = Image.fromarray(arr)
+        tiles.append(ref.mm_utils.process_anyres_image(img, proc, host.config.image_grid_pinpoints))
+        sizes.append(img.size)
+    L = max(len(r) for r in gi.GRAD_IDS)
+    ids = torch.full((len(gi.GRAD_IDS), L), 0, dtype=torch.long)
+    mask = torch.zeros(len(gi.GRAD_IDS), L, dtype=torch.bool)
+    for b, r in enumerate(gi.GRAD_IDS):
+        ids[b, :len(r)] = torch.tensor(r)
+        mask[b, :len(r)] = True
+    labels = torch.where(ids < 0, torch.full_like(ids, -100), ids)
+    pos = torch.arange(L)[None].expand(len(gi.GRAD_IDS), -1).contiguous()
+    out = host.prepare_inputs_labels_for_multimodal(ids, pos, mask, None, labels, tiles, ["image"] * len(tiles), sizes)
+    emb = out[4]
+    R = gi.grad_loss_weights(emb.shape)
+    (emb * R).sum().backward()
+    rows = np.linspace(0, emb.shape[1] - 1, 64).astype(np.int64)
+    res = {"embeds_rows": emb.detach()[:, rows].numpy().astype(np.float32), "rows": rows,
+           "embeds_shape": np.array(emb.shape), "tile_counts": np.array([t.shape[0] for t in tiles])}
+    n = 0
+    for name, p in host.named_parameters():
+        if p.grad is None:
+            continue
+        res["grad/" + name] = p.grad.detach().numpy().astype(np.float32)
+        n += 1
+    print("grad golden: embeds", tuple(emb.shape), "tiles", [t.shape[0] for t in tiles], n, "parameter gradients")
+    return res
+
+
 def main():
-    parts = set(sys.argv[1:]) or {"planner", "merge", "preprocess", "encoder"}
+    parts = set(sys.argv[1:]) or {"planner", "merge", "preprocess", "encoder", "grad"}
     ref = import_reference()
     if "planner" in parts:
         with open(os.path.join(HERE, "planner_golden.json"), "w") as f:
@@ -157,6 +200,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, "preprocess_golden.npz"), **arrays)
     if "encoder" in parts:
         np.savez_compressed(os.path.join(HERE, "encoder_golden.npz"), **encoder_golden())
+    if "grad" in parts:
+        np.savez_compressed(os.path.join(HERE, "grad_golden.npz"), **grad_golden(ref))
     print("golden vectors written to", HERE)
 
 

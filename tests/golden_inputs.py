@@ -132,3 +132,21 @@ def encoder_pixels(n: int, seed: int) -> torch.Tensor:
     u = rng.integers(0, 256, size=(n, 1, 384, 384), dtype=np.uint8)
     u = np.repeat(u, 3, axis=1)
     return torch.from_numpy(normalize_lut_f32()[u])
+
+
+# ---------------------------------------------------------------------------------------------- training (gradients)
+GRAD_SEED = 9
+GRAD_IMAGES = ["rgb_500x300_noise", "grad_1536_gray_mix"]     # 2x1 grid (crop, no pool) and 4x4 grid (bilinear pool)
+GRAD_IDS = [[11, 12, -200, 13, 14], [21, -200, 22, 23, 24, 25]]
+
+
+def grad_image(name) -> np.ndarray:
+    if name == "grad_1536_gray_mix":
+        return preprocess_image(dict(seed=21, size=(1536, 1536), kind="gray_mix"))
+    return preprocess_image(preprocess_cases()[name])
+
+
+def grad_loss_weights(shape) -> torch.Tensor:
+    """dL/d(inputs_embeds) of the synthetic loss  L = sum(inputs_embeds * R)"""
+    g = torch.Generator(device="cpu").manual_seed(4242)
+    return torch.randn(shape, generator=g)
