@@ -409,6 +409,126 @@ def run_b200_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# training-mode arm (BASELINE.json configs[4]): --mode train.  Not the driver's headline metric: an extra line.
+# ----------------------------------------------------------------------------------------------------------------
+def run_train_arm(args):
+    """Step = preprocess + tower/projector/merge/splice forward (activations saved) + backward with a random upstream
+    gradient on inputs_embeds + (N > 1) bucketed NCCL all-reduce of the tower / projector gradients, overlapped."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from radvlm_b200 import _lib, mm_arch, mm_utils, synthetic
+    from radvlm_b200.encoder import flops_per_tile
+    import golden_inputs as gi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    B = args.batch
+    host = synthetic.build_host(hidden_size=3584, vocab=4096, seed=0, dtype=torch.bfloat16, device=dev)
+    host.model.vision_tower.requires_grad_(True)      # mm_tunable_parts = mm_vision_tower, mm_mlp_adapter
+    host.model.mm_projector.requires_grad_(True)
+    host.model.image_newline.requires_grad_(True)
+    host.train()
+    enc = mm_arch._encoder_for(host)
+    enc.grad_allreduce_group = None if world > 1 else False
+    rng = np.random.default_rng(2000 + rank)
+    n_buf = 2
+    dev_imgs = []
+    for _ in range(n_buf):
+        gray = rng.integers(0, 256, size=(B, IMG, IMG, 1), dtype=np.uint8)
+        dev_imgs.append(torch.from_numpy(np.repeat(gray, 3, axis=3).copy()).to(dev))
+    Lp = 32
+    ids = torch.randint(1, 4000, (B, Lp), generator=torch.Generator().manual_seed(5))
+    ids[:, 7] = -200
+    ids_dev = ids.to(dev)
+    mask_dev = torch.ones_like(ids_dev, dtype=torch.bool)
+    labels_dev = torch.where(ids_dev < 0, torch.full_like(ids_dev, -100), ids_dev)
+    pos_dev = torch.arange(Lp, device=dev)[None].expand(B, -1).contiguous()
+    upstream = [None]
+    t_fwd = [0.0]
+
+    def step(images_u8, timed_fwd=None):
+        tiles, sizes, splits, _ = mm_utils.preprocess_anyres_batch(list(images_u8), gi.PINPOINTS, device=dev,
+                                                                   dtype=torch.bfloat16)
+        out = host.prepare_inputs_labels_for_multimodal(ids_dev, pos_dev, mask_dev, None, labels_dev,
+                                                        list(torch.split(tiles, splits)), ["image"] * B, sizes)
+        emb = out[4]
+        if upstream[0] is None:
+            upstream[0] = torch.randn(emb.shape, device=dev, dtype=emb.dtype, generator=torch.Generator(device=dev).manual_seed(3))
+        if timed_fwd is not None:
+            timed_fwd.record()
+        emb.backward(upstream[0])
+        host.zero_grad(set_to_none=True)
+
+    for i in range(args.warmup):
+        step(dev_imgs[i % n_buf])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    tw0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        starts[i].record()
+        step(dev_imgs[i % n_buf], mids[i])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    fwd_ms = sum(s.elapsed_time(m) for s, m in zip(starts, mids)) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop(tw0, tw1) if clocks else None
+    if rank == 0:
+        peaks, _ = _peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        tokens_step = B * world * TOKENS_PER_IMAGE
+        step_ms = ms / args.steps
+        # algorithmic FLOPs of a training step with per-layer recompute (SURVEY section 8(d)): forward + recomputed
+        # QKV / out_proj / fc1 + 2x every Linear + 2.5x attention for the tower, 3x for the projector
+        hidden, inter, seq, proj, L = 1152, 4304, 729, 3584, 26
+        lin = 2.0 * seq * (4 * hidden * hidden + 2 * hidden * inter)
+        attn = 4.0 * seq * seq * hidden
+        tower_fwd = L * (lin + attn) + 2.0 * seq * 588 * hidden
+        recompute = L * 2.0 * seq * (4 * hidden * hidden + hidden * inter)
+        bwd = L * (2 * lin + 2.5 * attn) + 2.0 * seq * 588 * hidden
+        proj_f = 2.0 * seq * (hidden * proj + proj * proj)
+        flops_step = (tower_fwd + recompute + bwd + proj_f * (1 + 0.35 + 2)) * TILES_PER_IMAGE * B
+        print(json.dumps({
+            "metric": "visual tokens/sec, training step (tower + projector + merge forward/backward)", "mode": "train",
+            "value": tokens_step / (step_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "forward_ms_per_step": fwd_ms,
+            "backward_ms_per_step": step_ms - fwd_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[4]: %d synthetic 1024x1024 CXR per GPU per step, SigLIP-so400m 26 "
+                                   "layers + mlp2x_gelu + unpad/newline merge + splice, forward + backward (layer "
+                                   "recompute) with a random upstream gradient on inputs_embeds" % B
+                                   + ("" if world == 1 else "; bucketed NCCL gradient all-reduce overlapped with the backward"),
+                       "images_per_gpu_per_step": B, "parallelism": "dp%d (replicas)" % world},
+            "clocks": clk,
+            "path_tflops": flops_step * world / (step_ms / 1e3) / 1e12,
+            "path_frac_of_peak": flops_step / (step_ms / 1e3) / 1e12 / peak,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def _ncu_traffic():
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json); {} if absent."""
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
@@ -427,10 +547,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="encode", choices=["encode", "train"],
+                    help="encode: the headline metric (BASELINE configs[1..3]); train: configs[4], forward + backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "train":
+        return run_train_arm(args)
     return run_b200_arm(args)
 
 

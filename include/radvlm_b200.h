@@ -244,6 +244,13 @@ size_t radvlm_tower_backward_workspace_bytes(const radvlm_siglip_weights* tw, in
 int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads, const void* pixels,
                                  int pixel_dtype, int n_tiles, const void* saved, size_t saved_bytes, float* d_hidden,
                                  void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for encoder layers [layer_lo, layer_hi) only (top down; the embeddings follow when layer_lo == 0).  Call it
+ * range by range from the top with the same d_hidden / workspace to overlap the gradient all-reduce of finished
+ * layers (radvlm_b200.dist.allreduce_gradients) with the backward of the next range. */
+int radvlm_siglip_tower_backward_range(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads,
+                                       const void* pixels, int pixel_dtype, int n_tiles, const void* saved,
+                                       size_t saved_bytes, float* d_hidden, void* workspace, size_t workspace_bytes,
+                                       int layer_lo, int layer_hi, void* stream);
 size_t radvlm_projector_backward_workspace_bytes(const radvlm_projector_weights* pw, int rows);
 /* hidden: fp32 [rows, in_dim] (the projector input); d_features: bf16 [rows, hidden];
  * d_hidden: fp32 [rows, in_dim] written (may be NULL when the tower is frozen). */

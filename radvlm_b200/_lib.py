@@ -146,6 +146,8 @@ SIGNATURES = {
     "radvlm_tower_backward_workspace_bytes": (_sz, [C.POINTER(SiglipWeights), _i]),
     "radvlm_siglip_tower_backward": (_i, [C.POINTER(SiglipWeights), C.POINTER(SiglipGrads), _vp, _i, _i, _vp, _sz, _vp,
                                           _vp, _sz, _vp]),
+    "radvlm_siglip_tower_backward_range": (_i, [C.POINTER(SiglipWeights), C.POINTER(SiglipGrads), _vp, _i, _i, _vp, _sz,
+                                                _vp, _vp, _sz, _i, _i, _vp]),
     "radvlm_projector_backward_workspace_bytes": (_sz, [C.POINTER(ProjectorWeights), _i]),
     "radvlm_projector_backward": (_i, [C.POINTER(ProjectorWeights), C.POINTER(ProjectorGrads), _vp, _vp, _i, _vp, _vp,
                                        _sz, _vp]),

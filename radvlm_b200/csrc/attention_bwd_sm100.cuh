@@ -254,10 +254,14 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
       tc_fence_before();
       mbar_arrive(bar_dqfree);
       if (q_ok) {
+        // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations of scalar adds.
+        // Columns >= hd are padding of the accumulator row: adding to them is harmless and keeps the vectors whole.
         float* dst = args.dq_acc + (static_cast<size_t>(th) * args.seq_pad + qrow) * 80 + half * 40;
 #pragma unroll
-        for (int e = 0; e < 40; ++e)
-          if (half * 40 + e < args.hd) atomicAdd(dst + e, __uint_as_float(dq[e]));
+        for (int e = 0; e < 40; e += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(dq[e])),
+                       "f"(__uint_as_float(dq[e + 1])), "f"(__uint_as_float(dq[e + 2])), "f"(__uint_as_float(dq[e + 3]))
+                       : "memory");
       }
     }
 

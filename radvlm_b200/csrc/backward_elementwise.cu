@@ -113,20 +113,17 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dy,
                      float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D,
-                     float eps) {
-  extern __shared__ float red[];  // [2][D]
+                     float eps, int rows_per_block) {
+  extern __shared__ float red[];  // [2][D]: this block's dgamma / dbeta partial sums
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 ag[NV], ab[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_d = 1.0f / static_cast<float>(D);
-  for (int row = warp_global; row < rows; row += nwarps) {
+  const int row_end = min(rows, (static_cast<int>(blockIdx.x) + 1) * rows_per_block);
+  for (int row = blockIdx.x * rows_per_block + warp; row < row_end; row += 8) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
     float4 v[NV], g[NV];
@@ -163,8 +160,11 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                                        __uint_as_float(d.y << 16), __uint_as_float(d.y & 0xFFFF0000u));
         const float4 gm = __ldg(g4 + idx);
         v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
-        ag[i].x += dyv.x * v[i].x; ag[i].y += dyv.y * v[i].y; ag[i].z += dyv.z * v[i].z; ag[i].w += dyv.w * v[i].w;
-        ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
+        // parameter gradients: shared-memory reductions (lanes hit distinct banks; warps of a block interleave)
+        atomicAdd(&red[4 * idx + 0], dyv.x * v[i].x); atomicAdd(&red[4 * idx + 1], dyv.y * v[i].y);
+        atomicAdd(&red[4 * idx + 2], dyv.z * v[i].z); atomicAdd(&red[4 * idx + 3], dyv.w * v[i].w);
+        atomicAdd(&red[D + 4 * idx + 0], dyv.x); atomicAdd(&red[D + 4 * idx + 1], dyv.y);
+        atomicAdd(&red[D + 4 * idx + 2], dyv.z); atomicAdd(&red[D + 4 * idx + 3], dyv.w);
         g[i] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
         m1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
         m2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
@@ -191,16 +191,6 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      atomicAdd(&red[4 * idx + 0], ag[i].x); atomicAdd(&red[4 * idx + 1], ag[i].y);
-      atomicAdd(&red[4 * idx + 2], ag[i].z); atomicAdd(&red[4 * idx + 3], ag[i].w);
-      atomicAdd(&red[D + 4 * idx + 0], ab[i].x); atomicAdd(&red[D + 4 * idx + 1], ab[i].y);
-      atomicAdd(&red[D + 4 * idx + 2], ab[i].z); atomicAdd(&red[D + 4 * idx + 3], ab[i].w);
-    }
-  }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     atomicAdd(dgamma + i, red[i]);
@@ -216,18 +206,21 @@ int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, flo
     return RADVLM_ERR_UNSUPPORTED_SHAPE;
   }
   const int threads = 256;
-  int blocks = (rows * 32 + threads - 1) / threads;
-  const int cap = device_sm_count() * 4;
-  if (blocks > cap) blocks = cap;
+  // rows per block: enough blocks to fill the GPU several times over, few enough that the per-block flush of
+  // 2*D global atomics stays negligible
+  int rows_per_block = (rows + device_sm_count() * 16 - 1) / (device_sm_count() * 16);
+  rows_per_block = (rows_per_block + 7) / 8 * 8;
+  if (rows_per_block < 32) rows_per_block = 32;
+  const int blocks = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = static_cast<size_t>(2) * D * sizeof(float);
   const int nv = (D / 4 + 31) / 32;
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dy);
   if (nv <= 3)
-    layernorm_bwd_kernel<3><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps);
+    layernorm_bwd_kernel<3><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps, rows_per_block);
   else if (nv <= 9)
-    layernorm_bwd_kernel<9><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps);
+    layernorm_bwd_kernel<9><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps, rows_per_block);
   else
-    layernorm_bwd_kernel<12><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps);
+    layernorm_bwd_kernel<12><<<blocks, threads, smem, stream>>>(x, gamma, d, dres, dgamma, dbeta, rows, D, eps, rows_per_block);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

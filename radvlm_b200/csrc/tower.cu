@@ -261,9 +261,12 @@ static int linear_dgrad(const void* dY, int ldy, const void* W, int ldw, int row
   return gemm_dispatch(dY, ldy, W, ldw, a, f32_out ? EPI_BIAS_F32 : EPI_BIAS_BF16, 0, stream);
 }
 
+// Layers [layer_lo, layer_hi) are processed from the top down; the embeddings follow when layer_lo == 0.  Calling it
+// range by range (top ranges first, same d_hidden buffer) lets the host overlap the gradient all-reduce of the
+// finished layers with the backward of the next ones.
 static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* gr, const void* pixels,
                                int pixel_dtype, int n_tiles, const TowerSaved& sv, float* dh, const EncodeLayout& L,
-                               const BackwardLayout& B, uint8_t* ws, cudaStream_t stream) {
+                               const BackwardLayout& B, uint8_t* ws, cudaStream_t stream, int layer_lo, int layer_hi) {
   const int D = tw->hidden, I = tw->intermediate, NL = tw->num_layers;
   const int M = static_cast<int>(L.M);
   void* xn1 = ws + B.off_xn1;
@@ -287,7 +290,7 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   const float scale = 1.0f / sqrtf(static_cast<float>(L.hd));
   const size_t MD = static_cast<size_t>(M) * D;
 
-  for (int l = NL - 1; l >= 0; --l) {
+  for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const radvlm_vit_layer_weights& w = tw->layers[l];
     const radvlm_vit_layer_grads* lg = (gr != nullptr && gr->layers != nullptr) ? &gr->layers[l] : nullptr;
     auto G = [&](float* radvlm_vit_layer_grads::*m) -> float* { return lg ? lg->*m : nullptr; };
@@ -351,7 +354,7 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     }
   }
   // ---- embeddings: hidden0 = im2col(pixels) Wp^T + bp + pos  (siglip_encoder.py:169-174)
-  if (gr != nullptr && (gr->patch_w || gr->patch_b || gr->pos_embed)) {
+  if (layer_lo == 0 && gr != nullptr && (gr->patch_w || gr->patch_b || gr->pos_embed)) {
     if (gr->pos_embed && (st = pos_embed_grad_launch(dh, gr->pos_embed, n_tiles, L.T, D, stream))) return st;
     if (gr->patch_w || gr->patch_b) {
       if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
@@ -502,16 +505,18 @@ extern "C" size_t radvlm_tower_backward_workspace_bytes(const radvlm_siglip_weig
   return B.total;
 }
 
-extern "C" int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads,
-                                            const void* pixels, int pixel_dtype, int n_tiles, const void* saved,
-                                            size_t saved_bytes, float* d_hidden, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
+extern "C" int radvlm_siglip_tower_backward_range(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads,
+                                                  const void* pixels, int pixel_dtype, int n_tiles, const void* saved,
+                                                  size_t saved_bytes, float* d_hidden, void* workspace,
+                                                  size_t workspace_bytes, int layer_lo, int layer_hi, void* stream) {
   int st = require_sm100();
   if (st) return st;
   EncodeLayout L;
   st = make_layout(tw, nullptr, n_tiles, &L);
   if (st) return st;
   RV_CHECK_ARG(pixels && saved && d_hidden && workspace, "tower_backward: null pointer");
+  RV_CHECK_ARG(0 <= layer_lo && layer_lo <= layer_hi && layer_hi <= tw->num_layers, "tower_backward: bad layer range [%d, %d)",
+               layer_lo, layer_hi);
   const TowerSaved sv = make_saved(tw, L, n_tiles, const_cast<void*>(saved));
   BackwardLayout B;
   make_bwd_layout(tw, L, n_tiles, &B);
@@ -521,7 +526,16 @@ extern "C" int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, con
     return RADVLM_ERR_WORKSPACE_TOO_SMALL;
   }
   return tower_backward_impl(tw, grads, pixels, pixel_dtype, n_tiles, sv, d_hidden, L, B,
-                             static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream));
+                             static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream), layer_lo, layer_hi);
+}
+
+extern "C" int radvlm_siglip_tower_backward(const radvlm_siglip_weights* tw, const radvlm_siglip_grads* grads,
+                                            const void* pixels, int pixel_dtype, int n_tiles, const void* saved,
+                                            size_t saved_bytes, float* d_hidden, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  RV_CHECK_ARG(tw != nullptr, "tower_backward: null weights");
+  return radvlm_siglip_tower_backward_range(tw, grads, pixels, pixel_dtype, n_tiles, saved, saved_bytes, d_hidden,
+                                            workspace, workspace_bytes, 0, tw->num_layers, stream);
 }
 
 extern "C" size_t radvlm_projector_backward_workspace_bytes(const radvlm_projector_weights* pw, int rows) {

@@ -80,3 +80,70 @@ def encode_images_sharded(images: Sequence, image_sizes: Sequence, tile_counts: 
     owned = shard_images_lpt(tile_counts, world)
     local = encode_and_merge(list(owned[rank]))
     return gather_visual_tokens(local, owned, token_counts, group=group)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training mode (BASELINE.json configs[4]): replicas of the tower + projector, gradients all-reduced in buckets
+# ---------------------------------------------------------------------------------------------------------------
+def plan_gradient_buckets(numels: Sequence[int], bucket_elems: int) -> List[List[int]]:
+    """Greedy buckets in the given order (the caller passes tensors in the order the backward finishes them:
+    top layers first), each at most ``bucket_elems`` elements unless a single tensor is larger."""
+    buckets: List[List[int]] = []
+    cur, cur_n = [], 0
+    for i, n in enumerate(numels):
+        if cur and cur_n + int(n) > bucket_elems:
+            buckets.append(cur)
+            cur, cur_n = [], 0
+        cur.append(i)
+        cur_n += int(n)
+    if cur:
+        buckets.append(cur)
+    return buckets
+
+
+class GradientAllReducer:
+    """Bucketed, asynchronous sum (then scale) of gradient tensors over the data-parallel group.
+
+    ``submit(tensors)`` may be called several times while the backward is still running (one call per finished
+    layer range); every bucket is flattened, all-reduced with ``async_op=True`` (NCCL runs it on its own stream, over
+    NVLink / NVSwitch) and written back in ``finish()``, which also applies the 1 / world_size average."""
+
+    def __init__(self, group=None, bucket_bytes: int = 64 << 20, average: bool = True):
+        self.group, self.bucket_bytes, self.average = group, bucket_bytes, average
+        self._pending = []
+
+    def submit(self, tensors: Sequence[torch.Tensor]) -> None:
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1 or not tensors:
+            return
+        tensors = list(tensors)
+        per = max(1, self.bucket_bytes // max(tensors[0].element_size(), 1))
+        for bucket in plan_gradient_buckets([t.numel() for t in tensors], per):
+            members = [tensors[i] for i in bucket]
+            flat = torch.cat([t.reshape(-1) for t in members]) if len(members) > 1 else members[0].reshape(-1)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((work, flat, members))
+
+    def finish(self) -> None:
+        if not self._pending:
+            return
+        scale = 1.0 / dist.get_world_size(self.group) if self.average else 1.0
+        for work, flat, members in self._pending:
+            work.wait()
+            off = 0
+            for t in members:
+                n = t.numel()
+                src = flat[off:off + n].view_as(t)
+                if src.data_ptr() != t.data_ptr():
+                    t.copy_(src)
+                if scale != 1.0:
+                    t.mul_(scale)
+                off += n
+        self._pending = []
+
+
+def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20,
+                        average: bool = True) -> None:
+    """One-shot form of :class:`GradientAllReducer` (blocking)."""
+    r = GradientAllReducer(group, bucket_bytes, average)
+    r.submit(tensors)
+    r.finish()

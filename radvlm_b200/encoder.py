@@ -117,6 +117,12 @@ class B200VisionEncoder:
         self.projector_module = projector_module  # nn.Sequential(Linear, GELU, Linear)
         self.num_heads, self.image_size, self.ln_eps = num_heads, image_size, ln_eps
         self.max_tiles_per_call = max_tiles_per_call
+        # training mode, data parallel: gradients are all-reduced (averaged) inside the backward, overlapped with it.
+        # False (default) leaves them local (e.g. when DistributedDataParallel / DeepSpeed owns the reduction);
+        # None = the default process group; or pass a process group.
+        self.grad_allreduce_group = False
+        self.grad_bucket_bytes = 64 << 20
+        self.backward_layers_per_range = 4
         self._packed: Optional[PackedWeights] = None
         self._key = None
         self._frozen = False
@@ -221,11 +227,21 @@ class _GradBuffers:
         psd = dict(enc.projector_module.named_parameters())
         pre = "vision_model."
         self.bufs: Dict[str, torch.Tensor] = {}
+        # one flat zero-filled allocation (one memset), carved into 256-byte aligned views
+        n_layers_alloc = sum(1 for _ in range(NL))
+        cap = NL * (3 * D * D + D * D + 2 * D * I + 9 * D + I + 64 * 12) + D * tw.patch_k_pad + D + pk.tokens_per_tile * D \
+            + pk.proj_hidden * (D + pk.proj_hidden + 2) + 64 * 8
+        flat = torch.zeros(cap, dtype=torch.float32, device=dev)
+        cursor = [0]
 
         def alloc(key, shape, *src_names, table=tsd):
             if not any(table[n].requires_grad for n in src_names):
                 return None
-            t = torch.zeros(shape, dtype=torch.float32, device=dev)
+            n = 1
+            for d in shape:
+                n *= int(d)
+            t = flat[cursor[0]:cursor[0] + n].view(shape)
+            cursor[0] += (n + 63) // 64 * 64
             self.bufs[key] = t
             return t.data_ptr()
 
@@ -260,6 +276,15 @@ class _GradBuffers:
         self.proj.w2 = alloc("p.w2", (P, P), "2.weight", table=psd)
         self.proj.b2 = alloc("p.b2", (P,), "2.bias", table=psd)
         self._D, self._NL, self._pre = D, NL, pre
+
+    def layer_buffers(self, lo: int, hi: int, include_embeddings: bool):
+        """fp32 buffers of layers [lo, hi), top layer first (the order the backward finishes them)."""
+        out = []
+        for i in range(hi - 1, lo - 1, -1):
+            out += [t for k, t in self.bufs.items() if k.startswith("l%d." % i)]
+        if include_embeddings:
+            out += [self.bufs[k] for k in ("patch_w", "patch_b", "pos") if k in self.bufs]
+        return out
 
     def for_parameter(self, name: str, p: torch.Tensor, is_tower: bool) -> Optional[torch.Tensor]:
         """Gradient of one module Parameter (its shape / dtype), or None when frozen."""
@@ -341,6 +366,12 @@ class _EncodeImagesFn(torch.autograd.Function):
         T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
         d_out = d_out.to(device=dev, dtype=torch.bfloat16).contiguous()
         gb = _GradBuffers(enc, pk, dev)
+        reducer = None
+        if enc.grad_allreduce_group is not False:   # False = off; None = default process group (when initialised)
+            from .dist import GradientAllReducer
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(enc.grad_allreduce_group) > 1:
+                reducer = GradientAllReducer(enc.grad_allreduce_group, enc.grad_bucket_bytes, average=True)
         with torch.cuda.device(dev):
             stream = _stream_ptr(dev)
             for s, m, saved in ctx.chunks:
@@ -353,10 +384,26 @@ class _EncodeImagesFn(torch.autograd.Function):
                 _lib.check(lib.radvlm_projector_backward(
                     C.byref(pk.projector), C.byref(gb.proj), hid_ptr, d_out[s:s + m].data_ptr(), rows,
                     None if d_hidden is None else d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                last_chunk = (s, m) == (ctx.chunks[-1][0], ctx.chunks[-1][1])
+                if last_chunk and reducer is not None:   # projector gradients are final: reduce them first
+                    reducer.submit([gb.bufs[k] for k in ("p.w2", "p.b2", "p.w1", "p.b1") if k in gb.bufs])
                 if gb.tower_trainable:
-                    _lib.check(lib.radvlm_siglip_tower_backward(
-                        C.byref(pk.tower), C.byref(gb.tower), images[s:s + m].data_ptr(), _DT[images.dtype], m,
-                        saved.data_ptr(), saved.numel(), d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                    NL = pk.tower.num_layers
+                    step_l = max(1, enc.backward_layers_per_range) if (last_chunk and reducer is not None) else NL
+                    hi = NL
+                    while hi > 0:
+                        lo = max(0, hi - step_l)
+                        _lib.check(lib.radvlm_siglip_tower_backward_range(
+                            C.byref(pk.tower), C.byref(gb.tower), images[s:s + m].data_ptr(), _DT[images.dtype], m,
+                            saved.data_ptr(), saved.numel(), d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), lo, hi,
+                            stream))
+                        if last_chunk and reducer is not None:   # overlap: these layers are done, the next range runs
+                            reducer.submit(gb.layer_buffers(lo, hi, include_embeddings=(lo == 0)))
+                        hi = lo
+        if reducer is not None:
+            if not gb.tower_trainable:
+                pass
+            reducer.finish()
         grads = []
         for idx, ((name, is_tower), p) in enumerate(zip(ctx.param_names, ctx.params)):
             grads.append(gb.for_parameter(name, p, is_tower) if ctx.needs_input_grad[4 + idx] else None)

@@ -63,3 +63,42 @@ def test_single_process_passthrough():
     toks = torch.cat([_fake_tokens(i, n, 8) for i, n in enumerate(counts)])
     out = rdist.gather_visual_tokens(toks, [[0, 1, 2]], counts)
     assert all(torch.equal(out[i], _fake_tokens(i, counts[i], 8)) for i in range(3))
+
+
+# ---------------------------------------------------------------------------------------------- training mode
+def test_gradient_bucket_plan():
+    assert rdist.plan_gradient_buckets([], 100) == []
+    assert rdist.plan_gradient_buckets([10, 20, 30], 100) == [[0, 1, 2]]
+    assert rdist.plan_gradient_buckets([60, 50, 50, 500, 10], 100) == [[0], [1, 2], [3], [4]]   # an oversized tensor stands alone
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shapes = [(7, 5), (3,), (64, 33), (1,), (129,)]
+        mk = lambda r: [torch.full(s, float(r + 1)) + torch.arange(int(torch.tensor(s).prod())).reshape(s) * 0.01 for s in shapes]
+        mine = mk(rank)
+        want = [sum(mk(r)[i] for r in range(world)) / world for i in range(len(shapes))]
+        red = rdist.GradientAllReducer(bucket_bytes=256 * 4, average=True)   # several buckets, one oversized tensor
+        red.submit(mine[:2])       # two submissions, as the layer-range backward does
+        red.submit(mine[2:])
+        red.finish()
+        ok = all(torch.allclose(a, b, rtol=0, atol=1e-6) for a, b in zip(mine, want))
+        mine2 = mk(rank)
+        rdist.allreduce_gradients(mine2, average=False)
+        ok = ok and all(torch.allclose(a, b * world, rtol=0, atol=1e-5) for a, b in zip(mine2, want))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) is True and ret.get(1) is True
