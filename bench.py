@@ -472,6 +472,8 @@ def run_train_arm(args):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+    _lib.profile_enable(True)
+    _lib.profile_read()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -493,6 +495,8 @@ def run_train_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clk = clocks.stop(tw0, tw1) if clocks else None
+    prof_ms, prof_n = _lib.profile_read()
+    _lib.profile_enable(False)
     if rank == 0:
         peaks, _ = _peaks()
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
@@ -520,6 +524,8 @@ def run_train_arm(args):
                                    + ("" if world == 1 else "; bucketed NCCL gradient all-reduce overlapped with the backward"),
                        "images_per_gpu_per_step": B, "parallelism": "dp%d (replicas)" % world},
             "clocks": clk,
+            "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in prof_ms.items() if v > 0},
+            "gpu_launches": int(sum(prof_n.values())),
             "path_tflops": flops_step * world / (step_ms / 1e3) / 1e12,
             "path_frac_of_peak": flops_step / (step_ms / 1e3) / 1e12 / peak,
         }))

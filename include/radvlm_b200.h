@@ -260,8 +260,9 @@ int radvlm_projector_backward(const radvlm_projector_weights* pw, const radvlm_p
 /* helpers exposed for tests */
 int radvlm_colsum_bf16(const void* x, int rows, int cols, int ld, float* out, void* stream);
 int radvlm_gelu_fwd_bwd_bf16(const void* u, void* da_du, void* a, int64_t n, int erf_form, void* stream);
+/* dres += dL/dx; dgamma / dbeta += (both NULL: frozen affine); row_stats_scratch: rows * 8 bytes */
 int radvlm_layernorm_bwd(const float* x, const float* gamma, const void* dy, float* dres, float* dgamma, float* dbeta,
-                         int rows, int D, float eps, void* stream);
+                         void* row_stats_scratch, int rows, int D, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Planner (CPU only, no CUDA): every integer decision of the path with the reference's Python

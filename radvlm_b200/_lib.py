@@ -153,7 +153,7 @@ SIGNATURES = {
                                        _sz, _vp]),
     "radvlm_colsum_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "radvlm_gelu_fwd_bwd_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
-    "radvlm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "radvlm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "radvlm_merge_splice_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "radvlm_plan_select_best_resolution": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _pi, _pi]),
     "radvlm_plan_image": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _i, _i, _i, C.POINTER(ImagePlan)]),
@@ -188,7 +188,8 @@ def load():
 
 
 PROF_CLASSES = ("gemm_patch_proj", "attention", "layernorm", "misc", "preprocess", "merge_splice",
-                "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2")
+                "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2",
+                "bwd_recompute", "bwd_dgrad", "bwd_wgrad", "bwd_attention", "bwd_elementwise")
 
 
 def profile_enable(on: bool):

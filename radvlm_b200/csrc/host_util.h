@@ -56,7 +56,12 @@ enum ProfClass : int {
   PROF_GEMM_OUT = 7,
   PROF_GEMM_FC1 = 8,
   PROF_GEMM_FC2 = 9,
-  PROF_NUM_CLASSES = 10
+  PROF_BWD_RECOMPUTE = 10,  // training mode: forward pieces recomputed inside the backward (LN, QKV, out_proj, fc1)
+  PROF_BWD_DGRAD = 11,      // dX = dY W
+  PROF_BWD_WGRAD = 12,      // dW += dY^T X (+ bias column sums)
+  PROF_BWD_ATTENTION = 13,
+  PROF_BWD_ELEMENTWISE = 14, // LayerNorm / GELU backward, casts, position-table sum
+  PROF_NUM_CLASSES = 15
 };
 struct ProfScope {
   ProfScope(int cls, cudaStream_t stream, int launches = 1);

@@ -203,7 +203,7 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
 // parameter (frozen, train.py:1642-1665 mm_tunable_parts).
 // =================================================================================================
 struct BackwardLayout {
-  size_t off_xn1, off_xn2, off_g, off_dx, off_h1, off_u, off_da, off_a, off_dqkv, off_q, off_k, off_vt, off_attn, total;
+  size_t off_xn1, off_xn2, off_g, off_dx, off_h1, off_u, off_da, off_a, off_dqkv, off_q, off_k, off_vt, off_attn, off_stats, total;
   size_t attn_bytes;
 };
 
@@ -225,6 +225,7 @@ static void make_bwd_layout(const radvlm_siglip_weights* tw, const EncodeLayout&
   B->off_vt = off;   off = align_up(off + L.qkv_bytes, 1024);
   B->attn_bytes = attention_bwd_workspace_bytes(n_tiles, tw->heads, L.seq_pad);
   B->off_attn = off; off = align_up(off + B->attn_bytes, 1024);
+  B->off_stats = off; off = align_up(off + M * 8 + 2 * D * sizeof(float), 1024);  // LayerNorm row stats + frozen-affine scratch
   B->total = off;
 }
 
@@ -244,10 +245,10 @@ static int linear_wgrad(const void* dY, int ldy, const void* X, int ldx, int row
     a.M = out_dim; a.N = in_dim; a.K = rows;
     a.out = dW; a.ldo = ldw;
     a.a_mn = 1; a.b_mn = 1; a.k_splits = pick_splits(out_dim, in_dim);
-    st = gemm_dispatch(dY, ldy, X, ldx, a, EPI_ATOMIC_F32, 0, stream);
+    { ProfScope ps(PROF_BWD_WGRAD, stream); st = gemm_dispatch(dY, ldy, X, ldx, a, EPI_ATOMIC_F32, 0, stream); }
     if (st) return st;
   }
-  if (db != nullptr) st = colsum_bf16_launch(dY, rows, out_dim, ldy, db, stream);
+  if (db != nullptr) { ProfScope ps(PROF_BWD_WGRAD, stream); st = colsum_bf16_launch(dY, rows, out_dim, ldy, db, stream); }
   return st;
 }
 
@@ -258,6 +259,7 @@ static int linear_dgrad(const void* dY, int ldy, const void* W, int ldw, int row
   a.M = rows; a.N = in_dim; a.K = out_dim;
   a.out = dX; a.ldo = ldx;
   a.b_mn = 1;
+  ProfScope ps(PROF_BWD_DGRAD, stream);
   return gemm_dispatch(dY, ldy, W, ldw, a, f32_out ? EPI_BIAS_F32 : EPI_BIAS_BF16, 0, stream);
 }
 
@@ -282,6 +284,8 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   void* k = ws + B.off_k;
   void* vt = ws + B.off_vt;
   void* attn_ws = ws + B.off_attn;
+  void* stats = ws + B.off_stats;
+  float* ln_scratch = reinterpret_cast<float*>(ws + B.off_stats + align_up(static_cast<size_t>(M) * 8, 16));
   int st;
   // q / k / vt padding must be zero; the backward attention wants plain zeros in the V^T padding rows (no ones row)
   RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
@@ -297,6 +301,8 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     const float* h0 = sv.h(l);
     const void* ao = sv.ao(l, NL);
     // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
+    {
+    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 5);
     if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
     {
       GemmArgs a{};
@@ -323,34 +329,42 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
       a.out = u; a.ldo = I;
       if ((st = gemm_dispatch(xn2, D, w.fc1_w, D, a, EPI_BIAS_BF16, 0, stream))) return st;
     }
+    }
     // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
-    if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
     if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream))) return st;           // dL/da
-    if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(M) * I, 0, stream))) return st;   // a, dL/du
+    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(M) * I, 0, stream))) return st; }  // a, dL/du
     if ((st = linear_wgrad(g, D, act, I, M, D, I, G(&radvlm_vit_layer_grads::fc2_w), I, G(&radvlm_vit_layer_grads::fc2_b), stream))) return st;
     if ((st = linear_wgrad(da, I, xn2, D, M, I, D, G(&radvlm_vit_layer_grads::fc1_w), D, G(&radvlm_vit_layer_grads::fc1_b), stream))) return st;
     if ((st = linear_dgrad(da, I, w.fc1_w, D, M, I, D, dx, D, false, stream))) return st;           // dL/dLN2
     {
       float* dg = G(&radvlm_vit_layer_grads::ln2_gamma);
       float* db = G(&radvlm_vit_layer_grads::ln2_beta);
-      float* scratch = reinterpret_cast<float*>(attn_ws);  // frozen LN: the parameter sums go to scratch
-      if (!dg || !db) RV_CUDA(cudaMemsetAsync(scratch, 0, 2 * D * sizeof(float), stream));
-      if ((st = layernorm_bwd_launch(h1, w.ln2_gamma, dx, dh, dg ? dg : scratch, db ? db : scratch + D, M, D, tw->ln_eps, stream))) return st;
+      if ((dg == nullptr) != (db == nullptr)) {  // one of the pair frozen: the other's sum goes to scratch
+        RV_CUDA(cudaMemsetAsync(ln_scratch, 0, 2 * D * sizeof(float), stream));
+        if (!dg) dg = ln_scratch; else db = ln_scratch + D;
+      }
+      ProfScope ps(PROF_BWD_ELEMENTWISE, stream, 2);
+      if ((st = layernorm_bwd_launch(h1, w.ln2_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream))) return st;
     }
     // ---- attention branch: h1 = h0 + out_proj(attn(LN1(h0)))
-    if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
     if ((st = linear_wgrad(g, D, ao, D, M, D, D, G(&radvlm_vit_layer_grads::out_w), D, G(&radvlm_vit_layer_grads::out_b), stream))) return st;
     if ((st = linear_dgrad(g, D, w.out_w, D, M, D, D, dx, D, false, stream))) return st;            // dL/d(attn out)
+    { ProfScope ps(PROF_BWD_ATTENTION, stream, 4);
     if ((st = attention_bwd_launch(q, k, vt, dx, ao, sv.lse(l, NL), dqkv, attn_ws, B.attn_bytes, n_tiles, tw->heads,
-                                   L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream))) return st;
+                                   L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream))) return st; }
     if ((st = linear_wgrad(dqkv, 3 * D, xn1, D, M, 3 * D, D, G(&radvlm_vit_layer_grads::qkv_w), D, G(&radvlm_vit_layer_grads::qkv_b), stream))) return st;
     if ((st = linear_dgrad(dqkv, 3 * D, w.qkv_w, D, M, 3 * D, D, dx, D, false, stream))) return st;  // dL/dLN1
     {
       float* dg = G(&radvlm_vit_layer_grads::ln1_gamma);
       float* db = G(&radvlm_vit_layer_grads::ln1_beta);
-      float* scratch = reinterpret_cast<float*>(attn_ws);
-      if (!dg || !db) RV_CUDA(cudaMemsetAsync(scratch, 0, 2 * D * sizeof(float), stream));
-      if ((st = layernorm_bwd_launch(h0, w.ln1_gamma, dx, dh, dg ? dg : scratch, db ? db : scratch + D, M, D, tw->ln_eps, stream))) return st;
+      if ((dg == nullptr) != (db == nullptr)) {
+        RV_CUDA(cudaMemsetAsync(ln_scratch, 0, 2 * D * sizeof(float), stream));
+        if (!dg) dg = ln_scratch; else db = ln_scratch + D;
+      }
+      ProfScope ps(PROF_BWD_ELEMENTWISE, stream, 2);
+      if ((st = layernorm_bwd_launch(h0, w.ln1_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream))) return st;
     }
   }
   // ---- embeddings: hidden0 = im2col(pixels) Wp^T + bp + pos  (siglip_encoder.py:169-174)

@@ -99,8 +99,9 @@ def test_colsum_gelu_layernorm_backward_vs_torch(lib):
     torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6).backward(dyn.float())
     dres = dres0.clone()
     dgamma, dbeta = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    stats = torch.empty(rows, 2, device="cuda")
     _lib.check(lib.radvlm_layernorm_bwd(x.data_ptr(), gamma.data_ptr(), dyn.data_ptr(), dres.data_ptr(), dgamma.data_ptr(),
-                                        dbeta.data_ptr(), rows, D, 1e-6, _stream()))
+                                        dbeta.data_ptr(), stats.data_ptr(), rows, D, 1e-6, _stream()))
     torch.testing.assert_close(dres, dres0 + xr.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dgamma, gr.grad, rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(dbeta, br.grad, rtol=1e-3, atol=2e-2)
