@@ -86,9 +86,10 @@ int radvlm_gemm_set_mode(int mode);
 /* QKV projection with the head-split scatter fused into the epilogue
  * (siglip_encoder.py:207-213: three Linear + view/transpose).  W is the row-concatenation
  * [q_proj; k_proj; v_proj] = [3*heads*hd, K]; bias likewise.  Outputs (bf16):
- *   q, k : bf16 [tiles, heads, seq_pad, hd_pad]       vt : bf16 [tiles, heads, hd_pad, seq_pad]  (V transposed)
+ *   q, k, v : bf16 [tiles, heads, seq_pad, hd_pad]  (the `vt` argument is V in the SAME layout as q / k: the
+ *   attention kernels read it as an MN-major tensor-core operand, no transposed copy exists)
  * Padding regions are never written: the caller zero-fills q / k once and prepares vt with
- * radvlm_attention_prepare_vt (zero padding + the ones row the attention kernel sums P with). */
+ * radvlm_attention_prepare_vt (zero padding + the ones column the attention kernel sums P with). */
 int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K,
                           const float* bias, void* q, void* k, void* vt, int seq, int seq_pad,
                           int heads, int hd, int hd_pad, int block_n, void* stream);
@@ -101,8 +102,8 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
  * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 384 == 0 (query blocks of 128, key blocks
  * of 96), 1 <= seq <= seq_pad.
  * ---------------------------------------------------------------------------------------------- */
-/* Zero the padded V^T buffer (bf16 [tiles, heads, hd_pad, seq_pad]) and write ones into row `hd` of every head
- * for the valid keys: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */
+/* Zero the padded V buffer (bf16 [tiles, heads, seq_pad, hd_pad]) and write a one into column `hd` of every valid
+ * key: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */
 int radvlm_attention_prepare_vt(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 void* stream);
 int radvlm_attention_fwd(const void* q, const void* k, const void* vt, void* out, int tiles, int heads,
@@ -113,7 +114,7 @@ int radvlm_attention_fwd_lse(const void* q, const void* k, const void* vt, void*
                              int seq, int seq_pad, int hd, int hd_pad, float scale, void* stream);
 
 /* Backward of the attention (autograd of siglip_encoder.py:216-235).  q, k: the padded head-major buffers of the
- * forward; vt: V^T prepared with plain ZEROS in its padding rows (no ones row); dout / out: gradient and value of the
+ * forward; vt: V ([tiles, heads, seq_pad, hd_pad]) with plain ZEROS in its padding (no ones column); dout / out: gradient and value of the
  * attention output, bf16 token-major [tiles*seq, heads*hd]; lse from radvlm_attention_fwd_lse.
  * dqkv: bf16 [tiles*seq, 3*heads*hd] = [dQ | dK | dV] in the column order of the concatenated QKV projection, i.e.
  * the dY of that Linear.  workspace: radvlm_attention_bwd_workspace_bytes (row dots + fp32 dQ accumulator). */

@@ -57,8 +57,7 @@ int attention_bwd_launch(const void* q, const void* k, const void* vt, const voi
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tk, k, hd_pad, th * seq_pad, pitch, 16, 128, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64, 80,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+  st = make_tmap_bf16_2d(&tv, vt, hd_pad, th * seq_pad, pitch, 16, 128, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tdo, dout, D, tokens, static_cast<uint64_t>(D) * 2, 16, 128, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;

@@ -11,13 +11,13 @@
 //     straight out of the token-major [tokens, heads*hd] gradient of the attention output).  The same bytes are a
 //     K-major operand when the contraction runs over head_dim (S, dP) and an MN-major operand when it runs over
 //     the rows (dV = P^T dO, dK = dS^T Q, dQ = dS K).
-//   * V_j is the forward's V^T tile ([80 x 128 keys], 128B swizzle) used as an MN-major B operand.
+//   * V_j is loaded like K_j (five chunks) and is a plain K-major B operand of dP = dO V^T.
 //   * P and dS are written by the softmax warps as bf16 [q][key] tiles (128B swizzle): K-major A for dQ = dS K,
 //     MN-major A for P^T dO and dS^T Q.
 // Warp roles: warp0 TMA, warp1 MMA issue (whole warp, elect.sync), warps 2..9 two threads per query row.
 // TMEM: S [0,128)  dP [128,256)  dV [256,336)  dK [336,416)  dQ [416,496).
 //
-// Padding contract: Q / K pad rows and head-dim pad columns are zero; V^T rows >= hd are zero (NO ones row: use a
+// Padding contract: Q / K / V pad rows and head-dim pad columns are zero (V WITHOUT the forward's ones column: use a
 // buffer prepared with plain zeros); rows of dO beyond this tile (the next tile's tokens) are neutralised by zeroing
 // the P / dS rows of invalid queries.
 #pragma once
@@ -36,7 +36,7 @@ struct AttnBwdArgs {
 };
 
 constexpr int kAbThreads = 320;
-constexpr int kAbTile = 128 * 80 * 2;   // 20480: Q / K / dO tiles (5 SW32 chunks) and the V^T tile (2 SW128 atoms)
+constexpr int kAbTile = 128 * 80 * 2;   // 20480: Q / K / V / dO tiles (5 SW32 chunks each)
 constexpr int kAbPTile = 128 * 128 * 2; // 32768: P and dS
 constexpr int kAbSmemBytes = 4 * kAbTile + 2 * kAbPTile + 128;
 constexpr int kAbTmemCols = 512;
@@ -47,22 +47,10 @@ __device__ __forceinline__ float ex2_approx_bwd(float x) {
   return y;
 }
 
-// shared-memory descriptor with an explicit leading-dimension byte offset (MN-major operands need it)
-__device__ __forceinline__ uint64_t make_smem_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                       uint32_t layout) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1u) << 46;
-  d |= static_cast<uint64_t>(layout) << 61;
-  return d;
-}
-
 __global__ void __launch_bounds__(kAbThreads, 1)
 siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  [th*seq_pad, 80]   box {16, 128} SW32
                             const __grid_constant__ CUtensorMap tmap_k,   // K  same
-                            const __grid_constant__ CUtensorMap tmap_vt,  // Vt [th*80, seq_pad]   box {64, 80} SW128
+                            const __grid_constant__ CUtensorMap tmap_v,   // V  same
                             const __grid_constant__ CUtensorMap tmap_do,  // dO [tiles*seq, heads*hd] box {16, 128} SW32
                             const AttnBwdArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +83,7 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_vt);
+    tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_do);
     mbar_init(bar_kv, 1);
     mbar_init(bar_qdo, 1);
@@ -123,9 +111,10 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
       const int k_row0 = th * args.seq_pad + jblk * 128;
       mbar_arrive_expect_tx(bar_kv, 2 * kAbTile);
 #pragma unroll
-      for (int c = 0; c < 5; ++c) tma_load_2d(sK + c * 4096, &tmap_k, bar_kv, c * 16, k_row0);
-      tma_load_2d(sV, &tmap_vt, bar_kv, jblk * 128, th * 80);
-      tma_load_2d(sV + 10240, &tmap_vt, bar_kv, jblk * 128 + 64, th * 80);
+      for (int c = 0; c < 5; ++c) {
+        tma_load_2d(sK + c * 4096, &tmap_k, bar_kv, c * 16, k_row0);
+        tma_load_2d(sV + c * 4096, &tmap_v, bar_kv, c * 16, k_row0);
+      }
       for (int i = 0; i < num_q; ++i) {
         if (i > 0) mbar_wait(bar_mma2, static_cast<uint32_t>((i - 1) & 1));  // Q / dO consumed
         mbar_arrive_expect_tx(bar_qdo, 2 * kAbTile);
@@ -142,7 +131,7 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
     // ===================== MMA issue (whole warp, elect.sync inside the asm blocks) =====================
     constexpr uint32_t kAMn = 1u << 15, kBMn = 1u << 16;
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);                  // S  = Q K^T      (K-major, K-major)
-    constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128) | kBMn;          // dP = dO V^T     (K-major, MN-major V^T)
+    constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128);                 // dP = dO V^T     (K-major, K-major)
     constexpr uint32_t idesc_kv = make_idesc_bf16(128, 80) | kAMn | kBMn;    // dV = P^T dO, dK = dS^T Q
     constexpr uint32_t idesc_dq = make_idesc_bf16(128, 80) | kBMn;           // dQ = dS K
     const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0);
@@ -154,8 +143,7 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
     const uint64_t q_mn = make_smem_desc_lbo(sQ, 4096, 256, kLayoutSw32);
     const uint64_t k_mn = make_smem_desc_lbo(sK, 4096, 256, kLayoutSw32);
     const uint64_t do_mn = make_smem_desc_lbo(sdO, 4096, 256, kLayoutSw32);
-    // V^T tile [80 x 128 keys] as MN-major B (N = keys): 64-key groups 10240 B apart, 8 head-dim rows per 1024 B atom
-    const uint64_t v_mn = make_smem_desc_lbo(sV, 10240, 1024, kLayoutSw128);
+    const uint64_t v_k = make_smem_desc(sV, 256, kLayoutSw32);
     // P / dS tiles [128 q x 128 keys]: K-major A (contraction over keys) and MN-major A (contraction over queries)
     const uint64_t ds_k = make_smem_desc(sdS, 1024, kLayoutSw128);
     const uint64_t p_mn = make_smem_desc_lbo(sP, 16384, 1024, kLayoutSw128);
@@ -170,8 +158,8 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
       for (int c = 0; c < 5; ++c)   // S: K step c = chunk c (4096 B)
         umma_bf16_ss_elect(tS_u, q_k + c * 256, k_k + c * 256, idesc_s, c != 0 ? 1u : 0u);
 #pragma unroll
-      for (int c = 0; c < 5; ++c)   // dP: K step c = 16 head-dim rows of V^T (2048 B)
-        umma_bf16_ss_elect(tdP_u, do_k + c * 256, v_mn + c * 128, idesc_dp, c != 0 ? 1u : 0u);
+      for (int c = 0; c < 5; ++c)   // dP: K step c = chunk c
+        umma_bf16_ss_elect(tdP_u, do_k + c * 256, v_k + c * 256, idesc_dp, c != 0 ? 1u : 0u);
       umma_commit_elect(bar_sdp);
 
       mbar_wait(bar_pds, par);                                  // P, dS in shared memory

@@ -27,7 +27,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
     configured = true;
   }
   const uint64_t th = static_cast<uint64_t>(tiles) * heads;
-  CUtensorMap tq, tq2, tk, tk2, tv, tv2;
+  CUtensorMap tq, tq2, tk, tk2, tv;
   const uint64_t pitch = static_cast<uint64_t>(hd_pad) * 2;
   st = make_tmap_bf16_2d(&tq, q, hd_pad, th * seq_pad, pitch, 64, kAttnBQ, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
@@ -37,11 +37,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
   if (st != RADVLM_OK) return st;
   st = make_tmap_bf16_2d(&tk2, k, hd_pad, th * seq_pad, pitch, 16, kAttnBKV, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tv, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 64, kAttnHdPad,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
-  if (st != RADVLM_OK) return st;
-  st = make_tmap_bf16_2d(&tv2, vt, seq_pad, th * hd_pad, static_cast<uint64_t>(seq_pad) * 2, 32, kAttnHdPad,
-                         CU_TENSOR_MAP_SWIZZLE_64B);
+  st = make_tmap_bf16_2d(&tv, vt, hd_pad, th * seq_pad, pitch, 16, kAttnBKV, CU_TENSOR_MAP_SWIZZLE_32B);
   if (st != RADVLM_OK) return st;
   AttnArgs a;
   a.out = static_cast<__nv_bfloat16*>(out);
@@ -54,7 +50,7 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
   a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
   a.total_items = tiles * heads * a.num_qblk;
   const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
-  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, tv2, a);
+  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

@@ -5,9 +5,10 @@
 //    matmul(q,k^T)*scale -> softmax(fp32) -> cast -> matmul(p,v) -> transpose/reshape)
 // with one fused kernel.  Layout contract (produced by the QKV GEMM epilogue, gemm_sm100.cuh):
 //    Q, K : [tiles*heads, seq_pad, hd_pad] bf16, zero padded (hd 72 -> 80, seq 729 -> 768)
-//    Vt   : [tiles*heads, hd_pad, seq_pad] bf16  (V transposed so the PV B-operand is K-major); row `hd` of
-//           every head holds ones for the valid keys, so the tensor core accumulates the softmax row sum
-//           (O[:, hd] = sum_j P_j 1) from exactly the bf16 P values the numerator uses
+//    V    : [tiles*heads, seq_pad, hd_pad] bf16, same layout as K (the QKV epilogue writes all three with 16-byte
+//           row stores); it is the B operand of O += P V as an MN-major tcgen05 operand (head_dim contiguous), so no
+//           transposed copy exists anywhere.  Column `hd` of every valid key holds a one, so the tensor core also
+//           accumulates the softmax row sum (O[:, hd] = sum_j P_j 1) from exactly the bf16 P values it multiplies
 //    out  : [tiles*seq, heads*hd] bf16 token-major (the A operand of out_proj)
 //
 // A work item = 128 query rows of one (tile, head).  The kernel is persistent: two CTAs are resident per SM (256
@@ -57,8 +58,8 @@ constexpr int kAttnQBytes = kAttnBQ * kAttnHdPad * 2;    // 20480 : [128 x 128 B
 constexpr int kAttnQ2Off = kAttnBQ * 128;                // offset of the SW32 slab (head dims [64,80))
 constexpr int kAttnKBytes = kAttnBKV * kAttnHdPad * 2;   // 15360 : [96 x 128 B] (SW128) + [96 x 32 B] (SW32)
 constexpr int kAttnK2Off = kAttnBKV * 128;
-constexpr int kAttnVBytes = kAttnHdPad * kAttnBKV * 2;   // 15360 : [80 x 128 B] (SW128, keys 0-63) + [80 x 64 B] (SW64, keys 64-95)
-constexpr int kAttnV2Off = kAttnHdPad * 128;
+constexpr int kAttnVBytes = kAttnBKV * kAttnHdPad * 2;   // 15360 : 5 chunks of [96 keys x 32 B] (SW32), MN-major B operand
+constexpr int kAttnVChunk = kAttnBKV * 32;               // 3072
 constexpr int kAttnStages = 3;                           // K / V ring depth
 constexpr int kAttnXchBytes = 2 * 2 * kAttnBQ * 2;       // 1024 : [block parity][column half][row] bf16 block maxima
 // No alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte aligned
@@ -105,19 +106,18 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
                         const __grid_constant__ CUtensorMap tmap_q2,   // Q  columns [64,80) : SW32  box {16, 128}
                         const __grid_constant__ CUtensorMap tmap_k,    // K  columns [0,64)  : SW128 box {64, 96}
                         const __grid_constant__ CUtensorMap tmap_k2,   // K  columns [64,80) : SW32  box {16, 96}
-                        const __grid_constant__ CUtensorMap tmap_vt,   // Vt keys [0,64) of a block  : SW128 box {64, 80}
-                        const __grid_constant__ CUtensorMap tmap_vt2,  // Vt keys [64,96) of a block : SW64  box {32, 80}
+                        const __grid_constant__ CUtensorMap tmap_v,    // V  16-column chunks : SW32  box {16, 96}
                         const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // swizzled operand tiles need 1024-byte alignment
   const uint32_t sQ = smem_base;
   const uint32_t sK = sQ + kAttnQBytes;               // ring: K_g lives in sK + (g % stages) * kAttnKBytes
-  const uint32_t sV = sK + kAttnStages * kAttnKBytes; // ring: Vt_g lives in sV + (g % stages) * kAttnVBytes
+  const uint32_t sV = sK + kAttnStages * kAttnKBytes; // ring: V_g lives in sV + (g % stages) * kAttnVBytes
   const uint32_t sX = sV + kAttnStages * kAttnVBytes; // [2 parities][2 halves][128 rows] bf16 block maxima
   const uint32_t bar_base = sX + kAttnXchBytes;
   const uint32_t bar_k = bar_base + 0;        // [stages] K_g landed
-  const uint32_t bar_v = bar_base + 32;       // [stages] Vt_g landed
+  const uint32_t bar_v = bar_base + 32;       // [stages] V_g landed
   const uint32_t bar_kfree = bar_base + 64;   // [stages] S_g complete: its K buffer may be refilled
   const uint32_t bar_vfree = bar_base + 96;   // [stages] PV_g complete: its V buffer may be refilled
   const uint32_t bar_s = bar_base + 128;      // S_g complete in TMEM
@@ -142,8 +142,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
     tma_prefetch_desc(&tmap_q2);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_k2);
-    tma_prefetch_desc(&tmap_vt);
-    tma_prefetch_desc(&tmap_vt2);
+    tma_prefetch_desc(&tmap_v);
     for (uint32_t i = 0; i < kAttnStages; ++i) {
       mbar_init(bar_k + 8 * i, 1);
       mbar_init(bar_v + 8 * i, 1);
@@ -193,9 +192,9 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
           tma_load_2d(sK + slot * kAttnKBytes + kAttnK2Off, &tmap_k2, bar_k + 8 * slot, 64, k_row0);
           if (g >= kAttnStages) mbar_wait(bar_vfree + 8 * slot, ring_par ^ 1u);  // PV_{g-stages} complete
           mbar_arrive_expect_tx(bar_v + 8 * slot, kAttnVBytes);
-          tma_load_2d(sV + slot * kAttnVBytes, &tmap_vt, bar_v + 8 * slot, j * kAttnBKV, th * kAttnHdPad);
-          tma_load_2d(sV + slot * kAttnVBytes + kAttnV2Off, &tmap_vt2, bar_v + 8 * slot, j * kAttnBKV + 64,
-                      th * kAttnHdPad);
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+            tma_load_2d(sV + slot * kAttnVBytes + c * kAttnVChunk, &tmap_v, bar_v + 8 * slot, c * 16, k_row0);
           if (++slot == kAttnStages) { slot = 0; ring_par ^= 1u; }
         }
       }
@@ -204,15 +203,16 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
     // ===================== MMA issuer: the whole warp runs this code converged, elect.sync picks the issuing lane
     // inside each asm block (see umma_bf16_ss_elect) =====================
     constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
-    constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad);
+    constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad) | (1u << 16);  // B (= V) is MN-major
     const uint32_t tS_u = __shfl_sync(0xffffffffu, tS, 0), tO_u = __shfl_sync(0xffffffffu, tO, 0);
     const uint32_t tP_u = __shfl_sync(0xffffffffu, tP, 0);
     const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);             // head dims [0,64): 32 B per K step
     const uint64_t qd32 = make_smem_desc(sQ + kAttnQ2Off, 256, kLayoutSw32);   // head dims [64,80)
     const uint64_t kd128 = make_smem_desc(sK, 1024, kLayoutSw128);
     const uint64_t kd32 = make_smem_desc(sK + kAttnK2Off, 256, kLayoutSw32);
-    const uint64_t vd128 = make_smem_desc(sV, 1024, kLayoutSw128);             // keys [0,64) of the block
-    const uint64_t vd64 = make_smem_desc(sV + kAttnV2Off, 512, kLayoutSw64);   // keys [64,96)
+    // V block [96 keys][80] as an MN-major B operand (N = head_dim): 16-column groups kAttnVChunk bytes apart (LBO),
+    // 8 keys per 256-byte swizzle atom (SBO), 512 bytes per 16-key K step
+    const uint64_t vd = make_smem_desc_lbo(sV, kAttnVChunk, 256, kLayoutSw32);
     const int total_blocks = num_items * num_kv;
     // ring bookkeeping for S issue (runs one block ahead of the PV issue)
     uint32_t s_slot = 0, s_par = 0;
@@ -246,11 +246,8 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
         tc_fence_after();
         const uint64_t voff = static_cast<uint64_t>(slot * (kAttnVBytes >> 4));
 #pragma unroll
-        for (int s = 0; s < 4; ++s)  // A = P_g from TMEM (8 columns = 16 bf16 per K step), keys [0,64)
-          umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(s * 8), vd128 + voff + 2 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int s = 0; s < 2; ++s)  // keys [64,96)
-          umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(32 + s * 8), vd64 + voff + 2 * s, idesc_o, 1u);
+        for (int s = 0; s < kAttnBKV / 16; ++s)  // A = P_g from TMEM (8 columns = 16 bf16 per K step)
+          umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(s * 8), vd + voff + 32 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
         umma_commit_elect(bar_o);
         umma_commit_elect(bar_vfree + 8 * slot);
         if (++slot == kAttnStages) { slot = 0; ring_par ^= 1u; }

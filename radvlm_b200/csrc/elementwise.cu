@@ -186,12 +186,12 @@ int im2col_launch(const void* pixels, int dtype, void* out, int n_tiles, int C, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// V^T padding for the attention kernel: zero everything, then ones in row `hd` for the valid keys
+// V padding for the attention kernel: zero everything, then a one in column `hd` of every valid key
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-vt_ones_row_kernel(__nv_bfloat16* __restrict__ vt, int hd, int hd_pad, int seq, int seq_pad) {
-  __nv_bfloat16* row = vt + (static_cast<size_t>(blockIdx.x) * hd_pad + hd) * seq_pad;
-  for (int t = threadIdx.x; t < seq; t += blockDim.x) row[t] = __float2bfloat16(1.0f);
+v_ones_column_kernel(__nv_bfloat16* __restrict__ v, int hd, int hd_pad, int seq, int seq_pad) {
+  __nv_bfloat16* base = v + static_cast<size_t>(blockIdx.x) * seq_pad * hd_pad + hd;
+  for (int t = threadIdx.x; t < seq; t += blockDim.x) base[static_cast<size_t>(t) * hd_pad] = __float2bfloat16(1.0f);
 }
 
 int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
@@ -199,7 +199,7 @@ int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq
   RV_CHECK_ARG(vt && tiles > 0 && heads > 0 && hd < hd_pad && seq <= seq_pad, "prepare_vt: bad arguments");
   const size_t bytes = static_cast<size_t>(tiles) * heads * hd_pad * seq_pad * 2;
   RV_CUDA(cudaMemsetAsync(vt, 0, bytes, stream));
-  vt_ones_row_kernel<<<tiles * heads, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(vt), hd, hd_pad, seq, seq_pad);
+  v_ones_column_kernel<<<tiles * heads, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(vt), hd, hd_pad, seq, seq_pad);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

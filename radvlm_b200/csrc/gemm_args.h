@@ -25,7 +25,7 @@ struct GemmArgs {
   // EPI_QKV_SPLIT
   __nv_bfloat16* q;   // [tiles, heads, seq_pad, hd_pad]
   __nv_bfloat16* k;   // [tiles, heads, seq_pad, hd_pad]
-  __nv_bfloat16* vt;  // [tiles, heads, hd_pad, seq_pad]
+  __nv_bfloat16* vt;  // V: [tiles, heads, seq_pad, hd_pad] (same layout as q / k)
   int seq, seq_pad, heads, hd, hd_pad;
   // Operand layouts (backward GEMMs read activations / weights as they are stored, no transposes):
   //   a_mn = 0: A is [M, K] row-major (K-major operand);  a_mn = 1: A is stored as [K, M] row-major (MN-major)

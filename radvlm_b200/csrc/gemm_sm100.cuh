@@ -6,7 +6,7 @@
 //     live in TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * Four epilogue warps read TMEM with tcgen05.ld (one output row per thread) and apply the fused
 //     epilogue: bias, GELU (tanh / erf), fp32 residual add, position-embedding add, or the QKV
-//     head-split scatter (Q,K -> [tile,head,seq_pad,hd_pad];  V -> transposed [tile,head,hd_pad,seq_pad]).
+//     head-split scatter (Q, K, V -> [tile,head,seq_pad,hd_pad]).
 //
 // Replaces the cuBLASLt / ATen elementwise launches behind nn.Linear / nn.Conv2d(k=14,s=14) in
 //   finetuning/llava/model/multimodal_encoder/siglip_encoder.py:156-173,192-194,207-209,237,252-254
@@ -142,19 +142,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
       const int head = rem / a.hd;
       const int d = rem - head * a.hd;
       const size_t th = static_cast<size_t>(tile) * a.heads + head;
-      if (which < 2) {
-        __nv_bfloat16* base = (which == 0 ? a.q : a.k) + (th * a.seq_pad + t) * a.hd_pad + d;
-        uint4 p;
-        p.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-        p.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-        p.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-        p.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-        *reinterpret_cast<uint4*>(base) = p;
-      } else {
-        __nv_bfloat16* base = a.vt + (th * a.hd_pad + d) * a.seq_pad + t;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) base[static_cast<size_t>(j) * a.seq_pad] = __float2bfloat16_rn(v[8 * g + j]);
-      }
+      __nv_bfloat16* base = (which == 0 ? a.q : (which == 1 ? a.k : a.vt)) + (th * a.seq_pad + t) * a.hd_pad + d;
+      uint4 p;
+      p.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+      p.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+      p.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+      p.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+      *reinterpret_cast<uint4*>(base) = p;
     }
   }
 }
@@ -275,6 +269,51 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
   __syncwarp();
 }
 
+// QKV head-split scatter, coalesced: 64 columns (two 32-column chunks) of 32 rows go through the swizzled staging
+// buffer; afterwards 8 lanes own one row and write its eight 16-byte pieces, which are contiguous in the destination
+// ([tile, head, seq_pad, hd_pad] rows of q / k / v) except at a head boundary.  The direct row-per-thread form made every
+// warp store touch 32 half-used 32-byte sectors.  Requires hd % 8 == 0 (a 16-byte piece never straddles heads).
+__device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
+                                                         const uint32_t* acc1, uint32_t stage, int lane) {
+  uint32_t pk[32];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t* acc = h ? acc1 : acc0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + 32 * h + 4 * j;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      pk[16 * h + 2 * j] = pack_bf16x2(__uint_as_float(acc[4 * j + 0]) + b.x, __uint_as_float(acc[4 * j + 1]) + b.y);
+      pk[16 * h + 2 * j + 1] = pack_bf16x2(__uint_as_float(acc[4 * j + 2]) + b.z, __uint_as_float(acc[4 * j + 3]) + b.w);
+    }
+  }
+  stage_store_row(stage, lane, pk);
+  __syncwarp();
+  const int v = lane & 7;
+  const int c = col0 + 8 * v;
+  if (c < a.N) {
+    const int D = a.heads * a.hd;
+    const int which = c / D;
+    const int rem = c - which * D;
+    const int head = rem / a.hd;
+    const int d = rem - head * a.hd;
+    __nv_bfloat16* dst = (which == 0 ? a.q : (which == 1 ? a.k : a.vt)) + d;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      const int grow = row0 + rr;
+      if (grow < a.M) {
+        const int tile = grow / a.seq;
+        const int t = grow - tile * a.seq;
+        const size_t th = static_cast<size_t>(tile) * a.heads + head;
+        *reinterpret_cast<uint4*>(dst + (th * a.seq_pad + t) * a.hd_pad) = stage_load_vec(stage, rr, v);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // Drain NCOLS accumulator columns of this thread's row: two tcgen05.ld in flight per wait.
 template <int EPI, int NCOLS>
 __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row,
@@ -298,6 +337,8 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
       }
     } else if (kBf16 && staged && two) {
       if constexpr (kBf16) gemm_epilogue_bf16_staged<EPI>(args, row0, col_base + c, r0, r1, stage, lane);
+    } else if (EPI == EPI_QKV_SPLIT && two && (args.N & 7) == 0 && (args.hd & 7) == 0) {
+      if constexpr (EPI == EPI_QKV_SPLIT) gemm_epilogue_qkv_staged(args, row0, col_base + c, r0, r1, stage, lane);
     } else {
       gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
       if (two) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);

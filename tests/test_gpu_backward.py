@@ -114,13 +114,13 @@ def test_attention_backward_vs_torch_autograd(lib):
     g = torch.Generator(device="cuda").manual_seed(6)
     q = torch.zeros(tiles, heads, Tp, hp, device="cuda", dtype=torch.bfloat16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(tiles, heads, hp, Tp, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros_like(q)                                     # V, same layout as q / k
     q[:, :, :T, :hd] = torch.randn(tiles, heads, T, hd, device="cuda", generator=g)
     k[:, :, :T, :hd] = torch.randn(tiles, heads, T, hd, device="cuda", generator=g)
-    vt[:, :, :hd, :T] = torch.randn(tiles, heads, hd, T, device="cuda", generator=g)
+    vt[:, :, :T, :hd] = torch.randn(tiles, heads, T, hd, device="cuda", generator=g)
     dout = torch.randn(tiles * T, D, device="cuda", generator=g).bfloat16()
     vt_fwd = vt.clone()
-    vt_fwd[:, :, hd, :T] = 1   # the forward sums P with a ones row; the backward wants plain zeros there
+    vt_fwd[:, :, :T, hd] = 1   # the forward sums P with a ones column; the backward wants plain zeros there
     out = torch.empty(tiles * T, D, device="cuda", dtype=torch.bfloat16)
     lse = torch.zeros(tiles * heads, Tp, device="cuda", dtype=torch.float32)
     scale = hd ** -0.5
@@ -128,7 +128,7 @@ def test_attention_backward_vs_torch_autograd(lib):
                                             tiles, heads, T, Tp, hd, hp, scale, _stream()))
     qf = q[:, :, :T, :hd].float().requires_grad_(True)
     kf = k[:, :, :T, :hd].float().requires_grad_(True)
-    vf = vt[:, :, :hd, :T].float().transpose(-1, -2).contiguous().requires_grad_(True)
+    vf = vt[:, :, :T, :hd].float().contiguous().requires_grad_(True)
     s = qf @ kf.transpose(-1, -2) * scale
     ref = (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(tiles * T, D)
     torch.testing.assert_close(lse.view(tiles, heads, Tp)[:, :, :T], torch.logsumexp(s, dim=-1).detach() * 1.4426950408889634,

@@ -101,20 +101,21 @@ def test_qkv_split_and_attention_vs_torch(lib):
     b = torch.randn(3 * D, device="cuda", generator=g) * 0.1
     q = torch.zeros(tiles, heads, Tp, hp, device="cuda", dtype=torch.bfloat16)
     k = torch.zeros_like(q)
-    vt = torch.empty(tiles, heads, hp, Tp, device="cuda", dtype=torch.bfloat16)
+    vt = torch.empty(tiles, heads, Tp, hp, device="cuda", dtype=torch.bfloat16)      # V, same layout as q / k
     _lib.check(lib.radvlm_attention_prepare_vt(vt.data_ptr(), tiles, heads, T, Tp, hd, hp, _stream()))
     _lib.check(lib.radvlm_gemm_qkv_split(X.data_ptr(), D, W.data_ptr(), D, tiles * T, D, b.data_ptr(), q.data_ptr(),
                                          k.data_ptr(), vt.data_ptr(), T, Tp, heads, hd, hp, 0, _stream()))
     qkv = (X.float() @ W.float().t() + b).view(tiles, T, 3, heads, hd).permute(2, 0, 3, 1, 4)  # [3,tiles,heads,T,hd]
     torch.testing.assert_close(q[:, :, :T, :hd].float(), qkv[0], rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(k[:, :, :T, :hd].float(), qkv[1], rtol=1e-2, atol=1e-2)
-    torch.testing.assert_close(vt[:, :, :hd, :T].float(), qkv[2].transpose(-1, -2), rtol=1e-2, atol=1e-2)
-    assert q[:, :, T:, :].abs().max() == 0 and q[:, :, :, hd:].abs().max() == 0 and vt[:, :, hd + 1:, :].abs().max() == 0
-    assert bool((vt[:, :, hd, :T] == 1).all()) and vt[:, :, hd, T:].abs().max() == 0   # ones row: P row sums
+    torch.testing.assert_close(vt[:, :, :T, :hd].float(), qkv[2], rtol=1e-2, atol=1e-2)
+    assert q[:, :, T:, :].abs().max() == 0 and q[:, :, :, hd:].abs().max() == 0
+    assert vt[:, :, T:, :].abs().max() == 0 and vt[:, :, :, hd + 1:].abs().max() == 0
+    assert bool((vt[:, :, :T, hd] == 1).all())   # ones column: P row sums come out of the tensor core
     out = torch.empty(tiles * T, D, device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.radvlm_attention_fwd(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), tiles, heads, T, Tp,
                                         hd, hp, hd ** -0.5, _stream()))
-    qf, kf, vf = q[:, :, :T, :hd].float(), k[:, :, :T, :hd].float(), vt[:, :, :hd, :T].float().transpose(-1, -2)
+    qf, kf, vf = q[:, :, :T, :hd].float(), k[:, :, :T, :hd].float(), vt[:, :, :T, :hd].float()
     p = torch.softmax(qf @ kf.transpose(-1, -2) * hd ** -0.5, dim=-1)
     ref = (p @ vf).transpose(1, 2).reshape(tiles * T, D)
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=1e-2)  # bf16 P and output rounding

@@ -52,7 +52,7 @@ __global__ void ref_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, co
     float p = expf(s * scale - mx);
     l += p;
     for (int d = 0; d < hd; ++d)
-      acc[d] += p * __bfloat162float(vt[((size_t)th * hd_pad + d) * seq_pad + j]);
+      acc[d] += p * __bfloat162float(vt[((size_t)th * seq_pad + j) * hd_pad + d]);
   }
   int tile = th / heads, head = th % heads;
   for (int d = 0; d < hd; ++d)
@@ -81,7 +81,7 @@ static int test_attention(int tiles, int heads, float amp) {
       for (int d = 0; d < hd; ++d) {
         hq[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
         hk[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
-        hv[((size_t)a * hd_pad + d) * seq_pad + t] = __float2bfloat16(frand() * 2.f);
+        hv[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * 2.f);
       }
   __nv_bfloat16 *dq, *dk, *dout;
   __nv_bfloat16* dv;
@@ -92,7 +92,7 @@ static int test_attention(int tiles, int heads, float amp) {
   CK(cudaMemcpy(dq, hq.data(), nq * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dk, hk.data(), nq * 2, cudaMemcpyHostToDevice));
   for (int a = 0; a < th; ++a)
-    for (int t = 0; t < seq; ++t) hv[((size_t)a * hd_pad + hd) * seq_pad + t] = __float2bfloat16(1.0f);  // ones row
+    for (int t = 0; t < seq; ++t) hv[((size_t)a * seq_pad + t) * hd_pad + hd] = __float2bfloat16(1.0f);  // ones row
   CK(cudaMemcpy(dv, hv.data(), nq * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xFF, nout * 2));
   const float scale = 1.0f / sqrtf((float)hd);
@@ -177,7 +177,7 @@ static int test_qkv_split(int tiles) {
           const size_t th = (size_t)tile * heads + h;
           float gq = __bfloat162float(hq[(th * seq_pad + t) * hd_pad + d]);
           float gk = __bfloat162float(hk[(th * seq_pad + t) * hd_pad + d]);
-          float gv = __bfloat162float(hv[(th * hd_pad + d) * seq_pad + t]);
+          float gv = __bfloat162float(hv[(th * seq_pad + t) * hd_pad + d]);
           if (t >= seq || d >= hd) {
             const float want_v = (d == hd && t < seq) ? 1.f : 0.f;  // ones row
             if (gq != 0.f || gk != 0.f || gv != want_v) ++nonzero_pad;
@@ -221,7 +221,7 @@ __global__ void ref_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k
     for (int d = 0; d < hd; ++d) s += __bfloat162float(qr[d]) * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
     float p = expf(s * scale - mx);
     l += p;
-    for (int d = 0; d < hd; ++d) o[d] += p * __bfloat162float(vt[((size_t)th * hd_pad + d) * seq_pad + j]);
+    for (int d = 0; d < hd; ++d) o[d] += p * __bfloat162float(vt[((size_t)th * seq_pad + j) * hd_pad + d]);
   }
   float delta = 0.f;
   for (int d = 0; d < hd; ++d) delta += (o[d] / l) * __bfloat162float(dor[d]);
@@ -229,7 +229,7 @@ __global__ void ref_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k
     float s = 0.f, dp = 0.f;
     for (int d = 0; d < hd; ++d) {
       s += __bfloat162float(qr[d]) * __bfloat162float(k[((size_t)th * seq_pad + j) * hd_pad + d]);
-      dp += __bfloat162float(dor[d]) * __bfloat162float(vt[((size_t)th * hd_pad + d) * seq_pad + j]);
+      dp += __bfloat162float(dor[d]) * __bfloat162float(vt[((size_t)th * seq_pad + j) * hd_pad + d]);
     }
     const float p = expf(s * scale - mx) / l;
     const float ds = p * (dp - delta) * scale;
@@ -253,12 +253,12 @@ static int test_attention_bwd(int tiles, int heads, float amp) {
       for (int d = 0; d < hd; ++d) {
         hq[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
         hk[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * amp);
-        hv[((size_t)a * hd_pad + d) * seq_pad + t] = __float2bfloat16(frand() * 2.f);
+        hv[((size_t)a * seq_pad + t) * hd_pad + d] = __float2bfloat16(frand() * 2.f);
       }
   for (auto& v : hdo) v = __float2bfloat16(frand());
   std::vector<__nv_bfloat16> hv1 = hv;  // forward copy with the ones row
   for (int a = 0; a < th; ++a)
-    for (int t = 0; t < seq; ++t) hv1[((size_t)a * hd_pad + hd) * seq_pad + t] = __float2bfloat16(1.0f);
+    for (int t = 0; t < seq; ++t) hv1[((size_t)a * seq_pad + t) * hd_pad + hd] = __float2bfloat16(1.0f);
   __nv_bfloat16 *dq, *dk, *dv, *dv1, *ddo, *dout, *dqkv;
   float *dlse, *rdq, *rdk, *rdv;
   void* ws;
