@@ -30,6 +30,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.MergeImage) == 12 * 4
     assert ctypes.sizeof(_lib.PreprocessImage) == 16 + 10 * 4
     assert ctypes.sizeof(_lib.VitLayerWeights) == 12 * 8
+    assert ctypes.sizeof(_lib.VitLayerGrads) == 12 * 8
 
 
 def test_gpu_entry_points_fail_loudly_without_a_device():
