@@ -38,7 +38,7 @@ struct AttnBwdArgs {
 constexpr int kAbThreads = 320;
 constexpr int kAbTile = 128 * 80 * 2;   // 20480: Q / K / V / dO tiles (5 SW32 chunks each)
 constexpr int kAbPTile = 128 * 128 * 2; // 32768: P and dS
-constexpr int kAbSmemBytes = 4 * kAbTile + 2 * kAbPTile + 128;
+constexpr int kAbSmemBytes = 6 * kAbTile + 2 * kAbPTile + 128;  // K, V, 2 x (Q, dO), P, dS
 constexpr int kAbTmemCols = 512;
 
 __device__ __forceinline__ float ex2_approx_bwd(float x) {
@@ -58,18 +58,20 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
   if ((smem_base & 1023u) != 0) __trap();
   const uint32_t sK = smem_base;
   const uint32_t sV = sK + kAbTile;
-  const uint32_t sQ = sV + kAbTile;
-  const uint32_t sdO = sQ + kAbTile;
-  const uint32_t sP = sdO + kAbTile;
+  const uint32_t sQ = sV + kAbTile;          // two buffers: Q_i in sQ + (i & 1) * 2 * kAbTile
+  const uint32_t sdO = sQ + kAbTile;         // ... dO_i right behind its Q_i
+  const uint32_t sP = sQ + 4 * kAbTile;
   const uint32_t sdS = sP + kAbPTile;
   const uint32_t bar_base = sdS + kAbPTile;
   const uint32_t bar_kv = bar_base + 0;       // K_j, Vt_j landed
-  const uint32_t bar_qdo = bar_base + 8;      // Q_i, dO_i landed
-  const uint32_t bar_sdp = bar_base + 16;     // S, dP complete in TMEM
-  const uint32_t bar_pds = bar_base + 24;     // P, dS written to shared memory (256 arrivals)
-  const uint32_t bar_mma2 = bar_base + 32;    // dV, dK, dQ products of this query block complete
-  const uint32_t bar_dqfree = bar_base + 40;  // dQ read out of TMEM (256 arrivals)
-  const uint32_t tmem_ptr_smem = bar_base + 48;
+  const uint32_t bar_qdo = bar_base + 8;      // [2] Q_i, dO_i landed in buffer i & 1
+  const uint32_t bar_sdp = bar_base + 24;     // S, dP complete in TMEM
+  const uint32_t bar_pds = bar_base + 32;     // P, dS written to shared memory (256 arrivals)
+  const uint32_t bar_mma2 = bar_base + 40;    // dV, dK, dQ products of this query block complete
+  const uint32_t bar_dqfree = bar_base + 48;  // dQ read out of TMEM (256 arrivals)
+  const uint32_t bar_qdofree = bar_base + 56; // [2] the products reading Q / dO buffer i & 1 are complete
+  const uint32_t bar_dq = bar_base + 72;      // dQ product of this query block complete (read out while dV / dK run)
+  const uint32_t tmem_ptr_smem = bar_base + 80;
 
   const int warp = threadIdx.x >> 5;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -87,9 +89,13 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
     tma_prefetch_desc(&tmap_do);
     mbar_init(bar_kv, 1);
     mbar_init(bar_qdo, 1);
+    mbar_init(bar_qdo + 8, 1);
+    mbar_init(bar_qdofree, 1);
+    mbar_init(bar_qdofree + 8, 1);
     mbar_init(bar_sdp, 1);
     mbar_init(bar_pds, 256);
     mbar_init(bar_mma2, 1);
+    mbar_init(bar_dq, 1);
     mbar_init(bar_dqfree, 256);
     fence_mbar_init();
   }
@@ -115,15 +121,16 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
         tma_load_2d(sK + c * 4096, &tmap_k, bar_kv, c * 16, k_row0);
         tma_load_2d(sV + c * 4096, &tmap_v, bar_kv, c * 16, k_row0);
       }
-      for (int i = 0; i < num_q; ++i) {
-        if (i > 0) mbar_wait(bar_mma2, static_cast<uint32_t>((i - 1) & 1));  // Q / dO consumed
-        mbar_arrive_expect_tx(bar_qdo, 2 * kAbTile);
+      for (int i = 0; i < num_q; ++i) {   // Q_i / dO_i -> buffer i & 1, one query block ahead of the compute
+        const uint32_t b = static_cast<uint32_t>(i & 1);
+        if (i >= 2) mbar_wait(bar_qdofree + 8 * b, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(bar_qdo + 8 * b, 2 * kAbTile);
         const int q_row0 = th * args.seq_pad + i * 128;
         const int do_row0 = tile * args.seq + i * 128;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          tma_load_2d(sQ + c * 4096, &tmap_q, bar_qdo, c * 16, q_row0);
-          tma_load_2d(sdO + c * 4096, &tmap_do, bar_qdo, head * args.hd + c * 16, do_row0);
+          tma_load_2d(sQ + b * 2 * kAbTile + c * 4096, &tmap_q, bar_qdo + 8 * b, c * 16, q_row0);
+          tma_load_2d(sdO + b * 2 * kAbTile + c * 4096, &tmap_do, bar_qdo + 8 * b, head * args.hd + c * 16, do_row0);
         }
       }
     }
@@ -149,32 +156,42 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
     const uint64_t p_mn = make_smem_desc_lbo(sP, 16384, 1024, kLayoutSw128);
     const uint64_t ds_mn = make_smem_desc_lbo(sdS, 16384, 1024, kLayoutSw128);
 
-    mbar_wait(bar_kv, 0);
-    for (int i = 0; i < num_q; ++i) {
-      const uint32_t par = static_cast<uint32_t>(i & 1);
-      mbar_wait(bar_qdo, par);
+    // S_{i+1} / dP_{i+1} are issued right behind the dV / dK / dQ products of block i (their TMEM columns are free once
+    // the softmax-gradient warps have published P_i / dS_i), so they run while block i's dQ is read out.
+    auto issue_sdp = [&](int i) {
+      const uint32_t b = static_cast<uint32_t>(i & 1);
+      mbar_wait(bar_qdo + 8 * b, static_cast<uint32_t>((i >> 1) & 1));
       tc_fence_after();
+      const uint64_t qoff = static_cast<uint64_t>(b * ((2 * kAbTile) >> 4));
 #pragma unroll
       for (int c = 0; c < 5; ++c)   // S: K step c = chunk c (4096 B)
-        umma_bf16_ss_elect(tS_u, q_k + c * 256, k_k + c * 256, idesc_s, c != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tS_u, q_k + qoff + c * 256, k_k + c * 256, idesc_s, c != 0 ? 1u : 0u);
 #pragma unroll
       for (int c = 0; c < 5; ++c)   // dP: K step c = chunk c
-        umma_bf16_ss_elect(tdP_u, do_k + c * 256, v_k + c * 256, idesc_dp, c != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tdP_u, do_k + qoff + c * 256, v_k + c * 256, idesc_dp, c != 0 ? 1u : 0u);
       umma_commit_elect(bar_sdp);
-
-      mbar_wait(bar_pds, par);                                  // P, dS in shared memory
+    };
+    mbar_wait(bar_kv, 0);
+    issue_sdp(0);
+    for (int i = 0; i < num_q; ++i) {
+      const uint32_t par = static_cast<uint32_t>(i & 1);
+      const uint64_t qoff = static_cast<uint64_t>(par * ((2 * kAbTile) >> 4));
+      mbar_wait(bar_pds, par);                                  // P, dS in shared memory; S / dP consumed
       if (i > 0) mbar_wait(bar_dqfree, par ^ 1u);               // previous dQ read out
       tc_fence_after();
 #pragma unroll
+      for (int s = 0; s < 8; ++s)   // dQ = dS K first: its read-out (atomics) then overlaps the dV / dK products
+        umma_bf16_ss_elect(tdQ_u, ds_k + (s >> 2) * 1024 + (s & 3) * 2, k_mn + s * 32, idesc_dq, s != 0 ? 1u : 0u);
+      umma_commit_elect(bar_dq);
+#pragma unroll
       for (int s = 0; s < 8; ++s)   // dV += P^T dO: K step s = 16 query rows (P: 2048 B, dO chunks: 512 B)
-        umma_bf16_ss_elect(tdV_u, p_mn + s * 128, do_mn + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tdV_u, p_mn + s * 128, do_mn + qoff + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
 #pragma unroll
       for (int s = 0; s < 8; ++s)   // dK += dS^T Q
-        umma_bf16_ss_elect(tdK_u, ds_mn + s * 128, q_mn + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
-#pragma unroll
-      for (int s = 0; s < 8; ++s)   // dQ = dS K: K step s = 16 keys (dS: 32 B inside its 64-key atom, K chunks: 512 B)
-        umma_bf16_ss_elect(tdQ_u, ds_k + (s >> 2) * 1024 + (s & 3) * 2, k_mn + s * 32, idesc_dq, s != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tdK_u, ds_mn + s * 128, q_mn + qoff + s * 32, idesc_kv, (i | s) != 0 ? 1u : 0u);
       umma_commit_elect(bar_mma2);
+      umma_commit_elect(bar_qdofree + 8 * par);
+      if (i + 1 < num_q) issue_sdp(i + 1);
     }
   } else {
     // ===================== softmax-gradient warps: two threads per query row =====================
@@ -186,18 +203,25 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
     const uint32_t row_off = static_cast<uint32_t>(half) * 16384u + static_cast<uint32_t>(r) * 128u;
     const int D = args.heads * args.hd;
 
+    // lse / delta of the first query block; the next block's pair is fetched one iteration ahead
+    float lse_n = 0.f, delta_n = 0.f;
+    if (r < args.seq) {
+      lse_n = __ldg(args.lse + static_cast<size_t>(th) * args.seq_pad + r);
+      delta_n = __ldg(args.delta + static_cast<size_t>(th) * args.seq_pad + r);
+    }
     for (int i = 0; i < num_q; ++i) {
       const uint32_t par = static_cast<uint32_t>(i & 1);
       const int qrow = i * 128 + r;
       const bool q_ok = qrow < args.seq;
-      float lse = 0.f, delta = 0.f;
-      if (q_ok) {
-        lse = __ldg(args.lse + static_cast<size_t>(th) * args.seq_pad + qrow);
-        delta = __ldg(args.delta + static_cast<size_t>(th) * args.seq_pad + qrow);
+      const float lse = lse_n, delta = delta_n;
+      if (i + 1 < num_q && qrow + 128 < args.seq) {
+        lse_n = __ldg(args.lse + static_cast<size_t>(th) * args.seq_pad + qrow + 128);
+        delta_n = __ldg(args.delta + static_cast<size_t>(th) * args.seq_pad + qrow + 128);
       }
       mbar_wait(bar_sdp, par);
       tc_fence_after();
       if (i > 0) mbar_wait(bar_mma2, par ^ 1u);  // the products that read the previous P / dS are complete
+      const float nds = -delta * args.scale;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32];
@@ -206,16 +230,26 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
         tmem_wait_ld();
         const int key0 = jblk * 128 + half * 64 + c * 32;
         uint32_t pk[16], dk[16];
+        if (q_ok && key0 + 32 <= args.seq) {   // common case: nothing to mask
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = ex2_approx_bwd(fmaf(__uint_as_float(s[e]), args.scale_log2e, -lse));
-          float p1 = ex2_approx_bwd(fmaf(__uint_as_float(s[e + 1]), args.scale_log2e, -lse));
-          if (!q_ok || key0 + e >= args.seq) p0 = 0.f;
-          if (!q_ok || key0 + e + 1 >= args.seq) p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[e]) - delta) * args.scale;
-          const float d1 = p1 * (__uint_as_float(dp[e + 1]) - delta) * args.scale;
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          dk[e >> 1] = pack_bf16x2(d0, d1);
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2_approx_bwd(fmaf(__uint_as_float(s[e]), args.scale_log2e, -lse));
+            const float p1 = ex2_approx_bwd(fmaf(__uint_as_float(s[e + 1]), args.scale_log2e, -lse));
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(dp[e]), args.scale, nds),
+                                     p1 * fmaf(__uint_as_float(dp[e + 1]), args.scale, nds));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = ex2_approx_bwd(fmaf(__uint_as_float(s[e]), args.scale_log2e, -lse));
+            float p1 = ex2_approx_bwd(fmaf(__uint_as_float(s[e + 1]), args.scale_log2e, -lse));
+            if (!q_ok || key0 + e >= args.seq) p0 = 0.f;
+            if (!q_ok || key0 + e + 1 >= args.seq) p1 = 0.f;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(dp[e]), args.scale, nds),
+                                     p1 * fmaf(__uint_as_float(dp[e + 1]), args.scale, nds));
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -233,7 +267,7 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
       mbar_arrive(bar_pds);
 
       // ---- dQ_i partial product of this key block -> fp32 atomics (columns [40*half, +40) < hd)
-      mbar_wait(bar_mma2, par);
+      mbar_wait(bar_dq, par);
       tc_fence_after();
       uint32_t dq[40];
 #pragma unroll
@@ -241,6 +275,7 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(bar_dqfree);
+#ifndef RV_ABWD_NO_ATOMICS
       if (q_ok) {
         // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations of scalar adds.
         // Columns >= hd are padding of the accumulator row: adding to them is harmless and keeps the vectors whole.
@@ -251,10 +286,13 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
                        "f"(__uint_as_float(dq[e + 1])), "f"(__uint_as_float(dq[e + 2])), "f"(__uint_as_float(dq[e + 3]))
                        : "memory");
       }
+#endif
     }
 
     // ---- dK_j, dV_j -> bf16 -> dqkv[(tile*seq + key), D + head*hd + d] and [.., 2D + head*hd + d]
-    //      (lanes are keys now; the last bar_mma2 wait above covers the final products)
+    //      (lanes are keys now)
+    mbar_wait(bar_mma2, static_cast<uint32_t>((num_q - 1) & 1));
+    tc_fence_after();
     const int key = jblk * 128 + r;
     uint32_t kk[40], vv[40];
 #pragma unroll
