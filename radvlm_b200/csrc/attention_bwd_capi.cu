@@ -44,8 +44,8 @@ int attention_bwd_launch(const void* q, const void* k, const void* vt, const voi
   const int D = heads * hd;
   RV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(th) * seq_pad * 80 * sizeof(float), stream));
   {
-    const long long warps = static_cast<long long>(tokens) * heads;
-    const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+    RV_CHECK_ARG(heads * (hd / 8) <= 256, "attention_bwd: heads * hd / 8 must be <= 256");
+    const int blocks = (tokens + 7) / 8;
     attn_delta_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout),
                                                   static_cast<const __nv_bfloat16*>(out), delta, tokens, seq, seq_pad,
                                                   heads, hd);

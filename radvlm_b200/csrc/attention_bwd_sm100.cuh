@@ -330,22 +330,36 @@ siglip_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q,   // Q  
   }
 }
 
-// delta[th, q] = sum_d dO[token, head*hd + d] * O[token, head*hd + d]: one warp per (token, head)
+// delta[th, q] = sum_d dO[token, head*hd + d] * O[token, head*hd + d].  One warp per token: the row is read with
+// coalesced 16-byte loads, every 16-byte piece belongs to one head (hd % 8 == 0), pieces are summed per head through
+// shared memory.  heads * hd / 8 <= 8 * 32 pieces per row.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, float* __restrict__ delta,
                   int tokens, int seq, int seq_pad, int heads, int hd) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= tokens * heads) return;
-  const int token = w / heads, head = w - token * heads;
-  const size_t off = static_cast<size_t>(token) * heads * hd + head * hd;
-  float acc = 0.f;
-  for (int d = lane; d < hd; d += 32) acc += __bfloat162float(dO[off + d]) * __bfloat162float(O[off + d]);
+  __shared__ float part[8][256];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int token = blockIdx.x * 8 + wib;
+  if (token >= tokens) return;
+  const int per_head = hd / 8;
+  const int pieces = heads * per_head;
+  const uint4* a = reinterpret_cast<const uint4*>(dO + static_cast<size_t>(token) * heads * hd);
+  const uint4* b = reinterpret_cast<const uint4*>(O + static_cast<size_t>(token) * heads * hd);
+  for (int v = lane; v < pieces; v += 32) {
+    const uint4 x = a[v], y = b[v];
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+    float acc = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    const int tile = token / seq, t = token - tile * seq;
-    delta[(static_cast<size_t>(tile) * heads + head) * seq_pad + t] = acc;
+    for (int j = 0; j < 4; ++j)
+      acc += __uint_as_float(xw[j] << 16) * __uint_as_float(yw[j] << 16) +
+             __uint_as_float(xw[j] & 0xFFFF0000u) * __uint_as_float(yw[j] & 0xFFFF0000u);
+    part[wib][v] = acc;
+  }
+  __syncwarp();
+  const int tile = token / seq, t = token - tile * seq;
+  for (int h = lane; h < heads; h += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < per_head; ++j) acc += part[wib][h * per_head + j];
+    delta[(static_cast<size_t>(tile) * heads + h) * seq_pad + t] = acc;
   }
 }
 

@@ -25,7 +25,18 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int 
   const int r1 = min(rows, r0 + kColsumRows);
   float s0 = 0.f, s1 = 0.f;
   const __nv_bfloat16* p = x + static_cast<size_t>(r0) * ld + c;
-  for (int r = r0; r < r1; ++r, p += ld) {
+  int r = r0;
+  for (; r + 8 <= r1; r += 8, p += 8 * static_cast<size_t>(ld)) {   // eight independent row loads in flight
+    uint32_t w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const uint32_t*>(p + static_cast<size_t>(u) * ld);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s0 += __uint_as_float(w[u] << 16);
+      s1 += __uint_as_float(w[u] & 0xFFFF0000u);
+    }
+  }
+  for (; r < r1; ++r, p += ld) {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
     s0 += __uint_as_float(w << 16);
     s1 += __uint_as_float(w & 0xFFFF0000u);
@@ -196,7 +207,26 @@ layernorm_bwd_params_kernel(const float* __restrict__ x, const __nv_bfloat16* __
   const int r0 = blockIdx.y * kLnParamRows;
   const int r1 = min(rows, r0 + kLnParamRows);
   float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {   // four independent row loads in flight per thread
+    float2 st[4], xv[4];
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      st[u] = __ldg(stats + r + u);
+      xv[u] = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r + u) * D + c);
+      w[u] = *reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(r + u) * D + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d0 = __uint_as_float(w[u] << 16), d1 = __uint_as_float(w[u] & 0xFFFF0000u);
+      g0 += d0 * (xv[u].x - st[u].x) * st[u].y;
+      g1 += d1 * (xv[u].y - st[u].x) * st[u].y;
+      b0 += d0;
+      b1 += d1;
+    }
+  }
+  for (; r < r1; ++r) {
     const float2 st = __ldg(stats + r);
     const float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * D + c);
     const uint32_t w = *reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(r) * D + c);
