@@ -11,6 +11,7 @@ source tensor, so optimizer steps / checkpoint loads are picked up and the Param
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Dict, Mapping, Optional
 
@@ -116,7 +117,7 @@ class B200VisionEncoder:
         self.tower_module = tower_module          # SigLipVisionModel (state-dict prefix "vision_model.")
         self.projector_module = projector_module  # nn.Sequential(Linear, GELU, Linear)
         self.num_heads, self.image_size, self.ln_eps = num_heads, image_size, ln_eps
-        self.max_tiles_per_call = max_tiles_per_call
+        self.max_tiles_per_call = int(os.environ.get("RADVLM_B200_MAX_TILES", max_tiles_per_call))   # tuning override
         # training mode, data parallel: gradients are all-reduced (averaged) inside the backward, overlapped with it.
         # False (default) leaves them local (e.g. when DistributedDataParallel / DeepSpeed owns the reduction);
         # None = the default process group; or pass a process group.
