@@ -238,3 +238,44 @@ def test_training_path_accumulates_and_respects_frozen_parts(lib):
     for n in ("model.mm_projector.0.weight", "model.mm_projector.2.bias", "model.image_newline"):
         cos, relmax = _metrics(dict(host.named_parameters())[n].grad, g1[n])
         assert cos > 0.9999 and relmax < 1e-2, "%s with a frozen tower: cos=%.6f relmax=%.3e" % (n, cos, relmax)
+
+
+def test_backward_full_size_vs_oracle_autograd(lib):
+    """BASELINE.json configs[4] at the real widths (SigLIP-so400m: 1152 / 4304 / 16 heads x 72, 26 layers; projector
+    1152 -> 3584 -> 3584): gradients of two tiles against fp32 CPU autograd of the oracle on the same (bf16) weights."""
+    from oracle import encoder_oracle as eo
+    from radvlm_b200 import synthetic
+    host = synthetic.build_host(hidden_size=3584, vocab=64, seed=gi.FULL_SEED, dtype=torch.bfloat16, device="cuda")
+    host.model.vision_tower.requires_grad_(True)
+    host.model.mm_projector.requires_grad_(True)
+    host.train()
+    x = gi.encoder_pixels(2, seed=31).bfloat16()
+    feat = host.encode_images(x.cuda())
+    assert feat.requires_grad and tuple(feat.shape) == (2, 729, 3584)
+    R = (torch.randn(feat.shape, generator=torch.Generator().manual_seed(8)) * 0.1).bfloat16()
+    feat.backward(R.cuda())
+    torch.cuda.synchronize()
+    tower = dict(host.model.vision_tower.vision_tower.named_parameters())
+    proj = dict(host.model.mm_projector.named_parameters())
+    watch_t = ["vision_model.encoder.layers.25.mlp.fc2.weight", "vision_model.encoder.layers.25.self_attn.out_proj.bias",
+               "vision_model.encoder.layers.12.layer_norm1.weight", "vision_model.encoder.layers.12.mlp.fc1.weight",
+               "vision_model.encoder.layers.0.self_attn.q_proj.weight", "vision_model.encoder.layers.0.self_attn.v_proj.weight",
+               "vision_model.embeddings.patch_embedding.weight", "vision_model.embeddings.position_embedding.weight"]
+    watch_p = ["0.weight", "2.weight", "2.bias"]
+    tsd = {k: v.detach().float().cpu() for k, v in host.model.vision_tower.vision_tower.state_dict().items()}
+    psd = {k: v.detach().float().cpu() for k, v in host.model.mm_projector.state_dict().items()}
+    for k in watch_t:
+        tsd[k].requires_grad_(True)
+    for k in watch_p:
+        psd[k].requires_grad_(True)
+    ref = eo.encode_images(tsd, psd, x.float())
+    ref.backward(R.float())
+    worst = (1.0, "")
+    for name, got, want in [(k, tower[k].grad, tsd[k].grad) for k in watch_t] + [(k, proj[k].grad, psd[k].grad) for k in watch_p]:
+        assert got is not None and torch.isfinite(got).all(), name
+        cos, relmax = _metrics(got.float(), want)
+        # bf16 .grad tensors (the Parameters are bf16) of a 26-layer bf16-operand backward
+        assert cos >= 0.999 and relmax <= 5e-2, "%s: cos=%.6f relmax=%.3e" % (name, cos, relmax)
+        if cos < worst[0]:
+            worst = (cos, name)
+    print("full-size gradient parity vs oracle autograd: worst cos=%.6f at %s" % worst)
