@@ -97,6 +97,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// Optional timeline for tuning (-DRV_ATTN_TIMELINE): clock64 stamps of the first two work items of a few CTAs go to
+// args.lse (reinterpreted as long long[], [cta][64]).  Compiled out by default.
+#ifdef RV_ATTN_TIMELINE
+#define RV_TL(slot)                                                                                                  \
+  do {                                                                                                                 \
+    if (args.lse != nullptr && it < 2 && (slot) < 64)                                                                  \
+      reinterpret_cast<long long*>(args.lse)[static_cast<size_t>(blockIdx.x) * 64 + (slot)] = clock64();              \
+  } while (0)
+#else
+#define RV_TL(slot) do { } while (0)
+#endif
+
 // Work item w = (tile * heads + head) * num_qblk + qblk; CTA c processes w = c, c + gridDim.x, ...  (consecutive
 // CTAs share a head's K / V through L2).  `g` counts key blocks over all of a CTA's items: the K / V rings and the
 // S / P / O barriers keep running across items, so the producer prefetches the next item's Q / K / V while the
@@ -227,6 +239,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
       umma_bf16_ss_elect(tS_u, qd32, kd32 + koff, idesc_s, 1u);
       umma_commit_elect(bar_s);
       umma_commit_elect(bar_kfree + 8 * s_slot);
+      if (lane == 0 && it == 0) RV_TL(48 + 2 * j);
       if (j == num_kv - 1) umma_commit_elect(bar_qfree);
       if (++s_slot == kAttnStages) { s_slot = 0; s_par ^= 1u; }
     };
@@ -250,6 +263,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
           umma_bf16_ts_elect(tO_u, tP_u + static_cast<uint32_t>(s * 8), vd + voff + 32 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
         umma_commit_elect(bar_o);
         umma_commit_elect(bar_vfree + 8 * slot);
+        if (lane == 0 && it == 0) RV_TL(49 + 2 * j);
         if (++slot == kAttnStages) { slot = 0; ring_par ^= 1u; }
       }
     }
@@ -272,6 +286,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
       for (int j = 0; j < num_kv; ++j, ++g) {
         mbar_wait(bar_s, static_cast<uint32_t>(g & 1));
         tc_fence_after();
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 0);
         // keys >= nvalid (relative to this thread's first column) are padding: last block only
         const int nvalid = args.seq - j * kAttnBKV - half * kAttnHalf;
 
@@ -283,6 +298,7 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(bar_sfree);
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 1);
         if (nvalid < kAttnHalf) {
 #pragma unroll
           for (int i = 0; i < kAttnHalf; ++i)
@@ -320,7 +336,9 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
         }
         // PV_{g-1} must be complete before the P region is overwritten or O is rescaled (it normally is: it was
         // issued a whole softmax block ago)
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 2);
         if (g > 0) mbar_wait(bar_o, static_cast<uint32_t>((g - 1) & 1));
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 3);
         if (__any_sync(0xffffffffu, need)) {  // rare: the reference moved, rescale this thread's 40 O columns
           tc_fence_after();
 #pragma unroll
@@ -351,11 +369,13 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
           }
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 4);
         tmem_st_x16(tPh, pk);
         tmem_st_x8(tPh + 16, pk + 16);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar_p);
+        if (warp == 2 && lane == 0 && it == 0) RV_TL(6 * j + 5);
       }
 
       // ---- item done: O / l -> registers (then the next item's PV_0 may overwrite O) -> bf16 ->
@@ -374,8 +394,10 @@ siglip_attention_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  col
       const int tile = th / args.heads, head = th - tile * args.heads;
       const int t = qblk * kAttnBQ + r;
       const float inv_l = 1.0f / __uint_as_float(l_bits);
+#ifndef RV_ATTN_TIMELINE
       if (args.lse != nullptr && half == 0 && t < args.seq)  // softmax = 2^(s * scale * log2e - lse)
         args.lse[static_cast<size_t>(th) * args.seq_pad + t] = m_ref + log2f(__uint_as_float(l_bits));
+#endif
       if (t < args.seq) {
         __nv_bfloat16* dst = args.out +
                              (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +
