@@ -1,7 +1,9 @@
 // C-ABI launcher for the fused SigLIP attention kernel (attention_sm100.cuh).
 #include <algorithm>
 
-#include "attention_sm100.cuh"
+#include <cstdlib>
+
+#include "attention_pp_sm100.cuh"
 #include "host_util.h"
 
 namespace rv {
@@ -24,6 +26,8 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
                                  kAttnSmemBytes));
     // two CTAs per SM need the full 228 KB shared-memory carveout
     RV_CUDA(cudaFuncSetAttribute(siglip_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    RV_CUDA(cudaFuncSetAttribute(siglip_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kPpSmemBytes));
     configured = true;
   }
   const uint64_t th = static_cast<uint64_t>(tiles) * heads;
@@ -47,10 +51,19 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
   a.hd = hd;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.lse = lse;
-  a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
-  a.total_items = tiles * heads * a.num_qblk;
-  const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
-  siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
+  // Tuning switch (bring-up A/B only): RADVLM_B200_ATTN=2cta selects the two-CTAs-per-SM kernel.
+  static const bool use_2cta = [] { const char* e = std::getenv("RADVLM_B200_ATTN"); return e && e[0] == '2'; }();
+  if (use_2cta) {
+    a.num_qblk = (seq + kAttnBQ - 1) / kAttnBQ;
+    a.total_items = tiles * heads * a.num_qblk;
+    const int grid = std::min(a.total_items, 2 * device_sm_count());  // persistent: two resident CTAs per SM
+    siglip_attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
+  } else {
+    a.num_qblk = (seq + kPpItemRows - 1) / kPpItemRows;
+    a.total_items = tiles * heads * a.num_qblk;
+    const int grid = std::min(a.total_items, device_sm_count());  // persistent: one CTA (two query groups) per SM
+    siglip_attention_pp_kernel<<<grid, kPpThreads, kPpSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
+  }
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

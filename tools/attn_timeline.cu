@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 #include "../include/radvlm_b200.h"
 
@@ -26,9 +27,21 @@ int main() {
   cudaDeviceSynchronize();
   std::vector<long long> h(ctas * 64);
   cudaMemcpy(h.data(), tl, h.size() * 8, cudaMemcpyDeviceToHost);
-  for (int c : {0, 100, 200}) {
+  // ping-pong kernel (default): [cta][group][8 * j + {S ready, S loaded, max, PV done, poly done, turn granted, turn passed, P published}], j < 4
+  const bool pp = !(getenv("RADVLM_B200_ATTN") && getenv("RADVLM_B200_ATTN")[0] == '2');
+  for (int c : {0, 100, 147}) {
     const long long* e = &h[c * 64];
     const long long t0 = e[0];
+    if (pp) {
+      printf("CTA %d, first work item (cycles from group A's first S ready)\n", c);
+      for (int grp = 0; grp < 2; ++grp)
+        for (int j = 0; j < 4; ++j) {
+          const long long* b = e + grp * 32 + 8 * j;
+          printf("  %c j=%d  S_rdy %6lld  loaded %6lld  max %6lld  o_done %6lld  poly %6lld  turn %6lld  pass %6lld  P_pub %6lld\n",
+                 'A' + grp, j, b[0] - t0, b[1] - t0, b[2] - t0, b[3] - t0, b[4] - t0, b[5] - t0, b[6] - t0, b[7] - t0);
+        }
+      continue;
+    }
     printf("CTA %d, first work item (cycles from the first S ready)\n", c);
     for (int j = 0; j < 8; ++j)
       printf("  j=%d  S_rdy %6lld  loaded %6lld  xchg %6lld  o_free %6lld  exp_done %6lld  P_pub %6lld | S_iss %6lld  PV_iss %6lld\n", j,
