@@ -99,8 +99,8 @@ int radvlm_gemm_qkv_split(const void* A, int64_t lda, const void* W, int64_t ldw
  * softmax(fp32) -> p v -> transpose/reshape).  Inputs in the layout radvlm_gemm_qkv_split writes;
  * out: bf16 [tiles*seq, heads*hd] token-major (A operand of out_proj).  vt must have been prepared with
  * radvlm_attention_prepare_vt before the QKV epilogue filled it.
- * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 384 == 0 (query blocks of 128, key blocks
- * of 96), 1 <= seq <= seq_pad.
+ * Supported geometry: hd_pad == 80, hd < hd_pad, hd % 8 == 0, seq_pad % 384 == 0 (query groups of 128 rows, two per
+ * work item; key blocks of 96), 1 <= seq <= seq_pad; out 16-byte aligned (it is written with TMA tile stores).
  * ---------------------------------------------------------------------------------------------- */
 /* Zero the padded V buffer (bf16 [tiles, heads, seq_pad, hd_pad]) and write a one into column `hd` of every valid
  * key: the PV tensor-core product then also accumulates the softmax row sum (O[:, hd]). */

@@ -1,4 +1,5 @@
-// C-ABI launcher for the fused SigLIP attention kernel (attention_sm100.cuh).
+// C-ABI launcher for the fused SigLIP attention kernels (attention_pp_sm100.cuh: the product path;
+// attention_sm100.cuh: the earlier two-CTAs-per-SM organisation, kept as the A/B baseline of tools/).
 #include <algorithm>
 
 #include <cstdlib>
@@ -62,7 +63,12 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
     a.num_qblk = (seq + kPpItemRows - 1) / kPpItemRows;
     a.total_items = tiles * heads * a.num_qblk;
     const int grid = std::min(a.total_items, device_sm_count());  // persistent: one CTA (two query groups) per SM
-    siglip_attention_pp_kernel<<<grid, kPpThreads, kPpSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, a);
+    CUtensorMap tout;  // out viewed as [tiles][seq][heads*hd]: the store of a 128-row tile is clipped at seq
+    const uint64_t row_bytes = static_cast<uint64_t>(heads) * hd * 2;
+    st = make_tmap_bf16_3d(&tout, out, static_cast<uint64_t>(heads) * hd, seq, tiles, row_bytes, row_bytes * seq, hd,
+                           kAttnBQ, 1);
+    if (st != RADVLM_OK) return st;
+    siglip_attention_pp_kernel<<<grid, kPpThreads, kPpSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, tout, a);
   }
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;

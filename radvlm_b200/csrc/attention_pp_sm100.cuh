@@ -28,9 +28,19 @@ constexpr int kPpGroups = 2;
 constexpr int kPpItemRows = kPpGroups * kAttnBQ;             // 256 query rows per work item
 constexpr int kPpSoftmaxWarps = 4 * kPpGroups;
 constexpr int kPpGroupThreads = 128;
-constexpr int kPpThreads = 64 + kPpSoftmaxWarps * 32;        // 320
+constexpr int kPpEpilogueWarps = 4;                          // read O out of TMEM and store it, off the softmax path
+constexpr int kPpEpilogueThreads = kPpEpilogueWarps * 32;
+constexpr int kPpFirstSoftmaxWarp = 4;                       // warpgroup 0: TMA producer, MMA issuer, two idle warps
+constexpr int kPpFirstEpilogueWarp = kPpFirstSoftmaxWarp + kPpSoftmaxWarps;
+constexpr int kPpThreads = (kPpFirstEpilogueWarp + kPpEpilogueWarps) * 32;  // 512 = 4 warpgroups
+// Register budget per warpgroup (setmaxnreg; 512 threads start at 128): 56 + 2 x 160 + 120 = 496 <= 512
+constexpr int kPpRegsIo = 56, kPpRegsSoftmax = 160, kPpRegsEpilogue = 120;
 constexpr int kPpStages = 4;                                 // K / V ring depth
-constexpr int kPpSmemBytes = kPpGroups * kAttnQBytes + kPpStages * (kAttnKBytes + kAttnVBytes) + 512;
+constexpr int kPpQBufs = 2;                                  // Q of the next item is prefetched during the current one
+constexpr int kPpMrefBytes = 2 * kPpGroups * kAttnBQ * 4;           // reference maxima handed to the epilogue warps (lse)
+constexpr int kPpOutBytes = kAttnBQ * (kAttnHdPad - 8) * 2;   // 18432 : [128 rows][hd <= 72] bf16 staging tile of the TMA store
+constexpr int kPpSmemBytes = kPpQBufs * kPpGroups * kAttnQBytes + kPpStages * (kAttnKBytes + kAttnVBytes) + kPpOutBytes +
+                             kPpMrefBytes + 512;
 static_assert(kPpSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kPpTmemCols = 512;
 constexpr int kPpTmemGroup = 256;  // per group: S [0,96)  P (bf16 pairs) [96,144)  O [160,240) (32-column aligned)
@@ -39,13 +49,19 @@ static_assert(kPpTmemP + kAttnBKV / 2 <= kPpTmemO, "P must not overlap O");
 static_assert(kPpTmemO + kAttnHdPad <= kPpTmemGroup && kPpGroups * kPpTmemGroup <= kPpTmemCols, "TMEM budget");
 // Exponentials per 16 computed on the FMA pipe (degree-3 polynomial) instead of MUFU.EX2.
 #ifndef RV_PP_POLY_PER_16
-#define RV_PP_POLY_PER_16 4
+#define RV_PP_POLY_PER_16 0
 #endif
 
 __device__ __forceinline__ float ex2_approx_v(float x) {  // volatile: stays behind the turn barrier
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {  // volatile: keeps its place in the burst
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
@@ -74,11 +90,21 @@ __device__ __forceinline__ void turn_pass(uint32_t zero) {  // `zero` ties the a
 #ifdef RV_ATTN_TIMELINE
 #define RV_PPTL(slot)                                                                                                \
   do {                                                                                                                 \
-    if (args.lse != nullptr && it == 0 && lane == 0 && quad == 2 && j < 4)                                                      \
+    if (args.lse != nullptr && it == RV_ATTN_TIMELINE && lane == 0 && quad == 2 && (slot) < 32)                         \
       reinterpret_cast<long long*>(args.lse)[static_cast<size_t>(blockIdx.x) * 64 + grp * 32 + (slot)] = clock64();   \
   } while (0)
 #else
 #define RV_PPTL(slot) do { } while (0)
+#endif
+#define RV_PPTL_J(slot) do { if (j < 3) RV_PPTL(slot); } while (0)
+#ifdef RV_ATTN_TIMELINE
+#define RV_PPTL_NEXT()                                                                                               \
+  do {                                                                                                                 \
+    if (args.lse != nullptr && it == RV_ATTN_TIMELINE + 1 && j < 2 && lane == 0 && quad == 2)                          \
+      reinterpret_cast<long long*>(args.lse)[static_cast<size_t>(blockIdx.x) * 64 + grp * 32 + 28 + j] = clock64();   \
+  } while (0)
+#else
+#define RV_PPTL_NEXT() do { } while (0)
 #endif
 
 // Work item w = (tile * heads + head) * num_qblk + qblk with 256-row query blocks; CTA c processes w = c,
@@ -89,14 +115,17 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
                            const __grid_constant__ CUtensorMap tmap_k,    // K  columns [0,64)  : SW128 box {64, 96}
                            const __grid_constant__ CUtensorMap tmap_k2,   // K  columns [64,80) : SW32  box {16, 96}
                            const __grid_constant__ CUtensorMap tmap_v,    // V  16-column chunks : SW32  box {16, 96}
+                           const __grid_constant__ CUtensorMap tmap_out,  // out [tiles][seq][heads*hd] : box {hd, 128, 1}
                            const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // swizzled operand tiles need 1024-byte alignment
-  const uint32_t sQ = smem_base;                          // [group][Q block]
-  const uint32_t sK = sQ + kPpGroups * kAttnQBytes;       // ring
+  const uint32_t sQ = smem_base;                          // [item parity][group][Q block]
+  const uint32_t sK = sQ + kPpQBufs * kPpGroups * kAttnQBytes;  // ring
   const uint32_t sV = sK + kPpStages * kAttnKBytes;       // ring
-  const uint32_t bar_base = sV + kPpStages * kAttnVBytes;
+  const uint32_t sO = sV + kPpStages * kAttnVBytes;       // output staging tile (epilogue warps)
+  const uint32_t sM = sO + kPpOutBytes;       // [item parity][group][row] fp32 reference maxima of a finished item
+  const uint32_t bar_base = sM + kPpMrefBytes;
   const uint32_t bar_k = bar_base + 0;        // [stages] K_g landed
   const uint32_t bar_v = bar_base + 32;       // [stages] V_g landed
   const uint32_t bar_kfree = bar_base + 64;   // [stages] S_A,g and S_B,g complete
@@ -105,11 +134,12 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
   const uint32_t bar_sfree = bar_base + 144;  // [group] S_g is in registers
   const uint32_t bar_p = bar_base + 160;      // [group] P_g in TMEM, O rescaled
   const uint32_t bar_o = bar_base + 176;      // [group] O += P_g V_g complete
-  const uint32_t bar_ofree = bar_base + 192;  // [group] the item's O is in registers
-  const uint32_t bar_q = bar_base + 208;      // Q (both groups) of item `it` landed
-  const uint32_t bar_qfree = bar_base + 216;  // last S of the item complete: Q may be overwritten
-  const uint32_t tmem_ptr_smem = bar_base + 224;
-  const uint32_t zero_smem = bar_base + 232;  // a zero word (see the turn barriers)
+  const uint32_t bar_ofree = bar_base + 192;  // [group] the item's O is in registers (epilogue warps)
+  const uint32_t bar_q = bar_base + 208;      // [item parity] Q (both groups) of item `it` landed
+  const uint32_t bar_qfree = bar_base + 224;  // [item parity] last S of the item complete: Q may be overwritten
+  const uint32_t bar_ofin = bar_base + 240;   // [group] last PV of the item complete: O is final
+  const uint32_t tmem_ptr_smem = bar_base + 256;
+  const uint32_t zero_smem = bar_base + 264;  // a zero word (see the turn barriers)
   static_assert(kPpStages <= 4, "barrier layout");
 
   const int warp = threadIdx.x >> 5;
@@ -125,6 +155,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_k2);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_out);
     for (uint32_t i = 0; i < kPpStages; ++i) {
       mbar_init(bar_k + 8 * i, 1);
       mbar_init(bar_v + 8 * i, 1);
@@ -136,10 +167,13 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
       mbar_init(bar_sfree + 8 * i, kPpGroupThreads);
       mbar_init(bar_p + 8 * i, kPpGroupThreads);
       mbar_init(bar_o + 8 * i, 1);
-      mbar_init(bar_ofree + 8 * i, kPpGroupThreads);
+      mbar_init(bar_ofree + 8 * i, kPpEpilogueThreads);
+      mbar_init(bar_ofin + 8 * i, 1);
     }
-    mbar_init(bar_q, 1);
-    mbar_init(bar_qfree, 1);
+    for (uint32_t i = 0; i < kPpQBufs; ++i) {
+      mbar_init(bar_q + 8 * i, 1);
+      mbar_init(bar_qfree + 8 * i, 1);
+    }
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(zero_smem), "r"(0u) : "memory");
     fence_mbar_init();
   }
@@ -153,6 +187,9 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+  if (warp_u < kPpFirstSoftmaxWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPpRegsIo));
+  }
   if (warp_u == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -161,13 +198,15 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
       for (int it = 0; it < num_items; ++it) {
         const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
         const int th = w / args.num_qblk, qblk = w - th * args.num_qblk;
-        if (it > 0) mbar_wait(bar_qfree, static_cast<uint32_t>((it - 1) & 1));
-        mbar_arrive_expect_tx(bar_q, kPpGroups * kAttnQBytes);
+        const uint32_t qb = static_cast<uint32_t>(it & 1), quse = static_cast<uint32_t>(it >> 1);
+        if (quse > 0) mbar_wait(bar_qfree + 8 * qb, (quse - 1) & 1u);  // item it-2's last S complete
+        const uint32_t bq = bar_q + 8 * qb, sQi = sQ + qb * (kPpGroups * kAttnQBytes);
+        mbar_arrive_expect_tx(bq, kPpGroups * kAttnQBytes);
         const int q_row0 = th * args.seq_pad + qblk * kPpItemRows;
 #pragma unroll
         for (int gq = 0; gq < kPpGroups; ++gq) {
-          tma_load_2d(sQ + gq * kAttnQBytes, &tmap_q, bar_q, 0, q_row0 + gq * kAttnBQ);
-          tma_load_2d(sQ + gq * kAttnQBytes + kAttnQ2Off, &tmap_q2, bar_q, 64, q_row0 + gq * kAttnBQ);
+          tma_load_2d(sQi + gq * kAttnQBytes, &tmap_q, bq, 0, q_row0 + gq * kAttnBQ);
+          tma_load_2d(sQi + gq * kAttnQBytes + kAttnQ2Off, &tmap_q2, bq, 64, q_row0 + gq * kAttnBQ);
         }
         for (int j = 0; j < num_kv; ++j, ++g) {
           if (g >= kPpStages) mbar_wait(bar_kfree + 8 * slot, ring_par ^ 1u);
@@ -198,12 +237,13 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
     uint32_t s_slot = 0, s_par = 0;  // ring position of the S issue (one block ahead of the PV issue)
     // S_{grp,g} = Q_grp K_g^T
     auto issue_s = [&](int grp, int g, int it, int j) {
-      if (j == 0) mbar_wait(bar_q, static_cast<uint32_t>(it & 1));
+      const uint32_t qb = static_cast<uint32_t>(it & 1);
+      if (j == 0) mbar_wait(bar_q + 8 * qb, static_cast<uint32_t>(it >> 1) & 1u);
       mbar_wait(bar_k + 8 * s_slot, s_par);
       if (g > 0) mbar_wait(bar_sfree + 8 * grp, static_cast<uint32_t>((g - 1) & 1));
       tc_fence_after();
       const uint32_t tS = tbase_u + static_cast<uint32_t>(grp * kPpTmemGroup);
-      const uint64_t qoff = static_cast<uint64_t>(grp * (kAttnQBytes >> 4));
+      const uint64_t qoff = static_cast<uint64_t>((qb * kPpGroups + grp) * (kAttnQBytes >> 4));
       const uint64_t koff = static_cast<uint64_t>(s_slot * (kAttnKBytes >> 4));
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -212,7 +252,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
       umma_commit_elect(bar_s + 8 * grp);
       if (grp == kPpGroups - 1) {
         umma_commit_elect(bar_kfree + 8 * s_slot);
-        if (j == num_kv - 1) umma_commit_elect(bar_qfree);
+        if (j == num_kv - 1) umma_commit_elect(bar_qfree + 8 * qb);
         if (++s_slot == kPpStages) { s_slot = 0; s_par ^= 1u; }
       }
     };
@@ -239,20 +279,22 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
           for (int s = 0; s < kAttnBKV / 16; ++s)
             umma_bf16_ts_elect(tO, tP + static_cast<uint32_t>(s * 8), vd + voff + 32 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
           umma_commit_elect(bar_o + 8 * grp);
+          if (wrap) umma_commit_elect(bar_ofin + 8 * grp);
           if (grp == kPpGroups - 1) umma_commit_elect(bar_vfree + 8 * slot);
         }
         if (++slot == kPpStages) { slot = 0; ring_par ^= 1u; }
       }
     }
-  } else {
-    // ===================== softmax / correction / output: 2 groups x 4 warps, one thread per query row ==========
+  } else if (warp_u >= kPpFirstSoftmaxWarp && warp_u < kPpFirstEpilogueWarp) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPpRegsSoftmax));
+    // ===================== softmax / correction: 2 groups x 4 warps, one thread per query row ==========
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - kPpFirstSoftmaxWarp) >> 2;
     const int r = quad * 32 + lane;          // row within the group's query block
     const uint32_t tG = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(grp * kPpTmemGroup);
     const uint32_t tS = tG, tP = tG + kPpTmemP, tO = tG + kPpTmemO;
     const uint32_t b_s = bar_s + 8 * grp, b_sfree = bar_sfree + 8 * grp, b_p = bar_p + 8 * grp;
-    const uint32_t b_o = bar_o + 8 * grp, b_ofree = bar_ofree + 8 * grp;
+    const uint32_t b_o = bar_o + 8 * grp;
     const float sc = args.scale_log2e;
     const int total_blocks = num_items * num_kv;
 
@@ -264,7 +306,8 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
       for (int j = 0; j < num_kv; ++j, ++g) {
         mbar_wait(b_s, static_cast<uint32_t>(g & 1));
         tc_fence_after();
-        RV_PPTL(8 * j + 0);
+        RV_PPTL_J(8 * j + 0);
+        RV_PPTL_NEXT();
         uint32_t s[kAttnBKV];
         tmem_ld_x32(tS + 0, s + 0);
         tmem_ld_x32(tS + 32, s + 32);
@@ -272,7 +315,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(b_sfree);  // S_{g+1} may be computed while this block's exponentials run
-        RV_PPTL(8 * j + 1);
+        RV_PPTL_J(8 * j + 1);
         const int nvalid = args.seq - j * kAttnBKV;  // keys beyond it are padding (last block only)
         if (nvalid < kAttnBKV) {
 #pragma unroll
@@ -295,11 +338,10 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
           m_ref = mb;
           need = (j > 0);
         }
-        RV_PPTL(8 * j + 2);
-        // PV_{g-1} must be complete before the P region is overwritten or O is rescaled
-        if (g > 0) mbar_wait(b_o, static_cast<uint32_t>((g - 1) & 1));
-        RV_PPTL(8 * j + 3);
+        RV_PPTL_J(8 * j + 2);
+        RV_PPTL_J(8 * j + 3);
         if (__any_sync(0xffffffffu, need)) {  // rare: the reference moved, rescale this row of O
+          mbar_wait(b_o, static_cast<uint32_t>((g - 1) & 1));  // PV_{g-1} complete
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < kAttnHdPad / 8; ++c) {
@@ -311,6 +353,8 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
             tmem_st_x8(tO + c * 8, o);
           }
         }
+        if (j == num_kv - 1 && args.lse != nullptr)  // final reference of the item, for the epilogue warps' lse
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sM + static_cast<uint32_t>(((it & 1) * kPpGroups + grp) * kAttnBQ + r) * 4u), "f"(m_ref) : "memory");
         const float neg_m = -m_ref;
         // ---- MUFU-free part: the polynomial share of the exponentials
         uint32_t psign = 0;  // polynomial results are never negative: (psign >> 31) == 0
@@ -321,7 +365,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
             psign |= s[i];
           }
         }
-        RV_PPTL(8 * j + 4);
+        RV_PPTL_J(8 * j + 4);
         // ---- this group's turn on the XU pipe.  ptxas schedules arithmetic freely across BAR instructions, so the
         //      burst is tied to the barriers by data: its exponents depend on a (zero) word loaded from shared
         //      memory behind the bar.sync, and the thread count of the bar.arrive depends on the last results.
@@ -329,13 +373,25 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
         float zero;
         asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(zero) : "r"(zero_smem) : "memory");
         const float neg_m2 = neg_m + zero;
-        RV_PPTL(8 * j + 5);
-        uint32_t sign = 0;
+        RV_PPTL_J(8 * j + 5);
+        // The packs of a 16-column group are issued one group behind its exponentials: a pack right behind its
+        // two MUFU.EX2 stalls this (only) MUFU-issuing warp of the scheduler until they complete and the XU queue
+        // drains meanwhile (measured: the burst ran at 65 % of the XU rate).
+        uint32_t pk[kAttnBKV / 2];
+        uint32_t sign = 0;  // no P is negative: (sign >> 31) == 0
 #pragma unroll
-        for (int i = 0; i < kAttnBKV; ++i) {
-          if ((i & 15) < 16 - RV_PP_POLY_PER_16) {
-            s[i] = __float_as_uint(ex2_approx_v(fmaf(__uint_as_float(s[i]), sc, neg_m2)));
-            if (i >= kAttnBKV - 16) sign |= s[i];  // never negative: (sign >> 31) == 0
+        for (int c = 0; c <= kAttnBKV / 16; ++c) {
+          if (c < kAttnBKV / 16) {
+#pragma unroll
+            for (int i = 16 * c; i < 16 * c + 16 - RV_PP_POLY_PER_16; ++i)
+              s[i] = __float_as_uint(ex2_approx_v(fmaf(__uint_as_float(s[i]), sc, neg_m2)));
+          }
+          if (c > 0) {
+#pragma unroll
+            for (int i = 16 * (c - 1); i < 16 * c; i += 2) {
+              pk[i >> 1] = pack_bf16x2_v(__uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+              sign |= pk[i >> 1];
+            }
           }
         }
         if (grp == 0) {
@@ -343,55 +399,81 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
         } else if (g + 1 < total_blocks) {
           turn_pass<1>(sign >> 31);
         }
-        RV_PPTL(8 * j + 6);
-        // ---- P -> bf16 pairs -> this row's 48 packed columns of the P region
-        uint32_t pk[kAttnBKV / 2];
-#pragma unroll
-        for (int i = 0; i < kAttnBKV; i += 2) pk[i >> 1] = pack_bf16x2(__uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        RV_PPTL_J(8 * j + 6);
+        // ---- this row's 48 packed columns of the P region (PV_{g-1} must have read it: it normally has, it was
+        //      issued a whole block ago)
+        if (g > 0) mbar_wait(b_o, static_cast<uint32_t>((g - 1) & 1));
         tmem_st_x32(tP, pk);
         tmem_st_x16(tP + 32, pk + 32);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(b_p);
-        RV_PPTL(8 * j + 7);
+        RV_PPTL_J(8 * j + 7);
       }
 
-      // ---- item done: O / l -> registers (then the next item's PV_0 may overwrite O) -> bf16 ->
-      //      out[(tile*seq + t), head*hd + d]
-      mbar_wait(b_o, static_cast<uint32_t>((g - 1) & 1));
-      tc_fence_after();
-      uint32_t o[kAttnHdPad];
-#pragma unroll
-      for (int c = 0; c < kAttnHdPad / 8; ++c) tmem_ld_x8(tO + c * 8, o + c * 8);
-      const float l = __uint_as_float(tmem_ld_x1(tO + static_cast<uint32_t>(args.hd)));  // ones column of V
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(b_ofree);
+    }
+  } else if (warp_u >= kPpFirstEpilogueWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPpRegsEpilogue));
+    // ===================== epilogue warps: O / l of a finished item -> registers (then the next item's PV_0 may
+    // overwrite O) -> bf16 -> out[(tile*seq + t), head*hd + d], off the softmax warps' critical path ===========
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    for (int it = 0; it < num_items; ++it) {
       const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
       const int th = w / args.num_qblk, qblk = w - th * args.num_qblk;
       const int tile = th / args.heads, head = th - tile * args.heads;
-      const int t = qblk * kPpItemRows + grp * kAttnBQ + r;
-      const float inv_l = 1.0f / l;
+#pragma unroll 1
+      for (int grp = 0; grp < kPpGroups; ++grp) {
+        const uint32_t tO = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                            static_cast<uint32_t>(grp * kPpTmemGroup + kPpTmemO);
+        mbar_wait(bar_ofin + 8 * grp, static_cast<uint32_t>(it & 1));  // last PV of the item complete
+        tc_fence_after();
+        RV_PPTL(24);
+        uint32_t o[kAttnHdPad];
+#pragma unroll
+        for (int c = 0; c < kAttnHdPad / 8; ++c) tmem_ld_x8(tO + c * 8, o + c * 8);
+        const float l = __uint_as_float(tmem_ld_x1(tO + static_cast<uint32_t>(args.hd)));  // ones column of V
+        tmem_wait_ld();
+        tc_fence_before();
+        float m_ref = 0.f;
+        if (args.lse != nullptr)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_ref)
+                       : "r"(sM + static_cast<uint32_t>(((it & 1) * kPpGroups + grp) * kAttnBQ + r) * 4u) : "memory");
+        mbar_arrive(bar_ofree + 8 * grp);
+        RV_PPTL(25);
+        const int t = qblk * kPpItemRows + grp * kAttnBQ + r;
+        const float inv_l = 1.0f / l;
 #ifndef RV_ATTN_TIMELINE
-      if (args.lse != nullptr && t < args.seq)  // softmax = 2^(s * scale * log2e - lse)
-        args.lse[static_cast<size_t>(th) * args.seq_pad + t] = m_ref + log2f(l);
+        if (args.lse != nullptr && t < args.seq)  // softmax = 2^(s * scale * log2e - lse)
+          args.lse[static_cast<size_t>(th) * args.seq_pad + t] = m_ref + log2f(l);
 #endif
-      if (t < args.seq) {
-        __nv_bfloat16* dst = args.out + (static_cast<size_t>(tile) * args.seq + t) * (args.heads * args.hd) +
-                             head * args.hd;
+        // rows -> staging tile [128][hd] (16-byte stores, conflict-free per quarter warp at a 144-byte pitch), then
+        // ONE TMA store of the tile: per-thread global stores of 144-byte rows 2304 bytes apart cost 288 sector
+        // writes per warp and stalled the softmax warps' TMEM loads behind them in the LSU / MIO queue.
+        named_bar_sync(3, kPpEpilogueThreads);  // the previous tile's store has finished reading the staging tile
+        const uint32_t row_smem = sO + static_cast<uint32_t>(r * args.hd) * 2u;
 #pragma unroll
         for (int c = 0; c < kAttnHdPad / 8; ++c) {
           if (c * 8 < args.hd) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
-            v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
-            v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
-            v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
-            reinterpret_cast<uint4*>(dst)[c] = v;
+            const uint32_t v0 = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
+            const uint32_t v1 = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
+            const uint32_t v2 = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
+            const uint32_t v3 = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_smem + c * 16), "r"(v0), "r"(v1), "r"(v2),
+                         "r"(v3) : "memory");
           }
         }
+        fence_proxy_async_smem();
+        named_bar_sync(4, kPpEpilogueThreads);
+        if (warp == kPpFirstEpilogueWarp && lane == 0) {
+          tma_store_3d(&tmap_out, sO, head * args.hd, qblk * kPpItemRows + grp * kAttnBQ, tile);  // rows >= seq dropped
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        RV_PPTL(26);
       }
     }
+    if (warp == kPpFirstEpilogueWarp && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

@@ -105,6 +105,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// shared -> global tile store (bulk async group of the issuing thread); out-of-range box rows are dropped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int32_t c0, int32_t c1,
+                                             int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the buffer may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk stores of this thread are complete (globally visible)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // TMEM allocation
 // ---------------------------------------------------------------------------------------------

@@ -99,6 +99,36 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return RADVLM_OK;
 }
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                      uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return RADVLM_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch1_bytes & 15u) != 0 || (pitch2_bytes & 15u) != 0 ||
+      ((box0 * 2u) & 15u) != 0) {
+    set_error("TMA operand must be 16-byte aligned with 16-byte-multiple pitches and box rows (base=%p pitches=%llu,%llu "
+              "box0=%u)", base, static_cast<unsigned long long>(pitch1_bytes),
+              static_cast<unsigned long long>(pitch2_bytes), box0);
+    return RADVLM_ERR_BAD_ARGUMENT;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (dims=%llu,%llu,%llu box=%u,%u,%u)", static_cast<int>(r),
+              static_cast<unsigned long long>(d0), static_cast<unsigned long long>(d1),
+              static_cast<unsigned long long>(d2), box0, box1, box2);
+    return RADVLM_ERR_CUDA;
+  }
+  return RADVLM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // profiling
 // ---------------------------------------------------------------------------------------------

@@ -43,6 +43,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
                       uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                       CUtensorMapSwizzle swizzle);  // (any 16-bit element type: the copy is bit-exact)
 
+// 3-D bf16 tensor map (d0 contiguous; byte pitches of d1 and d2), no swizzle.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                      uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+
 // Optional per-kernel-class device timing (CUDA events recorded on the launch stream).  Off by default;
 // bench.py turns it on to report the live duration / launch count of each kernel class.
 enum ProfClass : int {

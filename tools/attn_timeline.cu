@@ -8,7 +8,7 @@
 #include "../include/radvlm_b200.h"
 
 int main() {
-  const int tiles = 10, heads = 16, seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
+  const int tiles = 37, heads = 16, seq = 729, seq_pad = 768, hd = 72, hd_pad = 80;
   const size_t nq = (size_t)tiles * heads * seq_pad * hd_pad;
   __nv_bfloat16 *q, *k, *v, *out;
   long long* tl;
@@ -33,13 +33,17 @@ int main() {
     const long long* e = &h[c * 64];
     const long long t0 = e[0];
     if (pp) {
-      printf("CTA %d, first work item (cycles from group A's first S ready)\n", c);
-      for (int grp = 0; grp < 2; ++grp)
-        for (int j = 0; j < 4; ++j) {
+      printf("CTA %d, work item RV_ATTN_TIMELINE of the CTA (cycles from group A's first S ready)\n", c);
+      for (int grp = 0; grp < 2; ++grp) {
+        for (int j = 0; j < 3; ++j) {
           const long long* b = e + grp * 32 + 8 * j;
           printf("  %c j=%d  S_rdy %6lld  loaded %6lld  max %6lld  o_done %6lld  poly %6lld  turn %6lld  pass %6lld  P_pub %6lld\n",
                  'A' + grp, j, b[0] - t0, b[1] - t0, b[2] - t0, b[3] - t0, b[4] - t0, b[5] - t0, b[6] - t0, b[7] - t0);
         }
+        const long long* b = e + grp * 32 + 24;
+        printf("  %c item end (epilogue warps): O final %6lld  O read %6lld  stored %6lld | next item S_rdy j=0 %6lld  j=1 %6lld\n",
+               'A' + grp, b[0] - t0, b[1] - t0, b[2] - t0, b[4] - t0, b[5] - t0);
+      }
       continue;
     }
     printf("CTA %d, first work item (cycles from the first S ready)\n", c);
