@@ -325,6 +325,20 @@ int radvlm_plan_splice(const int64_t* input_ids, const uint8_t* attention_mask, 
 #define RADVLM_MERGE_ANYRES 0  /* base tile + unpadded (optionally pooled) grid with newline column */
 #define RADVLM_MERGE_SINGLE 1  /* one tile + one newline token (llava_arch.py:407-412) */
 #define RADVLM_MERGE_FLAT 2    /* tiles*T tokens, no newline ("flat", or a 4-D image batch) */
+/* Video sample (llava_arch.py:171-190 get_2dPool, :222-249 add_token_per_grid / _frame, :310-349): the entry's
+ * `grid_w` tiles are FRAMES; each S x S frame is pooled with stride 2 to out_h x out_w (`pool` = RADVLM_POOL_*:
+ * bilinear -> ceil(S/2) with ATen's align_corners=False taps, average / max -> floor(S/2) 2x2 windows) and the frames
+ * are laid out frame-major with image_newline rows placed as `reserved` = RADVLM_NEWLINE_* says.  The backward
+ * covers bilinear and average pooling (max pooling needs the forward argmax; the host mirror raises for it). */
+#define RADVLM_MERGE_VIDEO 3
+#define RADVLM_POOL_NONE 0
+#define RADVLM_POOL_BILINEAR 1 /* also the anyres_max pooling flag of RADVLM_MERGE_ANYRES */
+#define RADVLM_POOL_AVERAGE 2
+#define RADVLM_POOL_MAX 3
+#define RADVLM_NEWLINE_NONE 0  /* mm_newline_position "no_token" (and "one_token" without 'unpad', and "flat") */
+#define RADVLM_NEWLINE_ONE 1   /* "one_token": a single newline after the last frame */
+#define RADVLM_NEWLINE_FRAME 2 /* "frame": one newline after every frame */
+#define RADVLM_NEWLINE_GRID 3  /* "grid": one newline after every pooled row of every frame */
 typedef struct radvlm_merge_image {
   int32_t tile_base; /* index of the image's first (base) tile in the feature buffer */
   int32_t mode;      /* RADVLM_MERGE_* */
@@ -332,7 +346,7 @@ typedef struct radvlm_merge_image {
   int32_t crop_r0, crop_c0, crop_h, crop_w;
   int32_t pool, out_h, out_w;
   int32_t n_tokens;
-  int32_t reserved;
+  int32_t reserved;  /* RADVLM_MERGE_VIDEO: RADVLM_NEWLINE_* */
 } radvlm_merge_image;
 
 /* All pointers are DEVICE pointers.  dtype: element type of features / newline / embed table / out.

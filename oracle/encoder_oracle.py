@@ -94,6 +94,48 @@ def merge_image(feat: torch.Tensor, image_size, newline: torch.Tensor, possible_
     return torch.cat((base, x), dim=0)                                             # :405
 
 
+def get_2d_pool(feat: torch.Tensor, mode: str, stride: int = 2, unit: int = 27) -> torch.Tensor:
+    """llava_arch.py:171-190 (get_2dPool): [frames, unit*unit, C] -> [frames, h'*w', C]."""
+    frames, _, c = feat.shape
+    x = feat.view(frames, unit, unit, -1).permute(0, 3, 1, 2).contiguous()
+    if mode == "average":
+        x = F.avg_pool2d(x, stride)
+    elif mode == "max":
+        x = F.max_pool2d(x, stride)
+    elif mode == "bilinear":
+        h, w = x.shape[2:]
+        x = F.interpolate(x, size=[math.ceil(h / stride), math.ceil(w / stride)], mode="bilinear")
+    else:
+        raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")
+    return x.permute(0, 2, 3, 1).reshape(frames, -1, c)
+
+
+def merge_video(feat: torch.Tensor, newline: torch.Tensor, pool_mode: str = "bilinear", newline_position: str = "grid",
+                merge_type: str = "spatial_unpad", unit: int = 27) -> torch.Tensor:
+    """llava_arch.py:286-290 + 299-349 for one video sample: [frames, T, C] -> [N, C]."""
+    x = get_2d_pool(feat, pool_mode, 2, unit)                                      # :286-288 (default stride 2)
+    if merge_type == "flat":
+        return x.flatten(0, 1)                                                     # :299-300
+    frames, p2, c = x.shape
+    if newline_position == "grid":                                                 # :222-244 add_token_per_grid
+        h = int(math.sqrt(p2))
+        y = x.view(frames, 1, h, h, -1).permute(4, 0, 2, 1, 3).contiguous().flatten(1, 2).flatten(2, 3)
+        y = torch.cat((y, newline[:, None, None].expand(*y.shape[:-1], 1)), dim=-1)
+        return y.flatten(1, 2).transpose(0, 1)
+    if newline_position == "frame":                                                # :246-250 add_token_per_frame
+        y = x.permute(2, 0, 1).contiguous()
+        y = torch.cat((y, newline[:, None, None].expand(*y.shape[:-1], 1)), dim=-1)
+        return y.permute(1, 2, 0).contiguous().flatten(0, 1)
+    if newline_position == "one_token":                                            # :337-345
+        y = x.flatten(0, 1)
+        if "unpad" in merge_type:
+            y = torch.cat((y, newline[None]), dim=0)
+        return y
+    if newline_position == "no_token":                                             # :346-347
+        return x.flatten(0, 1)
+    raise ValueError(f"Unexpected mm_newline_position: {newline_position}")
+
+
 def prepare_inputs_labels(embed_table: torch.Tensor, image_features: List[torch.Tensor], input_ids: torch.Tensor,
                           attention_mask: Optional[torch.Tensor], labels: Optional[torch.Tensor],
                           max_length: Optional[int] = None, left_pad: bool = False,

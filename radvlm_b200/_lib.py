@@ -31,7 +31,9 @@ EPI_BIAS_F32 = 6
 EPI_ATOMIC_F32 = 7
 
 SEG_PAD, SEG_TEXT, SEG_IMAGE = 0, 1, 2
-MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT = 0, 1, 2
+MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT, MERGE_VIDEO = 0, 1, 2, 3
+POOL_NONE, POOL_BILINEAR, POOL_AVERAGE, POOL_MAX = 0, 1, 2, 3
+NEWLINE_NONE, NEWLINE_ONE, NEWLINE_FRAME, NEWLINE_GRID = 0, 1, 2, 3
 
 
 class RadvlmError(RuntimeError):

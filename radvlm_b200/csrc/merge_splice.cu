@@ -123,6 +123,72 @@ __device__ __forceinline__ size_t grid_src_row(const radvlm_merge_image& im, int
   return static_cast<size_t>(im.tile_base + 1 + tr * im.grid_w + tc) * T + (R - tr * S) * S + (C - tc * S);
 }
 
+
+// Video samples (llava_arch.py:171-190 get_2dPool with stride 2, :222-249 add_token_per_grid / add_token_per_frame,
+// :310-349): `grid_w` frames of S x S tokens are pooled to out_h x out_w (bilinear: ceil(S/2), ATen
+// upsample_bilinear2d align_corners=False; average / max: floor(S/2), 2x2 windows) and laid out frame-major with a
+// newline token per pooled row (GRID), per frame (FRAME), once at the end (ONE) or not at all (NONE).
+struct VideoTaps {
+  int newline;    // the token is the image_newline row
+  size_t row[4];  // feature rows of the (up to) four taps
+  float ly1, lx1; // bilinear weights of the second row / column
+};
+__device__ __forceinline__ VideoTaps video_source(const radvlm_merge_image& im, int t, int S, int T) {
+  VideoTaps v;
+  v.newline = 0;
+  v.ly1 = v.lx1 = 0.f;
+  const int per_frame = im.out_h * im.out_w;
+  int f, r, c;
+  if (im.reserved == RADVLM_NEWLINE_GRID) {
+    const int stride = im.out_h * (im.out_w + 1);
+    f = t / stride;
+    const int u = t - f * stride;
+    r = u / (im.out_w + 1);
+    c = u - r * (im.out_w + 1);
+    if (c == im.out_w) v.newline = 1;
+  } else if (im.reserved == RADVLM_NEWLINE_FRAME) {
+    f = t / (per_frame + 1);
+    const int u = t - f * (per_frame + 1);
+    if (u == per_frame) v.newline = 1;
+    r = u / im.out_w;
+    c = u - r * im.out_w;
+  } else {
+    f = t / per_frame;
+    if (f >= im.grid_w) v.newline = 1;  // the single trailing newline (ONE)
+    const int u = t - f * per_frame;
+    r = u / im.out_w;
+    c = u - r * im.out_w;
+  }
+  if (v.newline) {
+    v.row[0] = v.row[1] = v.row[2] = v.row[3] = 0;
+    return v;
+  }
+  int y0, y1, x0, x1;
+  if (im.pool == RADVLM_POOL_BILINEAR) {
+    const float sh = static_cast<float>(S) / static_cast<float>(im.out_h);
+    const float sw = static_cast<float>(S) / static_cast<float>(im.out_w);
+    float sy = sh * (static_cast<float>(r) + 0.5f) - 0.5f;
+    float sx = sw * (static_cast<float>(c) + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    y0 = static_cast<int>(sy);
+    x0 = static_cast<int>(sx);
+    y1 = y0 + (y0 < S - 1 ? 1 : 0);
+    x1 = x0 + (x0 < S - 1 ? 1 : 0);
+    v.ly1 = sy - static_cast<float>(y0);
+    v.lx1 = sx - static_cast<float>(x0);
+  } else {  // 2x2 window
+    y0 = 2 * r; y1 = y0 + 1;
+    x0 = 2 * c; x1 = x0 + 1;
+  }
+  const size_t base = static_cast<size_t>(im.tile_base + f) * T;
+  v.row[0] = base + y0 * S + x0;
+  v.row[1] = base + y0 * S + x1;
+  v.row[2] = base + y1 * S + x0;
+  v.row[3] = base + y1 * S + x1;
+  return v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 merge_splice_kernel(const MergeSpliceArgs a) {
@@ -157,6 +223,34 @@ merge_splice_kernel(const MergeSpliceArgs a) {
       const int t = seg.src_off + off;
       if (im.mode == RADVLM_MERGE_FLAT) {
         copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
+      } else if (im.mode == RADVLM_MERGE_VIDEO) {
+        const VideoTaps v = video_source(im, t, a.S, a.T);
+        if (v.newline) {
+          copy_row(a.newline, dst, a.nvec, lane);
+        } else {
+          const uint4* p00 = a.features + v.row[0] * a.nvec;
+          const uint4* p01 = a.features + v.row[1] * a.nvec;
+          const uint4* p10 = a.features + v.row[2] * a.nvec;
+          const uint4* p11 = a.features + v.row[3] * a.nvec;
+          const float ly0 = 1.f - v.ly1, lx0 = 1.f - v.lx1;
+          for (int i = lane; i < a.nvec; i += 32) {
+            float f00[Vec16<T>::N], f01[Vec16<T>::N], f10[Vec16<T>::N], f11[Vec16<T>::N], o[Vec16<T>::N];
+            Vec16<T>::unpack(ld_stream(p00 + i), f00);
+            Vec16<T>::unpack(ld_stream(p01 + i), f01);
+            Vec16<T>::unpack(ld_stream(p10 + i), f10);
+            Vec16<T>::unpack(ld_stream(p11 + i), f11);
+#pragma unroll
+            for (int e = 0; e < Vec16<T>::N; ++e) {
+              if (im.pool == RADVLM_POOL_BILINEAR)
+                o[e] = ly0 * (lx0 * f00[e] + v.lx1 * f01[e]) + v.ly1 * (lx0 * f10[e] + v.lx1 * f11[e]);
+              else if (im.pool == RADVLM_POOL_AVERAGE)
+                o[e] = (((f00[e] + f01[e]) + f10[e]) + f11[e]) * 0.25f;
+              else
+                o[e] = fmaxf(fmaxf(f00[e], f01[e]), fmaxf(f10[e], f11[e]));
+            }
+            st_stream(dst + i, Vec16<T>::pack(o));
+          }
+        }
       } else if (t < a.T) {  // base tile
         copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
       } else if (im.mode == RADVLM_MERGE_SINGLE) {
@@ -260,7 +354,21 @@ merge_splice_bwd_kernel(const MergeSpliceBwdArgs a) {
     }
     const radvlm_merge_image im = a.images[seg.image];
     const int t = seg.src_off + off;
-    if (im.mode == RADVLM_MERGE_FLAT || t < a.T) {
+    if (im.mode == RADVLM_MERGE_VIDEO) {  // bilinear / average pooling (max pooling has no backward here: see header)
+      const VideoTaps v = video_source(im, t, a.S, a.T);
+      if (v.newline) {
+        scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+      } else if (im.pool == RADVLM_POOL_BILINEAR) {
+        const float ly0 = 1.f - v.ly1, lx0 = 1.f - v.lx1;
+        scatter_row<T>(src, a.dfeat + v.row[0] * H, ly0 * lx0, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + v.row[1] * H, ly0 * v.lx1, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + v.row[2] * H, v.ly1 * lx0, a.nvec, lane);
+        scatter_row<T>(src, a.dfeat + v.row[3] * H, v.ly1 * v.lx1, a.nvec, lane);
+      } else if (im.pool == RADVLM_POOL_AVERAGE) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scatter_row<T>(src, a.dfeat + v.row[k] * H, 0.25f, a.nvec, lane);
+      }
+    } else if (im.mode == RADVLM_MERGE_FLAT || t < a.T) {
       scatter_row<T>(src, a.dfeat + (static_cast<size_t>(im.tile_base) * a.T + t) * H, 1.f, a.nvec, lane);
     } else if (im.mode == RADVLM_MERGE_SINGLE) {
       scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);

@@ -53,8 +53,46 @@ def encode_images(self, images: torch.Tensor) -> torch.Tensor:
     return enc.encode_images(images)
 
 
-def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool):
-    """Per-image merge descriptors + visual-token counts (llava_arch.py:294-413)."""
+_POOL_MODES = {"bilinear": _lib.POOL_BILINEAR, "average": _lib.POOL_AVERAGE, "max": _lib.POOL_MAX}
+
+
+def _video_entry(self, m, frames: int, S: int, merge_type: str):
+    """Merge descriptor of one video sample: get_2dPool with the default stride 2 (llava_arch.py:171-190, 286-288),
+    then the newline placement of llava_arch.py:310-349 (add_token_per_grid / add_token_per_frame :222-250)."""
+    cfg = self.config
+    if getattr(cfg, "add_faster_video", False):
+        raise NotImplementedError("radvlm_b200: add_faster_video (slow / fast video tokens) is not implemented")
+    mode = getattr(cfg, "mm_spatial_pool_mode", None)
+    if mode not in _POOL_MODES:
+        raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")
+    side = math.ceil(S / 2) if mode == "bilinear" else S // 2
+    m.mode, m.grid_w, m.pool, m.out_h, m.out_w = _lib.MERGE_VIDEO, frames, _POOL_MODES[mode], side, side
+    m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = 0, 0, S, S
+    per_frame = side * side
+    if merge_type == "flat":
+        m.reserved, m.n_tokens = _lib.NEWLINE_NONE, frames * per_frame
+    elif merge_type.startswith("spatial"):
+        position = getattr(cfg, "mm_newline_position", "one_token")
+        if position == "grid":
+            m.reserved, m.n_tokens = _lib.NEWLINE_GRID, frames * side * (side + 1)
+        elif position == "frame":
+            m.reserved, m.n_tokens = _lib.NEWLINE_FRAME, frames * (per_frame + 1)
+        elif position == "one_token":
+            if "unpad" in merge_type:
+                m.reserved, m.n_tokens = _lib.NEWLINE_ONE, frames * per_frame + 1
+            else:
+                m.reserved, m.n_tokens = _lib.NEWLINE_NONE, frames * per_frame
+        elif position == "no_token":
+            m.reserved, m.n_tokens = _lib.NEWLINE_NONE, frames * per_frame
+        else:
+            raise ValueError(f"Unexpected mm_newline_position: {position}")
+    else:
+        raise ValueError("Unexpected mm_patch_merge_type: %s" % merge_type)
+
+
+def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool, video_idx=()):
+    """Per-image merge descriptors + visual-token counts (llava_arch.py:294-413); entries whose index is in
+    `video_idx` are video samples (llava_arch.py:269-272, 283-290, 310-349)."""
     cfg = self.config
     tower = self.get_vision_tower()
     S = tower.num_patches_per_side
@@ -67,7 +105,9 @@ def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool):
     for i, tiles in enumerate(tile_counts):
         m = table[i]
         m.tile_base = base
-        if flat_batch or merge_type == "flat":
+        if i in video_idx and not flat_batch:
+            _video_entry(self, m, tiles, S, merge_type)
+        elif flat_batch or merge_type == "flat":
             m.mode, m.n_tokens = _lib.MERGE_FLAT, tiles * T
         elif merge_type.startswith("spatial"):
             if tiles > 1:
@@ -186,8 +226,7 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         return input_ids, position_ids, attention_mask, past_key_values, None, labels
     if isinstance(modalities, str):
         modalities = [modalities]
-    if any(m == "video" for m in modalities):
-        raise NotImplementedError("radvlm_b200: the video / get_2dPool branch is out of scope (SURVEY.md section 8(f) row 4)")
+    video_idx = {i for i, m in enumerate(modalities) if m == "video"}   # llava_arch.py:269-272
     lib = _lib.load()
 
     # ---- encode all tiles of all images in one call (llava_arch.py:261-279)
@@ -210,7 +249,11 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     features = features.to(device=dev, dtype=embed.dtype).contiguous()
     if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
         raise NotImplementedError
-    merge_table, image_tokens = _merge_table(self, tile_counts, image_sizes, flat_batch)
+    merge_table, image_tokens = _merge_table(self, tile_counts, image_sizes, flat_batch, video_idx)
+    if (video_idx and not flat_batch and getattr(self.config, "mm_spatial_pool_mode", None) == "max"
+            and torch.is_grad_enabled() and features.requires_grad):
+        raise NotImplementedError("radvlm_b200: max-pooled video tokens have no backward (radvlm_merge_splice_backward "
+                                  "covers bilinear and average pooling)")
 
     # ---- splice plan on the host: one D2H of the ids instead of 2 syncs per sample (llava_arch.py:428-493)
     _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask

@@ -88,6 +88,42 @@ def merge_splice_golden():
     return results
 
 
+def video_golden():
+    """Real prepare_inputs_labels_for_multimodal on video samples (get_2dPool, add_token_per_grid / _frame,
+    one_token / no_token; llava_arch.py:171-190, 222-250, 286-349), encode_images stubbed as above."""
+    C = gi.MERGE_HIDDEN
+    host, ref = build_reference_host(vocab=gi.MERGE_VOCAB, hidden_size=C, seed=0,
+                                     vision_kwargs=dict(hidden_size=16, intermediate_size=16, num_hidden_layers=2,
+                                                        num_attention_heads=1))
+    with torch.no_grad():
+        host.model.embed_tokens.weight.copy_(gi.merge_embed_table())
+        host.model.image_newline.copy_(gi.merge_newline())
+    results = {}
+    for name, case in gi.video_cases().items():
+        host.config.tokenizer_padding_side = "right"
+        host.config.tokenizer_model_max_length = 32768
+        host.config.image_aspect_ratio = "anyres_max_9"
+        host.config.mm_spatial_pool_mode = case["pool"]
+        host.config.mm_spatial_pool_stride = 2
+        host.config.mm_newline_position = case["newline"]
+        host.config.mm_patch_merge_type = case.get("merge_type", "spatial_unpad")
+        host.config.add_faster_video = False
+        feats = gi.merge_features(case)
+        host.encode_images = lambda images, _f=feats: _f
+        images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
+        ids, mask, labels = gi.merge_ids(case)
+        position_ids = torch.arange(ids.shape[1], dtype=torch.long)[None].expand(ids.shape[0], -1).contiguous()
+        out = host.prepare_inputs_labels_for_multimodal(
+            ids, position_ids, mask, None, labels, images, modalities=case["modalities"], image_sizes=case["sizes"])
+        _, pos, am, _, emb, lab = out
+        results[name + "/embeds"] = emb.detach().numpy().astype(np.float32)
+        results[name + "/labels"] = lab.numpy()
+        results[name + "/mask"] = am.numpy().astype(np.uint8)
+        results[name + "/pos"] = pos.numpy()
+        print("video", name, tuple(emb.shape))
+    return results
+
+
 def preprocess_golden(ref):
     from PIL import Image
     proc = ref.siglip_encoder.SigLipImageProcessor()
@@ -186,13 +222,15 @@ def grad_golden(ref):
 
 
 def main():
-    parts = set(sys.argv[1:]) or {"planner", "merge", "preprocess", "encoder", "grad"}
+    parts = set(sys.argv[1:]) or {"planner", "merge", "video", "preprocess", "encoder", "grad"}
     ref = import_reference()
     if "planner" in parts:
         with open(os.path.join(HERE, "planner_golden.json"), "w") as f:
             json.dump(planner_golden(ref), f)
     if "merge" in parts:
         np.savez_compressed(os.path.join(HERE, "merge_splice_golden.npz"), **merge_splice_golden())
+    if "video" in parts:
+        np.savez_compressed(os.path.join(HERE, "video_golden.npz"), **video_golden())
     if "preprocess" in parts:
         meta, arrays = preprocess_golden(ref)
         with open(os.path.join(HERE, "preprocess_golden.json"), "w") as f:

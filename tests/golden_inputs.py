@@ -55,6 +55,23 @@ def merge_cases():
     }
 
 
+def video_cases():
+    """Video / get_2dPool branch: `tiles` = frames for the entries whose modality is "video"."""
+    return {
+        "bilinear_grid": dict(seed=11, modalities=["video"], sizes=[(384, 384)], tiles=[4], lengths=[20],
+                              images_per_sample=[1], pad_to=20, pool="bilinear", newline="grid"),
+        "average_frame": dict(seed=12, modalities=["video"], sizes=[(384, 384)], tiles=[3], lengths=[16],
+                              images_per_sample=[1], pad_to=16, pool="average", newline="frame"),
+        "max_one_token": dict(seed=13, modalities=["video"], sizes=[(384, 384)], tiles=[2], lengths=[12],
+                              images_per_sample=[1], pad_to=12, pool="max", newline="one_token"),
+        "mixed_no_token": dict(seed=14, modalities=["video", "image", "image"], sizes=[(384, 384), (1024, 1024), (384, 384)],
+                               tiles=[5, 10, 1], lengths=[30, 22, 9], images_per_sample=[1, 1, 1], pad_to=30,
+                               pool="bilinear", newline="no_token"),
+        "flat_average": dict(seed=15, modalities=["video"], sizes=[(384, 384)], tiles=[2], lengths=[10],
+                             images_per_sample=[1], pad_to=10, pool="average", newline="grid", merge_type="flat"),
+    }
+
+
 def merge_features(case) -> torch.Tensor:
     g = torch.Generator().manual_seed(1000 + case["seed"])
     return _bf16_exact(torch.randn(sum(case["tiles"]), 729, MERGE_HIDDEN, generator=g))

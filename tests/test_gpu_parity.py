@@ -215,6 +215,66 @@ def test_merge_splice_vs_reference_golden(lib, golden_dir, name, dtype):
         assert exact_rows > 0.3                           # text rows, base tiles, newlines, un-pooled images
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", sorted(gi.video_cases()))
+def test_video_merge_vs_reference_golden(lib, golden_dir, name, dtype):
+    """video samples (get_2dPool + newline placement) through prepare_inputs_labels_for_multimodal."""
+    case = gi.video_cases()[name]
+    z = np.load(os.path.join(golden_dir, "video_golden.npz"))
+    host = _merge_host(dtype)
+    host.config.image_aspect_ratio = "anyres_max_9"
+    host.config.mm_spatial_pool_mode = case["pool"]
+    host.config.mm_spatial_pool_stride = 2
+    host.config.mm_newline_position = case["newline"]
+    host.config.mm_patch_merge_type = case.get("merge_type", "spatial_unpad")
+    feats = gi.merge_features(case).to("cuda", dtype)
+    host.encode_images = lambda images, _f=feats: _f
+    images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
+    ids, mask, labels = gi.merge_ids(case)
+    pos_in = torch.arange(ids.shape[1])[None].expand(ids.shape[0], -1).contiguous()
+    out = host.prepare_inputs_labels_for_multimodal(ids.cuda(), pos_in.cuda(), mask.cuda(), None, labels.cuda(), images,
+                                                    modalities=case["modalities"], image_sizes=case["sizes"])
+    _, pos, am, _, emb, lab = out
+    assert np.array_equal(lab.cpu().numpy(), z[name + "/labels"])
+    assert np.array_equal(am.cpu().numpy().astype(np.uint8), z[name + "/mask"])
+    assert np.array_equal(pos.cpu().numpy(), z[name + "/pos"])
+    ref = torch.from_numpy(z[name + "/embeds"])
+    got = emb.float().cpu()
+    assert got.shape == ref.shape
+    if case["pool"] == "max" and dtype == torch.float32:
+        assert torch.equal(got, ref)                      # max pooling copies values: bit-exact
+    elif case["pool"] == "max":
+        assert torch.equal(got, ref.to(dtype).float())
+    else:
+        tol = 3e-5 if dtype == torch.float32 else 2e-2    # 4-tap fp32 arithmetic / bf16 output rounding
+        assert (got - ref).abs().max() <= tol
+
+
+@pytest.mark.parametrize("pool,newline", [("bilinear", "grid"), ("average", "frame")])
+def test_video_merge_backward_vs_oracle_autograd(lib, pool, newline):
+    """Gradients of the video gather w.r.t. the visual features and image_newline vs the oracle's fp32 autograd."""
+    from oracle import encoder_oracle as eo
+    host = _merge_host(torch.float32)
+    host.config.mm_spatial_pool_mode, host.config.mm_newline_position = pool, newline
+    g = torch.Generator().manual_seed(21)
+    feats = torch.randn(3, 729, gi.MERGE_HIDDEN, generator=g)
+    nl = host.model.image_newline.detach().cpu().clone().requires_grad_(True)
+    f_ref = feats.clone().requires_grad_(True)
+    merged = eo.merge_video(f_ref, nl, pool, newline)
+    R = torch.randn(merged.shape, generator=g)
+    (merged * R).sum().backward()
+    f_dev = feats.cuda().requires_grad_(True)
+    host.model.image_newline.requires_grad_(True)
+    host.encode_images = lambda images: f_dev
+    ids = torch.tensor([[3, -200, 4]], device="cuda")
+    out = host.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, [torch.zeros(3, 3, 2, 2)], ["video"], [(384, 384)])
+    emb = out[4]
+    assert emb.shape[1] == merged.shape[0] + 2
+    (emb[0, 1:1 + merged.shape[0]] * R.cuda()).sum().backward()
+    assert (f_dev.grad.cpu() - f_ref.grad).abs().max() <= 1e-5
+    assert (host.model.image_newline.grad.cpu() - nl.grad).abs().max() <= 1e-4
+
+
 def _is_pooled(size, case):
     from radvlm_b200 import planner
     mx = 0 if case.get("aspect", "anyres_max_9") == "anyres" else 9

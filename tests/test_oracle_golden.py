@@ -71,6 +71,30 @@ def test_merge_splice_oracle_vs_reference(golden_dir, name):
     assert np.array_equal(emb.numpy(), z[name + "/embeds"])  # same torch ops as the reference -> bit-exact
 
 
+@pytest.mark.parametrize("name", sorted(gi.video_cases()))
+def test_video_merge_oracle_vs_reference(golden_dir, name):
+    """Video / get_2dPool branch (llava_arch.py:171-190, 222-250, 286-349) against the real reference's outputs."""
+    case = gi.video_cases()[name]
+    z = np.load(os.path.join(golden_dir, "video_golden.npz"))
+    feats = gi.merge_features(case)
+    newline = gi.merge_newline()
+    per_image, base = [], 0
+    for i, (n, size) in enumerate(zip(case["tiles"], case["sizes"])):
+        f = feats[base:base + n]
+        if case["modalities"][i] == "video":
+            per_image.append(eo.merge_video(f, newline, case["pool"], case["newline"], case.get("merge_type", "spatial_unpad")))
+        else:
+            per_image.append(eo.merge_image(f, size, newline, gi.PINPOINTS, max_num_patches=9))
+        base += n
+    ids, mask, labels = gi.merge_ids(case)
+    emb, lab, am, pos = eo.prepare_inputs_labels(gi.merge_embed_table(), per_image, ids, mask, labels, 32768, False)
+    assert tuple(emb.shape) == z[name + "/embeds"].shape
+    assert np.array_equal(lab.numpy(), z[name + "/labels"])
+    assert np.array_equal(am.numpy().astype(np.uint8), z[name + "/mask"])
+    assert np.array_equal(pos.numpy(), z[name + "/pos"])
+    assert np.array_equal(emb.numpy(), z[name + "/embeds"])  # same torch ops as the reference -> bit-exact
+
+
 def test_merge_source_map_closed_form():
     """The closed-form per-token source map (what the CUDA gather implements) == the tensor-op merge."""
     newline = gi.merge_newline()
