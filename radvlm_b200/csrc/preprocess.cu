@@ -18,6 +18,8 @@
 //   3. resample_v_tiles_kernel: vertical pass + paste + crop + normalise + CHW scatter
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -148,6 +150,233 @@ resample_coeffs_kernel(const radvlm_preprocess_image* __restrict__ imgs, uint8_t
 __device__ __forceinline__ uint8_t clip8(int v) {
   v >>= kPrecisionBits;
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2+3 fused: one CTA produces a 16-row x 128-column block of the output plane (canvas tiles, then the base tile):
+//   source rectangle -> shared memory with 16-byte loads -> horizontal pass -> uint8 intermediate (planar, shared
+//   memory; the same rounding to uint8 Pillow does between its passes) -> vertical pass -> LUT normalise -> CHW
+//   tile rows with 16-byte stores.  Same coefficient tables and the same integer arithmetic as the two-kernel
+//   path below, which stays as the fall-back for geometries whose source rectangle does not fit shared memory
+//   (down-scales beyond ~5x) or tile sizes that are not a multiple of 16.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFuBX = 128, kFuBY = 16, kFuThreads = 256;
+
+struct FusedSmem {   // identical maxima on host (sizing) and device (offsets)
+  int max_nr;        // source / intermediate rows held per block
+  int src_pitch;     // bytes per staged source row (16-byte multiple)
+  int max_ksx;       // horizontal taps
+};
+__host__ __device__ inline size_t fused_src_off() { return 0; }
+__host__ __device__ inline size_t fused_inter_off(const FusedSmem& f) { return al16(static_cast<size_t>(f.max_nr) * f.src_pitch); }
+__host__ __device__ inline size_t fused_kx_off(const FusedSmem& f) { return fused_inter_off(f) + al16(static_cast<size_t>(3) * f.max_nr * kFuBX); }
+__host__ __device__ inline size_t fused_bx_off(const FusedSmem& f) { return fused_kx_off(f) + al16(static_cast<size_t>(kFuBX) * f.max_ksx * 4); }
+__host__ __device__ inline size_t fused_shift_off(const FusedSmem& f) { return fused_bx_off(f) + 2 * kFuBX * 4; }
+__host__ __device__ inline size_t fused_lut_off(const FusedSmem& f) { return fused_shift_off(f) + al16(static_cast<size_t>(f.max_nr) * 4); }
+__host__ __device__ inline size_t fused_total(const FusedSmem& f) { return fused_lut_off(f) + 256 * 4; }
+
+// rows / columns of the input an output range of n samples can touch (scale = in / out, ksize taps per sample)
+__host__ __device__ inline int fused_span(int in, int out, int n) {
+  if (in == out) return n;
+  const double scale = static_cast<double>(in) / static_cast<double>(out);
+  return static_cast<int>(ceil((n - 1) * scale)) + resample_ksize(in, out) + 1;
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* dst, const float* v);
+template <>
+__device__ __forceinline__ void store8<float>(float* dst, const float* v) {
+  reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* dst, const float* v) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* dst, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFuThreads)
+resample_fused_kernel(const radvlm_preprocess_image* __restrict__ imgs, const uint8_t* __restrict__ src,
+                      const uint8_t* __restrict__ scratch, T* __restrict__ tiles, int S, FusedSmem fs) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  uint8_t* src_s = fsm + fused_src_off();
+  uint8_t* inter_s = fsm + fused_inter_off(fs);
+  int32_t* kx_s = reinterpret_cast<int32_t*>(fsm + fused_kx_off(fs));
+  int32_t* bx_s = reinterpret_cast<int32_t*>(fsm + fused_bx_off(fs));
+  int32_t* shift_s = reinterpret_cast<int32_t*>(fsm + fused_shift_off(fs));
+  float* lut = reinterpret_cast<float*>(fsm + fused_lut_off(fs));
+  const int tid = threadIdx.x;
+
+  const radvlm_preprocess_image im = imgs[blockIdx.z];
+  const int canvas_w = im.grid_w * S, canvas_h = im.grid_h * S;
+  const int Y0 = blockIdx.y * kFuBY, X0 = blockIdx.x * kFuBX;
+  const bool is_base = (Y0 >= canvas_h);          // S % kFuBY == 0: a block never straddles canvas and base rows
+  if (Y0 >= canvas_h + S) return;
+  const int plane_w = is_base ? S : canvas_w;
+  if (X0 >= plane_w) return;
+
+  // rescale: float32(float64(u8) * (1/255));  normalize: (x - 0.5f) / 0.5f
+  if (tid < 256) {
+    const float r = __double2float_rn(__dmul_rn(static_cast<double>(tid), 1.0 / 255.0));
+    lut[tid] = __fdiv_rn(__fsub_rn(r, 0.5f), 0.5f);
+  }
+
+  const PreLayout L = make_pre_layout(im.width, im.height, im.channels, im.resized_w, im.resized_h, S);
+  const uint8_t* base = scratch + im.scratch_offset;
+  const int C = im.channels, W = im.width, H = im.height;
+  const int out_w = is_base ? S : im.resized_w, out_h = is_base ? S : im.resized_h;
+  const int px = is_base ? 0 : im.paste_x, py = is_base ? canvas_h : im.paste_y;  // output -> resized coordinates
+  const AxisLayout Ax = is_base ? L.xb : L.xm, Ay = is_base ? L.yb : L.ym;
+  const int32_t* bxg = reinterpret_cast<const int32_t*>(base + Ax.bounds_off);
+  const int32_t* kxg = reinterpret_cast<const int32_t*>(base + Ax.kk_off);
+  const int32_t* byg = reinterpret_cast<const int32_t*>(base + Ay.bounds_off);
+  const int32_t* kyg = reinterpret_cast<const int32_t*>(base + Ay.kk_off);
+  const bool h_skip = (out_w == W), v_skip = (out_h == H);
+
+  // the part of this block that lies inside the pasted (resized) image
+  const int oy_lo = max(Y0 - py, 0), oy_hi = min(Y0 - py + kFuBY, out_h);
+  const int ox_lo = max(X0 - px, 0), ox_hi = min(X0 - px + kFuBX, out_w);
+  const bool empty = (oy_lo >= oy_hi) || (ox_lo >= ox_hi);
+  int r_lo = 0, nr = 0, c_lo = 0, nc = 0;
+  const int nox = empty ? 0 : ox_hi - ox_lo;
+  const int col0 = ox_lo - (X0 - px);  // intermediate column of ox_lo (columns are indexed by X - X0)
+  if (!empty) {
+    if (v_skip) { r_lo = oy_lo; nr = oy_hi - oy_lo; }
+    else { r_lo = byg[2 * oy_lo]; nr = byg[2 * (oy_hi - 1)] + byg[2 * (oy_hi - 1) + 1] - r_lo; }
+    if (h_skip) { c_lo = ox_lo; nc = nox; }
+    else { c_lo = bxg[2 * ox_lo]; nc = bxg[2 * (ox_hi - 1)] + bxg[2 * (ox_hi - 1) + 1] - c_lo; }
+    if (nr > fs.max_nr || nc * C + 32 > fs.src_pitch || Ax.ksize > fs.max_ksx) __trap();  // host sizing bug
+
+    // ---- phase 0: horizontal coefficients of this block's columns + the source rectangle (16-byte loads)
+    if (!h_skip) {
+      for (int i = tid; i < nox * Ax.ksize; i += kFuThreads) kx_s[i] = kxg[static_cast<size_t>(ox_lo) * Ax.ksize + i];
+      for (int i = tid; i < 2 * nox; i += kFuThreads) bx_s[i] = bxg[2 * ox_lo + i];
+    }
+    const uint8_t* img = src + im.src_offset;
+    const uint8_t* img_end = img + static_cast<size_t>(W) * H * C;
+    const int chunks = fs.src_pitch / 16;
+    for (int i = tid; i < nr * chunks; i += kFuThreads) {
+      const int r = i / chunks, ch = i - r * chunks;
+      const uint8_t* row = img + (static_cast<size_t>(r_lo + r) * W + c_lo) * C;
+      const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(row) & 15u);
+      if (ch == 0) shift_s[r] = static_cast<int>(a);
+      if (ch * 16 >= static_cast<int>(a) + nc * C) continue;  // past the row's bytes
+      const uint8_t* g = row - a + ch * 16;
+      uint4 v;
+      if (g >= img && g + 16 <= img_end) {
+        v = *reinterpret_cast<const uint4*>(g);
+      } else {  // first / last bytes of the image: stay inside it
+        uint8_t b[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = (g + e >= img && g + e < img_end) ? g[e] : 0;
+        v = *reinterpret_cast<const uint4*>(b);
+      }
+      *reinterpret_cast<uint4*>(src_s + static_cast<size_t>(r) * fs.src_pitch + ch * 16) = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: horizontal pass -> planar uint8 intermediate [channel][row][X - X0]
+  if (!empty) {
+    for (int i = tid; i < nr * nox; i += kFuThreads) {
+      const int r = i / nox, o = i - r * nox;
+      const uint8_t* rowp = src_s + static_cast<size_t>(r) * fs.src_pitch + shift_s[r];
+      uint8_t* dst = inter_s + static_cast<size_t>(r) * kFuBX + col0 + o;
+      const size_t plane = static_cast<size_t>(fs.max_nr) * kFuBX;
+      if (h_skip) {
+        const uint8_t* p = rowp + o * C;
+        dst[0] = p[0];
+        if (C == 3) { dst[plane] = p[1]; dst[2 * plane] = p[2]; }
+      } else {
+        const int xmin = bx_s[2 * o] - c_lo, cnt = bx_s[2 * o + 1];
+        const int32_t* k = kx_s + o * Ax.ksize;
+        if (C == 1) {
+          int s0 = 1 << (kPrecisionBits - 1);
+          for (int x = 0; x < cnt; ++x) s0 += static_cast<int>(rowp[xmin + x]) * k[x];
+          dst[0] = clip8(s0);
+        } else {
+          int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+          const uint8_t* p = rowp + xmin * 3;
+          for (int x = 0; x < cnt; ++x) {
+            const int kv = k[x];
+            s0 += static_cast<int>(p[3 * x]) * kv;
+            s1 += static_cast<int>(p[3 * x + 1]) * kv;
+            s2 += static_cast<int>(p[3 * x + 2]) * kv;
+          }
+          dst[0] = clip8(s0);
+          dst[plane] = clip8(s1);
+          dst[2 * plane] = clip8(s2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: vertical pass + paste (black outside) + normalise + CHW tile rows, 8 pixels per thread
+  const size_t plane = static_cast<size_t>(fs.max_nr) * kFuBX;
+  for (int i = tid; i < kFuBY * 3 * (kFuBX / 8); i += kFuThreads) {
+    const int g8 = i % (kFuBX / 8);
+    const int ch = (i / (kFuBX / 8)) % 3;
+    const int y = i / (3 * (kFuBX / 8));
+    const int Y = Y0 + y, X = X0 + g8 * 8;
+    if (X >= plane_w) continue;  // plane widths are multiples of 8
+    const int oy = Y - py;
+    int v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0;
+    if (!empty && oy >= oy_lo && oy < oy_hi) {
+      const uint8_t* pl = inter_s + (C == 1 ? 0 : ch) * plane + g8 * 8;
+      if (v_skip) {
+        const uint2 w = *reinterpret_cast<const uint2*>(pl + static_cast<size_t>(oy - r_lo) * kFuBX);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[e] = (w.x >> (8 * e)) & 0xFF; v[4 + e] = (w.y >> (8 * e)) & 0xFF; }
+      } else {
+        const int ymin = byg[2 * oy] - r_lo, cnt = byg[2 * oy + 1];
+        const int32_t* k = kyg + static_cast<size_t>(oy) * Ay.ksize;
+        int acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 1 << (kPrecisionBits - 1);
+        for (int t = 0; t < cnt; ++t) {
+          const uint2 w = *reinterpret_cast<const uint2*>(pl + static_cast<size_t>(ymin + t) * kFuBX);
+          const int kv = __ldg(k + t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[e] += static_cast<int>((w.x >> (8 * e)) & 0xFF) * kv;
+            acc[4 + e] += static_cast<int>((w.y >> (8 * e)) & 0xFF) * kv;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = clip8(acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // columns outside the pasted image are black
+        const int ox = X + e - px;
+        if (ox < ox_lo || ox >= ox_hi) v[e] = 0;
+      }
+    }
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = lut[v[e]];
+    int tile, ty, tx;
+    if (is_base) {
+      tile = im.tile_base; ty = Y - canvas_h; tx = X;
+    } else {
+      const int gy = Y / S, gx = X / S;
+      tile = im.tile_base + 1 + gy * im.grid_w + gx; ty = Y - gy * S; tx = X - gx * S;
+    }
+    store8<T>(tiles + (static_cast<size_t>(tile) * 3 + ch) * S * S + static_cast<size_t>(ty) * S + tx, f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,9 +572,47 @@ extern "C" int radvlm_preprocess_anyres(const uint8_t* src, const radvlm_preproc
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* scr = static_cast<uint8_t*>(scratch);
-  ProfScope ps(PROF_PREPROCESS, s, 3);
+  // shared-memory needs of the fused kernel over the batch (both targets of every image)
+  FusedSmem fs{kFuBY, 64, 1};
+  for (int i = 0; i < n_images; ++i) {
+    const radvlm_preprocess_image& im = images_host[i];
+    for (int target = 0; target < 2; ++target) {
+      const int ow = target ? tile_size : im.resized_w, oh = target ? tile_size : im.resized_h;
+      const int nr = fused_span(im.height, oh, kFuBY), nc = fused_span(im.width, ow, kFuBX);
+      const int pitch = static_cast<int>(al16(static_cast<size_t>(nc) * im.channels + 32));
+      const int ksx = resample_ksize(im.width, ow);
+      if (nr > fs.max_nr) fs.max_nr = nr;
+      if (pitch > fs.src_pitch) fs.src_pitch = pitch;
+      if (ksx > fs.max_ksx) fs.max_ksx = ksx;
+    }
+  }
+  const size_t fused_smem = fused_total(fs);
+  static const bool force_two_pass = [] { const char* e = std::getenv("RADVLM_B200_PREPROCESS"); return e && e[0] == '2'; }();
+  const bool fused = !force_two_pass && (tile_size % kFuBY) == 0 && (tile_size % 8) == 0 && fused_smem <= 200 * 1024;
+  ProfScope ps(PROF_PREPROCESS, s, fused ? 2 : 3);
   resample_coeffs_kernel<<<dim3((max_out + 63) / 64, 4, n_images), 64, 0, s>>>(images_dev, scr, tile_size);
   RV_CUDA(cudaGetLastError());
+  if (fused) {
+    dim3 fgrid((max_cw + kFuBX - 1) / kFuBX, (max_rows + kFuBY - 1) / kFuBY, n_images);
+    const int smem = static_cast<int>(fused_smem);
+#define RV_LAUNCH_FUSED(TYPE)                                                                                          \
+  do {                                                                                                                 \
+    RV_CUDA(cudaFuncSetAttribute(resample_fused_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+    resample_fused_kernel<TYPE><<<fgrid, kFuThreads, smem, s>>>(images_dev, src, scr, static_cast<TYPE*>(tiles_out),  \
+                                                                 tile_size, fs);                                        \
+  } while (0)
+    switch (out_dtype) {
+      case RADVLM_DT_F32: RV_LAUNCH_FUSED(float); break;
+      case RADVLM_DT_BF16: RV_LAUNCH_FUSED(__nv_bfloat16); break;
+      case RADVLM_DT_F16: RV_LAUNCH_FUSED(__half); break;
+      default:
+        set_error("preprocess: unknown out_dtype %d", out_dtype);
+        return RADVLM_ERR_BAD_ARGUMENT;
+    }
+#undef RV_LAUNCH_FUSED
+    RV_CUDA(cudaGetLastError());
+    return RADVLM_OK;
+  }
   resample_h_kernel<<<dim3((max_out + 127) / 128, max_h, n_images * 2), 128, 0, s>>>(images_dev, src, scr,
                                                                                    tile_size);
   RV_CUDA(cudaGetLastError());

@@ -233,6 +233,16 @@ int main(int argc, char** argv) {
     cases.push_back({29160, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, 256});
     cases.push_back({29160, 1152, 4304, RADVLM_EPI_RESID_F32, 0});
   }
+  if (argc > 1 && !strcmp(argv[1], "bn")) {  // ./test_gemm bn : tile width sweep on the N = 1152 GEMMs of a 80-tile call
+    radvlm_gemm_set_mode(2);
+    int f = 0;
+    for (int rep = 0; rep < 2; ++rep)
+      for (int bn : {256, 192, 128}) {
+        f += run_case({58320, 1152, 4304, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({58320, 1152, 1152, RADVLM_EPI_RESID_F32, bn});
+      }
+    return f;
+  }
   if (argc > 2 && !strcmp(argv[1], "perf")) {  // ./test_gemm perf <mode> : the three big shapes only (ncu target)
     radvlm_gemm_set_mode(atoi(argv[2]));
     int f = 0;
