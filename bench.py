@@ -383,7 +383,7 @@ def run_b200_arm(args):
                                    "frac": achieved_all / peak, "traffic": None,
                                    "algorithmic_flops_per_step": gemm_flops_step, "kernel_ms_per_step": gemm_ms_step,
                                    "share_of_step": gemm_total_ms / total_ms},
-            "roofline_attention": {"kernel": "siglip_attention_kernel", "bound": "tensor (MUFU co-limited, DESIGN.md)",
+            "roofline_attention": {"kernel": "siglip_attention_pp_kernel", "bound": "tensor (MUFU issue co-limited, DESIGN.md)",
                                    "achieved": at_flops / (at_ms * 1e-3) / 1e12 if at_ms > 0 else 0.0, "peak": peak,
                                    "unit": "TFLOP/s", "frac": (at_flops / (at_ms * 1e-3) / 1e12 / peak) if at_ms > 0 else 0.0,
                                    "traffic": traffic_of("attention", at_lps),
@@ -536,8 +536,11 @@ def run_train_arm(args):
 
 
 def _ncu_traffic():
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json); {} if absent."""
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01b_traffic.json, the latest committed capture); {} if absent."""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    p = os.path.join(d, "r01b_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(d, "r01_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)

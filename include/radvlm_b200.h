@@ -361,6 +361,32 @@ int radvlm_merge_splice(const void* features, const void* newline, const void* e
                         void* out_embeds, int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
                         int64_t ignore_index, void* stream);
 
+/* Fused merge + all-gather (one process per GPU, images sharded by rank): the same gather, but every
+ * embedding row is written to `n_peers` destinations, destination d = this rank's [total_rows, H] slot inside rank
+ * d's gathered buffer, through peer-mapped pointers (plain stores over NVLink / NVSwitch).  The merged tokens are read
+ * once and no separate collective moves them; labels / mask / position ids stay local.  max_ctas > 0 caps the grid so
+ * the kernel can run on a side stream beside the next step's tower.  The reference has no counterpart (its data
+ * parallelism lives in DeepSpeed); the NCCL all-gather of radvlm_b200/dist.py is the equivalent two-step form. */
+#define RADVLM_MAX_PEERS 8
+int radvlm_merge_splice_scatter(const void* features, const void* newline, const void* embed_table, int dtype,
+                                int hidden, int tokens_per_tile, int patches_per_side, const int64_t* input_ids,
+                                const int64_t* labels_in, const int32_t* text_src,
+                                const radvlm_splice_segment* segments, int n_segments,
+                                const radvlm_merge_image* images, int n_images, int64_t total_rows,
+                                void* const* out_peers, int n_peers, int max_ctas, int64_t* out_labels,
+                                uint8_t* out_mask, int64_t* out_pos, int64_t ignore_index, void* stream);
+/* Peer memory for the call above: radvlm_peer_alloc = cudaMalloc (zero-filled) + a 64-byte cudaIpc handle the host
+ * exchanges (e.g. torch.distributed.all_gather); radvlm_peer_open maps a peer's allocation into this process.
+ * radvlm_peer_signal_wait (on `stream`): publish `value` into slot [rank] of every rank's flag array (uint64[n],
+ * peer-mapped device pointers in the DEVICE array flags_peers_dev), then wait until all n slots of flags_local have
+ * reached it - the step barrier that orders the scattered rows of all ranks before any rank reads its buffer. */
+int radvlm_peer_alloc(size_t bytes, void** ptr, uint8_t* handle64);
+int radvlm_peer_open(const uint8_t* handle64, void** ptr);
+int radvlm_peer_close(void* ptr);
+int radvlm_peer_free(void* ptr);
+int radvlm_peer_signal_wait(void* const* flags_peers_dev, void* flags_local, int n, int rank,
+                            unsigned long long value, void* stream);
+
 /* Backward of radvlm_merge_splice (autograd of llava_arch.py:350-531).  d_out_embeds: [B*max_len, H] of `dtype`.
  *   d_features fp32 [tiles*T, H] and d_newline fp32 [H]: accumulated with atomics (zero or running sums on entry);
  *   d_text [n_text, H] of `dtype` (or NULL): gradient rows of the text tokens in text_src order. */

@@ -10,6 +10,8 @@
 // (align_corners=False): scale = in/out in fp32, src = max(scale*(i+0.5)-0.5, 0), 4-tap lerp in fp32.
 #include <cuda_fp16.h>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -96,6 +98,8 @@ struct MergeSpliceArgs {
   const radvlm_merge_image* images;
   int64_t total_rows;
   uint4* out;
+  uint4* out_peers[RADVLM_MAX_PEERS];  // scatter form: the slot of this rank in every rank's gathered buffer
+  int n_peers;
   int64_t* out_labels;
   uint8_t* out_mask;
   int64_t* out_pos;
@@ -115,6 +119,36 @@ __device__ __forceinline__ void copy_row(const uint4* __restrict__ src, uint4* _
     for (int u = 0; u < kMsUnroll; ++u) st_stream(dst + i + 32 * u, v[u]);
   }
   for (; i < nvec; i += 32) st_stream(dst + i, ld_stream(src + i));
+}
+
+// Destination row(s) of one output row.  kScatter = false: the local inputs_embeds tensor.  kScatter = true (fused
+// merge + all-gather): the same row of every rank's gathered buffer, written with plain stores through
+// peer-mapped pointers (NVLink / NVSwitch), so the source is read once and no separate collective moves the tokens.
+template <bool kScatter>
+struct RowDst {
+  uint4* p[kScatter ? RADVLM_MAX_PEERS : 1];
+  int n;
+  __device__ __forceinline__ void st(int i, const uint4& v) const {
+    if (kScatter) {
+#pragma unroll
+      for (int d = 0; d < RADVLM_MAX_PEERS; ++d)
+        if (d < n) st_stream(p[d] + i, v);
+    } else {
+      st_stream(p[0] + i, v);
+    }
+  }
+};
+template <bool kScatter>
+__device__ __forceinline__ void copy_row(const uint4* __restrict__ src, const RowDst<kScatter>& dst, int nvec, int lane) {
+  int i = lane;
+  for (; i + 32 * (kMsUnroll - 1) < nvec; i += 32 * kMsUnroll) {
+    uint4 v[kMsUnroll];
+#pragma unroll
+    for (int u = 0; u < kMsUnroll; ++u) v[u] = ld_stream(src + i + 32 * u);
+#pragma unroll
+    for (int u = 0; u < kMsUnroll; ++u) dst.st(i + 32 * u, v[u]);
+  }
+  for (; i < nvec; i += 32) dst.st(i, ld_stream(src + i));
 }
 
 // feature row (in 16-byte vectors) of grid position (R, C) of the un-cropped S*gh x S*gw map
@@ -189,7 +223,7 @@ __device__ __forceinline__ VideoTaps video_source(const radvlm_merge_image& im, 
   return v;
 }
 
-template <typename T>
+template <typename T, bool kScatter>
 __global__ void __launch_bounds__(256)
 merge_splice_kernel(const MergeSpliceArgs a) {
   const int lane = threadIdx.x & 31;
@@ -204,13 +238,21 @@ merge_splice_kernel(const MergeSpliceArgs a) {
     }
     const radvlm_splice_segment seg = a.segments[lo];
     const int off = static_cast<int>(row - seg.dst_row);
-    uint4* dst = a.out + static_cast<size_t>(row) * a.nvec;
+    RowDst<kScatter> dst;
+    if (kScatter) {
+      dst.n = a.n_peers;
+#pragma unroll
+      for (int d = 0; d < RADVLM_MAX_PEERS; ++d) dst.p[d] = (d < a.n_peers ? a.out_peers[d] : a.out) + static_cast<size_t>(row) * a.nvec;
+    } else {
+      dst.n = 1;
+      dst.p[0] = a.out + static_cast<size_t>(row) * a.nvec;
+    }
     int64_t label = a.ignore_index;
     uint8_t mask = 1;
     int64_t pos = seg.pos0 + off;
 
     if (seg.kind == RADVLM_SEG_PAD || off >= seg.length) {
-      for (int i = lane; i < a.nvec; i += 32) st_stream(dst + i, make_uint4(0, 0, 0, 0));
+      for (int i = lane; i < a.nvec; i += 32) dst.st(i, make_uint4(0, 0, 0, 0));
       mask = 0;
       pos = 0;
     } else if (seg.kind == RADVLM_SEG_TEXT) {
@@ -248,7 +290,7 @@ merge_splice_kernel(const MergeSpliceArgs a) {
               else
                 o[e] = fmaxf(fmaxf(f00[e], f01[e]), fmaxf(f10[e], f11[e]));
             }
-            st_stream(dst + i, Vec16<T>::pack(o));
+            dst.st(i, Vec16<T>::pack(o));
           }
         }
       } else if (t < a.T) {  // base tile
@@ -288,7 +330,7 @@ merge_splice_kernel(const MergeSpliceArgs a) {
 #pragma unroll
             for (int e = 0; e < Vec16<T>::N; ++e)
               o[e] = ly0 * (lx0 * f00[e] + lx1 * f01[e]) + ly1 * (lx0 * f10[e] + lx1 * f11[e]);
-            st_stream(dst + i, Vec16<T>::pack(o));
+            dst.st(i, Vec16<T>::pack(o));
           }
         }
       }
@@ -402,19 +444,20 @@ merge_splice_bwd_kernel(const MergeSpliceBwdArgs a) {
 
 }  // namespace rv
 
-extern "C" int radvlm_merge_splice(const void* features, const void* newline, const void* embed_table,
-                                   int dtype, int hidden, int tokens_per_tile, int patches_per_side,
-                                   const int64_t* input_ids, const int64_t* labels_in,
-                                   const int32_t* text_src, const radvlm_splice_segment* segments,
-                                   int n_segments, const radvlm_merge_image* images, int n_images,
-                                   int64_t total_rows, void* out_embeds, int64_t* out_labels,
-                                   uint8_t* out_mask, int64_t* out_pos, int64_t ignore_index,
-                                   void* stream) {
-  using namespace rv;
+namespace rv {
+
+static int merge_splice_launch(const void* features, const void* newline, const void* embed_table, int dtype, int hidden,
+                               int tokens_per_tile, int patches_per_side, const int64_t* input_ids,
+                               const int64_t* labels_in, const int32_t* text_src, const radvlm_splice_segment* segments,
+                               int n_segments, const radvlm_merge_image* images, int n_images, int64_t total_rows,
+                               void* out_embeds, void* const* out_peers, int n_peers, int max_ctas, int64_t* out_labels,
+                               uint8_t* out_mask, int64_t* out_pos, int64_t ignore_index, void* stream) {
   int st = require_sm100();
   if (st) return st;
-  RV_CHECK_ARG(segments && n_segments > 0 && out_embeds && total_rows > 0, "merge_splice: bad arguments");
+  RV_CHECK_ARG(segments && n_segments > 0 && (out_embeds || n_peers > 0) && total_rows > 0, "merge_splice: bad arguments");
   RV_CHECK_ARG(n_images == 0 || (images && features), "merge_splice: image table without features");
+  RV_CHECK_ARG(n_peers >= 0 && n_peers <= RADVLM_MAX_PEERS, "merge_splice: %d destinations (at most %d)", n_peers,
+               RADVLM_MAX_PEERS);
   const int esize = (dtype == RADVLM_DT_F32) ? 4 : 2;
   RV_CHECK_ARG((static_cast<long long>(hidden) * esize) % 16 == 0, "merge_splice: row bytes must be a multiple of 16");
   MergeSpliceArgs a;
@@ -432,22 +475,138 @@ extern "C" int radvlm_merge_splice(const void* features, const void* newline, co
   a.images = images;
   a.total_rows = total_rows;
   a.out = static_cast<uint4*>(out_embeds);
+  a.n_peers = n_peers;
+  for (int d = 0; d < RADVLM_MAX_PEERS; ++d) {
+    a.out_peers[d] = d < n_peers ? static_cast<uint4*>(out_peers[d]) : nullptr;
+    RV_CHECK_ARG(d >= n_peers || out_peers[d] != nullptr, "merge_splice: destination %d is null", d);
+  }
   a.out_labels = out_labels;
   a.out_mask = out_mask;
   a.out_pos = out_pos;
   a.ignore_index = ignore_index;
   const int threads = 256;
   const int64_t want = (total_rows * 32 + threads - 1) / threads;
-  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;  // 8 resident CTAs per SM
+  int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;  // 8 resident CTAs per SM
+  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
   const int blocks = static_cast<int>(want < cap ? want : cap);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ProfScope ps(PROF_MERGE_SPLICE, s);
+  const bool scatter = n_peers > 0;
+#define RV_MS_LAUNCH(TYPE)                                                            \
+  do {                                                                                \
+    if (scatter) merge_splice_kernel<TYPE, true><<<blocks, threads, 0, s>>>(a);       \
+    else merge_splice_kernel<TYPE, false><<<blocks, threads, 0, s>>>(a);              \
+  } while (0)
   switch (dtype) {
-    case RADVLM_DT_F32: merge_splice_kernel<float><<<blocks, threads, 0, s>>>(a); break;
-    case RADVLM_DT_BF16: merge_splice_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(a); break;
-    case RADVLM_DT_F16: merge_splice_kernel<__half><<<blocks, threads, 0, s>>>(a); break;
+    case RADVLM_DT_F32: RV_MS_LAUNCH(float); break;
+    case RADVLM_DT_BF16: RV_MS_LAUNCH(__nv_bfloat16); break;
+    case RADVLM_DT_F16: RV_MS_LAUNCH(__half); break;
     default: set_error("merge_splice: unknown dtype %d", dtype); return RADVLM_ERR_BAD_ARGUMENT;
   }
+#undef RV_MS_LAUNCH
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// Cross-rank step barrier over peer memory: rank `rank` publishes `value` into slot [rank] of every rank's flag
+// array (system-scope release after this stream's earlier kernels, i.e. after its scattered rows), then waits until
+// all `n` slots of its own array have reached `value`.  Bounded spin: a lost peer traps instead of hanging the GPU.
+__global__ void peer_signal_wait_kernel(unsigned long long* const* flags_peers, unsigned long long* flags_local, int n,
+                                        int rank, unsigned long long value, long long timeout_cycles) {
+  const int d = threadIdx.x;
+  if (d >= n) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags_peers[d] + rank), "l"(value) : "memory");
+  const long long t0 = clock64();
+  unsigned long long seen = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags_local + d) : "memory");
+    if (seen >= value) break;
+    if (clock64() - t0 > timeout_cycles) __trap();
+  } while (true);
+}
+
+}  // namespace rv
+
+extern "C" int radvlm_merge_splice(const void* features, const void* newline, const void* embed_table,
+                                   int dtype, int hidden, int tokens_per_tile, int patches_per_side,
+                                   const int64_t* input_ids, const int64_t* labels_in,
+                                   const int32_t* text_src, const radvlm_splice_segment* segments,
+                                   int n_segments, const radvlm_merge_image* images, int n_images,
+                                   int64_t total_rows, void* out_embeds, int64_t* out_labels,
+                                   uint8_t* out_mask, int64_t* out_pos, int64_t ignore_index,
+                                   void* stream) {
+  return rv::merge_splice_launch(features, newline, embed_table, dtype, hidden, tokens_per_tile, patches_per_side,
+                                 input_ids, labels_in, text_src, segments, n_segments, images, n_images, total_rows,
+                                 out_embeds, nullptr, 0, 0, out_labels, out_mask, out_pos, ignore_index, stream);
+}
+
+extern "C" int radvlm_merge_splice_scatter(const void* features, const void* newline, const void* embed_table,
+                                           int dtype, int hidden, int tokens_per_tile, int patches_per_side,
+                                           const int64_t* input_ids, const int64_t* labels_in,
+                                           const int32_t* text_src, const radvlm_splice_segment* segments,
+                                           int n_segments, const radvlm_merge_image* images, int n_images,
+                                           int64_t total_rows, void* const* out_peers, int n_peers, int max_ctas,
+                                           int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
+                                           int64_t ignore_index, void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(out_peers != nullptr && n_peers >= 1, "merge_splice_scatter: no destinations");
+  return merge_splice_launch(features, newline, embed_table, dtype, hidden, tokens_per_tile, patches_per_side, input_ids,
+                             labels_in, text_src, segments, n_segments, images, n_images, total_rows, nullptr, out_peers,
+                             n_peers, max_ctas, out_labels, out_mask, out_pos, ignore_index, stream);
+}
+
+// ---- peer memory (one process per GPU, same node): cudaIpc handles exchanged by the host through torch.distributed
+extern "C" int radvlm_peer_alloc(size_t bytes, void** ptr, uint8_t* handle64) {
+  using namespace rv;
+  RV_CHECK_ARG(bytes > 0 && ptr && handle64, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  RV_CUDA(cudaMalloc(&p, bytes));
+  RV_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return RADVLM_ERR_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return RADVLM_OK;
+}
+
+extern "C" int radvlm_peer_open(const uint8_t* handle64, void** ptr) {
+  using namespace rv;
+  RV_CHECK_ARG(handle64 && ptr, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  RV_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RADVLM_OK;
+}
+
+extern "C" int radvlm_peer_close(void* ptr) {
+  using namespace rv;
+  if (ptr) RV_CUDA(cudaIpcCloseMemHandle(ptr));
+  return RADVLM_OK;
+}
+
+extern "C" int radvlm_peer_free(void* ptr) {
+  using namespace rv;
+  if (ptr) RV_CUDA(cudaFree(ptr));
+  return RADVLM_OK;
+}
+
+extern "C" int radvlm_peer_signal_wait(void* const* flags_peers_dev, void* flags_local, int n, int rank,
+                                       unsigned long long value, void* stream) {
+  using namespace rv;
+  int st = require_sm100();
+  if (st) return st;
+  RV_CHECK_ARG(flags_peers_dev && flags_local && n >= 1 && n <= RADVLM_MAX_PEERS && rank >= 0 && rank < n,
+               "peer_signal_wait: bad arguments");
+  peer_signal_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long* const*>(flags_peers_dev), static_cast<unsigned long long*>(flags_local), n,
+      rank, value, 20000000000LL);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }
