@@ -58,6 +58,9 @@ def _workload_config(args, world):
         "visual_tokens_per_image": TOKENS_PER_IMAGE,
         "prompt_tokens": 32,
         "parallelism": "dp%d (image-sharded)" % world,
+        "gather": ("none" if world == 1 else
+                   ("fused merge + scatter over peer memory (radvlm_merge_splice_scatter)" if getattr(args, "gather", "nccl") == "peer"
+                    else "NCCL all-gather of inputs_embeds, asynchronous")),
         "l2": "per-step working set (0.83 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2; input images rotate over 3 buffers",
     }
 
@@ -253,10 +256,15 @@ def run_b200_arm(args):
     pos_dev = torch.arange(Lp, device=dev)[None].expand(B, -1).contiguous()
     # N > 1: the all-gather of step i runs asynchronously (NCCL's own stream) and overlaps the encode of step i+1;
     # two (embeddings, gathered) slots alternate, a slot is reused only after its collective has completed.
+    # --gather peer: no collective call at all - the merge kernel itself writes every embedding row into the other
+    # ranks' gathered buffers over NVLink (radvlm_merge_splice_scatter, dist.PeerGather), on a side stream.
     slots = [{"work": None, "emb": None, "out": None} for _ in range(2)]
     step_no = [0]
+    peer = [None]
 
     def drain_gathers():
+        if peer[0] is not None:
+            peer[0].drain()
         for sl in slots:
             if sl["work"] is not None:
                 sl["work"].wait()
@@ -268,7 +276,13 @@ def run_b200_arm(args):
         out = host.prepare_inputs_labels_for_multimodal(ids_dev, pos_dev, mask_dev, None, labels_dev,
                                                         list(torch.split(tiles, splits)), ["image"] * B, sizes)
         emb = out[4]
-        if world > 1:
+        if world > 1 and args.gather == "peer":
+            if peer[0] is None:   # first step: size the peer buffers from the embeddings, then redo the step into them
+                from radvlm_b200.dist import PeerGather
+                peer[0] = PeerGather(emb.shape[0] * emb.shape[1], emb.shape[2], emb.dtype, dev)
+                host.radvlm_b200_gather = peer[0]
+                return step(images_u8)
+        elif world > 1:
             sl = slots[step_no[0] & 1]
             step_no[0] += 1
             if sl["work"] is not None:
@@ -556,6 +570,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the embeddings are all-gathered (NCCL all-gather, or the fused merge + scatter "
+                         "kernel over peer memory)")
     ap.add_argument("--mode", default="encode", choices=["encode", "train"],
                     help="encode: the headline metric (BASELINE configs[1..3]); train: configs[4], forward + backward")
     args = ap.parse_args()

@@ -32,6 +32,7 @@ EPI_ATOMIC_F32 = 7
 
 SEG_PAD, SEG_TEXT, SEG_IMAGE = 0, 1, 2
 MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT, MERGE_VIDEO = 0, 1, 2, 3
+MAX_PEERS = 8
 POOL_NONE, POOL_BILINEAR, POOL_AVERAGE, POOL_MAX = 0, 1, 2, 3
 NEWLINE_NONE, NEWLINE_ONE, NEWLINE_FRAME, NEWLINE_GRID = 0, 1, 2, 3
 
@@ -164,6 +165,13 @@ SIGNATURES = {
                                 C.POINTER(C.c_int32), _pi]),
     "radvlm_merge_splice": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64,
                                  _vp, _vp, _vp, _vp, _i64, _vp]),
+    "radvlm_merge_splice_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64,
+                                         C.POINTER(C.c_void_p), _i, _i, _vp, _vp, _vp, _i64, _vp]),
+    "radvlm_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)]),
+    "radvlm_peer_open": (_i, [C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
+    "radvlm_peer_close": (_i, [_vp]),
+    "radvlm_peer_free": (_i, [_vp]),
+    "radvlm_peer_signal_wait": (_i, [_vp, _vp, _i, _i, C.c_uint64, _vp]),
     "radvlm_preprocess_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "radvlm_preprocess_anyres": (_i, [_vp, _vp, C.POINTER(PreprocessImage), _i, _i, _vp, _i, _vp, _sz, _vp]),
 }

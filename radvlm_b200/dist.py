@@ -147,3 +147,131 @@ def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None, bucket_byte
     r = GradientAllReducer(group, bucket_bytes, average)
     r.submit(tensors)
     r.finish()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused merge + all-gather over peer memory (radvlm_merge_splice_scatter): no collective call moves the tokens
+# ---------------------------------------------------------------------------------------------------------------
+class _DevicePtr:
+    """Minimal __cuda_array_interface__ wrapper so torch can view memory this library allocated."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Gathered ``[world, rows, H]`` buffers living in peer-mapped device memory, ``slots`` of them.
+
+    Every rank allocates one region (``radvlm_peer_alloc``), the 64-byte cudaIpc handles are exchanged once through
+    ``torch.distributed`` and opened on every rank (``radvlm_peer_open``; one process per GPU on one node, NVLink /
+    NVSwitch).  ``prepare_inputs_labels_for_multimodal`` writes the local ``inputs_embeds`` straight into slice
+    ``[rank]`` of its own buffer, then ``scatter()`` launches ``radvlm_merge_splice_scatter`` on a side stream: the same
+    gather kernel reads the merged visual tokens / text embeddings once more (L2 / HBM) and writes every row into
+    slice ``[rank]`` of all OTHER ranks' buffers with plain stores over NVLink, followed by the flag exchange of
+    ``radvlm_peer_signal_wait``.  After ``wait(slot)`` the whole ``[world, rows, H]`` tensor of that slot is valid.
+    """
+
+    def __init__(self, rows: int, hidden: int, dtype: torch.dtype, device, group=None, slots: int = 2, max_ctas: int = 32):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("PeerGather supports at most %d ranks (one node)" % _lib.MAX_PEERS)
+        self.rows, self.hidden, self.dtype, self.device = int(rows), int(hidden), dtype, torch.device(device)
+        self.slots, self.max_ctas = slots, max_ctas
+        self.esize = torch.empty(0, dtype=dtype).element_size()
+        self.slice_bytes = (self.rows * self.hidden * self.esize + 255) // 256 * 256
+        self.slot_bytes = self.world * self.slice_bytes
+        self.flag_off = slots * self.slot_bytes
+        total = self.flag_off + slots * 256
+        with torch.cuda.device(self.device):
+            base = C.c_void_p()
+            handle = (C.c_uint8 * 64)()
+            _lib.check(self.lib.radvlm_peer_alloc(total, C.byref(base), handle))
+            self.base = int(base.value)
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(self.world, 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().numpy()
+            self.peer_base = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                h = (C.c_uint8 * 64)(*[int(v) for v in allh[r]])
+                p = C.c_void_p()
+                _lib.check(self.lib.radvlm_peer_open(h, C.byref(p)))
+                self.peer_base.append(int(p.value))
+            self._bytes = torch.as_tensor(_DevicePtr(self.base, total), device=self.device)
+            # per slot: DEVICE array of every rank's flag array (uint64[world]) for radvlm_peer_signal_wait
+            self._flag_ptrs = [torch.tensor([b + self.flag_off + s * 256 for b in self.peer_base], dtype=torch.int64,
+                                            device=self.device) for s in range(slots)]
+            self.stream = torch.cuda.Stream(self.device)
+            self._events = [None] * slots
+        self._step = [0] * slots
+        self._turn = 0
+        dist.barrier(group)
+
+    # -- views
+    def gathered(self, slot: int) -> torch.Tensor:
+        """[world, rows, H] view of slot ``slot`` in this rank's buffer."""
+        off = slot * self.slot_bytes
+        flat = self._bytes[off: off + self.slot_bytes].view(self.world, self.slice_bytes)
+        return flat[:, : self.rows * self.hidden * self.esize].view(self.dtype).view(self.world, self.rows, self.hidden)
+
+    def local_rows(self, slot: int, n_rows: int) -> torch.Tensor:
+        """This rank's own slice (the tensor the merge kernel fills as ``inputs_embeds``)."""
+        return self.gathered(slot)[self.rank, :n_rows]
+
+    def next_slot(self) -> int:
+        s = self._turn % self.slots
+        self._turn += 1
+        return s
+
+    def remote_dests(self, slot: int):
+        """ctypes array of the slice [rank] of slot ``slot`` in every OTHER rank's buffer."""
+        C = self._C
+        ptrs = [b + slot * self.slot_bytes + self.rank * self.slice_bytes
+                for r, b in enumerate(self.peer_base) if r != self.rank]
+        return (C.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
+
+    def scatter(self, slot: int, launch) -> None:
+        """Run ``launch(dests, n_dests, max_ctas, cuda_stream)`` (the scatter form of the merge kernel) and the flag
+        exchange on the side stream, after everything queued so far on the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        dests, n = self.remote_dests(slot)
+        with torch.cuda.stream(self.stream):
+            if n > 0:
+                launch(dests, n, self.max_ctas, self.stream.cuda_stream)
+            self._step[slot] += 1
+            self._lib.check(self.lib.radvlm_peer_signal_wait(
+                self._flag_ptrs[slot].data_ptr(), self.base + self.flag_off + slot * 256, self.world, self.rank,
+                self._step[slot], self.stream.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self._events[slot] = ev
+
+    def wait(self, slot: int) -> torch.Tensor:
+        """Make the current stream wait until every rank's rows of ``slot`` have landed; returns the gathered view."""
+        if self._events[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._events[slot])
+        return self.gathered(slot)
+
+    def drain(self) -> None:
+        for s in range(self.slots):
+            self.wait(s)
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        for r, b in enumerate(self.peer_base):
+            if r != self.rank:
+                self.lib.radvlm_peer_close(b)
+        dist.barrier(self.group)
+        self._bytes = None
+        self.lib.radvlm_peer_free(self.base)

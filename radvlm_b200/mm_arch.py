@@ -166,8 +166,17 @@ class _MergeSpliceFn(torch.autograd.Function):
         lib = _lib.load()
         dev = embed.device
         H = embed.shape[1]
+        gather = m.get("gather")
         with torch.cuda.device(dev):
-            out = torch.empty(m["B"], m["max_len"], H, dtype=embed.dtype, device=dev)
+            if gather is not None:   # inputs_embeds lives in slice [rank] of a peer-memory gather slot (dist.PeerGather)
+                if m["total_rows"] > gather.rows or H != gather.hidden or embed.dtype != gather.dtype:
+                    raise ValueError("PeerGather(rows=%d, hidden=%d, %s) cannot hold %d rows of %d x %s" % (
+                        gather.rows, gather.hidden, gather.dtype, m["total_rows"], H, embed.dtype))
+                m["gather_slot"] = gather.next_slot()
+                gather.wait(m["gather_slot"])   # the previous use of this slot has been fully exchanged
+                out = gather.local_rows(m["gather_slot"], m["total_rows"]).view(m["B"], m["max_len"], H)
+            else:
+                out = torch.empty(m["B"], m["max_len"], H, dtype=embed.dtype, device=dev)
             out_labels = torch.empty(m["B"], m["max_len"], dtype=torch.int64, device=dev)
             out_mask = torch.empty(m["B"], m["max_len"], dtype=torch.uint8, device=dev)
             out_pos = torch.empty(m["B"], m["max_len"], dtype=torch.int64, device=dev)
@@ -180,6 +189,18 @@ class _MergeSpliceFn(torch.autograd.Function):
                     tables.data_ptr() + m["off_img"], m["n_images"], m["total_rows"],
                     out.data_ptr(), out_labels.data_ptr(), out_mask.data_ptr(), out_pos.data_ptr(), IGNORE_INDEX,
                     torch.cuda.current_stream(dev).cuda_stream))
+                if gather is not None:
+                    # fused merge + all-gather: the same gather kernel writes every row into slice [rank] of all other
+                    # ranks' buffers over NVLink, on the gather's side stream (radvlm_merge_splice_scatter)
+                    def launch(dests, n, max_ctas, stream):
+                        _lib.check(lib.radvlm_merge_splice_scatter(
+                            features.data_ptr(), newline.data_ptr(), embed.data_ptr(), _DT[embed.dtype], H, m["T"], m["S"],
+                            m["ids_dev"].data_ptr(), None, tables.data_ptr() + m["off_txt"], tables.data_ptr(),
+                            m["n_segments"], tables.data_ptr() + m["off_img"], m["n_images"], m["total_rows"],
+                            dests, n, max_ctas, None, None, None, IGNORE_INDEX, stream))
+                    for t in (features, newline, embed, tables, m["ids_dev"]):
+                        t.record_stream(gather.stream)
+                    gather.scatter(m["gather_slot"], launch)
         ctx.m = m
         ctx.feat_shape, ctx.feat_dtype = tuple(features.shape), features.dtype
         ctx.newline_dtype, ctx.embed_shape, ctx.embed_dtype = newline.dtype, tuple(embed.shape), embed.dtype
@@ -294,7 +315,8 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
             n_images=len(tile_counts), n_text=plan.n_text, total_rows=total_rows, B=B_eff, max_len=max_len,
             T=vision_tower.num_patches_per_side ** 2, S=vision_tower.num_patches_per_side,
             ids_dev=input_ids.detach().to(dev, torch.int64).contiguous(),
-            labels_dev=None if labels is None else labels.detach().to(dev, torch.int64).contiguous())
+            labels_dev=None if labels is None else labels.detach().to(dev, torch.int64).contiguous(),
+            gather=getattr(self, "radvlm_b200_gather", None))
     if torch.is_grad_enabled() and (features.requires_grad or newline.requires_grad or embed.requires_grad):
         out, out_labels, out_mask, out_pos = _MergeSpliceFn.apply(features, newline, embed, meta)
     else:

@@ -275,6 +275,52 @@ def test_video_merge_backward_vs_oracle_autograd(lib, pool, newline):
     assert (host.model.image_newline.grad.cpu() - nl.grad).abs().max() <= 1e-4
 
 
+def test_merge_splice_scatter_writes_every_destination(lib):
+    """radvlm_merge_splice_scatter (fused merge + all-gather): every destination gets exactly the rows of the plain
+    kernel.  One GPU: two local buffers stand in for the peer-mapped slices (tools/peer_gather_check.py is the
+    multi-GPU check over cudaIpc peer memory)."""
+    import ctypes as C
+    case = gi.merge_cases()["mixed"]
+    host = _merge_host(torch.bfloat16)
+    feats = gi.merge_features(case).to("cuda", torch.bfloat16)
+    host.encode_images = lambda images, _f=feats: _f
+    images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
+    ids, mask, labels = gi.merge_ids(case)
+    args = (ids.cuda(), None, mask.cuda(), None, labels.cuda(), images)
+    kw = dict(modalities=["image"] * ids.shape[0], image_sizes=case["sizes"])
+    ref = host.prepare_inputs_labels_for_multimodal(*args, **kw)[4]
+
+    class FakeGather:
+        rows, hidden, dtype = ref.shape[0] * ref.shape[1], ref.shape[2], ref.dtype
+        stream = torch.cuda.Stream()
+
+        def __init__(self):
+            self.own = torch.zeros(self.rows, self.hidden, dtype=self.dtype, device="cuda")
+            self.remote = [torch.full((self.rows, self.hidden), 7.0, dtype=self.dtype, device="cuda") for _ in range(2)]
+
+        def next_slot(self):
+            return 0
+
+        def wait(self, slot):
+            return None
+
+        def local_rows(self, slot, n):
+            return self.own[:n]
+
+        def scatter(self, slot, launch):
+            self.stream.wait_stream(torch.cuda.current_stream())
+            dests = (C.c_void_p * 2)(*[t.data_ptr() for t in self.remote])
+            launch(dests, 2, 16, self.stream.cuda_stream)
+
+    g = FakeGather()
+    host.radvlm_b200_gather = g
+    emb = host.prepare_inputs_labels_for_multimodal(*args, **kw)[4]
+    torch.cuda.synchronize()
+    assert torch.equal(emb, ref)
+    for t in g.remote:
+        assert torch.equal(t.view_as(ref), ref)
+
+
 def _is_pooled(size, case):
     from radvlm_b200 import planner
     mx = 0 if case.get("aspect", "anyres_max_9") == "anyres" else 9
