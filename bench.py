@@ -59,7 +59,7 @@ def _workload_config(args, world):
         "prompt_tokens": 32,
         "parallelism": "dp%d (image-sharded)" % world,
         "gather": ("none" if world == 1 else
-                   ("fused merge + scatter over peer memory (radvlm_merge_splice_scatter)" if getattr(args, "gather", "nccl") == "peer"
+                   ("fused merge + scatter over peer memory (radvlm_merge_splice_scatter)" if getattr(args, "gather", "nccl") in ("peer", "auto")
                     else "NCCL all-gather of inputs_embeds, asynchronous")),
         "l2": "per-step working set (0.83 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2; input images rotate over 3 buffers",
     }
@@ -276,10 +276,18 @@ def run_b200_arm(args):
         out = host.prepare_inputs_labels_for_multimodal(ids_dev, pos_dev, mask_dev, None, labels_dev,
                                                         list(torch.split(tiles, splits)), ["image"] * B, sizes)
         emb = out[4]
-        if world > 1 and args.gather == "peer":
+        if world > 1 and args.gather in ("peer", "auto"):
             if peer[0] is None:   # first step: size the peer buffers from the embeddings, then redo the step into them
                 from radvlm_b200.dist import PeerGather
-                peer[0] = PeerGather(emb.shape[0] * emb.shape[1], emb.shape[2], emb.dtype, dev)
+                try:
+                    peer[0] = PeerGather(emb.shape[0] * emb.shape[1], emb.shape[2], emb.dtype, dev)
+                except Exception as e:  # no cudaIpc / peer access on this box: the NCCL all-gather does the same job
+                    if args.gather == "peer":
+                        raise
+                    print("bench: peer-memory gather unavailable (%s); using the NCCL all-gather" % e, file=sys.stderr)
+                    args.gather = "nccl"
+                    return step(images_u8)
+                args.gather = "peer"
                 host.radvlm_b200_gather = peer[0]
                 return step(images_u8)
         elif world > 1:
@@ -570,7 +578,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"],
                     help="N > 1: how the embeddings are all-gathered (NCCL all-gather, or the fused merge + scatter "
                          "kernel over peer memory)")
     ap.add_argument("--mode", default="encode", choices=["encode", "train"],
