@@ -37,6 +37,44 @@ __global__ void __launch_bounds__(1024) k_own(long long* cycles, float* out, flo
   if (acc == 123.456f) out[0] = acc;
 }
 
+// Same with the packed half2 exponential: one MUFU instruction produces two results (two XU passes).
+template <int NF>
+__global__ void __launch_bounds__(1024) k_own_h2(long long* cycles, float* out, float seed) {
+  uint32_t x[kUnroll];
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < kUnroll; ++i) x[i] = 0x3c003c00u + threadIdx.x + i;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = seed * (threadIdx.x + i + 3) * 1e-3f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < kRounds; ++it) {
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[i]));
+#pragma unroll
+      for (int f = 0; f < NF; ++f) asm volatile("fma.rn.f32 %0, %0, 0f3F7FBE77, 0fBA83126F;" : "+f"(y[(i * NF + f) & 7]));
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < kUnroll; ++i) acc += __uint_as_float(x[i]) + y[i & 7];
+  if (acc == 123.456f) out[0] = acc;
+}
+
+template <int NF>
+void run_own_h2(int warps, int sms, long long* dc, float* d) {
+  k_own_h2<NF><<<sms, 128 * warps>>>(dc, d, 1.0f);
+  cudaDeviceSynchronize();
+  k_own_h2<NF><<<sms, 128 * warps>>>(dc, d, 1.0f);
+  long long c = 0;
+  cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+  printf("own-warp interleave, ex2.f16x2: %d FFMA per instr, %d warps/SMSP: %6.2f cycles per MUFU warp-instruction (2 results) per SMSP\n",
+         NF, warps, double(c) / (double(kRounds) * kUnroll * warps));
+}
+
 template <int NF>
 void run_own(int warps, int sms, long long* dc, float* d) {
   k_own<NF><<<sms, 128 * warps>>>(dc, d, 1.0f);
@@ -122,6 +160,13 @@ int main() {
     run_own<6>(w, sms, dc, d);
     run_own<8>(w, sms, dc, d);
     run_own<12>(w, sms, dc, d);
+  }
+  for (int w = 1; w <= 2; ++w) {
+    run_own_h2<0>(w, sms, dc, d);
+    run_own_h2<4>(w, sms, dc, d);
+    run_own_h2<8>(w, sms, dc, d);
+    run_own_h2<12>(w, sms, dc, d);
+    run_own_h2<16>(w, sms, dc, d);
   }
   cudaError_t err = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(err));
