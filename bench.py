@@ -216,6 +216,52 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # product arm
 # ----------------------------------------------------------------------------------------------------------------
+def _gpu_eager_incumbent(host, dev, n_tiles=80, reps=3):
+    """The GPU incumbent: torch eager bf16 on the same B200, op for op what the reference runs for the tower and the
+    projector (siglip_encoder.py:148-305: conv2d patch embedding, LayerNorm, q/k/v Linear, matmul * scale,
+    softmax(fp32), matmul, out_proj, tanh-GELU MLP; builder.py:44-48) on the same random-init parameters.  Only the
+    dense part: the reference's preprocessing and merge run on the CPU and are not charged to it.  Library kernels
+    (cuBLAS / ATen) only - none of this repo's code.  Returns (visual tokens/s at 7371 per 10 tiles, seconds per call)."""
+    import torch
+    import torch.nn.functional as F
+    vm = host.get_model().vision_tower.vision_tower.vision_model
+    proj = host.get_model().mm_projector
+    heads = host.get_model().vision_tower.config.num_attention_heads
+    x0 = torch.randn(n_tiles, 3, 384, 384, device=dev, dtype=torch.bfloat16)
+
+    @torch.no_grad()
+    def fwd(px):
+        x = vm.embeddings.patch_embedding(px).flatten(2).transpose(1, 2)
+        x = x + vm.embeddings.position_embedding.weight[None]
+        B, T, D = x.shape
+        hd = D // heads
+        for layer in vm.encoder.layers:
+            h = layer.layer_norm1(x)
+            a = layer.self_attn
+            q = a.q_proj(h).view(B, T, heads, hd).transpose(1, 2)
+            k = a.k_proj(h).view(B, T, heads, hd).transpose(1, 2)
+            v = a.v_proj(h).view(B, T, heads, hd).transpose(1, 2)
+            w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+            o = torch.matmul(w, v).transpose(1, 2).contiguous().reshape(B, T, D)
+            x = x + a.out_proj(o)
+            h = layer.layer_norm2(x)
+            x = x + layer.mlp.fc2(F.gelu(layer.mlp.fc1(h), approximate="tanh"))
+        return proj(x)
+
+    fwd(x0[:8])
+    fwd(x0)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fwd(x0)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) / 1e3 / reps
+    return n_tiles / TILES_PER_IMAGE * TOKENS_PER_IMAGE / sec, sec
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -424,6 +470,14 @@ def run_b200_arm(args):
             s, desc, kind, cores = _cpu_sample(False)
             line["cpu_baseline"] = {"value": TOKENS_PER_IMAGE / s, "unit": "tokens/s", "cores": cores, "kind": kind,
                                     "sample": desc}
+            try:   # context only: the same architecture in torch eager bf16 on this GPU (tower + projector alone)
+                v, sec = _gpu_eager_incumbent(host, dev)
+                line["gpu_eager_incumbent"] = {
+                    "value": v, "unit": "tokens/s",
+                    "what": "torch eager bf16 (cuBLAS / ATen), the reference's op sequence for SigLIP tower + mm_projector "
+                            "only (its CPU preprocessing and merge not charged), 80 tiles per call, %.1f ms" % (sec * 1e3)}
+            except Exception as e:  # e.g. out of memory on a shared box: the headline numbers do not depend on it
+                line["gpu_eager_incumbent"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
