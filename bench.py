@@ -480,6 +480,9 @@ def run_b200_arm(args):
                 line["gpu_eager_incumbent"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))
     if world > 1:
+        if peer[0] is not None:
+            host.radvlm_b200_gather = None
+            peer[0].close()   # unmap the peers' buffers, then free this rank's
         dist.barrier()
         dist.destroy_process_group()
     return 0
