@@ -153,19 +153,22 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2+3 fused: one CTA produces a 16-row x 128-column block of the output plane (canvas tiles, then the base tile):
+// 2+3 fused: one CTA produces a block of the output plane (canvas tiles: 16 rows x 128 columns, base tile: 32 x 64;
+// smaller blocks when a batch holds large down-scales, e.g. 2544x3056 MIMIC images, so the source rectangle fits):
 //   source rectangle -> shared memory with 16-byte loads -> horizontal pass -> uint8 intermediate (planar, shared
 //   memory; the same rounding to uint8 Pillow does between its passes) -> vertical pass -> LUT normalise -> CHW
 //   tile rows with 16-byte stores.  Same coefficient tables and the same integer arithmetic as the two-kernel
-//   path below, which stays as the fall-back for geometries whose source rectangle does not fit shared memory
-//   (down-scales beyond ~5x) or tile sizes that are not a multiple of 16.
+//   path below, which stays as the fall-back for geometries whose source rectangle does not fit shared memory even
+//   with 8 x 16 blocks (down-scales beyond ~20x) or tile sizes that are not a multiple of 32.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFuBX = 128, kFuBY = 16, kFuThreads = 256;
+constexpr int kFuBX = 128, kFuThreads = 256;  // kFuBX: widest block = row pitch of the intermediate planes
 
-struct FusedSmem {   // identical maxima on host (sizing) and device (offsets)
+struct FusedSmem {   // identical on host (sizing) and device (offsets)
   int max_nr;        // source / intermediate rows held per block
   int src_pitch;     // bytes per staged source row (16-byte multiple)
   int max_ksx;       // horizontal taps
+  int cbx, cby;      // output block of the canvas target (columns, rows)
+  int bbx, bby;      // output block of the base-tile target (its down-scale is larger: smaller blocks)
 };
 __host__ __device__ inline size_t fused_src_off() { return 0; }
 __host__ __device__ inline size_t fused_inter_off(const FusedSmem& f) { return al16(static_cast<size_t>(f.max_nr) * f.src_pitch); }
@@ -220,8 +223,11 @@ resample_fused_kernel(const radvlm_preprocess_image* __restrict__ imgs, const ui
 
   const radvlm_preprocess_image im = imgs[blockIdx.z];
   const int canvas_w = im.grid_w * S, canvas_h = im.grid_h * S;
-  const int Y0 = blockIdx.y * kFuBY, X0 = blockIdx.x * kFuBX;
-  const bool is_base = (Y0 >= canvas_h);          // S % kFuBY == 0: a block never straddles canvas and base rows
+  const int nb_canvas = canvas_h / fs.cby;        // S % cby == 0: a block never straddles canvas and base rows
+  const bool is_base = (static_cast<int>(blockIdx.y) >= nb_canvas);
+  const int BX = is_base ? fs.bbx : fs.cbx, BY = is_base ? fs.bby : fs.cby;
+  const int Y0 = is_base ? canvas_h + (static_cast<int>(blockIdx.y) - nb_canvas) * BY : static_cast<int>(blockIdx.y) * BY;
+  const int X0 = blockIdx.x * BX;
   if (Y0 >= canvas_h + S) return;
   const int plane_w = is_base ? S : canvas_w;
   if (X0 >= plane_w) return;
@@ -245,8 +251,8 @@ resample_fused_kernel(const radvlm_preprocess_image* __restrict__ imgs, const ui
   const bool h_skip = (out_w == W), v_skip = (out_h == H);
 
   // the part of this block that lies inside the pasted (resized) image
-  const int oy_lo = max(Y0 - py, 0), oy_hi = min(Y0 - py + kFuBY, out_h);
-  const int ox_lo = max(X0 - px, 0), ox_hi = min(X0 - px + kFuBX, out_w);
+  const int oy_lo = max(Y0 - py, 0), oy_hi = min(Y0 - py + BY, out_h);
+  const int ox_lo = max(X0 - px, 0), ox_hi = min(X0 - px + BX, out_w);
   const bool empty = (oy_lo >= oy_hi) || (ox_lo >= ox_hi);
   int r_lo = 0, nr = 0, c_lo = 0, nc = 0;
   const int nox = empty ? 0 : ox_hi - ox_lo;
@@ -325,12 +331,13 @@ resample_fused_kernel(const radvlm_preprocess_image* __restrict__ imgs, const ui
 
   // ---- phase 2: vertical pass + paste (black outside) + normalise + CHW tile rows, 8 pixels per thread
   const size_t plane = static_cast<size_t>(fs.max_nr) * kFuBX;
-  for (int i = tid; i < kFuBY * 3 * (kFuBX / 8); i += kFuThreads) {
-    const int g8 = i % (kFuBX / 8);
-    const int ch = (i / (kFuBX / 8)) % 3;
-    const int y = i / (3 * (kFuBX / 8));
+  const int groups = BX / 8;
+  for (int i = tid; i < BY * 3 * groups; i += kFuThreads) {
+    const int g8 = i % groups;
+    const int ch = (i / groups) % 3;
+    const int y = i / (3 * groups);
     const int Y = Y0 + y, X = X0 + g8 * 8;
-    if (X >= plane_w) continue;  // plane widths are multiples of 8
+    if (X >= plane_w || Y >= canvas_h + S) continue;  // plane widths are multiples of 8
     const int oy = Y - py;
     int v[8];
 #pragma unroll
@@ -572,28 +579,46 @@ extern "C" int radvlm_preprocess_anyres(const uint8_t* src, const radvlm_preproc
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* scr = static_cast<uint8_t*>(scratch);
-  // shared-memory needs of the fused kernel over the batch (both targets of every image)
-  FusedSmem fs{kFuBY, 64, 1};
-  for (int i = 0; i < n_images; ++i) {
-    const radvlm_preprocess_image& im = images_host[i];
-    for (int target = 0; target < 2; ++target) {
-      const int ow = target ? tile_size : im.resized_w, oh = target ? tile_size : im.resized_h;
-      const int nr = fused_span(im.height, oh, kFuBY), nc = fused_span(im.width, ow, kFuBX);
-      const int pitch = static_cast<int>(al16(static_cast<size_t>(nc) * im.channels + 32));
-      const int ksx = resample_ksize(im.width, ow);
-      if (nr > fs.max_nr) fs.max_nr = nr;
-      if (pitch > fs.src_pitch) fs.src_pitch = pitch;
-      if (ksx > fs.max_ksx) fs.max_ksx = ksx;
+  // Block shapes and shared-memory needs of the fused kernel over the batch (both targets of every image): the first
+  // candidate pair that fits twice per SM, else the first that fits at all, else the two-pass kernels.
+  static const int kCand[5][4] = {{128, 16, 64, 32}, {128, 16, 32, 16}, {64, 16, 32, 16}, {64, 8, 32, 8}, {32, 8, 16, 8}};
+  FusedSmem fs{};
+  size_t fused_smem = 0;
+  bool fused = false;
+  static const bool force_two_pass = [] { const char* e = std::getenv("RADVLM_B200_PREPROCESS"); return e && e[0] == '2'; }();
+  if (!force_two_pass && (tile_size % 32) == 0) {
+    for (int budget_pass = 0; budget_pass < 2 && !fused; ++budget_pass) {
+      const size_t budget = budget_pass == 0 ? 110 * 1024 : 200 * 1024;
+      for (int c = 0; c < 5 && !fused; ++c) {
+        FusedSmem f{1, 64, 1, kCand[c][0], kCand[c][1], kCand[c][2], kCand[c][3]};
+        for (int i = 0; i < n_images; ++i) {
+          const radvlm_preprocess_image& im = images_host[i];
+          for (int target = 0; target < 2; ++target) {
+            const int ow = target ? tile_size : im.resized_w, oh = target ? tile_size : im.resized_h;
+            const int nr = fused_span(im.height, oh, target ? f.bby : f.cby);
+            const int nc = fused_span(im.width, ow, target ? f.bbx : f.cbx);
+            const int pitch = static_cast<int>(al16(static_cast<size_t>(nc) * im.channels + 32));
+            const int ksx = resample_ksize(im.width, ow);
+            if (nr > f.max_nr) f.max_nr = nr;
+            if (pitch > f.src_pitch) f.src_pitch = pitch;
+            if (ksx > f.max_ksx) f.max_ksx = ksx;
+          }
+        }
+        if (fused_total(f) <= budget) {
+          fs = f;
+          fused_smem = fused_total(f);
+          fused = true;
+        }
+      }
     }
   }
-  const size_t fused_smem = fused_total(fs);
-  static const bool force_two_pass = [] { const char* e = std::getenv("RADVLM_B200_PREPROCESS"); return e && e[0] == '2'; }();
-  const bool fused = !force_two_pass && (tile_size % kFuBY) == 0 && (tile_size % 8) == 0 && fused_smem <= 200 * 1024;
   ProfScope ps(PROF_PREPROCESS, s, fused ? 2 : 3);
   resample_coeffs_kernel<<<dim3((max_out + 63) / 64, 4, n_images), 64, 0, s>>>(images_dev, scr, tile_size);
   RV_CUDA(cudaGetLastError());
   if (fused) {
-    dim3 fgrid((max_cw + kFuBX - 1) / kFuBX, (max_rows + kFuBY - 1) / kFuBY, n_images);
+    const int gx_c = (max_cw + fs.cbx - 1) / fs.cbx, gx_b = (tile_size + fs.bbx - 1) / fs.bbx;
+    const int gy = (max_rows - tile_size) / fs.cby + (tile_size + fs.bby - 1) / fs.bby;
+    dim3 fgrid(gx_c > gx_b ? gx_c : gx_b, gy, n_images);
     const int smem = static_cast<int>(fused_smem);
 #define RV_LAUNCH_FUSED(TYPE)                                                                                          \
   do {                                                                                                                 \
