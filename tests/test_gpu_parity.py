@@ -413,6 +413,55 @@ def test_encode_c2_vs_oracle_and_batch_invariance(lib, full_host):
     assert torch.equal(big[:10], feat) and torch.equal(big[80:], feat)
 
 
+def test_c3_batch256_sharded_equals_unsharded(lib, full_host):
+    """BASELINE.json config 3 at full size (256 synthetic 1024x1024 CXRs = 2560 tiles, 1,886,976 visual tokens) through
+    size-independent properties: the image-sharded encode (dist.shard_images_lpt over 8 ranks, run rank by rank on
+    this GPU) yields bit for bit the tokens of the unsharded run, in any batch order, and a checksum of per-image
+    checksums is invariant."""
+    from radvlm_b200 import dist as rdist, mm_arch, mm_utils
+    n_img, world = 256, 8
+    g = torch.Generator(device="cuda").manual_seed(77)
+    distinct = 24   # 24 distinct images, repeated: repeats must give identical tokens (idempotence)
+    base = torch.randint(0, 256, (distinct, 1024, 1024, 1), generator=g, device="cuda", dtype=torch.uint8)
+    order = torch.randperm(n_img, generator=torch.Generator().manual_seed(5)).tolist()
+    src = [i % distinct for i in range(n_img)]
+
+    def encode(indices):
+        """merged tokens [len(indices) * 7371, H] of the given images, through the public path"""
+        outs = []
+        for c0 in range(0, len(indices), 16):
+            chunk = indices[c0:c0 + 16]
+            imgs = [base[src[i]].expand(-1, -1, 3) for i in chunk]
+            tiles, sizes, splits, _ = mm_utils.preprocess_anyres_batch(imgs, gi.PINPOINTS, device="cuda", dtype=torch.bfloat16)
+            feats = full_host.encode_images(tiles)
+            outs.append(mm_arch.merge_images(full_host, feats, splits, sizes))
+        return torch.cat(outs)
+
+    N = 7371
+    ref = encode(list(range(distinct)))                       # one pass over the distinct images
+    assert ref.shape[0] == distinct * N
+    per_image = ref.view(distinct, N, -1)
+    # sharded run: every rank encodes its LPT shard (in its own order); gather back to global image order
+    owned = rdist.shard_images_lpt([10] * n_img, world)
+    assert sorted(i for o in owned for i in o) == list(range(n_img))
+    assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+    total_tokens, checksum = 0, torch.zeros((), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        mine = [i for i in order if i in set(owned[r])]        # arbitrary batch order inside the rank
+        tok = encode(mine).view(len(mine), N, -1)
+        for j, i in enumerate(mine):
+            if i % 37 == 0 or j == 0:                          # full comparison on a subset, checksums on all
+                assert torch.equal(tok[j], per_image[src[i]]), (r, i)
+        total_tokens += tok.shape[0] * N
+        checksum += tok.double().sum()
+        want = torch.stack([per_image[src[i]].double().sum() for i in mine]).sum()
+        assert torch.equal(tok.double().sum(dim=(1, 2)), torch.stack([per_image[src[i]].double().sum() for i in mine]))
+        del tok, want
+    assert total_tokens == 1886976
+    expect = sum(per_image[src[i]].double().sum() for i in range(n_img))
+    assert abs(float(checksum - expect)) <= 1e-6 * max(1.0, abs(float(expect)))
+
+
 def test_full_prepare_inputs_vs_oracle(lib, full_host):
     """BASELINE.json config 4 (reduced batch): full prepare_inputs_labels_for_multimodal vs the oracle."""
     from oracle import encoder_oracle as eo
