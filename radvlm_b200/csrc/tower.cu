@@ -64,6 +64,11 @@ struct TowerSaved {
     return reinterpret_cast<float*>(base + static_cast<size_t>(L + 1) * h_bytes + static_cast<size_t>(L) * ao_bytes +
                                     static_cast<size_t>(l) * lse_bytes);
   }
+  // mid-layer residual stream (after the attention branch): kept too - 87 MB per tile buys the out_proj recompute
+  float* hmid(int l, int L) const {
+    return reinterpret_cast<float*>(base + static_cast<size_t>(L + 1) * h_bytes +
+                                    static_cast<size_t>(L) * (ao_bytes + lse_bytes) + static_cast<size_t>(l) * h_bytes);
+  }
 };
 
 static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, void* base) {
@@ -71,7 +76,7 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
   s.h_bytes = align_up(L.M * tw->hidden * 4, 1024);
   s.ao_bytes = align_up(L.M * tw->hidden * 2, 1024);
   s.lse_bytes = align_up(static_cast<size_t>(n_tiles) * tw->heads * L.seq_pad * 4, 1024);
-  s.total = (tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes);
+  s.total = (2 * tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes);
   s.base = static_cast<uint8_t*>(base);
   return s;
 }
@@ -121,6 +126,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     const float* h_in = save ? save->h(l) : hidden;     // residual stream entering the layer
     float* h_out = save ? save->h(l + 1) : hidden;      // ... leaving it
     void* ao = save ? save->ao(l, NL) : xn;             // attention output (bf16)
+    float* h_mid = save ? save->hmid(l, NL) : hidden;   // residual stream after the attention branch
     // x = x + out_proj(attn(LN1(x)))
     { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
@@ -141,12 +147,12 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       GemmArgs a{};
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
-      a.out = hidden; a.ldo = D; a.aux = h_in;
+      a.out = h_mid; a.ldo = D; a.aux = h_in;
       { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(hidden, w.ln2_gamma, w.ln2_beta, xn, M, D, tw->ln_eps, stream); }
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
@@ -160,7 +166,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       GemmArgs a{};
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
-      a.out = h_out; a.ldo = D; a.aux = hidden;
+      a.out = h_out; a.ldo = D; a.aux = h_mid;
       { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
@@ -275,7 +281,6 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   void* xn2 = ws + B.off_xn2;
   void* g = ws + B.off_g;
   void* dx = ws + B.off_dx;
-  float* h1 = reinterpret_cast<float*>(ws + B.off_h1);
   void* u = ws + B.off_u;
   void* da = ws + B.off_da;
   void* act = ws + B.off_a;
@@ -299,10 +304,11 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     const radvlm_vit_layer_grads* lg = (gr != nullptr && gr->layers != nullptr) ? &gr->layers[l] : nullptr;
     auto G = [&](float* radvlm_vit_layer_grads::*m) -> float* { return lg ? lg->*m : nullptr; };
     const float* h0 = sv.h(l);
+    const float* h1 = sv.hmid(l, NL);   // saved by the forward: no out_proj recompute
     const void* ao = sv.ao(l, NL);
     // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
     {
-    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 5);
+    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 4);
     if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
     {
       GemmArgs a{};
@@ -313,13 +319,6 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
       a.vt = static_cast<__nv_bfloat16*>(vt);
       a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
       if ((st = gemm_dispatch(xn1, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream))) return st;
-    }
-    {
-      GemmArgs a{};
-      a.M = M; a.N = D; a.K = D;
-      a.bias = w.out_b;
-      a.out = h1; a.ldo = D; a.aux = h0;
-      if ((st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream))) return st;
     }
     if ((st = layernorm_launch(h1, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream))) return st;
     {
