@@ -194,6 +194,37 @@ v_ones_column_kernel(__nv_bfloat16* __restrict__ v, int hd, int hd_pad, int seq,
   for (int t = threadIdx.x; t < seq; t += blockDim.x) base[static_cast<size_t>(t) * hd_pad] = __float2bfloat16(1.0f);
 }
 
+// Padding of per-layer q / k / v slots (training keeps them for the backward): only the pad rows (t >= seq) and pad
+// columns (d >= hd) are written - the QKV epilogue fills the rest - and column `hd` of every valid V row gets `v_one`
+// (1 for the forward's row sums, 0 for the backward, whose dP = dO V^T must not see it).  q / k may be null.
+__global__ void __launch_bounds__(256)
+qkv_pad_prepare_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v, int hd,
+                       int hd_pad, int seq, int seq_pad, float v_one) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const __nv_bfloat16 one = __float2bfloat16(v_one);
+  const uint4 first = make_uint4(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&one)), 0, 0, 0);
+  const int row_vecs = hd_pad / 8, pad0 = hd / 8;
+  for (int t = threadIdx.x; t < seq_pad; t += blockDim.x) {
+    const size_t off = (static_cast<size_t>(blockIdx.x) * seq_pad + t) * hd_pad;
+    const int v0 = t < seq ? pad0 : 0;
+    for (int i = v0; i < row_vecs; ++i) {
+      if (q != nullptr) reinterpret_cast<uint4*>(q + off)[i] = zero;
+      if (k != nullptr) reinterpret_cast<uint4*>(k + off)[i] = zero;
+      reinterpret_cast<uint4*>(v + off)[i] = (t < seq && i == pad0) ? first : zero;
+    }
+  }
+}
+
+int qkv_pad_prepare_launch(void* q, void* k, void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
+                           float v_one, cudaStream_t stream) {
+  RV_CHECK_ARG(vt && tiles > 0 && heads > 0 && hd < hd_pad && (hd % 8) == 0 && (hd_pad % 8) == 0 && seq <= seq_pad,
+               "qkv_pad_prepare: bad arguments");
+  qkv_pad_prepare_kernel<<<tiles * heads, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k),
+                                                            static_cast<__nv_bfloat16*>(vt), hd, hd_pad, seq, seq_pad, v_one);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
 int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 cudaStream_t stream) {
   RV_CHECK_ARG(vt && tiles > 0 && heads > 0 && hd < hd_pad && seq <= seq_pad, "prepare_vt: bad arguments");

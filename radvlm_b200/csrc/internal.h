@@ -17,6 +17,8 @@ size_t attention_bwd_workspace_bytes(int tiles, int heads, int seq_pad);
 int attention_bwd_launch(const void* q, const void* k, const void* vt, const void* dout, const void* out,
                          const float* lse, void* dqkv, void* workspace, size_t workspace_bytes, int tiles, int heads,
                          int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
+int qkv_pad_prepare_launch(void* q, void* k, void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
+                           float v_one, cudaStream_t stream);
 int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq_pad, int hd, int hd_pad,
                                 cudaStream_t stream);
 int colsum_bf16_launch(const void* x, int rows, int cols, int ld, float* out, cudaStream_t stream);

@@ -56,7 +56,7 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
 // Everything else is recomputed layer by layer in tower_backward_impl (the reference checkpoints whole encoder
 // layers too: siglip_encoder.py:381-387).
 struct TowerSaved {
-  size_t h_bytes, ao_bytes, lse_bytes, total;
+  size_t h_bytes, ao_bytes, lse_bytes, qkv_bytes, total;
   uint8_t* base;
   float* h(int l) const { return reinterpret_cast<float*>(base + static_cast<size_t>(l) * h_bytes); }
   void* ao(int l, int L) const { return base + static_cast<size_t>(L + 1) * h_bytes + static_cast<size_t>(l) * ao_bytes; }
@@ -69,6 +69,11 @@ struct TowerSaved {
     return reinterpret_cast<float*>(base + static_cast<size_t>(L + 1) * h_bytes +
                                     static_cast<size_t>(L) * (ao_bytes + lse_bytes) + static_cast<size_t>(l) * h_bytes);
   }
+  // q / k / v of every layer (padded head-major): kept too, the backward does not recompute the QKV GEMM
+  void* qkv(int l, int which, int L) const {
+    return base + static_cast<size_t>(2 * L + 1) * h_bytes + static_cast<size_t>(L) * (ao_bytes + lse_bytes) +
+           (static_cast<size_t>(l) * 3 + which) * qkv_bytes;
+  }
 };
 
 static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, void* base) {
@@ -76,7 +81,8 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
   s.h_bytes = align_up(L.M * tw->hidden * 4, 1024);
   s.ao_bytes = align_up(L.M * tw->hidden * 2, 1024);
   s.lse_bytes = align_up(static_cast<size_t>(n_tiles) * tw->heads * L.seq_pad * 4, 1024);
-  s.total = (2 * tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes);
+  s.qkv_bytes = align_up(L.qkv_bytes, 1024);
+  s.total = (2 * tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes);
   s.base = static_cast<uint8_t*>(base);
   return s;
 }
@@ -96,8 +102,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   void* h1 = ws + L.off_h1;
   int st;
 
-  // padding of q/k/vt must be zero (never written by the QKV epilogue)
-  {
+  // padding of q/k/vt must be zero (never written by the QKV epilogue); training uses per-layer slots instead
+  if (save == nullptr) {
     ProfScope ps(PROF_MISC, stream, 0);
     RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
     RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
@@ -127,6 +133,11 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     float* h_out = save ? save->h(l + 1) : hidden;      // ... leaving it
     void* ao = save ? save->ao(l, NL) : xn;             // attention output (bf16)
     float* h_mid = save ? save->hmid(l, NL) : hidden;   // residual stream after the attention branch
+    if (save != nullptr) {                              // this layer's own q / k / v slots: pads + ones column only
+      q = save->qkv(l, 0, NL); k = save->qkv(l, 1, NL); vt = save->qkv(l, 2, NL);
+      ProfScope ps(PROF_MISC, stream);
+      if ((st = qkv_pad_prepare_launch(q, k, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 1.0f, stream))) return st;
+    }
     // x = x + out_proj(attn(LN1(x)))
     { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
     if (st) return st;
@@ -285,17 +296,10 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   void* da = ws + B.off_da;
   void* act = ws + B.off_a;
   void* dqkv = ws + B.off_dqkv;
-  void* q = ws + B.off_q;
-  void* k = ws + B.off_k;
-  void* vt = ws + B.off_vt;
   void* attn_ws = ws + B.off_attn;
   void* stats = ws + B.off_stats;
   float* ln_scratch = reinterpret_cast<float*>(ws + B.off_stats + align_up(static_cast<size_t>(M) * 8, 16));
   int st;
-  // q / k / vt padding must be zero; the backward attention wants plain zeros in the V^T padding rows (no ones row)
-  RV_CUDA(cudaMemsetAsync(q, 0, L.qkv_bytes, stream));
-  RV_CUDA(cudaMemsetAsync(k, 0, L.qkv_bytes, stream));
-  RV_CUDA(cudaMemsetAsync(vt, 0, L.qkv_bytes, stream));
   const float scale = 1.0f / sqrtf(static_cast<float>(L.hd));
   const size_t MD = static_cast<size_t>(M) * D;
 
@@ -305,21 +309,16 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     auto G = [&](float* radvlm_vit_layer_grads::*m) -> float* { return lg ? lg->*m : nullptr; };
     const float* h0 = sv.h(l);
     const float* h1 = sv.hmid(l, NL);   // saved by the forward: no out_proj recompute
+    void* q = sv.qkv(l, 0, NL);         // ... and no QKV recompute
+    void* k = sv.qkv(l, 1, NL);
+    void* vt = sv.qkv(l, 2, NL);
     const void* ao = sv.ao(l, NL);
     // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
     {
     ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 4);
     if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
-    {
-      GemmArgs a{};
-      a.M = M; a.N = 3 * D; a.K = D;
-      a.bias = w.qkv_b;
-      a.q = static_cast<__nv_bfloat16*>(q);
-      a.k = static_cast<__nv_bfloat16*>(k);
-      a.vt = static_cast<__nv_bfloat16*>(vt);
-      a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
-      if ((st = gemm_dispatch(xn1, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream))) return st;
-    }
+    // the backward attention wants plain zeros in the V padding (no ones column): clear it in the saved V
+    if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st;
     if ((st = layernorm_launch(h1, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream))) return st;
     {
       GemmArgs a{};
