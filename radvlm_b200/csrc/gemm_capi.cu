@@ -100,6 +100,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   RV_CHECK_ARG(lda >= (args.a_mn ? args.M : args.K) && ldw >= (args.b_mn ? args.N : args.K),
                "gemm: row pitch smaller than the stored row length");
   RV_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: operand pitches must be multiples of 8 elements");
+  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16 || args.out2 != nullptr, "gemm: the dual-output epilogue needs out2");
   const bool general = args.a_mn || args.b_mn || args.k_splits > 1;
   RV_CHECK_ARG(args.k_splits <= 1 || epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the atomic fp32 epilogue");
   // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs; the MN-major / split-K paths
@@ -139,6 +140,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_QKV_SPLIT: return launch_gemm2_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
       case EPI_BIAS_F32: return launch_gemm2_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
       case EPI_ATOMIC_F32: return launch_gemm2_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
+      case EPI_GELU_TANH_DUAL_BF16: return launch_gemm2_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -152,6 +154,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     case EPI_QKV_SPLIT: return launch_gemm_bn<EPI_QKV_SPLIT>(bn, ta, tb, args, stream);
     case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
     case EPI_ATOMIC_F32: return launch_gemm_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
+    case EPI_GELU_TANH_DUAL_BF16: return launch_gemm_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
   return RADVLM_ERR_BAD_ARGUMENT;
@@ -173,6 +176,7 @@ extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64
                                 const float* aux, int aux_period, int block_n, void* stream) {
   using namespace rv;
   RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
+  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16, "the dual-output GELU epilogue is internal to the training forward");
   RV_CHECK_ARG(out != nullptr && ldo >= N, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
   RV_CHECK_ARG((ldo % 8) == 0, "gemm: ldo must be a multiple of 8 elements");
   RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");
@@ -193,6 +197,7 @@ extern "C" int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, con
                                    const float* aux, int aux_period, int k_splits, void* stream) {
   using namespace rv;
   RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
+  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16, "the dual-output GELU epilogue is internal to the training forward");
   RV_CHECK_ARG(out != nullptr && ldo >= N && (ldo % 8) == 0, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
   RV_CHECK_ARG((a_layout | b_layout) >= 0 && a_layout <= 1 && b_layout <= 1, "gemm: layouts are 0 or 1");
   RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");

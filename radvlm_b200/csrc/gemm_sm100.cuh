@@ -65,7 +65,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
     }
   }
 
-  if constexpr (EPI == EPI_GELU_TANH_BF16) {
+  if constexpr (EPI == EPI_GELU_TANH_DUAL_BF16) {
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(row) * a.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) o2[j] = __float2bfloat16_rn(v[j]);
+  }
+  if constexpr (EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_TANH_DUAL_BF16) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
   }
@@ -74,7 +80,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
   }
 
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
+                EPI == EPI_GELU_TANH_DUAL_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
     if (full) {
       uint4* o4 = reinterpret_cast<uint4*>(o);
@@ -230,43 +237,50 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
                                                           const uint32_t* acc1, uint32_t stage, int lane) {
-  uint32_t pk[32];
+  // EPI_GELU_TANH_DUAL_BF16 runs two passes over the same accumulators: pre-activation -> out2, GELU -> out
+  constexpr int kPasses = (EPI == EPI_GELU_TANH_DUAL_BF16) ? 2 : 1;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint32_t* acc = h ? acc1 : acc0;
+  for (int pass = 0; pass < kPasses; ++pass) {
+    const bool act = (kPasses == 1) || (pass == 1);
+    uint32_t pk[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col0 + 32 * h + 4 * j;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
-      float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
-      if constexpr (EPI == EPI_GELU_TANH_BF16) {
-        v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
-      }
-      if constexpr (EPI == EPI_GELU_ERF_BF16) {
-        v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
-      }
-      pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
-      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
-    }
-  }
-  stage_store_row(stage, lane, pk);
-  __syncwarp();
-  const int v = lane & 7;
-  const int gcol = col0 + 8 * v;
-  if (gcol < a.N) {
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t* acc = h ? acc1 : acc0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + (lane >> 3);
-      const int grow = row0 + rr;
-      if (grow < a.M) {
-        const uint4 t = stage_load_vec(stage, rr, v);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol) = t;
+      for (int j = 0; j < 8; ++j) {
+        const int c = col0 + 32 * h + 4 * j;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+        float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
+        float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
+        if constexpr (EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_TANH_DUAL_BF16) {
+          if (act) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3); }
+        }
+        if constexpr (EPI == EPI_GELU_ERF_BF16) {
+          v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
+        }
+        pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
+        pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
       }
     }
+    stage_store_row(stage, lane, pk);
+    __syncwarp();
+    const int v = lane & 7;
+    const int gcol = col0 + 8 * v;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((kPasses == 2 && pass == 0) ? a.out2 : a.out);
+    if (gcol < a.N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int grow = row0 + rr;
+        if (grow < a.M) {
+          const uint4 t = stage_load_vec(stage, rr, v);
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(grow) * a.ldo + gcol) = t;
+        }
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // QKV head-split scatter, coalesced: 64 columns (two 32-column chunks) of 32 rows go through the swizzled staging
@@ -320,7 +334,8 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
                                                     uint32_t stage, int lane) {
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
   constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
-  constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16);
+  constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
+                          EPI == EPI_GELU_TANH_DUAL_BF16);
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;
 #pragma unroll 1

@@ -56,7 +56,7 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
 // Everything else is recomputed layer by layer in tower_backward_impl (the reference checkpoints whole encoder
 // layers too: siglip_encoder.py:381-387).
 struct TowerSaved {
-  size_t h_bytes, ao_bytes, lse_bytes, qkv_bytes, total;
+  size_t h_bytes, ao_bytes, lse_bytes, qkv_bytes, u_bytes, total;
   uint8_t* base;
   float* h(int l) const { return reinterpret_cast<float*>(base + static_cast<size_t>(l) * h_bytes); }
   void* ao(int l, int L) const { return base + static_cast<size_t>(L + 1) * h_bytes + static_cast<size_t>(l) * ao_bytes; }
@@ -74,6 +74,11 @@ struct TowerSaved {
     return base + static_cast<size_t>(2 * L + 1) * h_bytes + static_cast<size_t>(L) * (ao_bytes + lse_bytes) +
            (static_cast<size_t>(l) * 3 + which) * qkv_bytes;
   }
+  // fc1 pre-activation (bf16 [M, I]) of every layer: written by the dual-output GELU epilogue of the forward
+  void* u(int l, int L) const {
+    return base + static_cast<size_t>(2 * L + 1) * h_bytes +
+           static_cast<size_t>(L) * (ao_bytes + lse_bytes + 3 * qkv_bytes) + static_cast<size_t>(l) * u_bytes;
+  }
 };
 
 static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, void* base) {
@@ -82,7 +87,9 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
   s.ao_bytes = align_up(L.M * tw->hidden * 2, 1024);
   s.lse_bytes = align_up(static_cast<size_t>(n_tiles) * tw->heads * L.seq_pad * 4, 1024);
   s.qkv_bytes = align_up(L.qkv_bytes, 1024);
-  s.total = (2 * tw->num_layers + 1) * s.h_bytes + tw->num_layers * (s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes);
+  s.u_bytes = align_up(L.M * tw->intermediate * 2, 1024);
+  s.total = (2 * tw->num_layers + 1) * s.h_bytes +
+            tw->num_layers * (s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes + s.u_bytes);
   s.base = static_cast<uint8_t*>(base);
   return s;
 }
@@ -170,7 +177,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = I; a.K = D;
       a.bias = w.fc1_b;
       a.out = h1; a.ldo = I;
-      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, EPI_GELU_TANH_BF16, 0, stream); }
+      a.out2 = save ? save->u(l, NL) : nullptr;   // training: keep the pre-activation for the GELU backward
+      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
     {
@@ -292,7 +300,6 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   void* xn2 = ws + B.off_xn2;
   void* g = ws + B.off_g;
   void* dx = ws + B.off_dx;
-  void* u = ws + B.off_u;
   void* da = ws + B.off_da;
   void* act = ws + B.off_a;
   void* dqkv = ws + B.off_dqkv;
@@ -312,21 +319,15 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     void* q = sv.qkv(l, 0, NL);         // ... and no QKV recompute
     void* k = sv.qkv(l, 1, NL);
     void* vt = sv.qkv(l, 2, NL);
+    const void* u = sv.u(l, NL);        // ... and no fc1 recompute
     const void* ao = sv.ao(l, NL);
     // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
     {
-    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 4);
+    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 3);
     if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
     // the backward attention wants plain zeros in the V padding (no ones column): clear it in the saved V
     if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st;
     if ((st = layernorm_launch(h1, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream))) return st;
-    {
-      GemmArgs a{};
-      a.M = M; a.N = I; a.K = D;
-      a.bias = w.fc1_b;
-      a.out = u; a.ldo = I;
-      if ((st = gemm_dispatch(xn2, D, w.fc1_w, D, a, EPI_BIAS_BF16, 0, stream))) return st;
-    }
     }
     // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
     { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
