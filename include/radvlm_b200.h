@@ -208,8 +208,8 @@ int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvlm_projector
 /* ------------------------------------------------------------------------------------------------
  * Training mode (BASELINE config 5; mm_tunable_parts = mm_vision_tower, mm_mlp_adapter: train.py:1642-1665).
  * The forward keeps, per layer, the fp32 residual stream entering it and after its attention branch, q / k / v, the
- * attention output, the attention log-sum-exp and the fc1 pre-activation (`saved`, radvlm_tower_saved_bytes: 537 MB
- * per tile at the SigLIP-so400m widths); the backward recomputes only the two LayerNorm outputs layer by layer (the reference checkpoints whole encoder layers:
+ * attention output, the attention log-sum-exp, the fc1 pre-activation and both LayerNorm outputs (`saved`,
+ * radvlm_tower_saved_bytes: 624 MB per tile at the SigLIP-so400m widths); the backward recomputes nothing (the reference checkpoints whole encoder layers:
  * siglip_encoder.py:381-387).  Gradient pointers are fp32, same shapes as the
  * packed weights, ACCUMULATED (+=); a null pointer freezes that parameter.
  * ---------------------------------------------------------------------------------------------- */

@@ -79,6 +79,12 @@ struct TowerSaved {
     return base + static_cast<size_t>(2 * L + 1) * h_bytes +
            static_cast<size_t>(L) * (ao_bytes + lse_bytes + 3 * qkv_bytes) + static_cast<size_t>(l) * u_bytes;
   }
+  // LayerNorm outputs (bf16 [M, D]; which = 0: LN1, 1: LN2): the A operands of the qkv / fc1 weight gradients
+  void* xn(int l, int which, int L) const {
+    return base + static_cast<size_t>(2 * L + 1) * h_bytes +
+           static_cast<size_t>(L) * (ao_bytes + lse_bytes + 3 * qkv_bytes + u_bytes) +
+           (static_cast<size_t>(l) * 2 + which) * ao_bytes;
+  }
 };
 
 static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, void* base) {
@@ -89,7 +95,7 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
   s.qkv_bytes = align_up(L.qkv_bytes, 1024);
   s.u_bytes = align_up(L.M * tw->intermediate * 2, 1024);
   s.total = (2 * tw->num_layers + 1) * s.h_bytes +
-            tw->num_layers * (s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes + s.u_bytes);
+            tw->num_layers * (3 * s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes + s.u_bytes);
   s.base = static_cast<uint8_t*>(base);
   return s;
 }
@@ -146,7 +152,9 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       if ((st = qkv_pad_prepare_launch(q, k, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 1.0f, stream))) return st;
     }
     // x = x + out_proj(attn(LN1(x)))
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn, M, D, tw->ln_eps, stream); }
+    void* xn1 = save ? save->xn(l, 0, NL) : xn;
+    void* xn2 = save ? save->xn(l, 1, NL) : xn;
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
@@ -156,7 +164,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.k = static_cast<__nv_bfloat16*>(k);
       a.vt = static_cast<__nv_bfloat16*>(vt);
       a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
-      { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
+      { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn1, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
     { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, ao, save ? save->lse(l, NL) : nullptr, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
@@ -170,7 +178,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn, M, D, tw->ln_eps, stream); }
+    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
@@ -178,7 +186,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.bias = w.fc1_b;
       a.out = h1; a.ldo = I;
       a.out2 = save ? save->u(l, NL) : nullptr;   // training: keep the pre-activation for the GELU backward
-      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn, D, w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
+      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
     {
@@ -296,8 +304,7 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
                                const BackwardLayout& B, uint8_t* ws, cudaStream_t stream, int layer_lo, int layer_hi) {
   const int D = tw->hidden, I = tw->intermediate, NL = tw->num_layers;
   const int M = static_cast<int>(L.M);
-  void* xn1 = ws + B.off_xn1;
-  void* xn2 = ws + B.off_xn2;
+  void* xn_scratch = ws + B.off_xn1;   // im2col rows of the patch-embedding weight gradient
   void* g = ws + B.off_g;
   void* dx = ws + B.off_dx;
   void* da = ws + B.off_da;
@@ -320,15 +327,12 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     void* k = sv.qkv(l, 1, NL);
     void* vt = sv.qkv(l, 2, NL);
     const void* u = sv.u(l, NL);        // ... and no fc1 recompute
+    const void* xn1 = sv.xn(l, 0, NL);  // LayerNorm outputs: kept as well, nothing of the forward is recomputed
+    const void* xn2 = sv.xn(l, 1, NL);
     const void* ao = sv.ao(l, NL);
-    // ---- recompute the forward of the layer (siglip_encoder.py:285-305)
-    {
-    ProfScope ps_re(PROF_BWD_RECOMPUTE, stream, 3);
-    if ((st = layernorm_launch(h0, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream))) return st;
     // the backward attention wants plain zeros in the V padding (no ones column): clear it in the saved V
-    if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st;
-    if ((st = layernorm_launch(h1, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream))) return st;
-    }
+    { ProfScope ps_re(PROF_BWD_RECOMPUTE, stream);
+      if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st; }
     // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
     { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
     if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream))) return st;           // dL/da
@@ -371,9 +375,9 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     if (gr->pos_embed && (st = pos_embed_grad_launch(dh, gr->pos_embed, n_tiles, L.T, D, stream))) return st;
     if (gr->patch_w || gr->patch_b) {
       if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
-      if (gr->patch_w && (st = im2col_launch(pixels, pixel_dtype, xn1, n_tiles, tw->channels, tw->image_size,
+      if (gr->patch_w && (st = im2col_launch(pixels, pixel_dtype, xn_scratch, n_tiles, tw->channels, tw->image_size,
                                              tw->patch_size, tw->patch_k_pad, stream))) return st;
-      if ((st = linear_wgrad(g, D, xn1, tw->patch_k_pad, M, D, tw->patch_k_pad, gr->patch_w, tw->patch_k_pad, gr->patch_b, stream))) return st;
+      if ((st = linear_wgrad(g, D, xn_scratch, tw->patch_k_pad, M, D, tw->patch_k_pad, gr->patch_w, tw->patch_k_pad, gr->patch_b, stream))) return st;
     }
   }
   return RADVLM_OK;
