@@ -126,7 +126,8 @@ int gelu_fwd_bwd_launch(const void* u, void* da_du, void* a, size_t n, int erf_f
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dy,
-                        float* __restrict__ dres, float2* __restrict__ stats, int rows, int D, float eps) {
+                        float* __restrict__ dres, __nv_bfloat16* __restrict__ dres_bf16, float2* __restrict__ stats, int rows,
+                        int D, float eps) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -195,6 +196,9 @@ layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ g
       o.z += rstd * (__uint_as_float(d.y << 16) * gm.z - m1 - v[i].z * m2);
       o.w += rstd * (__uint_as_float(d.y & 0xFFFF0000u) * gm.w - m1 - v[i].w * m2);
       dr[idx] = o;
+      if (dres_bf16 != nullptr)  // bf16 copy of the updated residual gradient: the next dgrad / wgrad GEMMs read it
+        reinterpret_cast<uint2*>(dres_bf16 + static_cast<size_t>(row) * D)[idx] =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
 }
@@ -247,7 +251,7 @@ layernorm_bwd_params_kernel(const float* __restrict__ x, const __nv_bfloat16* __
 
 // stats: scratch of rows * 8 bytes
 int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, float* dres, float* dgamma, float* dbeta,
-                         void* stats, int rows, int D, float eps, cudaStream_t stream) {
+                         void* stats, int rows, int D, float eps, cudaStream_t stream, void* dres_bf16) {
   RV_CHECK_ARG(x && gamma && dy && dres && stats && rows > 0, "layernorm_bwd: bad arguments");
   if ((D % 4) != 0 || D > 12 * 128) {
     set_error("layernorm_bwd: D=%d unsupported (need D %% 4 == 0 and D <= 1536)", D);
@@ -259,11 +263,11 @@ int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, flo
   const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dy);
   float2* st = static_cast<float2*>(stats);
   if (nv <= 3)
-    layernorm_bwd_dx_kernel<3><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, st, rows, D, eps);
+    layernorm_bwd_dx_kernel<3><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, static_cast<__nv_bfloat16*>(dres_bf16), st, rows, D, eps);
   else if (nv <= 9)
-    layernorm_bwd_dx_kernel<9><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, st, rows, D, eps);
+    layernorm_bwd_dx_kernel<9><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, static_cast<__nv_bfloat16*>(dres_bf16), st, rows, D, eps);
   else
-    layernorm_bwd_dx_kernel<12><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, st, rows, D, eps);
+    layernorm_bwd_dx_kernel<12><<<blocks, threads, 0, stream>>>(x, gamma, d, dres, static_cast<__nv_bfloat16*>(dres_bf16), st, rows, D, eps);
   RV_CUDA(cudaGetLastError());
   if (dgamma != nullptr && dbeta != nullptr) {
     dim3 grid((D / 2 + 127) / 128, (rows + kLnParamRows - 1) / kLnParamRows);
@@ -316,5 +320,5 @@ extern "C" int radvlm_layernorm_bwd(const float* x, const float* gamma, const vo
   int st = rv::require_sm100();
   if (st != RADVLM_OK) return st;
   return rv::layernorm_bwd_launch(x, gamma, dy, dres, dgamma, dbeta, row_stats_scratch, rows, D, eps,
-                                  static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream), nullptr);
 }

@@ -24,7 +24,7 @@ int attention_prepare_vt_launch(void* vt, int tiles, int heads, int seq, int seq
 int colsum_bf16_launch(const void* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
 int gelu_fwd_bwd_launch(const void* u, void* da_du, void* a, size_t n, int erf_form, cudaStream_t stream);
 int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, float* dres, float* dgamma, float* dbeta,
-                         void* stats, int rows, int D, float eps, cudaStream_t stream);
+                         void* stats, int rows, int D, float eps, cudaStream_t stream, void* dres_bf16 = nullptr);
 int pos_embed_grad_launch(const float* dh, float* dpos, int tiles, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
                      float eps, cudaStream_t stream);

@@ -317,6 +317,7 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   const float scale = 1.0f / sqrtf(static_cast<float>(L.hd));
   const size_t MD = static_cast<size_t>(M) * D;
 
+  bool g_is_dh = false;  // g == bf16(dh)?  (false on entry: dh comes from the caller)
   for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const radvlm_vit_layer_weights& w = tw->layers[l];
     const radvlm_vit_layer_grads* lg = (gr != nullptr && gr->layers != nullptr) ? &gr->layers[l] : nullptr;
@@ -334,7 +335,7 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
     { ProfScope ps_re(PROF_BWD_RECOMPUTE, stream);
       if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st; }
     // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
-    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
+    if (!g_is_dh) { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
     if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream))) return st;           // dL/da
     { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(M) * I, 0, stream))) return st; }  // a, dL/du
     if ((st = linear_wgrad(g, D, act, I, M, D, I, G(&radvlm_vit_layer_grads::fc2_w), I, G(&radvlm_vit_layer_grads::fc2_b), stream))) return st;
@@ -348,10 +349,9 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
         if (!dg) dg = ln_scratch; else db = ln_scratch + D;
       }
       ProfScope ps(PROF_BWD_ELEMENTWISE, stream, 2);
-      if ((st = layernorm_bwd_launch(h1, w.ln2_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream))) return st;
+      if ((st = layernorm_bwd_launch(h1, w.ln2_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream, g))) return st;  // also g = bf16(dh)
     }
-    // ---- attention branch: h1 = h0 + out_proj(attn(LN1(h0)))
-    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
+    // ---- attention branch: h1 = h0 + out_proj(attn(LN1(h0)))   (g already holds bf16(dh): written by the LayerNorm backward)
     if ((st = linear_wgrad(g, D, ao, D, M, D, D, G(&radvlm_vit_layer_grads::out_w), D, G(&radvlm_vit_layer_grads::out_b), stream))) return st;
     if ((st = linear_dgrad(g, D, w.out_w, D, M, D, D, dx, D, false, stream))) return st;            // dL/d(attn out)
     { ProfScope ps(PROF_BWD_ATTENTION, stream, 4);
@@ -367,14 +367,15 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
         if (!dg) dg = ln_scratch; else db = ln_scratch + D;
       }
       ProfScope ps(PROF_BWD_ELEMENTWISE, stream, 2);
-      if ((st = layernorm_bwd_launch(h0, w.ln1_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream))) return st;
+      if ((st = layernorm_bwd_launch(h0, w.ln1_gamma, dx, dh, dg, db, stats, M, D, tw->ln_eps, stream, g))) return st;
+      g_is_dh = true;   // the next (lower) layer and the embeddings start from this bf16 copy
     }
   }
   // ---- embeddings: hidden0 = im2col(pixels) Wp^T + bp + pos  (siglip_encoder.py:169-174)
   if (layer_lo == 0 && gr != nullptr && (gr->patch_w || gr->patch_b || gr->pos_embed)) {
     if (gr->pos_embed && (st = pos_embed_grad_launch(dh, gr->pos_embed, n_tiles, L.T, D, stream))) return st;
     if (gr->patch_w || gr->patch_b) {
-      if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
+      if (!g_is_dh && (st = cast_f32_bf16_launch(dh, g, MD, stream))) return st;
       if (gr->patch_w && (st = im2col_launch(pixels, pixel_dtype, xn_scratch, n_tiles, tw->channels, tw->image_size,
                                              tw->patch_size, tw->patch_k_pad, stream))) return st;
       if ((st = linear_wgrad(g, D, xn_scratch, tw->patch_k_pad, M, D, tw->patch_k_pad, gr->patch_w, tw->patch_k_pad, gr->patch_b, stream))) return st;
