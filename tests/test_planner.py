@@ -155,3 +155,35 @@ def test_splice_index_error_semantics():
     ids3 = np.array([[5, 6, 7], [1, -200, 2]], dtype=np.int64)
     plan = planner.plan_splice(ids3, None, [9, 4], None, False)
     assert plan.lengths.tolist() == [3, 2 + 4]
+
+
+def test_video_merge_table_token_counts_match_oracle():
+    """Host logic of the video / get_2dPool branch (mm_arch._video_entry) on the CPU: descriptor fields and token
+    counts for every pooling mode x newline placement x merge type equal the oracle's merged sequence length."""
+    import itertools
+    import torch
+    from oracle import encoder_oracle as eo
+    from radvlm_b200 import _lib, mm_arch, synthetic
+    host = synthetic.build_host(hidden_size=8, vocab=16, dtype=torch.float32, device="cpu",
+                                vision_cfg=synthetic.siglip_config(hidden_size=144, intermediate_size=272,
+                                                                   num_hidden_layers=1, num_attention_heads=2))
+    newline = torch.zeros(8)
+    feat = torch.zeros(3, 729, 8)
+    for pool, pos, mt in itertools.product(["bilinear", "average", "max"], ["grid", "frame", "one_token", "no_token"],
+                                           ["spatial_unpad", "flat"]):
+        host.config.mm_spatial_pool_mode, host.config.mm_newline_position, host.config.mm_patch_merge_type = pool, pos, mt
+        table, tokens = mm_arch._merge_table(host, [3, 1], [(384, 384), (384, 384)], False, {0})
+        want = eo.merge_video(feat, newline, pool, pos, mt).shape[0]
+        assert tokens[0] == want, (pool, pos, mt, tokens[0], want)
+        m = table[0]
+        assert m.mode == _lib.MERGE_VIDEO and m.grid_w == 3 and m.tile_base == 0
+        assert m.out_h == m.out_w == (14 if pool == "bilinear" else 13)
+        assert table[1].tile_base == 3 and table[1].mode != _lib.MERGE_VIDEO   # the image after the video
+    host.config.add_faster_video = True
+    import pytest
+    with pytest.raises(NotImplementedError):
+        mm_arch._merge_table(host, [3], [(384, 384)], False, {0})
+    host.config.add_faster_video = False
+    host.config.mm_spatial_pool_mode = "median"
+    with pytest.raises(ValueError):
+        mm_arch._merge_table(host, [3], [(384, 384)], False, {0})
