@@ -227,6 +227,10 @@ class PeerGather:
         """This rank's own slice (the tensor the merge kernel fills as ``inputs_embeds``)."""
         return self.gathered(slot)[self.rank, :n_rows]
 
+    def peek_slot(self) -> int:
+        """The slot the next ``prepare_inputs_labels_for_multimodal`` call will fill."""
+        return self._turn % self.slots
+
     def next_slot(self) -> int:
         s = self._turn % self.slots
         self._turn += 1

@@ -46,7 +46,7 @@ def main():
         if gather is None:
             gather = PeerGather(ref.shape[0] * ref.shape[1], ref.shape[2], ref.dtype, dev)
         host.radvlm_b200_gather = gather
-        slot = gather._turn % gather.slots
+        slot = gather.peek_slot()
         emb = host.prepare_inputs_labels_for_multimodal(*args, **kw)[4]
         got = gather.wait(slot)
         torch.cuda.synchronize(dev)
