@@ -123,3 +123,12 @@ def process_anyres_image(img: np.ndarray, possible_resolutions=None, tile: int =
     """Full reference preprocessing: uint8 HWC -> fp32 [n, 3, tile, tile]."""
     t = anyres_tiles_uint8(img, possible_resolutions, tile)
     return np.ascontiguousarray(normalize_lut()[t].transpose(0, 3, 1, 2))
+
+
+def siglip_image_processor(img: np.ndarray, size: int = 384) -> np.ndarray:
+    """SigLipImageProcessor.preprocess for one image (siglip_encoder.py:47-67): convert_to_rgb -> resize((size, size),
+    BICUBIC; aspect is NOT preserved) -> rescale(1/255) -> normalize(0.5, 0.5) -> CHW fp32 [3, size, size]."""
+    if img.ndim == 2:
+        img = np.repeat(img[:, :, None], 3, axis=2)
+    r = pil_resize_bicubic(img, (size, size))
+    return np.ascontiguousarray(normalize_lut()[r].transpose(2, 0, 1))

@@ -109,3 +109,36 @@ def process_images(images, image_processor, model_cfg, device=None, dtype: torch
     if all(x.shape == new_images[0].shape for x in new_images):
         return torch.stack(new_images, dim=0)
     return new_images
+
+
+class SigLipImageProcessor:
+    """Drop-in for siglip_encoder.py:34-67: same constructor attributes; ``preprocess(images, return_tensors)`` returns
+    ``{"pixel_values": [n, 3, 384, 384]}`` (convert to RGB, aspect-distorting BICUBIC resize to ``size``, rescale 1/255,
+    normalise with mean = std = 0.5), computed by the fused preprocessing kernel (it is the base tile of the anyres
+    tiling), bit-exact with the reference.  Only the reference's constants are supported."""
+
+    def __init__(self, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), size=(384, 384), crop_size=None,
+                 resample=3, rescale_factor=1 / 255, data_format="channels_first"):
+        self.image_mean, self.image_std, self.size = image_mean, image_std, size
+        self.resample, self.rescale_factor, self.data_format = resample, rescale_factor, data_format
+        self.crop_size = crop_size if crop_size is not None else {"height": 384, "width": 384}
+        if (tuple(image_mean) != (0.5, 0.5, 0.5) or tuple(image_std) != (0.5, 0.5, 0.5) or int(resample) != 3
+                or abs(rescale_factor - 1 / 255) > 1e-12 or size[0] != size[1]):
+            raise NotImplementedError("radvlm_b200.SigLipImageProcessor implements the reference's constants "
+                                      "(mean = std = 0.5, BICUBIC, 1/255, square size)")
+
+    def preprocess(self, images, return_tensors="pt", device=None, dtype: torch.dtype = torch.float32):
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        side = int(self.size[0])
+        tiles, _, splits, _ = preprocess_anyres_batch(list(images), [[side, side]], device=device, dtype=dtype,
+                                                      tile_size=side, patches_per_side=side // 14)
+        firsts, base = [], 0
+        for n in splits:              # tile 0 of every image = the whole image resized to side x side
+            firsts.append(base)
+            base += n
+        pixel_values = tiles[torch.tensor(firsts, device=tiles.device)]
+        if return_tensors in (None, "np"):
+            pixel_values = pixel_values.float().cpu().numpy()
+            return {"pixel_values": list(pixel_values) if return_tensors is None else pixel_values}
+        return {"pixel_values": pixel_values}

@@ -124,6 +124,23 @@ def video_golden():
     return results
 
 
+def processor_golden(ref):
+    """Real SigLipImageProcessor.preprocess (siglip_encoder.py:47-67) on three of the preprocessing images."""
+    from PIL import Image
+    import importlib
+    enc = importlib.import_module("llava.model.multimodal_encoder.siglip_encoder")
+    proc = enc.SigLipImageProcessor()
+    meta = {}
+    cases = gi.preprocess_cases()
+    for name in ["rgb_500x300_noise", "c2_1024_gray_noise", "small_130x100_mix"]:
+        img = gi.preprocess_image(cases[name])
+        pil = Image.fromarray(img).convert("RGB")
+        out = proc.preprocess(pil, return_tensors="pt")["pixel_values"][0].numpy().astype(np.float32)
+        meta[name] = {"shape": list(out.shape), "sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()}
+        print("processor", name, out.shape)
+    return meta
+
+
 def preprocess_golden(ref):
     from PIL import Image
     proc = ref.siglip_encoder.SigLipImageProcessor()
@@ -222,7 +239,7 @@ def grad_golden(ref):
 
 
 def main():
-    parts = set(sys.argv[1:]) or {"planner", "merge", "video", "preprocess", "encoder", "grad"}
+    parts = set(sys.argv[1:]) or {"planner", "merge", "video", "preprocess", "processor", "encoder", "grad"}
     ref = import_reference()
     if "planner" in parts:
         with open(os.path.join(HERE, "planner_golden.json"), "w") as f:
@@ -231,6 +248,9 @@ def main():
         np.savez_compressed(os.path.join(HERE, "merge_splice_golden.npz"), **merge_splice_golden())
     if "video" in parts:
         np.savez_compressed(os.path.join(HERE, "video_golden.npz"), **video_golden())
+    if "processor" in parts:
+        with open(os.path.join(HERE, "processor_golden.json"), "w") as f:
+            json.dump(processor_golden(ref), f, indent=1)
     if "preprocess" in parts:
         meta, arrays = preprocess_golden(ref)
         with open(os.path.join(HERE, "preprocess_golden.json"), "w") as f:

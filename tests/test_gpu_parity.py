@@ -156,6 +156,25 @@ def test_preprocess_bit_exact_vs_reference_golden(lib, golden_dir, name):
     assert torch.equal(t16, tiles.bfloat16())
 
 
+def test_siglip_image_processor_bit_exact_vs_reference_golden(lib, golden_dir):
+    """Boundary row SigLipImageProcessor.preprocess (siglip_encoder.py:47-67) through the fused preprocessing kernel."""
+    import json
+    from radvlm_b200 import mm_utils
+    meta = json.load(open(os.path.join(golden_dir, "processor_golden.json")))
+    cases = gi.preprocess_cases()
+    proc = mm_utils.SigLipImageProcessor()
+    names = sorted(meta)
+    imgs = [torch.from_numpy(gi.preprocess_image(cases[n])) for n in names]
+    out = proc.preprocess(imgs, return_tensors="pt")["pixel_values"]
+    assert tuple(out.shape) == (len(names), 3, 384, 384) and out.dtype == torch.float32
+    for i, n in enumerate(names):
+        assert hashlib.sha256(out[i].cpu().numpy().tobytes()).hexdigest() == meta[n]["sha256"], n
+    one = proc.preprocess(imgs[0], return_tensors="pt")["pixel_values"]
+    assert torch.equal(one[0], out[0])
+    with pytest.raises(NotImplementedError):
+        mm_utils.SigLipImageProcessor(image_mean=(0.4, 0.5, 0.5))
+
+
 def test_preprocess_batch_equals_single_and_oracle(lib):
     from oracle import resample_oracle as ro
     from radvlm_b200 import mm_utils

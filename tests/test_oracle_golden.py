@@ -49,6 +49,18 @@ def test_normalize_lut_values():
     assert np.array_equal(lut, gi.normalize_lut_f32())
 
 
+def test_siglip_image_processor_oracle_vs_reference(golden_dir):
+    """SigLipImageProcessor.preprocess (siglip_encoder.py:47-67) restated in the oracle == the real reference (sha256)."""
+    import hashlib
+    import json
+    meta = json.load(open(os.path.join(golden_dir, "processor_golden.json")))
+    cases = gi.preprocess_cases()
+    for name, m in meta.items():
+        out = ro.siglip_image_processor(gi.preprocess_image(cases[name]))
+        assert list(out.shape) == m["shape"]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == m["sha256"], name
+
+
 # ------------------------------------------------------------------------------------------ merge + splice
 @pytest.mark.parametrize("name", sorted(gi.merge_cases()))
 def test_merge_splice_oracle_vs_reference(golden_dir, name):
