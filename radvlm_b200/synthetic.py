@@ -86,6 +86,17 @@ class SyntheticVisionTower(nn.Module):
         self.is_loaded = True
 
     @property
+    def image_processor(self):
+        """siglip_encoder.py:546: the tower carries its SigLipImageProcessor (here: the GPU mirror of it)."""
+        from .mm_utils import SigLipImageProcessor
+        s = self.config.image_size
+        return SigLipImageProcessor(size=(s, s), crop_size={"height": s, "width": s})
+
+    def load_model(self, device_map=None):
+        """siglip_encoder.py:559-574 loads and truncates the checkpoint; the synthetic tower is always 'loaded'."""
+        self.is_loaded = True
+
+    @property
     def num_patches_per_side(self):
         return self.config.image_size // self.config.patch_size
 
