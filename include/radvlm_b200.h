@@ -380,13 +380,20 @@ int radvlm_merge_splice_scatter(const void* features, const void* newline, const
  * exchanges (e.g. torch.distributed.all_gather); radvlm_peer_open maps a peer's allocation into this process.
  * radvlm_peer_signal_wait (on `stream`): publish `value` into slot [rank] of every rank's flag array (uint64[n],
  * peer-mapped device pointers in the DEVICE array flags_peers_dev), then wait until all n slots of flags_local have
- * reached it - the step barrier that orders the scattered rows of all ranks before any rank reads its buffer. */
+ * reached it - the step barrier that orders the scattered rows of all ranks before any rank reads its buffer (and,
+ * on a second flag array, the consumer-release barrier that orders every rank's reads of a slot before the slot is
+ * overwritten).  The wait is bounded by wall time: timeout_s <= 0 waits for ever; on a timeout the kernel stores
+ * 1 + (first missing rank) into *status (pinned host or device int, 0 on entry, may be NULL) and returns - it never
+ * traps, the CUDA context survives and the host decides.
+ * radvlm_peer_copy: cudaMemcpyAsync(cudaMemcpyDefault) of a finished slice into a peer's buffer: the copy-engine form
+ * of the exchange (DMA over NVLink, no SM). */
 int radvlm_peer_alloc(size_t bytes, void** ptr, uint8_t* handle64);
 int radvlm_peer_open(const uint8_t* handle64, void** ptr);
 int radvlm_peer_close(void* ptr);
 int radvlm_peer_free(void* ptr);
 int radvlm_peer_signal_wait(void* const* flags_peers_dev, void* flags_local, int n, int rank,
-                            unsigned long long value, void* stream);
+                            unsigned long long value, double timeout_s, int* status, void* stream);
+int radvlm_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 
 /* Backward of radvlm_merge_splice (autograd of llava_arch.py:350-531).  d_out_embeds: [B*max_len, H] of `dtype`.
  *   d_features fp32 [tiles*T, H] and d_newline fp32 [H]: accumulated with atomics (zero or running sums on entry);

@@ -171,7 +171,8 @@ SIGNATURES = {
     "radvlm_peer_open": (_i, [C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
     "radvlm_peer_close": (_i, [_vp]),
     "radvlm_peer_free": (_i, [_vp]),
-    "radvlm_peer_signal_wait": (_i, [_vp, _vp, _i, _i, C.c_uint64, _vp]),
+    "radvlm_peer_signal_wait": (_i, [_vp, _vp, _i, _i, C.c_uint64, C.c_double, _vp, _vp]),
+    "radvlm_peer_copy": (_i, [_vp, _vp, _sz, _vp]),
     "radvlm_preprocess_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "radvlm_preprocess_anyres": (_i, [_vp, _vp, C.POINTER(PreprocessImage), _i, _i, _vp, _i, _vp, _sz, _vp]),
 }

@@ -509,20 +509,38 @@ static int merge_splice_launch(const void* features, const void* newline, const 
 }
 
 // Cross-rank step barrier over peer memory: rank `rank` publishes `value` into slot [rank] of every rank's flag
-// array (system-scope release after this stream's earlier kernels, i.e. after its scattered rows), then waits until
-// all `n` slots of its own array have reached `value`.  Bounded spin: a lost peer traps instead of hanging the GPU.
+// array (system-scope release after this stream's earlier work, i.e. after its scattered rows), then waits until
+// all `n` slots of its own array have reached `value`.  The wait is bounded by wall time (%globaltimer, independent
+// of the SM clock); timeout_ns <= 0 waits for ever.  A peer that does not arrive in time does NOT kill the context:
+// the kernel records 1 + (first missing rank) in *status (host-pinned or device memory, may be null) and returns, and
+// the host raises when it next looks (dist.PeerGather.check).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void peer_signal_wait_kernel(unsigned long long* const* flags_peers, unsigned long long* flags_local, int n,
-                                        int rank, unsigned long long value, long long timeout_cycles) {
+                                        int rank, unsigned long long value, long long timeout_ns, int* status) {
   const int d = threadIdx.x;
   if (d >= n) return;
   __threadfence_system();
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags_peers[d] + rank), "l"(value) : "memory");
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_timer_ns();
   unsigned long long seen = 0;
+  unsigned spins = 0;
   do {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags_local + d) : "memory");
     if (seen >= value) break;
-    if (clock64() - t0 > timeout_cycles) __trap();
+    if ((++spins & 255u) == 0 && timeout_ns > 0 &&
+        global_timer_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
+      if (status != nullptr) {
+        atomicCAS(status, 0, 1 + d);   // first missing rank wins; a nonzero status is sticky until the host clears it
+        __threadfence_system();
+      }
+      break;
+    }
+    __nanosleep(200);
   } while (true);
 }
 
@@ -598,16 +616,26 @@ extern "C" int radvlm_peer_free(void* ptr) {
 }
 
 extern "C" int radvlm_peer_signal_wait(void* const* flags_peers_dev, void* flags_local, int n, int rank,
-                                       unsigned long long value, void* stream) {
+                                       unsigned long long value, double timeout_s, int* status, void* stream) {
   using namespace rv;
   int st = require_sm100();
   if (st) return st;
   RV_CHECK_ARG(flags_peers_dev && flags_local && n >= 1 && n <= RADVLM_MAX_PEERS && rank >= 0 && rank < n,
                "peer_signal_wait: bad arguments");
+  const long long timeout_ns = timeout_s > 0 ? static_cast<long long>(timeout_s * 1e9) : 0;
   peer_signal_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<unsigned long long* const*>(flags_peers_dev), static_cast<unsigned long long*>(flags_local), n,
-      rank, value, 20000000000LL);
+      rank, value, timeout_ns, status);
   RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// Copy-engine form of the exchange: this rank's finished [rows, H] slice is pushed into a peer's gathered buffer by a
+// DMA engine over NVLink (no SM is used; the pointers are UVA, the driver routes by their owning devices).
+extern "C" int radvlm_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(dst && src && bytes > 0, "peer_copy: bad arguments");
+  RV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return RADVLM_OK;
 }
 

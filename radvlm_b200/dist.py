@@ -123,12 +123,32 @@ class GradientAllReducer:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._pending.append((work, flat, members))
 
+    def submit_flat(self, flat: torch.Tensor) -> None:
+        """All-reduce a contiguous 1-D gradient slice IN PLACE, in ``bucket_bytes`` pieces (no flatten, no copy back):
+        the encoder keeps all gradient accumulators in one flat buffer, ordered so that what a layer range of the
+        backward finishes is one slice.  NCCL averages inside the collective (ReduceOp.AVG); other backends sum and
+        ``finish()`` scales."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1 or flat.numel() == 0:
+            return
+        assert flat.dim() == 1 and flat.is_contiguous()
+        per = max(1, self.bucket_bytes // flat.element_size())
+        avg_in_op = self.average and dist.get_backend(self.group) == "nccl"
+        op = dist.ReduceOp.AVG if avg_in_op else dist.ReduceOp.SUM
+        for off in range(0, flat.numel(), per):
+            piece = flat[off:off + per]
+            work = dist.all_reduce(piece, op=op, group=self.group, async_op=True)
+            self._pending.append((work, piece, None if avg_in_op or not self.average else "scale"))
+
     def finish(self) -> None:
         if not self._pending:
             return
         scale = 1.0 / dist.get_world_size(self.group) if self.average else 1.0
         for work, flat, members in self._pending:
             work.wait()
+            if members is None or isinstance(members, str):   # in-place slices (submit_flat)
+                if members == "scale" and scale != 1.0:
+                    flat.mul_(scale)
+                continue
             off = 0
             for t in members:
                 n = t.numel()
@@ -165,14 +185,34 @@ class PeerGather:
     Every rank allocates one region (``radvlm_peer_alloc``), the 64-byte cudaIpc handles are exchanged once through
     ``torch.distributed`` and opened on every rank (``radvlm_peer_open``; one process per GPU on one node, NVLink /
     NVSwitch).  ``prepare_inputs_labels_for_multimodal`` writes the local ``inputs_embeds`` straight into slice
-    ``[rank]`` of its own buffer, then ``scatter()`` launches ``radvlm_merge_splice_scatter`` on a side stream: the same
-    gather kernel reads the merged visual tokens / text embeddings once more (L2 / HBM) and writes every row into
-    slice ``[rank]`` of all OTHER ranks' buffers with plain stores over NVLink, followed by the flag exchange of
-    ``radvlm_peer_signal_wait``.  After ``wait(slot)`` the whole ``[world, rows, H]`` tensor of that slot is valid.
+    ``[rank]`` of its own buffer; ``exchange()`` then moves that slice into slice ``[rank]`` of all OTHER ranks'
+    buffers on a side stream, in one of two ways:
+
+      * ``mode="ce"`` (default): one ``radvlm_peer_copy`` (``cudaMemcpyAsync``) per peer — DMA engines over NVLink,
+        no SM is taken from the next step's persistent GEMM / attention kernels;
+      * ``mode="kernel"``: ``radvlm_merge_splice_scatter`` — the gather kernel itself recomputes every row and stores
+        it to all peers (fused merge + all-gather; ``max_ctas`` CTAs).
+
+    Two flag exchanges (``radvlm_peer_signal_wait``) bracket the transfer: before it, every rank publishes that it has
+    finished READING the previous contents of the slot (consumer release — so a slot is never overwritten under a
+    reader, whatever the drift between ranks) and waits for all peers' releases; after it, every rank publishes that
+    its rows have landed and waits for all peers'.  After ``wait(slot)`` the whole ``[world, rows, H]`` tensor of
+    that slot is valid.
+
+    Invariant the caller keeps: every read of a slot's tensors (``inputs_embeds`` returned while the gather is
+    attached, ``gathered(slot)``) is queued on the current stream before the ``slots``-th following call that takes a
+    slot.  Under autograd ``inputs_embeds`` is therefore COPIED out of the slot (``copy_out_when_grad``): saved
+    activations may live until a backward pass that runs arbitrarily late.
+
+    A peer that does not arrive within ``timeout_s`` (default 600 s, ``RADVLM_B200_PEER_TIMEOUT_S``; 0 = wait for ever)
+    does not kill the CUDA context: the wait kernel records the missing rank in a pinned status word and
+    ``check()`` (called by ``wait`` / ``drain`` / ``close``) raises ``RuntimeError`` on the host.
     """
 
-    def __init__(self, rows: int, hidden: int, dtype: torch.dtype, device, group=None, slots: int = 2, max_ctas: int = 32):
+    def __init__(self, rows: int, hidden: int, dtype: torch.dtype, device, group=None, slots: int = 2, max_ctas: int = 32,
+                 mode: str = "ce", timeout_s: Optional[float] = None, copy_out_when_grad: bool = True):
         import ctypes as C
+        import os
         from . import _lib
         self._C, self._lib = C, _lib
         self.lib = _lib.load()
@@ -181,13 +221,17 @@ class PeerGather:
         self.rank = dist.get_rank(group)
         if self.world > _lib.MAX_PEERS:
             raise ValueError("PeerGather supports at most %d ranks (one node)" % _lib.MAX_PEERS)
+        if mode not in ("ce", "kernel"):
+            raise ValueError("PeerGather mode must be 'ce' or 'kernel'")
+        self.mode, self.copy_out_when_grad = mode, copy_out_when_grad
+        self.timeout_s = float(os.environ.get("RADVLM_B200_PEER_TIMEOUT_S", 600.0)) if timeout_s is None else float(timeout_s)
         self.rows, self.hidden, self.dtype, self.device = int(rows), int(hidden), dtype, torch.device(device)
         self.slots, self.max_ctas = slots, max_ctas
         self.esize = torch.empty(0, dtype=dtype).element_size()
         self.slice_bytes = (self.rows * self.hidden * self.esize + 255) // 256 * 256
         self.slot_bytes = self.world * self.slice_bytes
         self.flag_off = slots * self.slot_bytes
-        total = self.flag_off + slots * 256
+        total = self.flag_off + slots * 256   # per slot: uint64 arrived[8] at +0, uint64 released[8] at +64
         with torch.cuda.device(self.device):
             base = C.c_void_p()
             handle = (C.c_uint8 * 64)()
@@ -207,9 +251,12 @@ class PeerGather:
                 _lib.check(self.lib.radvlm_peer_open(h, C.byref(p)))
                 self.peer_base.append(int(p.value))
             self._bytes = torch.as_tensor(_DevicePtr(self.base, total), device=self.device)
-            # per slot: DEVICE array of every rank's flag array (uint64[world]) for radvlm_peer_signal_wait
-            self._flag_ptrs = [torch.tensor([b + self.flag_off + s * 256 for b in self.peer_base], dtype=torch.int64,
-                                            device=self.device) for s in range(slots)]
+            # per slot: DEVICE arrays of every rank's flag arrays (uint64[world]) for radvlm_peer_signal_wait
+            self._arrive_ptrs = [torch.tensor([b + self.flag_off + s * 256 for b in self.peer_base], dtype=torch.int64,
+                                              device=self.device) for s in range(slots)]
+            self._release_ptrs = [torch.tensor([b + self.flag_off + s * 256 + 64 for b in self.peer_base],
+                                               dtype=torch.int64, device=self.device) for s in range(slots)]
+            self._status = torch.zeros(1, dtype=torch.int32).pin_memory()   # written by the wait kernel on a timeout
             self.stream = torch.cuda.Stream(self.device)
             self._events = [None] * slots
         self._step = [0] * slots
@@ -243,25 +290,51 @@ class PeerGather:
                 for r, b in enumerate(self.peer_base) if r != self.rank]
         return (C.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
 
-    def scatter(self, slot: int, launch) -> None:
-        """Run ``launch(dests, n_dests, max_ctas, cuda_stream)`` (the scatter form of the merge kernel) and the flag
-        exchange on the side stream, after everything queued so far on the current stream."""
+    def _signal_wait(self, ptrs: torch.Tensor, local: int, value: int) -> None:
+        self._lib.check(self.lib.radvlm_peer_signal_wait(
+            ptrs.data_ptr(), local, self.world, self.rank, value, self.timeout_s, self._status.data_ptr(),
+            self.stream.cuda_stream))
+
+    def exchange(self, slot: int, n_rows: int, launch_kernel) -> None:
+        """Move this rank's slice of ``slot`` to all peers on the side stream, after everything queued so far on the
+        current stream: release barrier, transfer (copy engines, or ``launch_kernel(dests, n_dests, max_ctas,
+        cuda_stream)`` = the scatter form of the merge kernel), arrival barrier."""
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         dests, n = self.remote_dests(slot)
+        flags_local = self.base + self.flag_off + slot * 256
         with torch.cuda.stream(self.stream):
-            if n > 0:
-                launch(dests, n, self.max_ctas, self.stream.cuda_stream)
             self._step[slot] += 1
-            self._lib.check(self.lib.radvlm_peer_signal_wait(
-                self._flag_ptrs[slot].data_ptr(), self.base + self.flag_off + slot * 256, self.world, self.rank,
-                self._step[slot], self.stream.cuda_stream))
+            gen = self._step[slot]
+            if gen > 1 and n > 0:   # every rank has finished reading generation gen-1 of this slot
+                self._signal_wait(self._release_ptrs[slot], flags_local + 64, gen - 1)
+            if n > 0:
+                if self.mode == "kernel":
+                    launch_kernel(dests, n, self.max_ctas, self.stream.cuda_stream)
+                else:
+                    src = self.base + slot * self.slot_bytes + self.rank * self.slice_bytes
+                    nbytes = int(n_rows) * self.hidden * self.esize
+                    for d in range(n):
+                        self._lib.check(self.lib.radvlm_peer_copy(dests[d], src, nbytes, self.stream.cuda_stream))
+            self._signal_wait(self._arrive_ptrs[slot], flags_local, gen)
             ev = torch.cuda.Event()
             ev.record(self.stream)
             self._events[slot] = ev
 
+    def scatter(self, slot: int, launch) -> None:   # round-1 name: the kernel form over all rows of the slot
+        self.exchange(slot, self.rows, launch)
+
+    def check(self) -> None:
+        """Raise if a flag exchange timed out (the status word is only looked at, never waited for)."""
+        st = int(self._status[0])
+        if st != 0:
+            self._status[0] = 0
+            raise RuntimeError("radvlm_b200.PeerGather: rank %d did not reach the exchange within %.0f s (rank %d gave up "
+                               "waiting; the gathered buffer of that step is incomplete)" % (st - 1, self.timeout_s, self.rank))
+
     def wait(self, slot: int) -> torch.Tensor:
         """Make the current stream wait until every rank's rows of ``slot`` have landed; returns the gathered view."""
+        self.check()
         if self._events[slot] is not None:
             torch.cuda.current_stream(self.device).wait_event(self._events[slot])
         return self.gathered(slot)
@@ -272,6 +345,7 @@ class PeerGather:
 
     def close(self) -> None:
         torch.cuda.synchronize(self.device)
+        self.check()
         dist.barrier(self.group)
         for r, b in enumerate(self.peer_base):
             if r != self.rank:

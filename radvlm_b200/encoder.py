@@ -5,8 +5,9 @@ Mirrors ``SigLipVisionTower.forward`` (siglip_encoder.py:576-589) followed by ``
 compute is done by the sm_100a kernels behind the C ABI (``libradvlm_b200.so``).
 
 Weights are consumed from the reference's own Parameters (state-dict names).  The
-bf16 matrices the tensor-core kernels read are *caches* keyed on ``(data_ptr, _version)`` of every
-source tensor, so optimizer steps / checkpoint loads are picked up and the Parameters stay in place.
+bf16 matrices the tensor-core kernels read are packed *copies* (or aliases of bf16 Parameters) that are refreshed
+in place: see ``B200VisionEncoder.packed`` for when (storage change -> rebuild; version bump -> refresh; any
+trainable Parameter -> refresh on every call, because DeepSpeed-style ``p.data`` updates bypass ``_version``).
 """
 from __future__ import annotations
 
@@ -27,32 +28,53 @@ def _stream_ptr(device) -> int:
 
 
 class PackedWeights:
-    """bf16 / fp32 device copies of tower + projector weights and the C structs pointing at them."""
+    """bf16 / fp32 device copies of tower + projector weights and the C structs pointing at them.
+
+    Every destination buffer is allocated once; ``refresh()`` re-copies the CURRENT contents of the source
+    Parameters into the same buffers (same device pointers: the C structs, cached TMA descriptors and captured CUDA
+    graphs stay valid).  A source that already is a contiguous tensor of the wanted dtype on the device is not copied
+    at all: the struct points at the Parameter's own storage (``alias``), so optimizer updates are seen for free."""
 
     def __init__(self, tower_sd: Mapping[str, torch.Tensor], proj_sd: Mapping[str, torch.Tensor], device,
                  num_heads: int = 16, image_size: int = 384, ln_eps: float = 1e-6,
                  num_layers: Optional[int] = None):
         dev = torch.device(device)
-        keep = []  # every device tensor referenced by the structs
+        keep = []       # every device tensor referenced by the structs
+        copies = []     # (destination view, source tensor): what refresh() re-copies
+        self.n_alias = 0
 
-        def w(t):  # matrix -> bf16 [out, in] contiguous
-            x = t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
-            keep.append(x)
-            return x
+        def bind(srcs, dtype, pad_cols: int = 0):
+            """rows of `srcs` stacked -> one contiguous [sum rows, cols (+ zero padding)] device tensor of `dtype`"""
+            srcs = [t.detach() for t in srcs]
+            if len(srcs) == 1 and pad_cols == 0 and srcs[0].device == dev and srcs[0].dtype == dtype \
+                    and srcs[0].is_contiguous():
+                keep.append(srcs[0])     # alias: the Parameter's own storage
+                self.n_alias += 1
+                return srcs[0]
+            flat = [t.reshape(t.shape[0], -1) if t.dim() > 1 else t for t in srcs]
+            rows = sum(t.shape[0] for t in flat)
+            if flat[0].dim() == 1:
+                dst = torch.empty(rows, dtype=dtype, device=dev)
+            else:
+                cols = flat[0].shape[1]
+                dst = torch.zeros(rows, cols + pad_cols, dtype=dtype, device=dev)
+            off = 0
+            for t in flat:
+                view = dst[off:off + t.shape[0]] if t.dim() == 1 else dst[off:off + t.shape[0], :t.shape[1]]
+                copies.append((view, t))
+                off += t.shape[0]
+            keep.append(dst)
+            return dst
 
-        def v(t):  # vector / table -> fp32 contiguous
-            x = t.detach().to(device=dev, dtype=torch.float32).contiguous()
-            keep.append(x)
-            return x
+        w = lambda *ts, pad=0: bind(ts, torch.bfloat16, pad)   # matrices -> bf16 [out, in]
+        v = lambda *ts: bind(ts, torch.float32)                # vectors / tables -> fp32
 
         pre = "vision_model."
         pw = tower_sd[pre + "embeddings.patch_embedding.weight"]  # [hidden, C, ps, ps]
         hidden, channels, ps, _ = pw.shape
         k = channels * ps * ps
         k_pad = (k + 63) // 64 * 64
-        patch_w = torch.zeros(hidden, k_pad, dtype=torch.bfloat16, device=dev)
-        patch_w[:, :k] = pw.detach().reshape(hidden, k).to(device=dev, dtype=torch.bfloat16)
-        keep.append(patch_w)
+        patch_w = w(pw, pad=k_pad - k)
         pos = v(tower_sd[pre + "embeddings.position_embedding.weight"])
         if num_layers is None:
             num_layers = 0
@@ -63,15 +85,11 @@ class PackedWeights:
         for i in range(num_layers):
             lp = pre + "encoder.layers.%d." % i
             g = lambda n: tower_sd[lp + n]
-            qkv_w = torch.cat([g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"),
-                               g("self_attn.v_proj.weight")], dim=0)
-            qkv_b = torch.cat([g("self_attn.q_proj.bias"), g("self_attn.k_proj.bias"),
-                               g("self_attn.v_proj.bias")], dim=0)
             L = layers[i]
             L.ln1_gamma = v(g("layer_norm1.weight")).data_ptr()
             L.ln1_beta = v(g("layer_norm1.bias")).data_ptr()
-            L.qkv_w = w(qkv_w).data_ptr()
-            L.qkv_b = v(qkv_b).data_ptr()
+            L.qkv_w = w(g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"), g("self_attn.v_proj.weight")).data_ptr()
+            L.qkv_b = v(g("self_attn.q_proj.bias"), g("self_attn.k_proj.bias"), g("self_attn.v_proj.bias")).data_ptr()
             L.out_w = w(g("self_attn.out_proj.weight")).data_ptr()
             L.out_b = v(g("self_attn.out_proj.bias")).data_ptr()
             L.ln2_gamma = v(g("layer_norm2.weight")).data_ptr()
@@ -98,15 +116,46 @@ class PackedWeights:
         pj.w2 = w(w2).data_ptr()
         pj.b2 = v(proj_sd["2.bias"]).data_ptr()
         self.tower, self.projector = tw, pj
-        self._layers, self._keep = layers, keep
+        self._layers, self._keep, self._copies = layers, keep, copies
         self.device = dev
         self.tokens_per_tile = (image_size // ps) ** 2
         self.patches_per_side = image_size // ps
         self.hidden, self.proj_hidden = hidden, pj.hidden
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        """Re-copy the current values of every non-aliased source into its packed buffer (dtype conversion included)."""
+        if not self._copies:
+            return
+        same = [(d, s) for d, s in self._copies if s.device == d.device]
+        if same:
+            torch._foreach_copy_([d for d, _ in same], [s.reshape(d.shape) for d, s in same])
+        for d, s in self._copies:
+            if s.device != d.device:
+                d.copy_(s.reshape(d.shape))
+
+
+def _layout_key(tensors) -> tuple:
+    """What the packed buffers / aliases depend on structurally: storage address, shape, dtype, device."""
+    return tuple((t.data_ptr(), tuple(t.shape), t.dtype, t.device) for t in tensors)
 
 
 def _version_key(tensors) -> tuple:
-    return tuple((t.data_ptr(), t._version) for t in tensors)
+    return tuple(t._version for t in tensors)
+
+
+def _check_materialised(named) -> None:
+    """DeepSpeed ZeRO-3 replaces the storage of partitioned Parameters by an empty placeholder outside of its own
+    module hooks (which this path does not go through: it reads the Parameters directly)."""
+    for name, p in named:
+        if p.numel() == 0 or hasattr(p, "ds_tensor") and getattr(p, "ds_status", None) is not None \
+                and "NOT_AVAILABLE" in str(p.ds_status):
+            raise RuntimeError(
+                "radvlm_b200: parameter %r is partitioned (DeepSpeed ZeRO-3) and not gathered.  Exclude the vision tower "
+                "and mm_projector from partitioning, or call encode_images / prepare_inputs_labels_for_multimodal inside "
+                "deepspeed.zero.GatheredParameters(list(tower.parameters()) + list(projector.parameters())) "
+                "(INTEGRATION.md, 'DeepSpeed')." % name)
 
 
 class B200VisionEncoder:
@@ -125,30 +174,61 @@ class B200VisionEncoder:
         self.grad_bucket_bytes = 64 << 20
         self.backward_layers_per_range = 4
         self._packed: Optional[PackedWeights] = None
-        self._key = None
+        self._layout = None
+        self._versions = None
+        self._stale = False
         self._frozen = False
+        self.n_repacks = 0     # diagnostics (tests): full rebuilds / in-place refreshes of the packed weights
+        self.n_refreshes = 0
         self._ws: Dict[torch.device, torch.Tensor] = {}
         _lib.load()  # fail loudly at construction time if the extension is missing
 
     # ---- weights -------------------------------------------------------------------------------
+    def _source_named(self):
+        return list(self.tower_module.named_parameters()) + list(self.projector_module.named_parameters())
+
     def _source_tensors(self):
-        return list(self.tower_module.parameters()) + list(self.projector_module.parameters())
+        return [p for _, p in self._source_named()]
 
     def freeze(self, flag: bool = True):
-        """Skip the per-call version check (inference: weights never change)."""
+        """Skip every per-call check (pure inference: the weights never change)."""
         self._frozen = flag
         return self
 
-    def packed(self, device) -> PackedWeights:
-        if self._packed is not None and self._frozen and self._packed.device == torch.device(device):
+    def invalidate(self):
+        """Force the packed copies to be refreshed on the next call.  Needed only when weights are changed through
+        ``p.data`` (no ``_version`` bump) while no Parameter requires grad, e.g. a manual ``p.data.copy_`` at inference."""
+        self._stale = True
+        return self
+
+    def packed(self, device, training: bool = False) -> PackedWeights:
+        """The packed weights, up to date with the source Parameters.
+
+        * a different storage / shape / dtype of any source (checkpoint load, ``p.data = ...``, ``.to()``) rebuilds;
+        * an in-place update seen by autograd's version counter (torch.optim) refreshes the copies in place;
+        * updates through ``p.data`` do NOT bump ``_version`` (DeepSpeed's optimizers, ZeRO gathers): while any source
+          Parameter requires grad (the model is being trained, also during its eval passes) the copies are therefore
+          refreshed on EVERY call (~0.4 ms for the full tower: one multi-tensor copy into the existing buffers)."""
+        dev = torch.device(device)
+        if self._packed is not None and self._frozen and self._packed.device == dev:
             return self._packed
-        key = (torch.device(device), _version_key(self._source_tensors()))
-        if self._packed is None or key != self._key:
+        named = self._source_named()
+        srcs = [p for _, p in named]
+        _check_materialised(named)
+        layout = (dev, _layout_key(srcs))
+        if self._packed is None or layout != self._layout:
             n_layers = len(self.tower_module.vision_model.encoder.layers)
             self._packed = PackedWeights(self.tower_module.state_dict(), self.projector_module.state_dict(),
                                          device, num_heads=self.num_heads, image_size=self.image_size,
                                          ln_eps=self.ln_eps, num_layers=n_layers)
-            self._key = key
+            self._layout, self._versions, self._stale = layout, _version_key(srcs), False
+            self.n_repacks += 1
+            return self._packed
+        versions = _version_key(srcs)
+        if training or self._stale or versions != self._versions or any(p.requires_grad for p in srcs):
+            self._packed.refresh()
+            self._versions, self._stale = versions, False
+            self.n_refreshes += 1
         return self._packed
 
     def _workspace(self, device, nbytes: int) -> torch.Tensor:
@@ -228,11 +308,15 @@ class _GradBuffers:
         psd = dict(enc.projector_module.named_parameters())
         pre = "vision_model."
         self.bufs: Dict[str, torch.Tensor] = {}
-        # one flat zero-filled allocation (one memset), carved into 256-byte aligned views
-        n_layers_alloc = sum(1 for _ in range(NL))
+        # ONE flat fp32 allocation carved into 256-byte aligned views, in the order [embeddings | layer 0 .. NL-1 |
+        # projector]: the gradients of a layer range (+ the embeddings when it starts at layer 0) are one contiguous
+        # slice, which the data-parallel all-reduce reduces IN PLACE (no flatten / copy back).  The object is cached on
+        # the encoder and re-zeroed per backward (one memset) instead of re-allocated.
         cap = NL * (3 * D * D + D * D + 2 * D * I + 9 * D + I + 64 * 12) + D * tw.patch_k_pad + D + pk.tokens_per_tile * D \
             + pk.proj_hidden * (D + pk.proj_hidden + 2) + 64 * 8
         flat = torch.zeros(cap, dtype=torch.float32, device=dev)
+        self.flat = flat
+        self.spans: Dict[str, tuple] = {}    # "emb" / "l<i>" / "proj" -> (start, end) element offsets in flat
         cursor = [0]
 
         def alloc(key, shape, *src_names, table=tsd):
@@ -246,10 +330,17 @@ class _GradBuffers:
             self.bufs[key] = t
             return t.data_ptr()
 
+        self.tower = _lib.SiglipGrads()
+        c0 = cursor[0]
+        self.tower.patch_w = alloc("patch_w", (D, tw.patch_k_pad), pre + "embeddings.patch_embedding.weight")
+        self.tower.patch_b = alloc("patch_b", (D,), pre + "embeddings.patch_embedding.bias")
+        self.tower.pos_embed = alloc("pos", (pk.tokens_per_tile, D), pre + "embeddings.position_embedding.weight")
+        self.spans["emb"] = (c0, cursor[0])
         self.layers = (_lib.VitLayerGrads * NL)()
         for i in range(NL):
             lp = pre + "encoder.layers.%d." % i
             L = self.layers[i]
+            c0 = cursor[0]
             L.ln1_gamma = alloc("l%d.ln1_g" % i, (D,), lp + "layer_norm1.weight")
             L.ln1_beta = alloc("l%d.ln1_b" % i, (D,), lp + "layer_norm1.bias")
             L.qkv_w = alloc("l%d.qkv_w" % i, (3 * D, D), lp + "self_attn.q_proj.weight", lp + "self_attn.k_proj.weight",
@@ -264,28 +355,28 @@ class _GradBuffers:
             L.fc1_b = alloc("l%d.fc1_b" % i, (I,), lp + "mlp.fc1.bias")
             L.fc2_w = alloc("l%d.fc2_w" % i, (D, I), lp + "mlp.fc2.weight")
             L.fc2_b = alloc("l%d.fc2_b" % i, (D,), lp + "mlp.fc2.bias")
-        self.tower = _lib.SiglipGrads()
-        self.tower.patch_w = alloc("patch_w", (D, tw.patch_k_pad), pre + "embeddings.patch_embedding.weight")
-        self.tower.patch_b = alloc("patch_b", (D,), pre + "embeddings.patch_embedding.bias")
-        self.tower.pos_embed = alloc("pos", (pk.tokens_per_tile, D), pre + "embeddings.position_embedding.weight")
+            self.spans["l%d" % i] = (c0, cursor[0])
         self.tower.layers = C.cast(self.layers, C.POINTER(_lib.VitLayerGrads))
         self.tower_trainable = bool(self.bufs)
         P = pk.proj_hidden
         self.proj = _lib.ProjectorGrads()
+        c0 = cursor[0]
         self.proj.w1 = alloc("p.w1", (P, D), "0.weight", table=psd)
         self.proj.b1 = alloc("p.b1", (P,), "0.bias", table=psd)
         self.proj.w2 = alloc("p.w2", (P, P), "2.weight", table=psd)
         self.proj.b2 = alloc("p.b2", (P,), "2.bias", table=psd)
+        self.spans["proj"] = (c0, cursor[0])
         self._D, self._NL, self._pre = D, NL, pre
 
-    def layer_buffers(self, lo: int, hi: int, include_embeddings: bool):
-        """fp32 buffers of layers [lo, hi), top layer first (the order the backward finishes them)."""
-        out = []
-        for i in range(hi - 1, lo - 1, -1):
-            out += [t for k, t in self.bufs.items() if k.startswith("l%d." % i)]
-        if include_embeddings:
-            out += [self.bufs[k] for k in ("patch_w", "patch_b", "pos") if k in self.bufs]
-        return out
+    def layer_slice(self, lo: int, hi: int, include_embeddings: bool) -> torch.Tensor:
+        """The contiguous slice of the flat buffer holding the gradients of layers [lo, hi) (+ the embeddings)."""
+        a = self.spans["emb"][0] if include_embeddings else self.spans["l%d" % lo][0]
+        b = self.spans["l%d" % (hi - 1)][1] if hi > lo else self.spans["emb"][1]
+        return self.flat[a:b]
+
+    def projector_slice(self) -> torch.Tensor:
+        a, b = self.spans["proj"]
+        return self.flat[a:b]
 
     def for_parameter(self, name: str, p: torch.Tensor, is_tower: bool) -> Optional[torch.Tensor]:
         """Gradient of one module Parameter (its shape / dtype), or None when frozen."""
@@ -319,16 +410,19 @@ class _GradBuffers:
                             g = b[k + "qkv_w"][j * D:(j + 1) * D]
                         elif leaf == "self_attn.%s.bias" % proj:
                             g = b[k + "qkv_b"][j * D:(j + 1) * D]
-        if g is None:   # a parameter the path does not use (post_layernorm, head, the dropped 27th layer)
-            return torch.zeros_like(p)
-        return g.to(p.dtype).reshape(p.shape)
+        if g is None:   # a parameter the path does not use (post_layernorm, head, the dropped 27th layer): like the
+            return None  # reference, whose autograd leaves .grad = None there (AdamW then skips it entirely)
+        out = g.to(p.dtype).reshape(p.shape)
+        if out.dtype == torch.float32:   # fp32 Parameters: `out` would alias the cached flat buffer, which the next
+            out = out.clone()            # backward zeroes while .grad may still be accumulating micro-batches
+        return out
 
 
 class _EncodeImagesFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, images, out_dtype, n_tower, *params):
         dev = images.device
-        pk = enc.packed(dev)
+        pk = enc.packed(dev, training=True)
         lib = _lib.load()
         n = images.shape[0]
         T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
@@ -366,7 +460,7 @@ class _EncodeImagesFn(torch.autograd.Function):
         lib = _lib.load()
         T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
         d_out = d_out.to(device=dev, dtype=torch.bfloat16).contiguous()
-        gb = _GradBuffers(enc, pk, dev)
+        gb = enc._grad_buffers(pk, dev)
         reducer = None
         if enc.grad_allreduce_group is not False:   # False = off; None = default process group (when initialised)
             from .dist import GradientAllReducer
@@ -387,7 +481,7 @@ class _EncodeImagesFn(torch.autograd.Function):
                     None if d_hidden is None else d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), stream))
                 last_chunk = (s, m) == (ctx.chunks[-1][0], ctx.chunks[-1][1])
                 if last_chunk and reducer is not None:   # projector gradients are final: reduce them first
-                    reducer.submit([gb.bufs[k] for k in ("p.w2", "p.b2", "p.w1", "p.b1") if k in gb.bufs])
+                    reducer.submit_flat(gb.projector_slice())
                 if gb.tower_trainable:
                     NL = pk.tower.num_layers
                     step_l = max(1, enc.backward_layers_per_range) if (last_chunk and reducer is not None) else NL
@@ -399,11 +493,9 @@ class _EncodeImagesFn(torch.autograd.Function):
                             saved.data_ptr(), saved.numel(), d_hidden.data_ptr(), ws.data_ptr(), ws.numel(), lo, hi,
                             stream))
                         if last_chunk and reducer is not None:   # overlap: these layers are done, the next range runs
-                            reducer.submit(gb.layer_buffers(lo, hi, include_embeddings=(lo == 0)))
+                            reducer.submit_flat(gb.layer_slice(lo, hi, include_embeddings=(lo == 0)))
                         hi = lo
         if reducer is not None:
-            if not gb.tower_trainable:
-                pass
             reducer.finish()
         grads = []
         for idx, ((name, is_tower), p) in enumerate(zip(ctx.param_names, ctx.params)):
@@ -432,7 +524,22 @@ def _param_names(self: "B200VisionEncoder"):
            [(n, False) for n, _ in self.projector_module.named_parameters()]
 
 
+def _grad_buffers(self: "B200VisionEncoder", pk: PackedWeights, dev) -> _GradBuffers:
+    """The cached gradient accumulators (one flat fp32 allocation), zeroed; rebuilt when the packed weights or the
+    set of trainable Parameters changed."""
+    key = (id(pk), torch.device(dev), tuple(p.requires_grad for p in self._source_tensors()))
+    gb = getattr(self, "_gb", None)
+    if gb is None or self._gb_key != key:
+        self._gb = gb = None   # release the old allocation first
+        gb = _GradBuffers(self, pk, dev)   # freshly zero-filled
+        self._gb, self._gb_key = gb, key
+    else:
+        gb.flat.zero_()
+    return gb
+
+
 B200VisionEncoder.encode_images_train = _encode_images_train
+B200VisionEncoder._grad_buffers = _grad_buffers
 B200VisionEncoder._param_names = _param_names
 
 

@@ -200,7 +200,10 @@ class _MergeSpliceFn(torch.autograd.Function):
                             dests, n, max_ctas, None, None, None, IGNORE_INDEX, stream))
                     for t in (features, newline, embed, tables, m["ids_dev"]):
                         t.record_stream(gather.stream)
-                    gather.scatter(m["gather_slot"], launch)
+                    gather.exchange(m["gather_slot"], m["total_rows"], launch)
+                    if getattr(gather, "copy_out_when_grad", False) and not isinstance(ctx, _NullCtx):
+                        # under autograd the result may be kept (saved activations) far beyond the slot's reuse
+                        out = out.clone()
         ctx.m = m
         ctx.feat_shape, ctx.feat_dtype = tuple(features.shape), features.dtype
         ctx.newline_dtype, ctx.embed_shape, ctx.embed_dtype = newline.dtype, tuple(embed.shape), embed.dtype
@@ -219,7 +222,9 @@ class _MergeSpliceFn(torch.autograd.Function):
             n_rows = ctx.feat_shape[0] * ctx.feat_shape[1] if len(ctx.feat_shape) == 3 else ctx.feat_shape[0]
             d_feat = torch.zeros(max(n_rows, 1), H, dtype=torch.float32, device=dev)
             d_newline = torch.zeros(H, dtype=torch.float32, device=dev)
-            d_text = torch.empty(max(m["n_text"], 1), H, dtype=ctx.embed_dtype, device=dev) if need_e else None
+            # zeros, not empty: text tokens cut off by tokenizer_model_max_length are listed in text_src but covered by
+            # no segment, so the kernel never writes their rows; the reference gives them zero gradient
+            d_text = torch.zeros(max(m["n_text"], 1), H, dtype=ctx.embed_dtype, device=dev) if need_e else None
             if m["total_rows"] > 0:
                 tables = m["tables"]
                 _lib.check(lib.radvlm_merge_splice_backward(

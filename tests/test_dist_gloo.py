@@ -89,6 +89,17 @@ def _grad_worker(rank, world, port, ret):
         mine2 = mk(rank)
         rdist.allreduce_gradients(mine2, average=False)
         ok = ok and all(torch.allclose(a, b * world, rtol=0, atol=1e-5) for a, b in zip(mine2, want))
+        # in-place form: a contiguous slice of one flat buffer, cut into buckets, averaged without any copy
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        ptr = flat.data_ptr()
+        red = rdist.GradientAllReducer(bucket_bytes=96 * 4, average=True)
+        red.submit_flat(flat[100:700])
+        red.submit_flat(flat[700:1000])
+        red.finish()
+        mean = sum(r + 1 for r in range(world)) / world
+        want_flat = torch.arange(1000, dtype=torch.float32)
+        want_flat = torch.cat([want_flat[:100] * (rank + 1), want_flat[100:] * mean])
+        ok = ok and flat.data_ptr() == ptr and torch.allclose(flat, want_flat, rtol=1e-6, atol=1e-4)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -279,3 +279,68 @@ def test_backward_full_size_vs_oracle_autograd(lib):
         if cos < worst[0]:
             worst = (cos, name)
     print("full-size gradient parity vs oracle autograd: worst cos=%.6f at %s" % worst)
+
+
+@pytest.mark.parametrize("padding_side", ["right", "left"])
+def test_splice_backward_with_truncation_vs_oracle(lib, padding_side):
+    """tokenizer_model_max_length shorter than a sample (llava_arch.py:495-498): the text tokens that were cut off get
+    ZERO gradient in embed_tokens (their rows of the compact d_text buffer are written by no segment), the surviving
+    ones, the visual features and image_newline get the oracle's fp32 autograd gradient."""
+    from oracle import encoder_oracle as eo
+    from radvlm_b200 import synthetic
+    vcfg = synthetic.siglip_config(hidden_size=144, intermediate_size=272, num_hidden_layers=1, num_attention_heads=2)
+    host = synthetic.build_host(hidden_size=gi.MERGE_HIDDEN, vocab=gi.MERGE_VOCAB, seed=0, dtype=torch.float32,
+                                device="cuda", vision_cfg=vcfg)
+    with torch.no_grad():
+        host.model.embed_tokens.weight.copy_(gi.merge_embed_table())
+        host.model.image_newline.copy_(gi.merge_newline())
+    host.model.embed_tokens.requires_grad_(True)
+    host.model.image_newline.requires_grad_(True)
+    host.config.tokenizer_padding_side = padding_side
+    sizes, tiles = [(500, 300), (1024, 1024)], [3, 10]
+    g = torch.Generator().manual_seed(77)
+    feats = torch.randn(sum(tiles), 729, gi.MERGE_HIDDEN, generator=g)
+    lengths, L = [30, 50], 50
+    ids = torch.zeros(2, L, dtype=torch.long)
+    mask = torch.zeros(2, L, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        ids[b, :n] = torch.randint(1, gi.MERGE_VOCAB, (n,), generator=g)
+        mask[b, :n] = True
+    ids[0, 4] = -200      # sample 0: 4 text + image + 25 text; the cut falls inside the trailing text
+    ids[1, 45] = -200     # sample 1: 45 text + image + 4 text; the cut falls inside the image, all trailing text is lost
+    labels = torch.where(ids < 0, torch.full_like(ids, -100), ids)
+    # oracle side (fp32 CPU autograd)
+    f_ref = feats.clone().requires_grad_(True)
+    nl_ref = gi.merge_newline().clone().requires_grad_(True)
+    tab_ref = gi.merge_embed_table().clone().requires_grad_(True)
+    per_image, base = [], 0
+    for n, size in zip(tiles, sizes):
+        per_image.append(eo.merge_image(f_ref[base:base + n], size, nl_ref, gi.PINPOINTS))
+        base += n
+    n0 = int(per_image[0].shape[0])
+    max_length = 4 + n0 + 10           # sample 0 keeps 10 of its 25 trailing text tokens
+    assert 45 + int(per_image[1].shape[0]) > max_length > 45 + 100
+    host.config.tokenizer_model_max_length = max_length
+    r_emb, _, r_mask, _ = eo.prepare_inputs_labels(tab_ref, per_image, ids, mask, labels, max_length, padding_side == "left")
+    R = torch.randn(r_emb.shape, generator=g)
+    (r_emb * R).sum().backward()
+    # product side
+    f_dev = feats.cuda().requires_grad_(True)
+    host.encode_images = lambda images: f_dev
+    images = [torch.zeros(n, 3, 2, 2) for n in tiles]
+    out = host.prepare_inputs_labels_for_multimodal(ids.cuda(), None, mask.cuda(), None, labels.cuda(), images,
+                                                    ["image", "image"], sizes)
+    emb = out[4]
+    assert tuple(emb.shape) == tuple(r_emb.shape) and emb.shape[1] == max_length
+    assert torch.equal(emb.detach().cpu(), r_emb.detach())
+    (emb * R.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    got = host.model.embed_tokens.weight.grad.cpu()
+    assert torch.isfinite(got).all()
+    torch.testing.assert_close(got, tab_ref.grad, rtol=1e-5, atol=1e-5)
+    # tokens that only occur behind the cut have exactly zero gradient
+    kept = set(ids[0, :4].tolist()) | set(ids[0, 5:15].tolist()) | set(ids[1, :45].tolist())
+    lost = (set(ids[0, 15:30].tolist()) | set(ids[1, 46:50].tolist())) - kept
+    assert lost and all(float(got[t].abs().max()) == 0.0 for t in lost)
+    torch.testing.assert_close(f_dev.grad.cpu(), f_ref.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(host.model.image_newline.grad.cpu(), nl_ref.grad, rtol=1e-4, atol=1e-4)

@@ -326,7 +326,8 @@ def test_merge_splice_scatter_writes_every_destination(lib):
         def local_rows(self, slot, n):
             return self.own[:n]
 
-        def scatter(self, slot, launch):
+        def exchange(self, slot, n_rows, launch):
+            assert n_rows == self.rows
             self.stream.wait_stream(torch.cuda.current_stream())
             dests = (C.c_void_p * 2)(*[t.data_ptr() for t in self.remote])
             launch(dests, 2, 16, self.stream.cuda_stream)
