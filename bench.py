@@ -14,8 +14,12 @@ times per GPU; at N > 1 the images are sharded by rank and the embeddings are al
 `value`   : inputs resident in HBM when the timed region starts (device-timed, max over ranks).
 `e2e`     : same metric through the public API with HOST (pinned) uint8 images, H2D inside the timed region and a
             D2H read of a slice of the result every step.
-`roofline`: the dominant kernel class (tcgen05 GEMM) timed live with CUDA events on the launch stream.
-`cpu_baseline`: the oracle port (or the real reference when /root/reference exists) on the host cores, bounded sample.
+`roofline`: the dominant kernel (the fc2 tcgen05 GEMM) timed live with CUDA events on the launch stream, in a
+            profiled pass of its own (the timed regions run with that instrumentation off).
+`cpu_baseline`: the oracle port on the host cores, one whole image (10 tiles, nothing extrapolated).
+Extra keys of the same line: `train` (configs[4]: forward + backward, N > 1 with the NCCL gradient all-reduce),
+`c3_strong` (configs[2]: global batch 256, strong scaling), `batch1` (one 10-tile image per call), `gather_check`
+(N > 1: checksum proof that every rank received every rank's rows).
 """
 from __future__ import annotations
 
@@ -59,8 +63,11 @@ def _workload_config(args, world):
         "prompt_tokens": 32,
         "parallelism": "dp%d (image-sharded)" % world,
         "gather": ("none" if world == 1 else
-                   ("fused merge + scatter over peer memory (radvlm_merge_splice_scatter)" if getattr(args, "gather", "nccl") in ("peer", "auto")
-                    else "NCCL all-gather of inputs_embeds, asynchronous")),
+                   {"peer": "fused merge + scatter kernel over peer memory (radvlm_merge_splice_scatter)",
+                    "nccl": "NCCL all-gather of inputs_embeds, asynchronous"}.get(
+                       getattr(args, "gather", "auto"),
+                       "merge kernel writes into peer-mapped memory, copy engines push the slice to every peer over NVLink "
+                       "(dist.PeerGather mode=ce)")),
         "l2": "per-step working set (0.83 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2; input images rotate over 3 buffers",
     }
 
@@ -68,15 +75,30 @@ def _workload_config(args, world):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arms (oracle port / real reference)
 # ----------------------------------------------------------------------------------------------------------------
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms run on rank 0 alone and may use the whole host."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def _cpu_sample(use_reference: bool):
-    """One bounded sample of the CPU path: preprocess 1 image, tower+projector on 1 tile, merge+splice of 1 image.
-    Returns (seconds per image extrapolated to 10 tiles, description, kind, cores)."""
+    """One bounded sample of the CPU path = ONE whole image of the workload, nothing extrapolated: preprocess a
+    1024x1024 image (10 tiles), tower + projector on all 10 tiles (fp32), merge + splice with a 32-token prompt.
+    Returns (seconds per image, description, kind, cores)."""
     import numpy as np
     import torch
     import golden_inputs as gi
-    cores = torch.get_num_threads()
+    cores = _use_all_host_threads()
     rng = np.random.default_rng(0)
     gray = rng.integers(0, 256, size=(IMG, IMG), dtype=np.uint8)
+    ids = torch.randint(1, 1000, (1, 32), generator=torch.Generator().manual_seed(5))
+    ids[0, 7] = -200
     if use_reference:
         from PIL import Image
         st = _cpu_state(True)
@@ -86,20 +108,14 @@ def _cpu_sample(use_reference: bool):
         tiles = ref.mm_utils.process_anyres_image(pil, host.get_vision_tower().image_processor, gi.PINPOINTS)
         t_pre = time.perf_counter() - t0
         t0 = time.perf_counter()
-        with torch.no_grad():
-            feat1 = host.encode_images(tiles[:1])
-        t_tile = time.perf_counter() - t0
-        feats = feat1.expand(TILES_PER_IMAGE, -1, -1).contiguous()
-        host.encode_images = lambda images, _f=feats: _f
-        ids = torch.randint(1, 1000, (1, 32))
-        ids[0, 5] = -200
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            host.prepare_inputs_labels_for_multimodal(ids, None, torch.ones_like(ids, dtype=torch.bool), None, ids.clone(),
-                                                      [tiles], ["image"], [(IMG, IMG)])
-        t_merge = time.perf_counter() - t0
-        del host.encode_images
+        with torch.no_grad():   # the reference's own entry point: encode_images (10 tiles) + merge + splice inside
+            out = host.prepare_inputs_labels_for_multimodal(ids, None, torch.ones_like(ids, dtype=torch.bool), None,
+                                                            ids.clone(), [tiles], ["image"], [(IMG, IMG)])
+        t_enc = time.perf_counter() - t0
+        assert out[4].shape[1] == 31 + TOKENS_PER_IMAGE
         kind = "reference"
+        desc = ("1 whole image: process_anyres_image (%.2fs) + prepare_inputs_labels_for_multimodal = SigLIP tower + "
+                "projector fp32 on all 10 tiles + merge/splice (%.2fs)" % (t_pre, t_enc))
     else:
         from oracle import encoder_oracle as eo
         from oracle import resample_oracle as ro
@@ -109,20 +125,16 @@ def _cpu_sample(use_reference: bool):
         t_pre = time.perf_counter() - t0
         t0 = time.perf_counter()
         with torch.no_grad():
-            feat1 = eo.encode_images(st["tsd"], st["psd"], tiles[:1])
-        t_tile = time.perf_counter() - t0
-        feats = feat1.expand(TILES_PER_IMAGE, -1, -1).contiguous()
-        ids = torch.randint(1, 1000, (1, 32))
-        ids[0, 5] = -200
-        t0 = time.perf_counter()
-        merged = eo.merge_image(feats, (IMG, IMG), st["newline"], gi.PINPOINTS)
-        eo.prepare_inputs_labels(st["table"], [merged], ids, torch.ones_like(ids, dtype=torch.bool), ids.clone(), 32768, False)
-        t_merge = time.perf_counter() - t0
+            feats = eo.encode_images(st["tsd"], st["psd"], tiles)
+            merged = eo.merge_image(feats, (IMG, IMG), st["newline"], gi.PINPOINTS)
+            emb = eo.prepare_inputs_labels(st["table"], [merged], ids, torch.ones_like(ids, dtype=torch.bool), ids.clone(),
+                                           32768, False)[0]
+        t_enc = time.perf_counter() - t0
+        assert emb.shape[1] == 31 + TOKENS_PER_IMAGE
         kind = "port"
-    per_image = t_pre + TILES_PER_IMAGE * t_tile + t_merge
-    desc = ("1 image: process_anyres_image (%.2fs) + tower/projector fp32 on 1 of 10 tiles (%.2fs, x10 extrapolated) + "
-            "merge/splice (%.2fs)" % (t_pre, t_tile, t_merge))
-    return per_image, desc, kind, cores
+        desc = ("1 whole image: preprocess (%.2fs) + SigLIP tower + projector fp32 on all 10 tiles + merge/splice (%.2fs), "
+                "oracle port of the reference path" % (t_pre, t_enc))
+    return t_pre + t_enc, desc, kind, cores
 
 
 _CPU_STATE = {}
@@ -147,12 +159,15 @@ def _cpu_state(use_reference: bool):
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the box's host cores (the real Python reference when
+    /root/reference exists, else the oracle port).  Each step = one whole 1024x1024 image (10 tiles, nothing
+    extrapolated).  Under torchrun rank 0 alone runs it, with ALL host threads; the other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle.ref_loader import reference_available
     use_ref = reference_available()
-    for _ in range(args.warmup):
+    for _ in range(max(1, min(args.warmup, 2))):   # the first call pages the weights in; more warm-up buys nothing on a CPU
         _cpu_sample(use_ref)
     t_total, per_image_s, desc, kind, cores = 0.0, [], "", "", 1
     for _ in range(args.steps):
@@ -160,17 +175,20 @@ def run_reference_arm(args):
         s, desc, kind, cores = _cpu_sample(use_ref)
         t_total += time.perf_counter() - t0
         per_image_s.append(s)
-    per_image = sorted(per_image_s)[len(per_image_s) // 2]
+    per_image = sum(per_image_s) / len(per_image_s)
     value = TOKENS_PER_IMAGE / per_image
+    cfg = _workload_config(args, max(args.gpus, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _workload_config(args, max(args.gpus, 1)),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": kind,
-                         "sample": "each step = " + desc + "; value = 7371 tokens / median extrapolated seconds per image"},
+                         "sample": "each step = " + desc + "; value = 7371 tokens / mean seconds per image over %d steps" % args.steps},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "CPU path, rank 0 only, %d threads; each step = 1 image of the workload (the CPU does not scale with the "
+                "GPU count: the same value at every N)" % cores,
     }
     print(json.dumps(line))
     return 0
@@ -262,6 +280,30 @@ def _gpu_eager_incumbent(host, dev, n_tiles=80, reps=3):
     return n_tiles / TILES_PER_IMAGE * TOKENS_PER_IMAGE / sec, sec
 
 
+def _init_dist():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def _prompt(B, dev, Lp=32):
+    import torch
+    ids = torch.randint(1, 4000, (B, Lp), generator=torch.Generator().manual_seed(5))
+    ids[:, 7] = -200
+    ids_dev = ids.to(dev)
+    mask_dev = torch.ones_like(ids_dev, dtype=torch.bool)
+    labels_dev = torch.where(ids_dev < 0, torch.full_like(ids_dev, -100), ids_dev)
+    pos_dev = torch.arange(Lp, device=dev)[None].expand(B, -1).contiguous()
+    return ids_dev, pos_dev, mask_dev, labels_dev
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -270,19 +312,13 @@ def run_b200_arm(args):
     from radvlm_b200.encoder import flops_per_tile
     import golden_inputs as gi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = _init_dist()
     _lib.load()
 
     B = args.batch
     host = synthetic.build_host(hidden_size=3584, vocab=4096, seed=0, dtype=torch.bfloat16, device=dev)
     from radvlm_b200 import mm_arch
-    mm_arch._encoder_for(host).freeze()
+    enc = mm_arch._encoder_for(host).freeze()
 
     # synthetic chest-X-ray-shaped inputs: 1024x1024 grayscale replicated to RGB, uint8, 3 rotating batches
     rng = np.random.default_rng(1000 + rank)
@@ -294,19 +330,16 @@ def run_b200_arm(args):
         host_imgs.append(rgb)
         dev_imgs.append(rgb.to(dev))
     Lp = 32
-    ids = torch.randint(1, 4000, (B, Lp), generator=torch.Generator().manual_seed(5))
-    ids[:, 7] = -200
-    ids_dev = ids.to(dev)
-    mask_dev = torch.ones_like(ids_dev, dtype=torch.bool)
-    labels_dev = torch.where(ids_dev < 0, torch.full_like(ids_dev, -100), ids_dev)
-    pos_dev = torch.arange(Lp, device=dev)[None].expand(B, -1).contiguous()
-    # N > 1: the all-gather of step i runs asynchronously (NCCL's own stream) and overlaps the encode of step i+1;
-    # two (embeddings, gathered) slots alternate, a slot is reused only after its collective has completed.
-    # --gather peer: no collective call at all - the merge kernel itself writes every embedding row into the other
-    # ranks' gathered buffers over NVLink (radvlm_merge_splice_scatter, dist.PeerGather), on a side stream.
+    prompt = _prompt(B, dev, Lp)
+    # N > 1: every rank's inputs_embeds are gathered on every rank, overlapping the next step's encode.
+    #   --gather ce     : dist.PeerGather(mode="ce"): the merge kernel writes into peer-mapped memory, DMA engines push
+    #                     the finished slice to every peer over NVLink (no SM, no collective call)
+    #   --gather peer   : dist.PeerGather(mode="kernel"): the fused merge + scatter kernel stores every row to all peers
+    #   --gather nccl   : asynchronous NCCL all_gather_into_tensor, two alternating slots
     slots = [{"work": None, "emb": None, "out": None} for _ in range(2)]
     step_no = [0]
     peer = [None]
+    last = {"emb": None, "slot": None}
 
     def drain_gathers():
         if peer[0] is not None:
@@ -316,27 +349,32 @@ def run_b200_arm(args):
                 sl["work"].wait()
                 sl["work"] = None
 
-    def step(images_u8):
+    def step(images_u8, pr=prompt):
+        n = len(images_u8)
         tiles, sizes, splits, _ = mm_utils.preprocess_anyres_batch(list(images_u8), gi.PINPOINTS, device=dev,
                                                                    dtype=torch.bfloat16)
-        out = host.prepare_inputs_labels_for_multimodal(ids_dev, pos_dev, mask_dev, None, labels_dev,
-                                                        list(torch.split(tiles, splits)), ["image"] * B, sizes)
+        if peer[0] is not None:
+            last["slot"] = peer[0].peek_slot()
+        out = host.prepare_inputs_labels_for_multimodal(pr[0], pr[1], pr[2], None, pr[3],
+                                                        list(torch.split(tiles, splits)), ["image"] * n, sizes)
         emb = out[4]
-        if world > 1 and args.gather in ("peer", "auto"):
+        last["emb"] = emb
+        if world > 1 and args.gather in ("peer", "ce", "auto") and n == B:
             if peer[0] is None:   # first step: size the peer buffers from the embeddings, then redo the step into them
                 from radvlm_b200.dist import PeerGather
+                mode = "kernel" if args.gather == "peer" else "ce"
                 try:
-                    peer[0] = PeerGather(emb.shape[0] * emb.shape[1], emb.shape[2], emb.dtype, dev)
+                    peer[0] = PeerGather(emb.shape[0] * emb.shape[1], emb.shape[2], emb.dtype, dev, mode=mode)
                 except Exception as e:  # no cudaIpc / peer access on this box: the NCCL all-gather does the same job
-                    if args.gather == "peer":
+                    if args.gather != "auto":
                         raise
                     print("bench: peer-memory gather unavailable (%s); using the NCCL all-gather" % e, file=sys.stderr)
                     args.gather = "nccl"
-                    return step(images_u8)
-                args.gather = "peer"
+                    return step(images_u8, pr)
+                args.gather = "peer" if mode == "kernel" else "ce"
                 host.radvlm_b200_gather = peer[0]
-                return step(images_u8)
-        elif world > 1:
+                return step(images_u8, pr)
+        elif world > 1 and n == B:
             sl = slots[step_no[0] & 1]
             step_no[0] += 1
             if sl["work"] is not None:
@@ -345,6 +383,7 @@ def run_b200_arm(args):
                 sl["out"] = torch.empty((world,) + tuple(emb.shape), dtype=emb.dtype, device=dev)
             sl["emb"] = emb
             sl["work"] = dist.all_gather_into_tensor(sl["out"], emb, async_op=True)
+            last["slot"] = sl
         return emb
 
     def sync():
@@ -352,17 +391,18 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(src_list, steps, read_back):
+    def timed(fn, steps, read_back=False):
+        """device time of `steps` calls of fn(i), bracketed by barrier + synchronize, max over ranks"""
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
         e0.record()
         chk = 0.0
         for i in range(steps):
-            emb = step(src_list[i % n_buf])
+            emb = fn(i)
             if read_back:
                 chk += float(emb[0, -1, :8].float().sum().item())   # D2H read of a slice of the result
-        drain_gathers()   # the timed region ends when the last all-gather has landed
+        drain_gathers()   # the timed region ends when the last exchange has landed
         e1.record()
         sync()
         ms = e0.elapsed_time(e1)
@@ -377,20 +417,81 @@ def run_b200_arm(args):
     drain_gathers()
     sync()
 
-    # ---- device-resident arm, with live per-kernel-class timing (CUDA events on the launch stream)
-    _lib.profile_enable(True)
-    _lib.profile_read()
+    # ---- device-resident arm: the headline `value`.  The per-class CUDA-event instrumentation is OFF here.
     clocks = ClockSampler(local) if rank == 0 else None
-    ms, tw0, tw1, _ = timed(dev_imgs, args.steps, read_back=False)
+    ms, tw0, tw1, _ = timed(lambda i: step(dev_imgs[i % n_buf]), args.steps)
     clk = clocks.stop(tw0, tw1) if clocks else None
-    prof_ms, prof_n = _lib.profile_read()
-    _lib.profile_enable(False)
 
     # ---- end-to-end arm: pinned host uint8 in, slice of the result out, every step
     for i in range(min(2, args.warmup)):
         step(host_imgs[i % n_buf])
-    ms_e2e, _, _, _ = timed(host_imgs, args.steps, read_back=True)
+    ms_e2e, _, _, _ = timed(lambda i: step(host_imgs[i % n_buf]), args.steps, read_back=True)
 
+    # ---- profiled pass (separate from the timed regions): live duration / launch count of every kernel class,
+    #      CUDA events recorded around each launch on the launch stream (radvlm_profile_*)
+    prof_steps = max(1, min(args.steps, 5))
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    ms_prof, _, _, _ = timed(lambda i: step(dev_imgs[i % n_buf]), prof_steps)
+    prof_ms, prof_n = _lib.profile_read()
+    _lib.profile_enable(False)
+
+    # ---- N > 1: prove the exchange delivered every rank's rows (checksum of checksums over the gathered buffer)
+    gather_check = None
+    if world > 1:
+        emb = step(dev_imgs[0])
+        drain_gathers()
+        torch.cuda.synchronize(dev)
+        rows = emb.shape[0] * emb.shape[1]
+        if peer[0] is not None:
+            gathered = peer[0].gathered(last["slot"])[:, :rows]
+        else:
+            gathered = last["slot"]["out"].view(world, rows, -1)
+        mine = emb.reshape(rows, -1).view(torch.int32).sum(dtype=torch.int64).reshape(1)    # bit-level checksum
+        theirs = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(theirs, mine)
+        seen = torch.stack([gathered[r].reshape(rows, -1).view(torch.int32).sum(dtype=torch.int64) for r in range(world)])
+        ok = torch.tensor([1 if torch.equal(seen, theirs) and len(set(theirs.tolist())) == world else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = "ok" if int(ok.item()) == 1 else "FAILED"
+        gather_check += (": every rank holds all %d ranks' [%d, %d] slices, int32-sum checksums equal to the owners' "
+                         "(all ranks agree, %d distinct batches)" % (world, rows, emb.shape[2], len(set(theirs.tolist()))))
+
+    # ---- strong scaling, BASELINE.json configs[2]: a fixed global batch of 256 images, 256 / N per rank in
+    #      micro-batches of B, embeddings exchanged per micro-batch
+    c3 = None
+    if args.c3 and 256 % (world * B) == 0:
+        micro = 256 // (world * B)
+        reps = 2
+        timed(lambda i: step(dev_imgs[i % n_buf]), micro)   # one untimed global batch
+        ms_c3, _, _, _ = timed(lambda i: step(dev_imgs[i % n_buf]), micro * reps)
+        c3 = {"value": 256 * TOKENS_PER_IMAGE / (ms_c3 / reps / 1e3), "unit": "tokens/s", "scaling": "strong",
+              "ms_per_global_batch": ms_c3 / reps, "global_batch": 256, "images_per_rank": 256 // world,
+              "micro_batches_per_rank": micro, "repeats": reps,
+              "workload": "BASELINE.json configs[2]: 256 synthetic 1024x1024 CXR = 2560 tiles -> 1,886,976 visual tokens "
+                          "per global batch, image-sharded over %d GPU(s)" % world}
+
+    # ---- batch 1 (the reference trains and serves at per-device batch 1: ONE 10-tile image per call)
+    b1 = None
+    if args.batch1:
+        p1 = _prompt(1, dev, Lp)
+        one = [dev_imgs[k][j:j + 1] for k in range(n_buf) for j in range(min(B, 4))]
+        saved_gather = getattr(host, "radvlm_b200_gather", None)
+        host.radvlm_b200_gather = None
+        for i in range(5):
+            step(one[i % len(one)], p1)
+        reps1 = 40
+        ms_b1, _, _, _ = timed(lambda i: step(one[i % len(one)], p1), reps1)
+        host.radvlm_b200_gather = saved_gather
+        peaks1, _ = _peaks()
+        pk1 = float(peaks1.get("bf16_tflops_sustained", peaks1["bf16_tflops"]))
+        b1 = {"ms_per_image": ms_b1 / reps1, "value": TOKENS_PER_IMAGE / (ms_b1 / reps1 / 1e3), "unit": "tokens/s",
+              "tiles_per_call": TILES_PER_IMAGE, "calls": reps1,
+              "path_frac_of_peak": flops_per_tile() * TILES_PER_IMAGE / (ms_b1 / reps1 / 1e3) / 1e12 / pk1,
+              "what": "one 1024x1024 image per call through preprocess + prepare_inputs_labels_for_multimodal, device "
+                      "resident, per rank (no exchange)"}
+
+    line = None
     if rank == 0:
         peaks, peak_src = _peaks()
         tokens_step = B * world * TOKENS_PER_IMAGE
@@ -402,7 +503,7 @@ def run_b200_arm(args):
         attn_flops = 26 * 4.0 * 729 * 729 * 1152
         gemm_flops_step = (flops_per_tile() - attn_flops) * TILES_PER_IMAGE * B
         gemm_total_ms = sum(v for k, v in prof_ms.items() if k.startswith("gemm"))
-        gemm_ms_step = gemm_total_ms / args.steps
+        gemm_ms_step = gemm_total_ms / prof_steps
         achieved_all = gemm_flops_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         hbm_peak = float(peaks.get("hbm_gbs", 6545.0))
@@ -412,7 +513,7 @@ def run_b200_arm(args):
 
         def per_launch(cls, work_step):
             n = max(prof_n.get(cls, 0), 1)
-            return work_step * args.steps / n, prof_ms.get(cls, 0.0) / n, n / args.steps
+            return work_step * prof_steps / n, prof_ms.get(cls, 0.0) / n, n / prof_steps
 
         def traffic_of(cls, launches_per_step):
             """DRAM bytes of one launch from the ncu capture, if it was taken at this run's tiles-per-launch."""
@@ -424,11 +525,22 @@ def run_b200_arm(args):
                 return None
             return (t["dram_read_mb"] + t["dram_write_mb"]) * 1e6
 
-        fc2_flops, fc2_ms, fc2_lps = per_launch("gemm_fc2", 26 * 2.0 * rows_step * 1152 * 4304)
-        fc2_ach = fc2_flops / (fc2_ms * 1e-3) / 1e12 if fc2_ms > 0 else 0.0
+        def tensor_roofline(cls, kernel, flops_step_cls):
+            fl, ms_l, lps = per_launch(cls, flops_step_cls)
+            ach = fl / (ms_l * 1e-3) / 1e12 if ms_l > 0 else 0.0
+            return {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": traffic_of(cls, lps), "algorithmic_flops_per_launch": fl,
+                    "ms_per_launch": ms_l, "launches_per_step": lps,
+                    "share_of_step": prof_ms.get(cls, 0.0) / total_ms}
+
+        fc2 = tensor_roofline("gemm_fc2", "tcgen05 cta_group::2 GEMM as fc2 ([rows,4304] x [1152,4304]^T, fp32 residual "
+                              "epilogue)", 26 * 2.0 * rows_step * 1152 * 4304)
+        fc2["peak_source"] = "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src
+        fc2["measured"] = ("separate profiled pass of %d steps right after the timed regions (CUDA events around every "
+                           "launch; the timed regions run with the instrumentation off)" % prof_steps)
         ln_bytes, ln_ms, ln_lps = per_launch("layernorm", 52 * 6.0 * rows_step * 1152)
         ln_ach = ln_bytes / (ln_ms * 1e-3) / 1e9 if ln_ms > 0 else 0.0
-        at_flops, at_ms, at_lps = per_launch("attention", attn_flops * TILES_PER_IMAGE * B)
+        launches_step = sum(prof_n.values()) / prof_steps
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -436,39 +548,40 @@ def run_b200_arm(args):
             "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * IMG * IMG * 3 + B * 128 + 4096,
                     "d2h_bytes_per_step": B * Lp * 8 + 4},
-            "gpu_launches": int(sum(prof_n.values())),
+            "gpu_launches": int(round(launches_step * args.steps)),
             "clocks": clk,
-            "roofline": {"kernel": "gemm_bf16_tn_2cta_kernel<192,3> as the fc2 GEMM (tcgen05 cta_group::2, fp32 residual "
-                                   "epilogue)", "bound": "tensor",
-                         "achieved": fc2_ach, "peak": peak, "unit": "TFLOP/s", "frac": fc2_ach / peak,
-                         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
-                         "traffic": traffic_of("gemm_fc2", fc2_lps),
-                         "algorithmic_flops_per_launch": fc2_flops, "ms_per_launch": fc2_ms,
-                         "launches_per_step": fc2_lps,
-                         "share_of_step": prof_ms.get("gemm_fc2", 0.0) / total_ms},
+            "roofline": fc2,
             "roofline_all_gemms": {"kernel": "all tcgen05 GEMM launches of a step (patch, qkv, out, fc1, fc2, projector)",
                                    "bound": "tensor", "achieved": achieved_all, "peak": peak, "unit": "TFLOP/s",
                                    "frac": achieved_all / peak, "traffic": None,
                                    "algorithmic_flops_per_step": gemm_flops_step, "kernel_ms_per_step": gemm_ms_step,
                                    "share_of_step": gemm_total_ms / total_ms},
-            "roofline_attention": {"kernel": "siglip_attention_pp_kernel", "bound": "tensor (MUFU issue co-limited, DESIGN.md)",
-                                   "achieved": at_flops / (at_ms * 1e-3) / 1e12 if at_ms > 0 else 0.0, "peak": peak,
-                                   "unit": "TFLOP/s", "frac": (at_flops / (at_ms * 1e-3) / 1e12 / peak) if at_ms > 0 else 0.0,
-                                   "traffic": traffic_of("attention", at_lps),
-                                   "share_of_step": prof_ms.get("attention", 0.0) / total_ms},
+            "roofline_gemm_qkv": tensor_roofline("gemm_qkv", "QKV GEMM (head-split epilogue)", 26 * 2.0 * rows_step * 1152 * 3456),
+            "roofline_gemm_out": tensor_roofline("gemm_out", "out_proj GEMM (fp32 residual epilogue)", 26 * 2.0 * rows_step * 1152 * 1152),
+            "roofline_gemm_fc1": tensor_roofline("gemm_fc1", "fc1 GEMM (GELU-tanh epilogue)", 26 * 2.0 * rows_step * 1152 * 4304),
+            "roofline_attention": tensor_roofline("attention", "siglip_attention_pp_kernel (MUFU issue co-limited, DESIGN.md)",
+                                                  attn_flops * TILES_PER_IMAGE * B),
             "roofline_layernorm": {"kernel": "layernorm_f32_to_bf16_kernel", "bound": "hbm", "achieved": ln_ach,
                                    "peak": hbm_peak, "unit": "GB/s", "frac": ln_ach / hbm_peak,
                                    "traffic": traffic_of("layernorm", ln_lps),
                                    "algorithmic_bytes_per_launch": ln_bytes, "ms_per_launch": ln_ms,
                                    "share_of_step": prof_ms.get("layernorm", 0.0) / total_ms},
-            "kernel_ms_per_step": {k: v / args.steps for k, v in prof_ms.items()},
-            "kernel_launches_per_step": {k: v / args.steps for k, v in prof_n.items()},
+            "kernel_ms_per_step": {k: v / prof_steps for k, v in prof_ms.items()},
+            "kernel_launches_per_step": {k: v / prof_steps for k, v in prof_n.items()},
+            "profiled_pass": {"steps": prof_steps, "ms_per_step": ms_prof / prof_steps,
+                              "sum_of_kernels_ms_per_step": total_ms / prof_steps},
             "path_tflops": flops_per_tile() * TILES_PER_IMAGE * B * world / (ms / args.steps / 1e3) / 1e12,
             "path_frac_of_peak": flops_per_tile() * TILES_PER_IMAGE * B / (ms / args.steps / 1e3) / 1e12 / peak,
         }
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+        if c3 is not None:
+            line["c3_strong"] = c3
+        if b1 is not None:
+            line["batch1"] = b1
         if world == 1 and not args.no_cpu_baseline:
-            s, desc, kind, cores = _cpu_sample(False)
-            line["cpu_baseline"] = {"value": TOKENS_PER_IMAGE / s, "unit": "tokens/s", "cores": cores, "kind": kind,
+            s_img, desc, kind, cores = _cpu_sample(False)
+            line["cpu_baseline"] = {"value": TOKENS_PER_IMAGE / s_img, "unit": "tokens/s", "cores": cores, "kind": kind,
                                     "sample": desc}
             try:   # context only: the same architecture in torch eager bf16 on this GPU (tower + projector alone)
                 v, sec = _gpu_eager_incumbent(host, dev)
@@ -478,44 +591,51 @@ def run_b200_arm(args):
                             "only (its CPU preprocessing and merge not charged), 80 tiles per call, %.1f ms" % (sec * 1e3)}
             except Exception as e:  # e.g. out of memory on a shared box: the headline numbers do not depend on it
                 line["gpu_eager_incumbent"] = {"unavailable": str(e)[:200]}
+    if world > 1 and peer[0] is not None:
+        host.radvlm_b200_gather = None
+        peer[0].close()   # unmap the peers' buffers, then free this rank's
+        peer[0] = None
+    # ---- training mode (BASELINE.json configs[4]) as a key of the same line
+    if args.train_steps > 0:
+        del dev_imgs, host_imgs
+        torch.cuda.empty_cache()
+        tr = _train_measure(args, host, world, rank, local, dev, steps=args.train_steps, warmup=3)
+        if line is not None:
+            line["train"] = tr
+    if rank == 0:
+        if args.workload == "c3" and line.get("c3_strong"):   # the strong-scaling configuration as the headline of this line
+            c = line["c3_strong"]
+            line["weak_scaling_value"] = line["value"]
+            line.update({"value": c["value"], "scaling": "strong", "ms_per_step": c["ms_per_global_batch"],
+                         "steps": c["repeats"], "e2e": None})
+            line["config"]["workload"] = c["workload"] + " (a step = one global batch)"
         print(json.dumps(line))
     if world > 1:
-        if peer[0] is not None:
-            host.radvlm_b200_gather = None
-            peer[0].close()   # unmap the peers' buffers, then free this rank's
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# training-mode arm (BASELINE.json configs[4]): --mode train.  Not the driver's headline metric: an extra line.
+# training mode (BASELINE.json configs[4]): a `train` key of the main line, or a line of its own with --mode train
 # ----------------------------------------------------------------------------------------------------------------
-def run_train_arm(args):
+def _train_measure(args, host, world, rank, local, dev, steps, warmup):
     """Step = preprocess + tower/projector/merge/splice forward (activations saved) + backward with a random upstream
-    gradient on inputs_embeds + (N > 1) bucketed NCCL all-reduce of the tower / projector gradients, overlapped."""
+    gradient on inputs_embeds + (N > 1) NCCL all-reduce (average) of the tower / projector gradients, issued per layer
+    range from inside the backward, in place on the flat gradient buffer."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from radvlm_b200 import _lib, mm_arch, mm_utils, synthetic
+    from radvlm_b200 import _lib, mm_arch, mm_utils
     from radvlm_b200.encoder import flops_per_tile
     import golden_inputs as gi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-    B = args.batch
-    host = synthetic.build_host(hidden_size=3584, vocab=4096, seed=0, dtype=torch.bfloat16, device=dev)
+    B = args.train_batch
     host.model.vision_tower.requires_grad_(True)      # mm_tunable_parts = mm_vision_tower, mm_mlp_adapter
     host.model.mm_projector.requires_grad_(True)
     host.model.image_newline.requires_grad_(True)
     host.train()
-    enc = mm_arch._encoder_for(host)
+    enc = mm_arch._encoder_for(host).freeze(False)
     enc.grad_allreduce_group = None if world > 1 else False
     rng = np.random.default_rng(2000 + rank)
     n_buf = 2
@@ -523,20 +643,13 @@ def run_train_arm(args):
     for _ in range(n_buf):
         gray = rng.integers(0, 256, size=(B, IMG, IMG, 1), dtype=np.uint8)
         dev_imgs.append(torch.from_numpy(np.repeat(gray, 3, axis=3).copy()).to(dev))
-    Lp = 32
-    ids = torch.randint(1, 4000, (B, Lp), generator=torch.Generator().manual_seed(5))
-    ids[:, 7] = -200
-    ids_dev = ids.to(dev)
-    mask_dev = torch.ones_like(ids_dev, dtype=torch.bool)
-    labels_dev = torch.where(ids_dev < 0, torch.full_like(ids_dev, -100), ids_dev)
-    pos_dev = torch.arange(Lp, device=dev)[None].expand(B, -1).contiguous()
+    pr = _prompt(B, dev)
     upstream = [None]
-    t_fwd = [0.0]
 
     def step(images_u8, timed_fwd=None):
         tiles, sizes, splits, _ = mm_utils.preprocess_anyres_batch(list(images_u8), gi.PINPOINTS, device=dev,
                                                                    dtype=torch.bfloat16)
-        out = host.prepare_inputs_labels_for_multimodal(ids_dev, pos_dev, mask_dev, None, labels_dev,
+        out = host.prepare_inputs_labels_for_multimodal(pr[0], pr[1], pr[2], None, pr[3],
                                                         list(torch.split(tiles, splits)), ["image"] * B, sizes)
         emb = out[4]
         if upstream[0] is None:
@@ -546,68 +659,86 @@ def run_train_arm(args):
         emb.backward(upstream[0])
         host.zero_grad(set_to_none=True)
 
-    for i in range(args.warmup):
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(warmup):
         step(dev_imgs[i % n_buf])
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    _lib.profile_enable(True)
-    _lib.profile_read()
+    sync()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     tw0 = time.time()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         starts[i].record()
         step(dev_imgs[i % n_buf], mids[i])
     e1.record()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    sync()
     tw1 = time.time()
     ms = e0.elapsed_time(e1)
-    fwd_ms = sum(s.elapsed_time(m) for s, m in zip(starts, mids)) / args.steps
+    fwd_ms = sum(s.elapsed_time(m) for s, m in zip(starts, mids)) / steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clk = clocks.stop(tw0, tw1) if clocks else None
+    # per-class kernel times: separate profiled pass
+    prof_steps = max(1, min(steps, 3))
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    for i in range(prof_steps):
+        step(dev_imgs[i % n_buf])
+    sync()
     prof_ms, prof_n = _lib.profile_read()
     _lib.profile_enable(False)
+    host.model.vision_tower.requires_grad_(False)
+    host.model.mm_projector.requires_grad_(False)
+    host.model.image_newline.requires_grad_(False)
+    host.eval()
+    peaks, _ = _peaks()
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    tokens_step = B * world * TOKENS_PER_IMAGE
+    step_ms = ms / steps
+    # algorithmic FLOPs of a training step, nothing recomputed: forward + (dgrad + wgrad) of every Linear and the
+    # 4 backward GEMMs of attention (dV, dP, dQ, dK) = 3 x forward, minus the dgrad the patch embedding does not need
+    flops_step = (3.0 * flops_per_tile() - 2.0 * 729 * 588 * 1152) * TILES_PER_IMAGE * B
+    return {
+        "metric": "visual tokens/sec, training step (tower + projector + merge forward/backward)", "mode": "train",
+        "value": tokens_step / (step_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": step_ms, "forward_ms_per_step": fwd_ms,
+        "backward_ms_per_step": step_ms - fwd_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[4]: %d synthetic 1024x1024 CXR per GPU per step (%d tiles), "
+                               "SigLIP-so400m 26 layers + mlp2x_gelu + unpad/newline merge + splice, forward (activations "
+                               "kept, nothing recomputed) + backward with a random upstream gradient on inputs_embeds"
+                               % (B, B * TILES_PER_IMAGE)
+                               + ("" if world == 1 else "; NCCL gradient all-reduce (average, in place on the flat fp32 "
+                                                        "gradient buffer) per layer range, overlapped with the backward"),
+                   "images_per_gpu_per_step": B, "parallelism": "dp%d (replicas)" % world},
+        "clocks": clk,
+        "kernel_ms_per_step": {k: round(v / prof_steps, 3) for k, v in prof_ms.items() if v > 0},
+        "gpu_launches": int(sum(prof_n.values()) / prof_steps * steps),
+        "algorithmic_flops_per_step": flops_step,
+        "path_tflops": flops_step * world / (step_ms / 1e3) / 1e12,
+        "path_frac_of_peak": flops_step / (step_ms / 1e3) / 1e12 / peak,
+    }
+
+
+def run_train_arm(args):
+    import torch
+    import torch.distributed as dist
+    from radvlm_b200 import _lib, synthetic
+    world, rank, local, dev = _init_dist()
+    _lib.load()
+    host = synthetic.build_host(hidden_size=3584, vocab=4096, seed=0, dtype=torch.bfloat16, device=dev)
+    args.train_batch = args.train_batch if args.batch == 16 else args.batch   # --mode train --batch B keeps working
+    tr = _train_measure(args, host, world, rank, local, dev, steps=args.steps, warmup=args.warmup)
     if rank == 0:
-        peaks, _ = _peaks()
-        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        tokens_step = B * world * TOKENS_PER_IMAGE
-        step_ms = ms / args.steps
-        # algorithmic FLOPs of a training step with per-layer recompute: forward + recomputed
-        # QKV / out_proj / fc1 + 2x every Linear + 2.5x attention for the tower, 3x for the projector
-        hidden, inter, seq, proj, L = 1152, 4304, 729, 3584, 26
-        lin = 2.0 * seq * (4 * hidden * hidden + 2 * hidden * inter)
-        attn = 4.0 * seq * seq * hidden
-        tower_fwd = L * (lin + attn) + 2.0 * seq * 588 * hidden
-        recompute = L * 2.0 * seq * (4 * hidden * hidden + hidden * inter)
-        bwd = L * (2 * lin + 2.5 * attn) + 2.0 * seq * 588 * hidden
-        proj_f = 2.0 * seq * (hidden * proj + proj * proj)
-        flops_step = (tower_fwd + recompute + bwd + proj_f * (1 + 0.35 + 2)) * TILES_PER_IMAGE * B
-        print(json.dumps({
-            "metric": "visual tokens/sec, training step (tower + projector + merge forward/backward)", "mode": "train",
-            "value": tokens_step / (step_ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "forward_ms_per_step": fwd_ms,
-            "backward_ms_per_step": step_ms - fwd_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[4]: %d synthetic 1024x1024 CXR per GPU per step, SigLIP-so400m 26 "
-                                   "layers + mlp2x_gelu + unpad/newline merge + splice, forward + backward (layer "
-                                   "recompute) with a random upstream gradient on inputs_embeds" % B
-                                   + ("" if world == 1 else "; bucketed NCCL gradient all-reduce overlapped with the backward"),
-                       "images_per_gpu_per_step": B, "parallelism": "dp%d (replicas)" % world},
-            "clocks": clk,
-            "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in prof_ms.items() if v > 0},
-            "gpu_launches": int(sum(prof_n.values())),
-            "path_tflops": flops_step * world / (step_ms / 1e3) / 1e12,
-            "path_frac_of_peak": flops_step / (step_ms / 1e3) / 1e12 / peak,
-        }))
+        print(json.dumps(tr))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -635,9 +766,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"],
-                    help="N > 1: how the embeddings are all-gathered (NCCL all-gather, or the fused merge + scatter "
-                         "kernel over peer memory)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer", "ce"],
+                    help="N > 1: how the embeddings are all-gathered: ce = copy-engine push over peer memory (auto), "
+                         "peer = fused merge + scatter kernel over peer memory, nccl = NCCL all-gather")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps for the `train` key (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=4, help="images per GPU per training step")
+    ap.add_argument("--no-c3", dest="c3", action="store_false", help="skip the strong-scaling (global batch 256) key")
+    ap.add_argument("--no-batch1", dest="batch1", action="store_false", help="skip the batch-1 latency key")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
+                    help="c1 (default): BASELINE configs[1] x batch per GPU, weak scaling; c3: configs[2], a fixed global "
+                         "batch of 256 images (strong scaling) as the line's value")
     ap.add_argument("--mode", default="encode", choices=["encode", "train"],
                     help="encode: the headline metric (BASELINE configs[1..3]); train: configs[4], forward + backward")
     args = ap.parse_args()

@@ -61,6 +61,7 @@ int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_
 #define RADVLM_EPI_POS_F32 4        /* out f32  = acc + bias + aux[row % aux_period, N]  siglip_encoder.py:173 */
 #define RADVLM_EPI_BIAS_F32 6       /* out f32  = acc + bias */
 #define RADVLM_EPI_ATOMIC_F32 7     /* out f32 += acc (atomic; split-K partial sums, gradient accumulation) */
+#define RADVLM_EPI_BIAS_F16 9       /* out f16  = acc + bias                 (fp16 serving: model_worker.py:124-127) */
 
 int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                      const float* bias, int epilogue, void* out, int64_t ldo, const float* aux,
@@ -195,7 +196,7 @@ int radvlm_siglip_tower_forward(const radvlm_siglip_weights* tw, const void* pix
                                 int n_tiles, float* hidden_out, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
-/* hidden: fp32 [rows, in_dim] -> features_out: [rows, hidden] of out_dtype (RADVLM_DT_BF16 | RADVLM_DT_F32) */
+/* hidden: fp32 [rows, in_dim] -> features_out: [rows, hidden] of out_dtype (RADVLM_DT_BF16 | RADVLM_DT_F16 | RADVLM_DT_F32) */
 int radvlm_projector_forward(const radvlm_projector_weights* pw, const float* hidden, int rows,
                              void* features_out, int out_dtype, void* workspace, size_t workspace_bytes,
                              void* stream);

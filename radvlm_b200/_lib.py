@@ -29,6 +29,7 @@ EPI_RESID_F32 = 3
 EPI_POS_F32 = 4
 EPI_BIAS_F32 = 6
 EPI_ATOMIC_F32 = 7
+EPI_BIAS_F16 = 9
 
 SEG_PAD, SEG_TEXT, SEG_IMAGE = 0, 1, 2
 MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT, MERGE_VIDEO = 0, 1, 2, 3

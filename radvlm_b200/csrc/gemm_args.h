@@ -15,6 +15,8 @@ enum GemmEpilogue : int {
   EPI_ATOMIC_F32 = 7,      // out_f32 += acc (red.global.add; split-K partial sums, weight-gradient accumulation)
   EPI_GELU_TANH_DUAL_BF16 = 8,  // out_bf16 = gelu_tanh(acc + bias) and out2_bf16 = acc + bias (training forward of fc1:
                                 // the pre-activation is kept for the backward instead of recomputing the GEMM)
+  EPI_BIAS_F16 = 9,        // out_f16 = acc + bias (projector output when the model serves in fp16,
+                           // serve/model_worker.py:124-127, model/builder.py:289-294)
 };
 
 struct GemmArgs {

@@ -141,6 +141,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_BIAS_F32: return launch_gemm2_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
       case EPI_ATOMIC_F32: return launch_gemm2_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
       case EPI_GELU_TANH_DUAL_BF16: return launch_gemm2_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
+      case EPI_BIAS_F16: return launch_gemm2_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -155,6 +156,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, ta, tb, args, stream);
     case EPI_ATOMIC_F32: return launch_gemm_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
     case EPI_GELU_TANH_DUAL_BF16: return launch_gemm_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
+    case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
   return RADVLM_ERR_BAD_ARGUMENT;

@@ -13,6 +13,8 @@
 //   finetuning/llava/model/multimodal_projector/builder.py:44-48
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "gemm_args.h"
 
@@ -80,7 +82,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
   }
 
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
+  if constexpr (EPI == EPI_BIAS_F16) {
+    __half* o = reinterpret_cast<__half*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) o[j] = __float2half_rn(v[j]);
+  } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
                 EPI == EPI_GELU_TANH_DUAL_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
     if (full) {
@@ -259,15 +266,20 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
         if constexpr (EPI == EPI_GELU_ERF_BF16) {
           v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
         }
-        pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
-        pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
+        if constexpr (EPI == EPI_BIAS_F16) {
+          pk[16 * h + 2 * j] = pack_f16x2(v0, v1);
+          pk[16 * h + 2 * j + 1] = pack_f16x2(v2, v3);
+        } else {
+          pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
+          pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
+        }
       }
     }
     stage_store_row(stage, lane, pk);
     __syncwarp();
     const int v = lane & 7;
     const int gcol = col0 + 8 * v;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((kPasses == 2 && pass == 0) ? a.out2 : a.out);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((kPasses == 2 && pass == 0) ? a.out2 : a.out);  // (any 16-bit type)
     if (gcol < a.N) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -335,7 +347,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
   constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
   constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
-                          EPI == EPI_GELU_TANH_DUAL_BF16);
+                          EPI == EPI_GELU_TANH_DUAL_BF16 || EPI == EPI_BIAS_F16);  // 16-bit outputs
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;
 #pragma unroll 1

@@ -203,8 +203,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
 
 static int projector_forward_impl(const radvlm_projector_weights* pw, const float* hidden, int rows,
                                   void* out, int out_dtype, void* xn, void* h1, cudaStream_t stream) {
-  RV_CHECK_ARG(out_dtype == RADVLM_DT_BF16 || out_dtype == RADVLM_DT_F32,
-               "projector: out_dtype must be bf16 or f32");
+  RV_CHECK_ARG(out_dtype == RADVLM_DT_BF16 || out_dtype == RADVLM_DT_F32 || out_dtype == RADVLM_DT_F16,
+               "projector: out_dtype must be bf16, f16 or f32");
   RV_CHECK_ARG((pw->in_dim % 8) == 0 && (pw->hidden % 8) == 0, "projector: dims must be multiples of 8");
   int st;
   { ProfScope ps(PROF_MISC, stream); st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream); }
@@ -223,7 +223,8 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
     a.bias = pw->b2;
     a.out = out; a.ldo = pw->hidden;
     { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(h1, pw->hidden, pw->w2, pw->hidden, a,
-                       out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32, 0, stream); }
+                       out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : (out_dtype == RADVLM_DT_F16 ? EPI_BIAS_F16 : EPI_BIAS_F32),
+                       0, stream); }
     if (st) return st;
   }
   return RADVLM_OK;

@@ -257,7 +257,7 @@ class B200VisionEncoder:
         lib = _lib.load()
         n = images.shape[0]
         T, Hp = pk.tokens_per_tile, pk.proj_hidden
-        kernel_out = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        kernel_out = out_dtype if out_dtype in _DT else torch.float32
         out = torch.empty(n, T, Hp, dtype=kernel_out, device=dev)
         with torch.cuda.device(dev):
             stream = _stream_ptr(dev)
@@ -426,7 +426,7 @@ class _EncodeImagesFn(torch.autograd.Function):
         lib = _lib.load()
         n = images.shape[0]
         T, Hp, D = pk.tokens_per_tile, pk.proj_hidden, pk.hidden
-        kernel_out = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        kernel_out = out_dtype if out_dtype in _DT else torch.float32
         out = torch.empty(n, T, Hp, dtype=kernel_out, device=dev)
         chunks = []
         with torch.cuda.device(dev):

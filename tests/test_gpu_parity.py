@@ -520,3 +520,219 @@ def test_full_prepare_inputs_vs_oracle(lib, full_host):
     assert torch.equal(got[~r_mask], torch.zeros_like(got[~r_mask]))  # padding rows are zero
     cos, relmax = _assert_close_features(got[r_mask], r_emb[r_mask], "C4 inputs_embeds")
     print("C4 parity: cos=%.6f relmax=%.4f" % (cos, relmax))
+
+
+def _c4_batch(seed=404):
+    """BASELINE.json configs[3] / SURVEY 8(d) C4: batch 32, prompt lengths U[32, 512], one -200 per sample at a random
+    position except 2 text-only samples (which still consume a dummy one-tile image, llava_arch.py:449-455) and one
+    sample with 2 images; image sizes drawn from the parity list."""
+    rng = np.random.default_rng(seed)
+    B, vocab = 32, 152064
+    lengths = rng.integers(32, 513, size=B)
+    L = int(lengths.max())
+    text_only = {5, 20}
+    two_images = 11
+    ids = np.zeros((B, L), dtype=np.int64)
+    mask = np.zeros((B, L), dtype=bool)
+    sizes = []
+    for b in range(B):
+        n = int(lengths[b])
+        ids[b, :n] = rng.integers(0, vocab, size=n)
+        mask[b, :n] = True
+        if b in text_only:
+            sizes.append((384, 384))                       # dummy image of a text-only sample
+            continue
+        k = 2 if b == two_images else 1
+        ids[b, np.sort(rng.choice(np.arange(1, n - 1), size=k, replace=False))] = -200
+        for _ in range(k):
+            sizes.append(gi.PARITY_SIZES[int(rng.integers(0, len(gi.PARITY_SIZES)))])
+    labels = np.where(ids < 0, -100, ids)
+    labels[rng.random(labels.shape) < 0.3] = -100
+    return torch.from_numpy(ids), torch.from_numpy(mask), torch.from_numpy(labels), sizes, text_only
+
+
+def test_c4_full_prepare_inputs_at_spec(lib, full_host):
+    """BASELINE.json configs[3] at spec (llava_arch.py:428-531): variable-length batch 32 spliced into Qwen2-7B-sized
+    input embeddings (embed_tokens [152064, 3584] bf16).  labels / mask / position ids / max_len bit-exact vs the
+    oracle's splice layout; every text row bit-exact vs the embedding table; every visual row vs the oracle's merge of
+    the same bf16 features (copies bit-exact, pooled rows within bf16 rounding); and the visual rows of two sampled
+    images vs the full fp32 oracle (tower + projector + merge) with cos >= 0.999."""
+    from oracle import encoder_oracle as eo
+    from oracle import planner_oracle as po
+    from oracle import resample_oracle as ro
+    from radvlm_b200 import mm_utils
+    ids, mask, labels, sizes, text_only = _c4_batch()
+    B = ids.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    table = (torch.randn(152064, 3584, device="cuda", generator=g) * 0.02).bfloat16()
+    old_embed = full_host.model.embed_tokens
+    full_host.model.embed_tokens = torch.nn.Embedding.from_pretrained(table, freeze=True)
+    try:
+        # images: seeded uint8 noise at the drawn sizes (text-only samples: the all-zero dummy tile of train.py:1214-1217)
+        rng = np.random.default_rng(7)
+        u8, dummy_idx, img_i = [], [], 0
+        for b in range(B):
+            n_img = 1 if b in text_only else int((ids[b] == -200).sum())
+            for _ in range(n_img):
+                W, H = sizes[img_i]
+                if b in text_only:
+                    dummy_idx.append(img_i)
+                    u8.append(torch.zeros(H, W, 3, dtype=torch.uint8))
+                else:
+                    u8.append(torch.from_numpy(rng.integers(0, 256, size=(H, W, 1), dtype=np.uint8)).expand(-1, -1, 3))
+                img_i += 1
+        assert img_i == len(sizes) == 33
+        tiles, psizes, splits, _ = mm_utils.preprocess_anyres_batch(u8, gi.PINPOINTS, device="cuda", dtype=torch.bfloat16)
+        assert psizes == sizes
+        images = list(torch.split(tiles, splits))
+        for i in dummy_idx:                                  # the reference's dummy is ONE tile (not anyres-tiled)
+            images[i] = images[i][:1]
+        tile_counts = [int(t.shape[0]) for t in images]
+        pos_in = torch.arange(ids.shape[1])[None].expand(B, -1).contiguous()
+        feats = full_host.encode_images(torch.cat(images))
+        full_host.encode_images = lambda x, _f=feats: _f     # keep the features for the row-level checks below
+        _, pos, am, _, emb, lab = full_host.prepare_inputs_labels_for_multimodal(
+            ids.cuda(), pos_in.cuda(), mask.cuda(), None, labels.cuda(), images, ["image"] * B, sizes)
+        del full_host.encode_images
+        # ---- integers vs the oracle layout
+        plans = [po.plan_image(s, gi.PINPOINTS) for s in sizes]
+        n_tok = [730 if tc == 1 else p["n_tokens"] for tc, p in zip(tile_counts, plans)]
+        lay = po.splice_layout(ids.tolist(), mask.tolist(), n_tok, 32768, False, B)
+        max_len = lay["max_len"]
+        assert tuple(emb.shape) == (B, max_len, 3584) and emb.dtype == torch.bfloat16
+        r_lab = np.full((B, max_len), -100, dtype=np.int64)
+        r_mask = np.zeros((B, max_len), dtype=bool)
+        r_pos = np.zeros((B, max_len), dtype=np.int64)
+        text_rows, text_tok, img_rows = [], [], {}
+        for b, row in enumerate(lay["rows"]):
+            n = lay["lengths"][b]
+            r_mask[b, :n] = True
+            r_pos[b, :n] = np.arange(n)
+            for p, src in enumerate(row):
+                if src[0] == "text":
+                    r_lab[b, p] = int(labels[src[1], src[2]])
+                    text_rows.append(b * max_len + p)
+                    text_tok.append(int(ids[src[1], src[2]]))
+                elif src[0] == "image" and src[2] == 0:
+                    img_rows[src[1]] = b * max_len + p      # first row of this image's token block
+        assert np.array_equal(lab.cpu().numpy(), r_lab)
+        assert np.array_equal(am.cpu().numpy(), r_mask)
+        assert np.array_equal(pos.cpu().numpy(), r_pos)
+        # ---- text rows: exact rows of the embedding table; padding rows: zero
+        flat = emb.view(B * max_len, 3584)
+        assert torch.equal(flat[torch.tensor(text_rows, device="cuda")], table[torch.tensor(text_tok, device="cuda")])
+        assert int(flat[~torch.from_numpy(r_mask).cuda().view(-1)].abs().max()) == 0
+        # ---- every visual row vs the oracle's merge of the same bf16 features
+        newline = full_host.model.image_newline.float().cpu()
+        base, worst_pooled = 0, 0.0
+        for i, (tc, size, plan) in enumerate(zip(tile_counts, sizes, plans)):
+            f = feats[base:base + tc].float().cpu()
+            base += tc
+            if i in dummy_idx:
+                assert i not in img_rows                     # its tokens are sliced [0:0] (llava_arch.py:453-455)
+                continue
+            merged = eo.merge_image(f, size, newline, gi.PINPOINTS)
+            got = flat[img_rows[i]: img_rows[i] + merged.shape[0]].float().cpu()
+            if not plan["pool"]:
+                assert torch.equal(got, merged), "image %d %s" % (i, size)
+            else:
+                assert torch.equal(got[:729], merged[:729])
+                d = float((got - merged.bfloat16().float()).abs().max() / merged.abs().max())
+                worst_pooled = max(worst_pooled, d)
+                assert d <= 8e-3, "image %d %s pooled rows: %.3e" % (i, size, d)   # one bf16 ulp of the 4-tap lerp
+        # ---- two sampled images through the full fp32 oracle
+        tsd = {k: v.float().cpu() for k, v in full_host.model.vision_tower.vision_tower.state_dict().items()}
+        psd = {k: v.float().cpu() for k, v in full_host.model.mm_projector.state_dict().items()}
+        sampled = [i for i, (tc, s) in enumerate(zip(tile_counts, sizes)) if s in ((384, 384), (500, 300)) and i not in dummy_idx][:2]
+        assert sampled, "the seeded batch holds no small image to sample"
+        for i in sampled:
+            px = torch.from_numpy(ro.process_anyres_image(u8[i].numpy(), gi.PINPOINTS)).bfloat16().float()
+            ref = eo.merge_image(eo.encode_images(tsd, psd, px), sizes[i], newline, gi.PINPOINTS)
+            got = flat[img_rows[i]: img_rows[i] + ref.shape[0]].float().cpu()
+            cos, relmax = _assert_close_features(got, ref, "C4 visual rows of image %d %s" % (i, sizes[i]))
+        print("C4 at spec: %d tiles, max_len %d, %d text rows exact, pooled rows <= %.2e, sampled cos=%.6f relmax=%.4f"
+              % (sum(tile_counts), max_len, len(text_rows), worst_pooled, cos, relmax))
+    finally:
+        full_host.model.embed_tokens = old_embed
+
+
+def test_fp16_serving_dtype_encode_and_merge(lib):
+    """The reference serves in fp16 (serve/model_worker.py:124-127, model/builder.py:289-294: torch_dtype=float16):
+    fp16 pixels in -> fp16 features out of the projector epilogue (EPI_BIAS_F16, no fp32 detour) -> fp16
+    inputs_embeds; checked against the fp32 oracle on the same fp16 weights, text rows / labels bit-exact."""
+    from oracle import encoder_oracle as eo
+    from radvlm_b200 import mm_utils
+    host = _small_host(torch.float16)
+    img = gi.preprocess_image(gi.preprocess_cases()["rgb_500x300_noise"])
+    tiles, sizes, splits, _ = mm_utils.preprocess_anyres_batch([torch.from_numpy(img)], gi.PINPOINTS, dtype=torch.float16)
+    assert tiles.dtype == torch.float16
+    feat = host.encode_images(tiles)
+    assert feat.dtype == torch.float16 and tuple(feat.shape) == (3, 729, gi.SMALL_PROJ)
+    tsd = {k: v.float().cpu() for k, v in host.model.vision_tower.vision_tower.state_dict().items()}
+    psd = {k: v.float().cpu() for k, v in host.model.mm_projector.state_dict().items()}
+    ref = eo.encode_images(tsd, psd, tiles.float().cpu(), num_heads=gi.SMALL_VISION["num_attention_heads"])
+    _assert_close_features(feat, ref, "fp16 features")
+    ids = torch.tensor([[11, 12, -200, 13, 14, 15]], device="cuda")
+    mask = torch.ones_like(ids, dtype=torch.bool)
+    labels = torch.where(ids < 0, torch.full_like(ids, -100), ids)
+    _, pos, am, _, emb, lab = host.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, [tiles], ["image"], sizes)
+    assert emb.dtype == torch.float16 and pos is None
+    merged = eo.merge_image(ref, sizes[0], host.model.image_newline.float().cpu(), gi.PINPOINTS)
+    table = host.model.embed_tokens.weight
+    r_emb, r_lab, r_mask, _ = eo.prepare_inputs_labels(table.float().cpu(), [merged], ids.cpu(), mask.cpu(), labels.cpu(), 32768, False)
+    assert torch.equal(lab.cpu(), r_lab) and torch.equal(am.cpu(), r_mask)
+    assert torch.equal(emb[0, :2], table[ids[0, :2]]) and torch.equal(emb[0, -3:], table[ids[0, -3:]])   # fp16 rows, bit-exact
+    _assert_close_features(emb, r_emb, "fp16 inputs_embeds")
+    # the visual rows are exactly the fp16 features the encoder produced (pure gather for this un-pooled image)
+    nl = host.model.image_newline.detach()
+    again = eo.merge_image(feat.float().cpu(), sizes[0], nl.float().cpu(), gi.PINPOINTS)
+    assert torch.equal(emb[0, 2:2 + again.shape[0]].float().cpu(), again)
+
+
+def test_peer_signal_wait_times_out_with_a_status_instead_of_trapping(lib):
+    """A peer that never arrives must not kill the CUDA context (round 1: __trap()): the wait kernel gives up after
+    timeout_s, records 1 + (missing rank) in the pinned status word, and the context stays usable."""
+    from radvlm_b200 import _lib
+    flags_mine = torch.zeros(8, dtype=torch.int64, device="cuda")       # this rank's flag array
+    flags_other = torch.zeros(8, dtype=torch.int64, device="cuda")      # stands in for the absent peer's array
+    ptrs = torch.tensor([flags_mine.data_ptr(), flags_other.data_ptr()], dtype=torch.int64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32).pin_memory()
+    # rank 0 of 2 publishes step 1 to both arrays, then waits for rank 1's flag in its own array: never comes
+    _lib.check(lib.radvlm_peer_signal_wait(ptrs.data_ptr(), flags_mine.data_ptr(), 2, 0, 1, 0.2, status.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert int(status[0]) == 2                                          # 1 + rank 1
+    assert flags_mine[0].item() == 1 and flags_other[0].item() == 1     # the publish half still happened
+    assert float((torch.ones(4, device="cuda") * 2).sum()) == 8.0       # the context survived
+    # with the peer's flag present the same call returns at once and leaves the status alone
+    status[0] = 0
+    flags_mine[1] = 1
+    _lib.check(lib.radvlm_peer_signal_wait(ptrs.data_ptr(), flags_mine.data_ptr(), 2, 0, 1, 5.0, status.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert int(status[0]) == 0
+
+
+def _run_torchrun(script, nproc, timeout=600):
+    import subprocess, sys, socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, script)]
+    return subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_peer_gather_equals_nccl_all_gather():
+    """Both forms of the exchange over cudaIpc peer memory (copy engines; fused merge + scatter kernel), 2 ranks,
+    5 steps each (slots reused: consumer-release barrier), bit-exact against all_gather_into_tensor."""
+    r = _run_torchrun("tools/peer_gather_check.py", 2)
+    assert r.returncode == 0 and "PEER GATHER CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_training_gradients_equal_rank_average():
+    """configs[4] data parallel: the in-backward NCCL all-reduce (in place on the flat gradient buffer) gives every
+    rank the average of the per-rank gradients (57 tensors vs a single-process recomputation)."""
+    r = _run_torchrun("tools/dp_train_check.py", 2)
+    assert r.returncode == 0 and "OK" in r.stdout and "MISMATCH" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -23,13 +23,27 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     import golden_inputs as gi
     from radvlm_b200 import synthetic
-    from radvlm_b200.dist import PeerGather
     vcfg = synthetic.siglip_config(hidden_size=144, intermediate_size=272, num_hidden_layers=1, num_attention_heads=2)
     host = synthetic.build_host(hidden_size=64, vocab=gi.MERGE_VOCAB, seed=0, dtype=torch.bfloat16, device=dev, vision_cfg=vcfg)
     case = gi.merge_cases()["mixed"]
     ids, mask, labels = gi.merge_ids(case)
     pos = torch.arange(ids.shape[1])[None].expand(ids.shape[0], -1).contiguous()
     images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
+    ok = True
+    for mode in ("ce", "kernel"):
+        ok = run_mode(mode, host, case, ids, mask, labels, pos, images, dev, rank, world) and ok
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("PEER GATHER CHECK", "PASSED" if int(t.item()) == 1 else "FAILED", flush=True)
+    dist.destroy_process_group()
+    return 0 if int(t.item()) == 1 else 1
+
+
+def run_mode(mode, host, case, ids, mask, labels, pos, images, dev, rank, world):
+    """5 steps (both slots, reused twice -> the consumer-release barrier is exercised) with a different batch per rank
+    and step; `mode`: "ce" = copy-engine push of the finished slice, "kernel" = the fused merge + scatter kernel."""
+    from radvlm_b200.dist import PeerGather
     ok = True
     gather = None
     for it in range(5):
@@ -44,7 +58,7 @@ def main():
         want = torch.empty((world,) + tuple(ref.shape), dtype=ref.dtype, device=dev)
         dist.all_gather_into_tensor(want, ref.contiguous())
         if gather is None:
-            gather = PeerGather(ref.shape[0] * ref.shape[1], ref.shape[2], ref.dtype, dev)
+            gather = PeerGather(ref.shape[0] * ref.shape[1], ref.shape[2], ref.dtype, dev, mode=mode, timeout_s=60)
         host.radvlm_b200_gather = gather
         slot = gather.peek_slot()
         emb = host.prepare_inputs_labels_for_multimodal(*args, **kw)[4]
@@ -53,14 +67,10 @@ def main():
         same_local = torch.equal(emb, ref)
         same_all = torch.equal(got.view(world, *ref.shape), want)
         ok = ok and same_local and same_all
-        print("rank %d iter %d slot %d: local %s gathered %s" % (rank, it, slot, same_local, same_all), flush=True)
-    t = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        print("rank %d mode %s iter %d slot %d: local %s gathered %s" % (rank, mode, it, slot, same_local, same_all), flush=True)
+    host.radvlm_b200_gather = None
     gather.close()
-    if rank == 0:
-        print("PEER GATHER CHECK", "PASSED" if int(t.item()) == 1 else "FAILED", flush=True)
-    dist.destroy_process_group()
-    return 0 if int(t.item()) == 1 else 1
+    return ok
 
 
 if __name__ == "__main__":
