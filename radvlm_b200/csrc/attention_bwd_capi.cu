@@ -7,12 +7,16 @@
 
 namespace rv {
 
+#ifdef RV_ABWD_TIMELINE
+static long long* g_abwd_timeline = nullptr;
+#endif
+
 static size_t attn_bwd_delta_bytes(int tiles, int heads, int seq_pad) {
   return align_up(static_cast<size_t>(tiles) * heads * seq_pad * sizeof(float), 1024);
 }
 
 size_t attention_bwd_workspace_bytes(int tiles, int heads, int seq_pad) {
-  return attn_bwd_delta_bytes(tiles, heads, seq_pad) + static_cast<size_t>(tiles) * heads * seq_pad * 80 * sizeof(float);
+  return attn_bwd_delta_bytes(tiles, heads, seq_pad) + static_cast<size_t>(tiles) * heads * seq_pad * kAbDqPitch * sizeof(float);
 }
 
 int attention_bwd_launch(const void* q, const void* k, const void* vt, const void* dout, const void* out,
@@ -42,7 +46,7 @@ int attention_bwd_launch(const void* q, const void* k, const void* vt, const voi
   const uint64_t th = static_cast<uint64_t>(tiles) * heads;
   const int tokens = tiles * seq;
   const int D = heads * hd;
-  RV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(th) * seq_pad * 80 * sizeof(float), stream));
+  RV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(th) * seq_pad * kAbDqPitch * sizeof(float), stream));
   {
     RV_CHECK_ARG(heads * (hd / 8) <= 256, "attention_bwd: heads * hd / 8 must be <= 256");
     const int blocks = (tokens + 7) / 8;
@@ -69,6 +73,9 @@ int attention_bwd_launch(const void* q, const void* k, const void* vt, const voi
   a.seq = seq; a.seq_pad = seq_pad; a.heads = heads; a.hd = hd;
   a.scale = scale;
   a.scale_log2e = scale * 1.4426950408889634f;
+#ifdef RV_ABWD_TIMELINE
+  a.timeline = g_abwd_timeline;
+#endif
   dim3 grid((seq + 127) / 128, heads, tiles);
   siglip_attention_bwd_kernel<<<grid, kAbThreads, kAbSmemBytes, stream>>>(tq, tk, tv, tdo, a);
   RV_CUDA(cudaGetLastError());
@@ -93,3 +100,7 @@ extern "C" int radvlm_attention_bwd(const void* q, const void* k, const void* vt
   return rv::attention_bwd_launch(q, k, vt, dout, out, lse, dqkv, workspace, workspace_bytes, tiles, heads, seq,
                                   seq_pad, hd, hd_pad, scale, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef RV_ABWD_TIMELINE
+extern "C" void radvlm_debug_abwd_timeline(void* buffer) { rv::g_abwd_timeline = static_cast<long long*>(buffer); }
+#endif

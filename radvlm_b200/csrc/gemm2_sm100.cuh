@@ -141,14 +141,22 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int num_n = (args.N + BN - 1) / BN;
   const int num_mn = num_m * num_n;
   const int num_k_all = (args.K + kGemmBK - 1) / kGemmBK;
-  // split-K: work item t = split * num_mn + tile; split s covers K slabs [s * k_per, min(num_k_all, (s+1) * k_per))
+  // Work items.  Whole tiles (k_splits <= 1): cluster c takes tiles c, c + C, ...  Split-K (k_splits > 1, atomic fp32
+  // epilogue only): item t = split * num_mn + tile, split s covers K slabs [s * k_per, min(num_k_all, (s+1) * k_per)).
+  // Items are dealt round-robin, so the clusters of a wave work on the SAME K range of different tiles: every operand
+  // slab is fetched from HBM once and shared through L2.  (A "stream-K" deal - equal contiguous (tile, slab) ranges per
+  // cluster - was measured: perfectly balanced but 21 % slower, the clusters then sit at different K offsets and each
+  // re-reads its operand rows from HBM.)  for_each_segment is evaluated identically by the producer, the MMA issuer and
+  // the epilogue warps.
   const int k_splits = args.k_splits > 1 ? args.k_splits : 1;
   const int k_per = (num_k_all + k_splits - 1) / k_splits;
-  const int num_tiles = num_mn * k_splits;
-  auto k_range = [&](int t, int& kb0, int& kb1) {
-    const int split = t / num_mn;
-    kb0 = split * k_per;
-    kb1 = min(num_k_all, kb0 + k_per);
+  auto for_each_segment = [&](auto&& body) {
+    const int num_items = num_mn * k_splits;
+    for (int t = cluster_id; t < num_items; t += num_clusters) {
+      const int split = t / num_mn;
+      const int kb0 = split * k_per;
+      body(t - split * num_mn, kb0, min(num_k_all, kb0 + k_per));
+    }
   };
 
   if (warp == 0 && lane == 0) {
@@ -180,14 +188,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int tile = t % num_mn;
+      for_each_segment([&](int tile, int kb0, int kb1) {
         const int m_blk = tile / num_n;
         const int n_blk = tile - m_blk * num_n;
         const int row_a = m_blk * kTileM + static_cast<int>(rank) * kGemmBM;
         const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
-        int kb0, kb1;
-        k_range(t, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -213,7 +218,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             phase ^= 1u;
           }
         }
-      }
+      });
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -234,9 +239,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int kb0, kb1;
-        k_range(t, kb0, kb1);
+      for_each_segment([&](int /*tile*/, int kb0, int kb1) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * BN);
@@ -260,7 +263,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           acc = 0;
           acc_phase ^= 1u;
         }
-      }
+      });
     }
   } else {
     // ===================== epilogue (4 warps in each CTA) =====================
@@ -268,8 +271,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int tile = t % num_mn;
+    for_each_segment([&](int tile, int /*kb0*/, int /*kb1*/) {
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -289,7 +291,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         acc = 0;
         acc_phase ^= 1u;
       }
-    }
+    });
   }
 
   tc_fence_before();

@@ -226,11 +226,9 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
         o.z = __uint_as_float(t.z) + b.z + xr[i].z;
         o.w = __uint_as_float(t.w) + b.w + xr[i].w;
         float* dst = reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol;
-        if constexpr (EPI == EPI_ATOMIC_F32) {
-          atomicAdd(dst + 0, o.x);
-          atomicAdd(dst + 1, o.y);
-          atomicAdd(dst + 2, o.z);
-          atomicAdd(dst + 3, o.w);
+        if constexpr (EPI == EPI_ATOMIC_F32) {   // one 16-byte vector reduction instead of four scalar atomics
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                       : "memory");
         } else {
           *reinterpret_cast<float4*>(dst) = o;
         }

@@ -263,11 +263,23 @@ static void make_bwd_layout(const radvlm_siglip_weights* tw, const EncodeLayout&
   B->total = off;
 }
 
-static int pick_splits(int M, int N) {  // wgrad tiles are few (weights are small): cut K so ~3 waves of CTA pairs run
+// Weight-gradient GEMMs have few output tiles (25..85 for 74 CTA pairs): the K range (= the rows of the batch) is cut
+// into `splits` partial products so that tiles * splits items fill whole waves of CTA pairs.  Chosen to maximise
+// items / (waves * pairs) with a small charge per extra split (one more atomic epilogue per tile), keeping at least
+// 12 K slabs per item.
+static int pick_splits(int M, int N, int K) {
   const int pairs = (device_sm_count() > 0 ? device_sm_count() : 148) / 2;
   const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
-  int sp = (3 * pairs + tiles - 1) / tiles;
-  return sp < 1 ? 1 : (sp > 16 ? 16 : sp);
+  const int slabs = (K + 63) / 64;
+  int best = 1;
+  double best_score = -1.0;
+  for (int sp = 1; sp <= 32 && (sp == 1 || slabs / sp >= 12); ++sp) {
+    const int items = tiles * sp;
+    const int waves = (items + pairs - 1) / pairs;
+    const double score = static_cast<double>(items) / (static_cast<double>(waves) * pairs) - 0.004 * sp;
+    if (score > best_score) { best_score = score; best = sp; }
+  }
+  return best;
 }
 
 // dW[out, in] += dY^T[out, rows] X[rows, in];  db[out] += colsum(dY)
@@ -278,7 +290,7 @@ static int linear_wgrad(const void* dY, int ldy, const void* X, int ldx, int row
     GemmArgs a{};
     a.M = out_dim; a.N = in_dim; a.K = rows;
     a.out = dW; a.ldo = ldw;
-    a.a_mn = 1; a.b_mn = 1; a.k_splits = pick_splits(out_dim, in_dim);
+    a.a_mn = 1; a.b_mn = 1; a.k_splits = pick_splits(out_dim, in_dim, rows);
     { ProfScope ps(PROF_BWD_WGRAD, stream); st = gemm_dispatch(dY, ldy, X, ldx, a, EPI_ATOMIC_F32, 0, stream); }
     if (st) return st;
   }

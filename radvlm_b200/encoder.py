@@ -367,6 +367,7 @@ class _GradBuffers:
         self.proj.b2 = alloc("p.b2", (P,), "2.bias", table=psd)
         self.spans["proj"] = (c0, cursor[0])
         self._D, self._NL, self._pre = D, NL, pre
+        self._locs: Dict[tuple, object] = {}
 
     def layer_slice(self, lo: int, hi: int, include_embeddings: bool) -> torch.Tensor:
         """The contiguous slice of the flat buffer holding the gradients of layers [lo, hi) (+ the embeddings)."""
@@ -378,44 +379,64 @@ class _GradBuffers:
         a, b = self.spans["proj"]
         return self.flat[a:b]
 
-    def for_parameter(self, name: str, p: torch.Tensor, is_tower: bool) -> Optional[torch.Tensor]:
-        """Gradient of one module Parameter (its shape / dtype), or None when frozen."""
-        if not p.requires_grad:
-            return None
+    def _locate(self, name: str, is_tower: bool):
+        """(buffer key, q/k/v index or None) of one module Parameter, or None when the path does not use it."""
         D, b = self._D, self.bufs
-        g = None
         if not is_tower:
-            g = b.get({"0.weight": "p.w1", "0.bias": "p.b1", "2.weight": "p.w2", "2.bias": "p.b2"}.get(name, ""))
-        elif name == self._pre + "embeddings.patch_embedding.weight":
-            g = b["patch_w"][:, :p[0].numel()].reshape(p.shape)
-        elif name == self._pre + "embeddings.patch_embedding.bias":
-            g = b["patch_b"]
-        elif name == self._pre + "embeddings.position_embedding.weight":
-            g = b["pos"]
-        elif name.startswith(self._pre + "encoder.layers."):
-            rest = name[len(self._pre + "encoder.layers."):]
-            i, leaf = rest.split(".", 1)
-            i = int(i)
-            if i < self._NL:
-                k = "l%d." % i
-                simple = {"layer_norm1.weight": "ln1_g", "layer_norm1.bias": "ln1_b", "layer_norm2.weight": "ln2_g",
-                          "layer_norm2.bias": "ln2_b", "self_attn.out_proj.weight": "out_w",
-                          "self_attn.out_proj.bias": "out_b", "mlp.fc1.weight": "fc1_w", "mlp.fc1.bias": "fc1_b",
-                          "mlp.fc2.weight": "fc2_w", "mlp.fc2.bias": "fc2_b"}
-                if leaf in simple:
-                    g = b[k + simple[leaf]]
-                else:
-                    for j, proj in enumerate(("q_proj", "k_proj", "v_proj")):
-                        if leaf == "self_attn.%s.weight" % proj:
-                            g = b[k + "qkv_w"][j * D:(j + 1) * D]
-                        elif leaf == "self_attn.%s.bias" % proj:
-                            g = b[k + "qkv_b"][j * D:(j + 1) * D]
-        if g is None:   # a parameter the path does not use (post_layernorm, head, the dropped 27th layer): like the
-            return None  # reference, whose autograd leaves .grad = None there (AdamW then skips it entirely)
-        out = g.to(p.dtype).reshape(p.shape)
-        if out.dtype == torch.float32:   # fp32 Parameters: `out` would alias the cached flat buffer, which the next
-            out = out.clone()            # backward zeroes while .grad may still be accumulating micro-batches
-        return out
+            key = {"0.weight": "p.w1", "0.bias": "p.b1", "2.weight": "p.w2", "2.bias": "p.b2"}.get(name)
+            return (key, None) if key in b else None
+        emb = {"embeddings.patch_embedding.weight": "patch_w", "embeddings.patch_embedding.bias": "patch_b",
+               "embeddings.position_embedding.weight": "pos"}
+        rel = name[len(self._pre):] if name.startswith(self._pre) else name
+        if rel in emb:
+            return (emb[rel], None) if emb[rel] in b else None
+        if rel.startswith("encoder.layers."):
+            i, leaf = rel[len("encoder.layers."):].split(".", 1)
+            if int(i) >= self._NL:
+                return None
+            k = "l%d." % int(i)
+            simple = {"layer_norm1.weight": "ln1_g", "layer_norm1.bias": "ln1_b", "layer_norm2.weight": "ln2_g",
+                      "layer_norm2.bias": "ln2_b", "self_attn.out_proj.weight": "out_w",
+                      "self_attn.out_proj.bias": "out_b", "mlp.fc1.weight": "fc1_w", "mlp.fc1.bias": "fc1_b",
+                      "mlp.fc2.weight": "fc2_w", "mlp.fc2.bias": "fc2_b"}
+            if leaf in simple:
+                return (k + simple[leaf], None) if k + simple[leaf] in b else None
+            for j, proj in enumerate(("q_proj", "k_proj", "v_proj")):
+                if leaf == "self_attn.%s.weight" % proj:
+                    return (k + "qkv_w", j) if k + "qkv_w" in b else None
+                if leaf == "self_attn.%s.bias" % proj:
+                    return (k + "qkv_b", j) if k + "qkv_b" in b else None
+        return None   # post_layernorm, head, the dropped 27th layer
+
+    def export(self, param_names, params, needs):
+        """Gradients of the module Parameters (their shapes / dtypes; None when frozen or off the path, like the
+        reference's autograd, so AdamW skips those entirely).  The whole flat buffer is converted / copied ONCE per
+        dtype and the results are views of that copy: one kernel instead of one cast per Parameter (420 of them), and
+        nothing aliases the cached accumulators, which the next backward zeroes while .grad may still be summing
+        micro-batches."""
+        D = self._D
+        conv: Dict[torch.dtype, torch.Tensor] = {}
+        outs = []
+        for (name, is_tower), p, need in zip(param_names, params, needs):
+            loc = self._locs.get((name, is_tower), False)
+            if loc is False:
+                loc = self._locs[(name, is_tower)] = self._locate(name, is_tower)
+            if not need or not p.requires_grad or loc is None:
+                outs.append(None)
+                continue
+            key, j = loc
+            src = conv.get(p.dtype)
+            if src is None:
+                src = conv[p.dtype] = self.flat.clone() if p.dtype == torch.float32 else self.flat.to(p.dtype)
+            buf = self.bufs[key]
+            start = (buf.data_ptr() - self.flat.data_ptr()) // 4
+            t = src[start:start + buf.numel()].view(buf.shape)
+            if key == "patch_w":
+                t = t[:, :p[0].numel()]
+            elif j is not None:
+                t = t[j * D:(j + 1) * D]
+            outs.append(t.reshape(p.shape))
+        return outs
 
 
 class _EncodeImagesFn(torch.autograd.Function):
@@ -497,9 +518,7 @@ class _EncodeImagesFn(torch.autograd.Function):
                         hi = lo
         if reducer is not None:
             reducer.finish()
-        grads = []
-        for idx, ((name, is_tower), p) in enumerate(zip(ctx.param_names, ctx.params)):
-            grads.append(gb.for_parameter(name, p, is_tower) if ctx.needs_input_grad[4 + idx] else None)
+        grads = gb.export(ctx.param_names, ctx.params, ctx.needs_input_grad[4:])
         ctx.chunks = None
         return (None, None, None, None, *grads)
 
