@@ -361,6 +361,17 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return fmaf(hx, tanh_approx(u), hx);
 }
 
+// gelu_pytorch_tanh and its derivative from ONE tanh:
+//   y = 0.5 x (1 + t),  dy/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) sqrt(2/pi) (1 + 3 * 0.044715 x^2),  t = tanh(u(x))
+__device__ __forceinline__ void gelu_tanh_both_f(float x, float& y, float& dy) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(k01, x2, k0));
+  const float hx = 0.5f * x;
+  y = fmaf(hx, t, hx);
+  dy = fmaf(hx * fmaf(-t, t, 1.0f), fmaf(3.0f * k01, x2, k0), fmaf(0.5f, t, 0.5f));
+}
+
 // exact-erf GELU (nn.GELU()): erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), two MUFU ops.
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float z = fabsf(x) * 0.7071067811865476f;

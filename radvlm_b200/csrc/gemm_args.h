@@ -13,8 +13,10 @@ enum GemmEpilogue : int {
   EPI_QKV_SPLIT = 5,       // head split scatter of q/k/v                (siglip_encoder.py:207-213)
   EPI_BIAS_F32 = 6,        // out_f32  = acc + bias
   EPI_ATOMIC_F32 = 7,      // out_f32 += acc (red.global.add; split-K partial sums, weight-gradient accumulation)
-  EPI_GELU_TANH_DUAL_BF16 = 8,  // out_bf16 = gelu_tanh(acc + bias) and out2_bf16 = acc + bias (training forward of fc1:
-                                // the pre-activation is kept for the backward instead of recomputing the GEMM)
+  EPI_GELU_TANH_DUAL_BF16 = 8,  // out_bf16 = gelu_tanh(u) and out2_bf16 = gelu_tanh'(u), u = acc + bias (training forward
+                                // of fc1: the derivative is kept for the backward, one tanh serves both)
+  EPI_MUL_BF16 = 10,       // out_bf16 = bf16(acc) * m, m = out2 (bf16 [M, ldo], READ): the fc2 data gradient times the
+                           // kept gelu'(u) = the GELU backward fused into the GEMM (replaces a separate HBM pass)
   EPI_BIAS_F16 = 9,        // out_f16 = acc + bias (projector output when the model serves in fp16,
                            // serve/model_worker.py:124-127, model/builder.py:289-294)
 };
@@ -23,7 +25,7 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;  // [N] or nullptr
   void* out;          // [M, ldo] bf16 or f32 depending on the epilogue
-  void* out2;         // EPI_GELU_TANH_DUAL_BF16: pre-activation [M, ldo] bf16
+  void* out2;         // EPI_GELU_TANH_DUAL_BF16: gelu'(u) [M, ldo] bf16 (written); EPI_MUL_BF16: the multiplier (read)
   int ldo;
   const float* aux;  // EPI_RESID_F32: residual [M, ldo];  EPI_POS_F32: table [aux_period, N]
   int aux_period;

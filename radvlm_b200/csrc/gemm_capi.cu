@@ -1,4 +1,6 @@
 // C-ABI launchers for the tcgen05 GEMM (see gemm_sm100.cuh).
+#include <cstdlib>
+
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
@@ -89,6 +91,16 @@ int gemm_pick_block_n(int M, int N, int cta_group) {
   return best;
 }
 
+// MN-major B is fetched in 64-column boxes per CTA (BN/2 % 64 == 0): 256- or 128-wide tiles.  256 always: 128-wide
+// tiles waste no padding at N = 1152 (9 x 128 against 5 x 256 = 1280 columns) but were measured 22 % slower on the
+// data- and weight-gradient GEMMs of a 40-tile step (dgrad 19.0 -> 23.6 ms, wgrad 25.5 -> 31.3 ms): a 256 x 128 pair tile
+// streams 96 B/clk of operands per SM, at the shared-memory limit.
+int gemm_bmn_block_n(int N) {
+  static const int force = getenv("RADVLM_B200_BMN_BN") ? atoi(getenv("RADVLM_B200_BMN_BN")) : 0;   // tuning only
+  (void)N;
+  return force == 128 ? 128 : 256;
+}
+
 int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args_in,
                   int epilogue, int block_n, cudaStream_t stream) {
   int st = require_sm100();
@@ -100,14 +112,15 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   RV_CHECK_ARG(lda >= (args.a_mn ? args.M : args.K) && ldw >= (args.b_mn ? args.N : args.K),
                "gemm: row pitch smaller than the stored row length");
   RV_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: operand pitches must be multiples of 8 elements");
-  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16 || args.out2 != nullptr, "gemm: the dual-output epilogue needs out2");
+  RV_CHECK_ARG((epilogue != EPI_GELU_TANH_DUAL_BF16 && epilogue != EPI_MUL_BF16) || args.out2 != nullptr,
+               "gemm: the dual-output / GELU-backward epilogues need out2");
   const bool general = args.a_mn || args.b_mn || args.k_splits > 1;
   RV_CHECK_ARG(args.k_splits <= 1 || epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the atomic fp32 epilogue");
   // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs; the MN-major / split-K paths
   // exist in the pair kernel only
   const bool pair = general || g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
   int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N, pair ? 2 : 1);
-  if (args.b_mn && bn == 192) bn = 256;  // MN-major B is fetched in 64-column boxes per CTA: BN/2 % 64 == 0
+  if (args.b_mn && block_n <= 0) bn = gemm_bmn_block_n(args.N);
   if (args.k_splits > 1) {  // no empty split: (splits - 1) * ceil(slabs / splits) < slabs
     const int slabs = (args.K + kGemmBK - 1) / kGemmBK;
     int sp = args.k_splits < slabs ? args.k_splits : slabs;
@@ -142,6 +155,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_ATOMIC_F32: return launch_gemm2_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
       case EPI_GELU_TANH_DUAL_BF16: return launch_gemm2_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
       case EPI_BIAS_F16: return launch_gemm2_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
+      case EPI_MUL_BF16: return launch_gemm2_bn<EPI_MUL_BF16>(bn, ta, tb, args, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -157,6 +171,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     case EPI_ATOMIC_F32: return launch_gemm_bn<EPI_ATOMIC_F32>(bn, ta, tb, args, stream);
     case EPI_GELU_TANH_DUAL_BF16: return launch_gemm_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
     case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
+    case EPI_MUL_BF16: return launch_gemm_bn<EPI_MUL_BF16>(bn, ta, tb, args, stream);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
   return RADVLM_ERR_BAD_ARGUMENT;
@@ -178,7 +193,8 @@ extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64
                                 const float* aux, int aux_period, int block_n, void* stream) {
   using namespace rv;
   RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
-  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16, "the dual-output GELU epilogue is internal to the training forward");
+  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16 && epilogue != EPI_MUL_BF16,
+               "the dual-output GELU / GELU-backward epilogues are internal to the training path");
   RV_CHECK_ARG(out != nullptr && ldo >= N, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
   RV_CHECK_ARG((ldo % 8) == 0, "gemm: ldo must be a multiple of 8 elements");
   RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");
@@ -199,7 +215,8 @@ extern "C" int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, con
                                    const float* aux, int aux_period, int k_splits, void* stream) {
   using namespace rv;
   RV_CHECK_ARG(epilogue != EPI_QKV_SPLIT, "use radvlm_gemm_qkv_split for the QKV epilogue");
-  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16, "the dual-output GELU epilogue is internal to the training forward");
+  RV_CHECK_ARG(epilogue != EPI_GELU_TANH_DUAL_BF16 && epilogue != EPI_MUL_BF16,
+               "the dual-output GELU / GELU-backward epilogues are internal to the training path");
   RV_CHECK_ARG(out != nullptr && ldo >= N && (ldo % 8) == 0, "gemm: bad output (ldo=%lld N=%d)", (long long)ldo, N);
   RV_CHECK_ARG((a_layout | b_layout) >= 0 && a_layout <= 1 && b_layout <= 1, "gemm: layouts are 0 or 1");
   RV_CHECK_ARG(epilogue != EPI_RESID_F32 || aux != nullptr, "gemm: residual epilogue needs aux");

@@ -70,10 +70,14 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
   if constexpr (EPI == EPI_GELU_TANH_DUAL_BF16) {
     __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(row) * a.ldo + col0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < a.N) o2[j] = __float2bfloat16_rn(v[j]);
+    for (int j = 0; j < 32; ++j) {
+      float y, dy;
+      gelu_tanh_both_f(v[j], y, dy);
+      if (col0 + j < a.N) o2[j] = __float2bfloat16_rn(dy);
+      v[j] = y;
+    }
   }
-  if constexpr (EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_TANH_DUAL_BF16) {
+  if constexpr (EPI == EPI_GELU_TANH_BF16) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
   }
@@ -82,13 +86,19 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
   }
 
+  if constexpr (EPI == EPI_MUL_BF16) {
+    const __nv_bfloat16* m = reinterpret_cast<const __nv_bfloat16*>(a.out2) + static_cast<size_t>(row) * a.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) v[j] = __bfloat162float(__float2bfloat16_rn(v[j])) * __bfloat162float(m[j]);
+  }
   if constexpr (EPI == EPI_BIAS_F16) {
     __half* o = reinterpret_cast<__half*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (col0 + j < a.N) o[j] = __float2half_rn(v[j]);
   } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
-                EPI == EPI_GELU_TANH_DUAL_BF16) {
+                EPI == EPI_GELU_TANH_DUAL_BF16 || EPI == EPI_MUL_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
     if (full) {
       uint4* o4 = reinterpret_cast<uint4*>(o);
@@ -242,49 +252,81 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
                                                           const uint32_t* acc1, uint32_t stage, int lane) {
-  // EPI_GELU_TANH_DUAL_BF16 runs two passes over the same accumulators: pre-activation -> out2, GELU -> out
+  // EPI_GELU_TANH_DUAL_BF16 produces two tiles from the same accumulators: gelu(u) -> out and gelu'(u) -> out2 (one tanh
+  // for both); they go through the staging buffer one after the other.
   constexpr int kPasses = (EPI == EPI_GELU_TANH_DUAL_BF16) ? 2 : 1;
+  uint32_t pk[32], pk2[kPasses == 2 ? 32 : 1];
 #pragma unroll
-  for (int pass = 0; pass < kPasses; ++pass) {
-    const bool act = (kPasses == 1) || (pass == 1);
-    uint32_t pk[32];
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t* acc = h ? acc1 : acc0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t* acc = h ? acc1 : acc0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = col0 + 32 * h + 4 * j;
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-        float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
-        float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
-        if constexpr (EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_TANH_DUAL_BF16) {
-          if (act) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3); }
-        }
-        if constexpr (EPI == EPI_GELU_ERF_BF16) {
-          v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
-        }
-        if constexpr (EPI == EPI_BIAS_F16) {
-          pk[16 * h + 2 * j] = pack_f16x2(v0, v1);
-          pk[16 * h + 2 * j + 1] = pack_f16x2(v2, v3);
-        } else {
-          pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
-          pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
-        }
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + 32 * h + 4 * j;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
+      float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
+      if constexpr (EPI == EPI_GELU_TANH_BF16) {
+        v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
+      }
+      if constexpr (EPI == EPI_GELU_TANH_DUAL_BF16) {
+        float d0, d1, d2, d3;
+        gelu_tanh_both_f(v0, v0, d0); gelu_tanh_both_f(v1, v1, d1);
+        gelu_tanh_both_f(v2, v2, d2); gelu_tanh_both_f(v3, v3, d3);
+        pk2[16 * h + 2 * j] = pack_bf16x2(d0, d1);
+        pk2[16 * h + 2 * j + 1] = pack_bf16x2(d2, d3);
+      }
+      if constexpr (EPI == EPI_GELU_ERF_BF16) {
+        v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
+      }
+      if constexpr (EPI == EPI_BIAS_F16) {
+        pk[16 * h + 2 * j] = pack_f16x2(v0, v1);
+        pk[16 * h + 2 * j + 1] = pack_f16x2(v2, v3);
+      } else {
+        pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
+        pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
       }
     }
-    stage_store_row(stage, lane, pk);
+  }
+  // EPI_MUL_BF16: all eight multiplier pieces of this lane are requested up front (one L2 round trip, overlapped with
+  // the transposition) - loads issued inside the store loop would each wait behind the previous iteration's store
+  uint4 mm[EPI == EPI_MUL_BF16 ? 8 : 1];
+  if constexpr (EPI == EPI_MUL_BF16) {
+    const int gc = col0 + 8 * (lane & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grow = row0 + i * 4 + (lane >> 3);
+      mm[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (gc < a.N && grow < a.M)
+        mm[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out2) +
+                                                static_cast<size_t>(grow) * a.ldo + gc);
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < kPasses; ++pass) {
+    stage_store_row(stage, lane, pass == 0 ? pk : pk2);
     __syncwarp();
     const int v = lane & 7;
     const int gcol = col0 + 8 * v;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((kPasses == 2 && pass == 0) ? a.out2 : a.out);  // (any 16-bit type)
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(pass == 0 ? a.out : a.out2);  // (any 16-bit type)
     if (gcol < a.N) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3);
         const int grow = row0 + rr;
         if (grow < a.M) {
-          const uint4 t = stage_load_vec(stage, rr, v);
+          uint4 t = stage_load_vec(stage, rr, v);
+          if constexpr (EPI == EPI_MUL_BF16) {
+            // out = bf16(acc) * m, m = out2 read coalesced (the 16-byte piece the result is stored to).  Used as
+            // dL/du = dL/da * gelu'(u): dL/da is rounded to bf16 first, like a stand-alone GELU backward pass would see it.
+            const uint32_t mw[4] = {mm[i].x, mm[i].y, mm[i].z, mm[i].w};
+            uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tw[q] = pack_bf16x2(__uint_as_float(tw[q] << 16) * __uint_as_float(mw[q] << 16),
+                                  __uint_as_float(tw[q] & 0xFFFF0000u) * __uint_as_float(mw[q] & 0xFFFF0000u));
+            t = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+          }
           *reinterpret_cast<uint4*>(dst + static_cast<size_t>(grow) * a.ldo + gcol) = t;
         }
       }
@@ -345,7 +387,8 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
   constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
   constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
-                          EPI == EPI_GELU_TANH_DUAL_BF16 || EPI == EPI_BIAS_F16);  // 16-bit outputs
+                          EPI == EPI_GELU_TANH_DUAL_BF16 || EPI == EPI_BIAS_F16 ||
+                          EPI == EPI_MUL_BF16);  // 16-bit outputs
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;
 #pragma unroll 1

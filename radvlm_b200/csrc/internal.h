@@ -11,6 +11,7 @@ namespace rv {
 int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args,
                   int epilogue, int block_n, cudaStream_t stream);
 int gemm_pick_block_n(int M, int N, int cta_group);
+int gemm_bmn_block_n(int N);  // tile width of the GEMMs whose B operand is MN-major (data / weight gradients)
 int attention_launch(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles, int heads,
                      int seq, int seq_pad, int hd, int hd_pad, float scale, cudaStream_t stream);
 size_t attention_bwd_workspace_bytes(int tiles, int heads, int seq_pad);

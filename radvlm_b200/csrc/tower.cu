@@ -74,7 +74,7 @@ struct TowerSaved {
     return base + static_cast<size_t>(2 * L + 1) * h_bytes + static_cast<size_t>(L) * (ao_bytes + lse_bytes) +
            (static_cast<size_t>(l) * 3 + which) * qkv_bytes;
   }
-  // fc1 pre-activation (bf16 [M, I]) of every layer: written by the dual-output GELU epilogue of the forward
+  // gelu'(fc1 pre-activation) (bf16 [M, I]) of every layer: written by the dual-output GELU epilogue of the forward
   void* u(int l, int L) const {
     return base + static_cast<size_t>(2 * L + 1) * h_bytes +
            static_cast<size_t>(L) * (ao_bytes + lse_bytes + 3 * qkv_bytes) + static_cast<size_t>(l) * u_bytes;
@@ -84,6 +84,12 @@ struct TowerSaved {
     return base + static_cast<size_t>(2 * L + 1) * h_bytes +
            static_cast<size_t>(L) * (ao_bytes + lse_bytes + 3 * qkv_bytes + u_bytes) +
            (static_cast<size_t>(l) * 2 + which) * ao_bytes;
+  }
+  // MLP activation gelu(u) (bf16 [M, I]): the fc1 epilogue writes it here instead of a shared scratch buffer (same
+  // traffic), the backward uses it as the A operand of the fc2 weight gradient instead of recomputing it
+  void* act(int l, int L) const {
+    return base + static_cast<size_t>(2 * L + 1) * h_bytes +
+           static_cast<size_t>(L) * (3 * ao_bytes + lse_bytes + 3 * qkv_bytes + u_bytes) + static_cast<size_t>(l) * u_bytes;
   }
 };
 
@@ -95,7 +101,7 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
   s.qkv_bytes = align_up(L.qkv_bytes, 1024);
   s.u_bytes = align_up(L.M * tw->intermediate * 2, 1024);
   s.total = (2 * tw->num_layers + 1) * s.h_bytes +
-            tw->num_layers * (3 * s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes + s.u_bytes);
+            tw->num_layers * (3 * s.ao_bytes + s.lse_bytes + 3 * s.qkv_bytes + 2 * s.u_bytes);
   s.base = static_cast<uint8_t*>(base);
   return s;
 }
@@ -184,8 +190,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       GemmArgs a{};
       a.M = M; a.N = I; a.K = D;
       a.bias = w.fc1_b;
-      a.out = h1; a.ldo = I;
-      a.out2 = save ? save->u(l, NL) : nullptr;   // training: keep the pre-activation for the GELU backward
+      a.out = save ? save->act(l, NL) : h1; a.ldo = I;   // training: the activation is kept too (fc2 weight gradient)
+      a.out2 = save ? save->u(l, NL) : nullptr;          // training: keep gelu'(u) for the GELU backward
       { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
@@ -194,7 +200,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
       a.out = h_out; a.ldo = D; a.aux = h_mid;
-      { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
+      { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(save ? save->act(l, NL) : h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
   }
@@ -237,26 +243,21 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
 // parameter (frozen, train.py:1642-1665 mm_tunable_parts).
 // =================================================================================================
 struct BackwardLayout {
-  size_t off_xn1, off_xn2, off_g, off_dx, off_h1, off_u, off_da, off_a, off_dqkv, off_q, off_k, off_vt, off_attn, off_stats, total;
+  size_t off_xn1, off_g, off_dx, off_da, off_dqkv, off_attn, off_stats, total;
   size_t attn_bytes;
 };
 
+// Nothing of the forward is recomputed (every operand of the backward GEMMs was kept by the forward), so the workspace
+// only holds gradients in flight.
 static void make_bwd_layout(const radvlm_siglip_weights* tw, const EncodeLayout& L, int n_tiles, BackwardLayout* B) {
   const size_t M = L.M, D = tw->hidden, I = tw->intermediate;
   const size_t xn_cols = D > static_cast<size_t>(tw->patch_k_pad) ? D : tw->patch_k_pad;
   size_t off = 0;
-  B->off_xn1 = off;  off = align_up(off + M * xn_cols * 2, 1024);  // LN1 output / im2col rows
-  B->off_xn2 = off;  off = align_up(off + M * D * 2, 1024);        // LN2 output
+  B->off_xn1 = off;  off = align_up(off + M * xn_cols * 2, 1024);  // im2col rows (patch-embedding weight gradient)
   B->off_g = off;    off = align_up(off + M * D * 2, 1024);        // bf16 copy of the residual gradient
   B->off_dx = off;   off = align_up(off + M * D * 2, 1024);        // dgrad outputs of width D
-  B->off_h1 = off;   off = align_up(off + M * D * 4, 1024);        // recomputed mid-layer residual (fp32)
-  B->off_u = off;    off = align_up(off + M * I * 2, 1024);        // fc1 pre-activation
-  B->off_da = off;   off = align_up(off + M * I * 2, 1024);        // dL/da -> dL/du
-  B->off_a = off;    off = align_up(off + M * I * 2, 1024);        // gelu(u)
+  B->off_da = off;   off = align_up(off + M * I * 2, 1024);        // dL/du (fc2 data gradient x gelu')
   B->off_dqkv = off; off = align_up(off + M * 3 * D * 2, 1024);    // [dQ | dK | dV]
-  B->off_q = off;    off = align_up(off + L.qkv_bytes, 1024);
-  B->off_k = off;    off = align_up(off + L.qkv_bytes, 1024);
-  B->off_vt = off;   off = align_up(off + L.qkv_bytes, 1024);
   B->attn_bytes = attention_bwd_workspace_bytes(n_tiles, tw->heads, L.seq_pad);
   B->off_attn = off; off = align_up(off + B->attn_bytes, 1024);
   B->off_stats = off; off = align_up(off + M * 8 + 2 * D * sizeof(float), 1024);  // LayerNorm row stats + frozen-affine scratch
@@ -269,7 +270,8 @@ static void make_bwd_layout(const radvlm_siglip_weights* tw, const EncodeLayout&
 // 12 K slabs per item.
 static int pick_splits(int M, int N, int K) {
   const int pairs = (device_sm_count() > 0 ? device_sm_count() : 148) / 2;
-  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  const int bn = gemm_bmn_block_n(N);
+  const int tiles = ((M + 255) / 256) * ((N + bn - 1) / bn);
   const int slabs = (K + 63) / 64;
   int best = 1;
   double best_score = -1.0;
@@ -299,14 +301,17 @@ static int linear_wgrad(const void* dY, int ldy, const void* X, int ldx, int row
 }
 
 // dX[rows, in] = dY[rows, out] W[out, in]   (W read as stored)
+// gelu_u != nullptr (bf16 [rows, ldx], the gelu'(u) the forward kept): dX is multiplied by it in the epilogue
+// (fc2 data gradient -> dL/du)
 static int linear_dgrad(const void* dY, int ldy, const void* W, int ldw, int rows, int out_dim, int in_dim, void* dX,
-                        int ldx, bool f32_out, cudaStream_t stream) {
+                        int ldx, bool f32_out, cudaStream_t stream, const void* gelu_u = nullptr) {
   GemmArgs a{};
   a.M = rows; a.N = in_dim; a.K = out_dim;
   a.out = dX; a.ldo = ldx;
+  a.out2 = const_cast<void*>(gelu_u);
   a.b_mn = 1;
   ProfScope ps(PROF_BWD_DGRAD, stream);
-  return gemm_dispatch(dY, ldy, W, ldw, a, f32_out ? EPI_BIAS_F32 : EPI_BIAS_BF16, 0, stream);
+  return gemm_dispatch(dY, ldy, W, ldw, a, gelu_u ? EPI_MUL_BF16 : (f32_out ? EPI_BIAS_F32 : EPI_BIAS_BF16), 0, stream);
 }
 
 // Layers [layer_lo, layer_hi) are processed from the top down; the embeddings follow when layer_lo == 0.  Calling it
@@ -321,7 +326,6 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
   void* g = ws + B.off_g;
   void* dx = ws + B.off_dx;
   void* da = ws + B.off_da;
-  void* act = ws + B.off_a;
   void* dqkv = ws + B.off_dqkv;
   void* attn_ws = ws + B.off_attn;
   void* stats = ws + B.off_stats;
@@ -349,8 +353,9 @@ static int tower_backward_impl(const radvlm_siglip_weights* tw, const radvlm_sig
       if ((st = qkv_pad_prepare_launch(nullptr, nullptr, vt, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, 0.0f, stream))) return st; }
     // ---- MLP branch: h2 = h1 + fc2(gelu(fc1(LN2(h1))))
     if (!g_is_dh) { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = cast_f32_bf16_launch(dh, g, MD, stream))) return st; }
-    if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream))) return st;           // dL/da
-    { ProfScope ps(PROF_BWD_ELEMENTWISE, stream); if ((st = gelu_fwd_bwd_launch(u, da, act, static_cast<size_t>(M) * I, 0, stream))) return st; }  // a, dL/du
+    // dL/du = (g W2) o gelu'(u): one multiply in the epilogue of the data-gradient GEMM; gelu'(u) and a = gelu(u) were kept
+    if ((st = linear_dgrad(g, D, w.fc2_w, I, M, D, I, da, I, false, stream, u))) return st;
+    const void* act = sv.act(l, NL);
     if ((st = linear_wgrad(g, D, act, I, M, D, I, G(&radvlm_vit_layer_grads::fc2_w), I, G(&radvlm_vit_layer_grads::fc2_b), stream))) return st;
     if ((st = linear_wgrad(da, I, xn2, D, M, I, D, G(&radvlm_vit_layer_grads::fc1_w), D, G(&radvlm_vit_layer_grads::fc1_b), stream))) return st;
     if ((st = linear_dgrad(da, I, w.fc1_w, D, M, I, D, dx, D, false, stream))) return st;           // dL/dLN2
