@@ -86,6 +86,75 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row statistics of the bf16 copy of the residual stream: (mean, rstd) per row, for the LayerNorm that is folded into
+// the QKV / fc1 GEMM (gemm_args.h: ln_stats).  Reads 2 B per element (the LayerNorm kernel above moves 6); the
+// statistics are those of the values the tensor core will multiply, so the fold's mean subtraction is exact for them.
+// One warp per row, two passes over registers like the kernel above.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, int rows, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * D);
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < nvec) u = xr[idx];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[i][2 * q] = __uint_as_float(w[q] << 16);
+      v[i][2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+      sum += v[i][2 * q] + v[i][2 * q + 1];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0) stats[warp] = make_float2(mean, rsqrtf(sq / static_cast<float>(D) + eps));
+}
+
+int ln_row_stats_launch(const void* x, void* stats, int rows, int D, float eps, cudaStream_t stream) {
+  RV_CHECK_ARG(x && stats && rows > 0, "ln_row_stats: bad arguments");
+  if ((D % 8) != 0 || D > 6 * 256) {
+    set_error("ln_row_stats: D=%d unsupported (need D %% 8 == 0 and D <= 1536)", D);
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  }
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int nv = (D / 8 + 31) / 32;
+  const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+  float2* st = static_cast<float2*>(stats);
+  if (nv <= 2)
+    ln_row_stats_bf16_kernel<2><<<blocks, threads, 0, stream>>>(xx, st, rows, D, eps);
+  else if (nv <= 5)
+    ln_row_stats_bf16_kernel<5><<<blocks, threads, 0, stream>>>(xx, st, rows, D, eps);
+  else
+    ln_row_stats_bf16_kernel<6><<<blocks, threads, 0, stream>>>(xx, st, rows, D, eps);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp32 -> bf16 cast (tower output -> projector A operand)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -249,6 +318,12 @@ extern "C" int radvlm_layernorm_f32_bf16(const float* x, const float* gamma, con
   int st = rv::require_sm100();
   if (st != RADVLM_OK) return st;
   return rv::layernorm_launch(x, gamma, beta, y, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_ln_row_stats_bf16(const void* x, void* stats, int rows, int D, float eps, void* stream) {
+  int st = rv::require_sm100();
+  if (st != RADVLM_OK) return st;
+  return rv::ln_row_stats_launch(x, stats, rows, D, eps, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int radvlm_cast_f32_bf16(const float* x, void* y, size_t n, void* stream) {

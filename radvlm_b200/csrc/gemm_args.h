@@ -25,7 +25,9 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;  // [N] or nullptr
   void* out;          // [M, ldo] bf16 or f32 depending on the epilogue
-  void* out2;         // EPI_GELU_TANH_DUAL_BF16: gelu'(u) [M, ldo] bf16 (written); EPI_MUL_BF16: the multiplier (read)
+  void* out2;         // EPI_GELU_TANH_DUAL_BF16: gelu'(u) [M, ldo] bf16 (written); EPI_MUL_BF16: the multiplier (read);
+                      // EPI_RESID_F32 / EPI_POS_F32: optional bf16 copy of the fp32 result, [M, ldo] (written) - the A
+                      // operand of the next GEMM when LayerNorm is folded into it (ln_stats below)
   int ldo;
   const float* aux;  // EPI_RESID_F32: residual [M, ldo];  EPI_POS_F32: table [aux_period, N]
   int aux_period;
@@ -39,6 +41,11 @@ struct GemmArgs {
   //   b_mn = 0: W is [N, K] row-major;                    b_mn = 1: W is stored as [K, N] row-major
   int a_mn, b_mn;
   int k_splits;  // >= 1: the K range is cut into k_splits partial products (EPI_ATOMIC_F32 only)
+  // LayerNorm folded into this GEMM (EPI_QKV_SPLIT, EPI_GELU_TANH_BF16, EPI_BIAS_BF16):  with A = bf16(x) (NOT
+  // normalised), W = bf16(gamma o W0), ln_s[n] = sum_k W[n, k], bias = b0 + W0 beta and ln_stats[row] = (mean, rstd) of
+  // row `row` of x,   out = rstd * (acc - mean * ln_s[n]) + bias[n]  ==  LayerNorm(x) W0^T + b0.   nullptr: plain GEMM.
+  const float2* ln_stats;
+  const float* ln_s;
 };
 
 }  // namespace rv

@@ -1,7 +1,10 @@
 // C-ABI launchers for the tcgen05 GEMM (see gemm_sm100.cuh).
 #include <cstdlib>
 
+#include <vector>
+
 #include "gemm2_sm100.cuh"
+#include "gemm3_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -44,6 +47,61 @@ static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
   return RADVLM_OK;
 }
 
+// ---- scheduled variable-width pair kernel (gemm3_sm100.cuh) --------------------------------------------------------
+// List scheduling, simulated once per (M, N, pairs): tiles in row-block-major order, each to the least loaded CTA pair
+// (what a dynamic tile counter would do), a 128-wide tile charged 0.82 of a full one (measured; its MMAs last 64 cycles
+// but its operands stream at the shared-memory / L2 limit).  Returns nullptr when the shape does not fit the parameter block.
+static const GemmSched* gemm_sched_for(int M, int N, int pairs) {
+  struct Item { int M, N, pairs; GemmSched s; };
+  static thread_local std::vector<Item*> cache;
+  for (const Item* it : cache)
+    if (it->M == M && it->N == N && it->pairs == pairs) return &it->s;
+  const int num_m = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int num_n = (N + kSchedBN - 1) / kSchedBN;
+  const int last_w = (N - (num_n - 1) * kSchedBN <= 128) ? 128 : kSchedBN;
+  const long entries = static_cast<long>(num_m) * num_n;
+  if (entries > kSchedMaxEntries || num_n > 32 || num_m > 2048 || pairs < 1) return nullptr;
+  const int clusters = static_cast<int>(entries < pairs ? entries : pairs) < kSchedMaxClusters
+                           ? static_cast<int>(entries < pairs ? entries : pairs) : kSchedMaxClusters;
+  std::vector<std::vector<uint16_t>> lists(clusters);
+  std::vector<long> load(clusters, 0);
+  for (int m = 0; m < num_m; ++m)
+    for (int n = 0; n < num_n; ++n) {
+      int best = 0;
+      for (int c = 1; c < clusters; ++c)
+        if (load[c] < load[best]) best = c;
+      lists[best].push_back(static_cast<uint16_t>(m * 32 + n));
+      load[best] += (n == num_n - 1 && last_w == 128) ? 82 : 100;  // measured: 0.112 vs 0.137 ms (tools/test_gemm sched)
+    }
+  Item* it = new Item();
+  it->M = M; it->N = N; it->pairs = pairs;
+  int pos = 0;
+  for (int c = 0; c <= kSchedMaxClusters; ++c) {
+    it->s.off[c] = static_cast<uint16_t>(pos);
+    if (c < clusters)
+      for (uint16_t v : lists[c]) it->s.ent[pos++] = v;
+  }
+  if (cache.size() >= 64) { delete cache.front(); cache.erase(cache.begin()); }
+  cache.push_back(it);
+  return &it->s;
+}
+
+template <int EPI>
+static int launch_gemm3_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb64, const GemmArgs& args,
+                             const GemmSched& sched, cudaStream_t stream) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    RV_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_sched_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Gemm3Cfg::kSmemBytes));
+    configured = true;
+  }
+  int clusters = 0;
+  while (clusters < kSchedMaxClusters && sched.off[clusters + 1] > sched.off[clusters]) ++clusters;
+  gemm_bf16_tn_2cta_sched_kernel<EPI><<<2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream>>>(ta, tb, tb64, args, sched);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
 template <int EPI>
 static int launch_gemm2_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
                            cudaStream_t stream) {
@@ -70,6 +128,12 @@ static int launch_gemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, 
 
 // Wave-quantisation aware tile-width choice: cost = waves * BN (MMA cycles per K step scale with BN).
 static int g_gemm_mode = 0;  // 0 auto, 1 force single-CTA tiles, 2 force CTA-pair tiles
+// scheduled variable-width tiles (gemm3_sm100.cuh) for the pair GEMMs whose A is K-major; RADVLM_B200_GEMM_SCHED=0
+// keeps the round-robin 256 x BN kernel (A/B switch)
+static bool gemm_sched_enabled() {
+  static const bool on = !(getenv("RADVLM_B200_GEMM_SCHED") && atoi(getenv("RADVLM_B200_GEMM_SCHED")) == 0);
+  return on;
+}
 
 int gemm_pick_block_n(int M, int N, int cta_group) {
   const int sms = (device_sm_count() > 0 ? device_sm_count() : 148) / cta_group;
@@ -118,7 +182,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   RV_CHECK_ARG(args.k_splits <= 1 || epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the atomic fp32 epilogue");
   // CTA pairs (256 x BN tiles) whenever there is enough work to fill the 74 pairs; the MN-major / split-K paths
   // exist in the pair kernel only
-  const bool pair = general || g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
+  const bool pair = general || block_n < 0 || g_gemm_mode == 2 || (g_gemm_mode == 0 && args.M >= 4 * kGemmBM);
   int bn = block_n > 0 ? block_n : gemm_pick_block_n(args.M, args.N, pair ? 2 : 1);
   if (args.b_mn && block_n <= 0) bn = gemm_bmn_block_n(args.N);
   if (args.k_splits > 1) {  // no empty split: (splits - 1) * ceil(slabs / splits) < slabs
@@ -127,6 +191,12 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     while (sp > 1 && (sp - 1) * ((slabs + sp - 1) / sp) >= slabs) --sp;
     args.k_splits = sp;
   }
+  // block_n < 0 forces the scheduled kernel (tests), block_n > 0 the round-robin one
+  const GemmSched* sched = nullptr;
+  if (pair && !args.a_mn && args.k_splits <= 1 && epilogue != EPI_ATOMIC_F32 &&
+      (block_n < 0 || (block_n == 0 && gemm_sched_enabled())))
+    sched = gemm_sched_for(args.M, args.N, device_sm_count() / 2);
+  RV_CHECK_ARG(block_n >= 0 || sched != nullptr, "gemm: the scheduled kernel does not cover this shape / layout");
   CUtensorMap ta, tb;
   if (!args.a_mn)
     st = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M),
@@ -137,12 +207,34 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   if (st != RADVLM_OK) return st;
   if (!args.b_mn)
     st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
-                           static_cast<uint64_t>(ldw) * 2, kGemmBK, static_cast<uint32_t>(pair ? bn / 2 : bn),
-                           CU_TENSOR_MAP_SWIZZLE_128B);
+                           static_cast<uint64_t>(ldw) * 2, kGemmBK,
+                           static_cast<uint32_t>(sched ? 128 : (pair ? bn / 2 : bn)), CU_TENSOR_MAP_SWIZZLE_128B);
   else
     st = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(args.N), static_cast<uint64_t>(args.K),
                            static_cast<uint64_t>(ldw) * 2, 64, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != RADVLM_OK) return st;
+  if (sched != nullptr) {
+    CUtensorMap tb64 = tb;   // 128-wide tiles: each CTA of the pair fetches 64 rows of W
+    if (!args.b_mn) {
+      st = make_tmap_bf16_2d(&tb64, W, static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N),
+                             static_cast<uint64_t>(ldw) * 2, kGemmBK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st != RADVLM_OK) return st;
+    }
+    switch (epilogue) {
+      case EPI_BIAS_BF16: return launch_gemm3_inst<EPI_BIAS_BF16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_GELU_TANH_BF16: return launch_gemm3_inst<EPI_GELU_TANH_BF16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_GELU_ERF_BF16: return launch_gemm3_inst<EPI_GELU_ERF_BF16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_RESID_F32: return launch_gemm3_inst<EPI_RESID_F32>(ta, tb, tb64, args, *sched, stream);
+      case EPI_POS_F32: return launch_gemm3_inst<EPI_POS_F32>(ta, tb, tb64, args, *sched, stream);
+      case EPI_QKV_SPLIT: return launch_gemm3_inst<EPI_QKV_SPLIT>(ta, tb, tb64, args, *sched, stream);
+      case EPI_BIAS_F32: return launch_gemm3_inst<EPI_BIAS_F32>(ta, tb, tb64, args, *sched, stream);
+      case EPI_GELU_TANH_DUAL_BF16: return launch_gemm3_inst<EPI_GELU_TANH_DUAL_BF16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_BIAS_F16: return launch_gemm3_inst<EPI_BIAS_F16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_MUL_BF16: return launch_gemm3_inst<EPI_MUL_BF16>(ta, tb, tb64, args, *sched, stream);
+    }
+    set_error("gemm: unknown epilogue %d", epilogue);
+    return RADVLM_ERR_BAD_ARGUMENT;
+  }
   if (pair) {
     switch (epilogue) {
       case EPI_BIAS_BF16: return launch_gemm2_bn<EPI_BIAS_BF16>(bn, ta, tb, args, stream);

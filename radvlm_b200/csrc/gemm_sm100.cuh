@@ -49,6 +49,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   const bool full = (col0 + 32 <= a.N);
 
+  if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM (gemm_args.h)
+    const float2 st = a.ln_stats[row];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) v[j] = st.y * fmaf(-st.x, __ldg(a.ln_s + col0 + j), v[j]);
+  }
   if (a.bias != nullptr) {
     if (full) {
       const float4* b4 = reinterpret_cast<const float4*>(a.bias + col0);
@@ -236,6 +242,11 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
         o.z = __uint_as_float(t.z) + b.z + xr[i].z;
         o.w = __uint_as_float(t.w) + b.w + xr[i].w;
         float* dst = reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol;
+        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32) {
+          if (a.out2 != nullptr)  // bf16 copy of the new residual stream (8 lanes x 8 B = 64 contiguous bytes per row)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(grow) * a.ldo + gcol) =
+                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
         if constexpr (EPI == EPI_ATOMIC_F32) {   // one 16-byte vector reduction instead of four scalar atomics
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
                        : "memory");
@@ -251,7 +262,8 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
 // bf16 outputs (EPI_BIAS_BF16 / EPI_GELU_*): two 32-column chunks = 64 columns = 128 B per row, requires N % 8 == 0
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
-                                                          const uint32_t* acc1, uint32_t stage, int lane) {
+                                                          const uint32_t* acc1, uint32_t stage, int lane,
+                                                          float ln_nmean = 0.f, float ln_rstd = 1.f) {
   // EPI_GELU_TANH_DUAL_BF16 produces two tiles from the same accumulators: gelu(u) -> out and gelu'(u) -> out2 (one tanh
   // for both); they go through the staging buffer one after the other.
   constexpr int kPasses = (EPI == EPI_GELU_TANH_DUAL_BF16) ? 2 : 1;
@@ -264,8 +276,15 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
       const int c = col0 + 32 * h + 4 * j;
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      float v0 = __uint_as_float(acc[4 * j + 0]) + b.x, v1 = __uint_as_float(acc[4 * j + 1]) + b.y;
-      float v2 = __uint_as_float(acc[4 * j + 2]) + b.z, v3 = __uint_as_float(acc[4 * j + 3]) + b.w;
+      float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
+      float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
+      if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n])
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
+        v0 = ln_rstd * fmaf(ln_nmean, s4.x, v0); v1 = ln_rstd * fmaf(ln_nmean, s4.y, v1);
+        v2 = ln_rstd * fmaf(ln_nmean, s4.z, v2); v3 = ln_rstd * fmaf(ln_nmean, s4.w, v3);
+      }
+      v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
       if constexpr (EPI == EPI_GELU_TANH_BF16) {
         v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
       }
@@ -340,7 +359,8 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
 // ([tile, head, seq_pad, hd_pad] rows of q / k / v) except at a head boundary.  The direct row-per-thread form made every
 // warp store touch 32 half-used 32-byte sectors.  Requires hd % 8 == 0 (a 16-byte piece never straddles heads).
 __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
-                                                         const uint32_t* acc1, uint32_t stage, int lane) {
+                                                         const uint32_t* acc1, uint32_t stage, int lane,
+                                                         float ln_nmean = 0.f, float ln_rstd = 1.f) {
   uint32_t pk[32];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -350,8 +370,16 @@ __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int 
       const int c = col0 + 32 * h + 4 * j;
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      pk[16 * h + 2 * j] = pack_bf16x2(__uint_as_float(acc[4 * j + 0]) + b.x, __uint_as_float(acc[4 * j + 1]) + b.y);
-      pk[16 * h + 2 * j + 1] = pack_bf16x2(__uint_as_float(acc[4 * j + 2]) + b.z, __uint_as_float(acc[4 * j + 3]) + b.w);
+      float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
+      float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
+      if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n])
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
+        v0 = ln_rstd * fmaf(ln_nmean, s4.x, v0); v1 = ln_rstd * fmaf(ln_nmean, s4.y, v1);
+        v2 = ln_rstd * fmaf(ln_nmean, s4.z, v2); v3 = ln_rstd * fmaf(ln_nmean, s4.w, v3);
+      }
+      pk[16 * h + 2 * j] = pack_bf16x2(v0 + b.x, v1 + b.y);
+      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2 + b.z, v3 + b.w);
     }
   }
   stage_store_row(stage, lane, pk);
@@ -391,6 +419,14 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
                           EPI == EPI_MUL_BF16);  // 16-bit outputs
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;
+  float ln_nmean = 0.f, ln_rstd = 1.f;  // this thread's row statistics when LayerNorm is folded into the GEMM
+  if constexpr (kBf16 || EPI == EPI_QKV_SPLIT) {
+    if (args.ln_stats != nullptr && row < args.M) {
+      const float2 st = __ldg(args.ln_stats + row);
+      ln_nmean = -st.x;
+      ln_rstd = st.y;
+    }
+  }
 #pragma unroll 1
   for (int c = 0; c < NCOLS; c += 64) {
     uint32_t r0[32], r1[32];
@@ -404,9 +440,9 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
         if (two) gemm_epilogue_f32_staged<EPI>(args, row0, col_base + c + 32, r1, stage, lane);
       }
     } else if (kBf16 && staged && two) {
-      if constexpr (kBf16) gemm_epilogue_bf16_staged<EPI>(args, row0, col_base + c, r0, r1, stage, lane);
+      if constexpr (kBf16) gemm_epilogue_bf16_staged<EPI>(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
     } else if (EPI == EPI_QKV_SPLIT && two && (args.N & 7) == 0 && (args.hd & 7) == 0) {
-      if constexpr (EPI == EPI_QKV_SPLIT) gemm_epilogue_qkv_staged(args, row0, col_base + c, r0, r1, stage, lane);
+      if constexpr (EPI == EPI_QKV_SPLIT) gemm_epilogue_qkv_staged(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
     } else {
       gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
       if (two) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);

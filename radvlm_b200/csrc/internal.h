@@ -29,6 +29,7 @@ int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, flo
 int pos_embed_grad_launch(const float* dh, float* dpos, int tiles, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
                      float eps, cudaStream_t stream);
+int ln_row_stats_launch(const void* x, void* stats, int rows, int D, float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream);
 int im2col_launch(const void* pixels, int dtype, void* out, int n_tiles, int C, int S, int ps,
                   int Kpad, cudaStream_t stream);

@@ -243,6 +243,43 @@ int main(int argc, char** argv) {
       }
     return f;
   }
+  if (argc > 1 && !strcmp(argv[1], "schedncu")) {  // ncu target: round-robin vs scheduled kernel on the fc1 / fc2 shapes
+    int f = 0;
+    for (int bn : {256, -1}) f += run_case({58320, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, bn});
+    for (int bn : {192, -1}) f += run_case({58320, 1152, 4304, RADVLM_EPI_RESID_F32, bn});
+    return f;
+  }
+  if (argc > 1 && !strcmp(argv[1], "sched")) {  // ./test_gemm sched : scheduled variable-width tiles (block_n = -1)
+    int f = 0;                                   // correctness on ragged shapes, then the N = 1152 / 3456 shapes timed
+    for (int epi : {RADVLM_EPI_BIAS_F32, RADVLM_EPI_RESID_F32, RADVLM_EPI_BIAS_BF16, RADVLM_EPI_GELU_TANH_BF16}) {
+      f += run_case({300, 200, 136, epi, -1});
+      f += run_case({1458, 1152, 1152, epi, -1});
+      f += run_case({729, 384, 4304, epi, -1});
+      f += run_case({2000, 648, 200, epi, -1});
+    }
+    f += run_case({729, 1152, 588 + 4, RADVLM_EPI_POS_F32, -1});
+    f += run_case({7290, 3456, 1152, RADVLM_EPI_BIAS_BF16, -1});
+    f += run_case({7290, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, -1});
+    f += run_case({7290, 1152, 4304, RADVLM_EPI_RESID_F32, -1});
+    // cost of a 128-wide tile against a full one: N = 128 (strips only) vs N = 256 (full tiles only), same M and K
+    for (int K : {4304, 1152})
+      for (int bn : {-1, 128, 256}) {
+        f += run_case({58320, 128, K, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({58320, 256, K, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({58320, 1280, K, RADVLM_EPI_RESID_F32, bn});
+      }
+    for (int rep = 0; rep < 2; ++rep)
+      for (int bn : {-1, 192, 256}) {
+        f += run_case({58320, 1152, 4304, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({58320, 1152, 1152, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({58320, 3456, 1152, RADVLM_EPI_BIAS_BF16, bn});
+        f += run_case({58320, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, bn});
+        f += run_case({7290, 1152, 4304, RADVLM_EPI_RESID_F32, bn});
+        f += run_case({7290, 1152, 1152, RADVLM_EPI_RESID_F32, bn});
+      }
+    printf("%s (%d failing cases)\n", f ? "SCHED GEMM TEST FAILED" : "SCHED GEMM TEST PASSED", f);
+    return f;
+  }
   if (argc > 2 && !strcmp(argv[1], "perf")) {  // ./test_gemm perf <mode> : the three big shapes only (ncu target)
     radvlm_gemm_set_mode(atoi(argv[2]));
     int f = 0;
