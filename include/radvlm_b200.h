@@ -80,6 +80,14 @@ int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, const void* W,
                         int K, const float* bias, int epilogue, void* out, int64_t ldo, const float* aux,
                         int aux_period, int k_splits, void* stream);
 
+/* The same GEMM with a LayerNorm folded in (siglip_encoder.py:264,266,287,296 followed by a Linear):
+ *   A = bf16(x) (not normalised), W = bf16(gamma o W0), ln_s[n] = sum_k W[n, k], bias = b0 + W0 beta,
+ *   ln_stats[row] = (mean, rstd) of row `row` of x (radvlm_ln_row_stats_bf16):
+ *   out = epilogue( rstd * (acc - mean * ln_s[n]) + bias[n] )  ==  epilogue( LayerNorm(x) W0^T + b0 ).
+ * epilogue: RADVLM_EPI_BIAS_BF16 | RADVLM_EPI_GELU_TANH_BF16 | RADVLM_EPI_GELU_ERF_BF16; N % 8 == 0. */
+int radvlm_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const float* bias,
+                        const void* ln_stats, const float* ln_s, int epilogue, void* out, int64_t ldo, void* stream);
+
 /* Tile-shape policy of the GEMM: 0 = auto (CTA pairs, tcgen05 cta_group::2, 256 x BN tiles when M >= 512),
  * 1 = force single-CTA 128 x BN tiles, 2 = force CTA-pair tiles.  Process-wide; meant for tests / tuning. */
 int radvlm_gemm_set_mode(int mode);
@@ -137,6 +145,9 @@ int radvlm_layernorm_f32_bf16(const float* x, const float* gamma, const float* b
 int radvlm_patch_im2col(const void* pixels, int dtype, void* out, int n_tiles, int channels,
                         int image_size, int patch_size, int k_pad, void* stream);
 int radvlm_cast_f32_bf16(const float* x, void* y, size_t n, void* stream);
+/* (mean, rstd) of every row of a bf16 [rows, D] matrix -> stats: fp32 [rows][2].  The LayerNorm statistics when the
+ * normalisation itself is folded into the consuming GEMM (radvlm_vit_layer_weights.qkv_wf). */
+int radvlm_ln_row_stats_bf16(const void* x, void* stats, int rows, int D, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-path entry points: SigLIP tower (SigLipVisionTower.forward, siglip_encoder.py:576-589,
@@ -160,6 +171,17 @@ typedef struct radvlm_vit_layer_weights {
   const float* fc1_b;
   const void* fc2_w;   /* bf16 [hidden, intermediate] */
   const float* fc2_b;
+  /* LayerNorm folded into the QKV / fc1 GEMMs (inference; all six NULL = stand-alone LayerNorm kernels).
+   *   LN(x) W^T + b  =  rstd * (x (gamma o W)^T - mean * s) + b',   s[n] = sum_k (gamma o W)[n, k],  b' = b + W beta
+   * qkv_wf / fc1_wf: bf16 [out, hidden] = bf16(gamma o W);  *_sf: fp32 [out] row sums of the bf16 matrix;
+   * *_bf: fp32 [out].  The residual GEMM epilogues then also emit a bf16 copy of the stream (the A operand) and a
+   * 2 B/element pass (radvlm_ln_row_stats_bf16) supplies (mean, rstd); siglip_encoder.py:264,266,287,296. */
+  const void* qkv_wf;
+  const float* qkv_sf;
+  const float* qkv_bf;
+  const void* fc1_wf;
+  const float* fc1_sf;
+  const float* fc1_bf;
 } radvlm_vit_layer_weights;
 
 typedef struct radvlm_siglip_weights {

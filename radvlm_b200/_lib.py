@@ -53,6 +53,9 @@ class VitLayerWeights(C.Structure):
         ("ln2_gamma", C.c_void_p), ("ln2_beta", C.c_void_p),
         ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
         ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+        # LayerNorm folded into the QKV / fc1 GEMMs (all None: stand-alone LayerNorm kernels)
+        ("qkv_wf", C.c_void_p), ("qkv_sf", C.c_void_p), ("qkv_bf", C.c_void_p),
+        ("fc1_wf", C.c_void_p), ("fc1_sf", C.c_void_p), ("fc1_bf", C.c_void_p),
     ]
 
 
@@ -130,6 +133,7 @@ SIGNATURES = {
     "radvlm_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int64), _i]),
     "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_bf16_ex": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
+    "radvlm_gemm_bf16_ln": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "radvlm_gemm_set_mode": (_i, [_i]),
     "radvlm_gemm_qkv_split": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "radvlm_attention_prepare_vt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -140,6 +144,7 @@ SIGNATURES = {
     "radvlm_layernorm_f32_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "radvlm_patch_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "radvlm_cast_f32_bf16": (_i, [_vp, _vp, _sz, _vp]),
+    "radvlm_ln_row_stats_bf16": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "radvlm_encode_workspace_bytes": (_sz, [C.POINTER(SiglipWeights), C.POINTER(ProjectorWeights), _i]),
     "radvlm_siglip_tower_forward": (_i, [C.POINTER(SiglipWeights), _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "radvlm_projector_forward": (_i, [C.POINTER(ProjectorWeights), _vp, _i, _vp, _i, _vp, _sz, _vp]),

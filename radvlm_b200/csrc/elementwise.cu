@@ -133,6 +133,33 @@ ln_row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict
   if (lane == 0) stats[warp] = make_float2(mean, rsqrtf(sq / static_cast<float>(D) + eps));
 }
 
+// (sum, sum of squares) partials written by the residual GEMM epilogues ([rows][slots] float2) -> (mean, rstd) per row
+__global__ void __launch_bounds__(256)
+ln_finalize_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int rows, int slots, float inv_d,
+                         float eps) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float2* p = part + static_cast<size_t>(r) * slots;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < slots; ++i) {
+    const float2 v = p[i];
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * inv_d;
+  const float var = fmaxf(fmaf(-mean, mean, q * inv_d), 0.f);
+  stats[r] = make_float2(mean, rsqrtf(var + eps));
+}
+
+int ln_finalize_stats_launch(const void* part, void* stats, int rows, int slots, int D, float eps, cudaStream_t stream) {
+  RV_CHECK_ARG(part && stats && rows > 0 && slots > 0 && D > 0, "ln_finalize_stats: bad arguments");
+  ln_finalize_stats_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(static_cast<const float2*>(part),
+                                                                     static_cast<float2*>(stats), rows, slots,
+                                                                     1.0f / static_cast<float>(D), eps);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
 int ln_row_stats_launch(const void* x, void* stats, int rows, int D, float eps, cudaStream_t stream) {
   RV_CHECK_ARG(x && stats && rows > 0, "ln_row_stats: bad arguments");
   if ((D % 8) != 0 || D > 6 * 256) {

@@ -279,8 +279,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
+      float ln_nmean, ln_rstd;
+      gemm_ln_row_stats(args, row, ln_nmean, ln_rstd);
       gemm_epilogue_drain<EPI, BN / 2>(args, row, n_blk * BN + half * (BN / 2), t_row,
-                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane);
+                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane, -1,
+                                       ln_nmean, ln_rstd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

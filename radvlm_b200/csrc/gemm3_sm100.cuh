@@ -210,14 +210,18 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       int m_blk, n0, w;
       tile_of(e, m_blk, n0, w);
       if (e + 1 < e_end) prefetch_resid(e + 1);
+      const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
+      float ln_nmean, ln_rstd;  // LayerNorm fold: this row's statistics, fetched while the tile's MMAs still run
+      gemm_ln_row_stats(args, row, ln_nmean, ln_rstd);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * kSchedBN + half * (w / 2));
       const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes;
-      if (w == kSchedBN) gemm_epilogue_drain<EPI, kSchedBN / 2>(args, row, n0 + half * (kSchedBN / 2), t_row, stg, lane);
-      else gemm_epilogue_drain<EPI, 64>(args, row, n0 + half * 64, t_row, stg, lane);
+      const int ln_slot = 2 * (n0 / kSchedBN) + half;  // one statistics slot per (column tile, half): gemm_args.h ln_part
+      if (w == kSchedBN) gemm_epilogue_drain<EPI, kSchedBN / 2>(args, row, n0 + half * (kSchedBN / 2), t_row, stg, lane, ln_slot,
+                                                                ln_nmean, ln_rstd);
+      else gemm_epilogue_drain<EPI, 64>(args, row, n0 + half * 64, t_row, stg, lane, ln_slot, ln_nmean, ln_rstd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

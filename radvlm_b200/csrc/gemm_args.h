@@ -46,6 +46,14 @@ struct GemmArgs {
   // row `row` of x,   out = rstd * (acc - mean * ln_s[n]) + bias[n]  ==  LayerNorm(x) W0^T + b0.   nullptr: plain GEMM.
   const float2* ln_stats;
   const float* ln_s;
+  // Producer side of the fold (EPI_RESID_F32 / EPI_POS_F32, scheduled kernel only): partial (sum, sum of squares) of every
+  // output row over the columns one epilogue warp drains, one slot per (column tile, half): [M][ln_slots] float2, written
+  // without atomics (every slot has exactly one writer); ln_finalize_stats_kernel turns them into (mean, rstd).
+  float2* ln_part;
+  int ln_slots;
+  // Consumer side without a finalize pass: ln_stats == nullptr, ln_s != nullptr and ln_part != nullptr -> every epilogue
+  // thread adds up the ln_slots partials of its row itself: mean = sum / ln_dim, rstd = rsqrt(E[x^2] - mean^2 + ln_eps).
+  float ln_inv_dim, ln_eps;
 };
 
 }  // namespace rv

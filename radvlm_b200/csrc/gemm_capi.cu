@@ -165,6 +165,12 @@ int gemm_bmn_block_n(int N) {
   return force == 128 ? 128 : 256;
 }
 
+int gemm_ln_part_slots(int M, int N) {
+  if (!gemm_sched_enabled() || g_gemm_mode == 1 || M < 4 * kGemmBM || (N & 7) != 0) return 0;
+  if (gemm_sched_for(M, N, device_sm_count() / 2) == nullptr) return 0;
+  return 2 * ((N + kSchedBN - 1) / kSchedBN);
+}
+
 int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmArgs& args_in,
                   int epilogue, int block_n, cudaStream_t stream) {
   int st = require_sm100();
@@ -300,6 +306,25 @@ extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64
   a.aux = aux;
   a.aux_period = aux_period;
   return gemm_dispatch(A, lda, W, ldw, a, epilogue, block_n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int radvlm_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                                   const float* bias, const void* ln_stats, const float* ln_s, int epilogue, void* out,
+                                   int64_t ldo, void* stream) {
+  using namespace rv;
+  RV_CHECK_ARG(epilogue == EPI_BIAS_BF16 || epilogue == EPI_GELU_TANH_BF16 || epilogue == EPI_GELU_ERF_BF16,
+               "gemm_ln: the LayerNorm fold exists for the bf16 epilogues (and the QKV head split inside the tower)");
+  RV_CHECK_ARG(out != nullptr && ldo >= N && (ldo % 8) == 0 && (N % 8) == 0, "gemm_ln: bad output (ldo=%lld N=%d)",
+               (long long)ldo, N);
+  RV_CHECK_ARG(ln_stats != nullptr && ln_s != nullptr, "gemm_ln: null statistics / row sums");
+  GemmArgs a{};
+  a.M = M; a.N = N; a.K = K;
+  a.bias = bias;
+  a.out = out;
+  a.ldo = static_cast<int>(ldo);
+  a.ln_stats = static_cast<const float2*>(ln_stats);
+  a.ln_s = ln_s;
+  return gemm_dispatch(A, lda, W, ldw, a, epilogue, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int radvlm_gemm_bf16_ex(const void* A, int64_t lda, int a_layout, const void* W, int64_t ldw, int b_layout,

@@ -39,6 +39,30 @@ struct GemmCfg {
       kStages * kStageBytes + kGemmStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// (-mean, rstd) of output row `row` when LayerNorm is folded into this GEMM (gemm_args.h); (0, 1) otherwise.  Issued by
+// the epilogue warps BEFORE they wait for the accumulator, so the loads cost nothing on the critical path.
+__device__ __forceinline__ void gemm_ln_row_stats(const GemmArgs& a, int row, float& nmean, float& rstd) {
+  nmean = 0.f;
+  rstd = 1.f;
+  if (a.ln_s == nullptr || row >= a.M) return;
+  if (a.ln_stats != nullptr) {
+    const float2 st = __ldg(a.ln_stats + row);
+    nmean = -st.x;
+    rstd = st.y;
+  } else if (a.ln_part != nullptr) {
+    const float2* p = a.ln_part + static_cast<size_t>(row) * a.ln_slots;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < a.ln_slots; ++i) {
+      const float2 v = p[i];   // written by the previous kernel's epilogue (plain load: not read-only for the program)
+      s += v.x;
+      q += v.y;
+    }
+    const float mean = s * a.ln_inv_dim;
+    nmean = -mean;
+    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, q * a.ln_inv_dim), 0.f) + a.ln_eps);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, int col0,
                                                     const uint32_t* acc) {
@@ -49,11 +73,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   const bool full = (col0 + 32 <= a.N);
 
-  if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM (gemm_args.h)
-    const float2 st = a.ln_stats[row];
+  if (a.ln_s != nullptr) {  // LayerNorm folded into the GEMM (gemm_args.h)
+    float nmean, rstd;
+    gemm_ln_row_stats(a, row, nmean, rstd);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (col0 + j < a.N) v[j] = st.y * fmaf(-st.x, __ldg(a.ln_s + col0 + j), v[j]);
+      if (col0 + j < a.N) v[j] = rstd * fmaf(nmean, __ldg(a.ln_s + col0 + j), v[j]);
   }
   if (a.bias != nullptr) {
     if (full) {
@@ -208,9 +233,12 @@ __device__ __forceinline__ uint4 stage_load_vec(uint32_t stage, int rr, int v) {
 }
 
 // fp32 outputs (EPI_RESID_F32 / EPI_POS_F32 / EPI_BIAS_F32): one 32-column chunk, requires N % 4 == 0
-template <int EPI>
+// kStats: also accumulate, per output row this thread touches (8 of them: rows i * 4 + lane / 8), the sum and the sum of
+// squares of the values it stores (ps / pq); the caller reduces them over the 8 lanes that share a row once per tile.
+template <int EPI, bool kStats = false>
 __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc,
-                                                         uint32_t stage, int lane) {
+                                                         uint32_t stage, int lane, float* ps = nullptr,
+                                                         float* pq = nullptr) {
   stage_store_row(stage, lane, acc);
   __syncwarp();
   const int v = lane & 7;
@@ -242,6 +270,10 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
         o.z = __uint_as_float(t.z) + b.z + xr[i].z;
         o.w = __uint_as_float(t.w) + b.w + xr[i].w;
         float* dst = reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol;
+        if constexpr (kStats) {
+          ps[i] += (o.x + o.y) + (o.z + o.w);
+          pq[i] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, pq[i]))));
+        }
         if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32) {
           if (a.out2 != nullptr)  // bf16 copy of the new residual stream (8 lanes x 8 B = 64 contiguous bytes per row)
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(grow) * a.ldo + gcol) =
@@ -260,7 +292,10 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
 }
 
 // bf16 outputs (EPI_BIAS_BF16 / EPI_GELU_*): two 32-column chunks = 64 columns = 128 B per row, requires N % 8 == 0
-template <int EPI>
+// kLn: LayerNorm folded into the GEMM (gemm_args.h).  A template parameter, not a run-time test: a (uniform) branch
+// inside the unrolled column loop kept ptxas from hoisting the bias / row-sum loads, and the 32 serialised L1 round
+// trips per 64 columns made the epilogue of the K = 1152 GEMMs their critical path (QKV + 17 %, fc1 + 14 % in-step).
+template <int EPI, bool kLn>
 __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
                                                           const uint32_t* acc1, uint32_t stage, int lane,
                                                           float ln_nmean = 0.f, float ln_rstd = 1.f) {
@@ -278,13 +313,14 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
       float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
       float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
-      if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n])
+      if constexpr (kLn) {  // rstd * (acc - mean * s[n]) + b'[n]
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
-        v0 = ln_rstd * fmaf(ln_nmean, s4.x, v0); v1 = ln_rstd * fmaf(ln_nmean, s4.y, v1);
-        v2 = ln_rstd * fmaf(ln_nmean, s4.z, v2); v3 = ln_rstd * fmaf(ln_nmean, s4.w, v3);
+        v0 = fmaf(ln_rstd, fmaf(ln_nmean, s4.x, v0), b.x); v1 = fmaf(ln_rstd, fmaf(ln_nmean, s4.y, v1), b.y);
+        v2 = fmaf(ln_rstd, fmaf(ln_nmean, s4.z, v2), b.z); v3 = fmaf(ln_rstd, fmaf(ln_nmean, s4.w, v3), b.w);
+      } else {
+        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
       }
-      v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
       if constexpr (EPI == EPI_GELU_TANH_BF16) {
         v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
       }
@@ -358,6 +394,7 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
 // buffer; afterwards 8 lanes own one row and write its eight 16-byte pieces, which are contiguous in the destination
 // ([tile, head, seq_pad, hd_pad] rows of q / k / v) except at a head boundary.  The direct row-per-thread form made every
 // warp store touch 32 half-used 32-byte sectors.  Requires hd % 8 == 0 (a 16-byte piece never straddles heads).
+template <bool kLn>
 __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
                                                          const uint32_t* acc1, uint32_t stage, int lane,
                                                          float ln_nmean = 0.f, float ln_rstd = 1.f) {
@@ -372,14 +409,16 @@ __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int 
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
       float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
       float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
-      if (a.ln_stats != nullptr) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n])
+      if constexpr (kLn) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n]) + b'[n]
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
-        v0 = ln_rstd * fmaf(ln_nmean, s4.x, v0); v1 = ln_rstd * fmaf(ln_nmean, s4.y, v1);
-        v2 = ln_rstd * fmaf(ln_nmean, s4.z, v2); v3 = ln_rstd * fmaf(ln_nmean, s4.w, v3);
+        v0 = fmaf(ln_rstd, fmaf(ln_nmean, s4.x, v0), b.x); v1 = fmaf(ln_rstd, fmaf(ln_nmean, s4.y, v1), b.y);
+        v2 = fmaf(ln_rstd, fmaf(ln_nmean, s4.z, v2), b.z); v3 = fmaf(ln_rstd, fmaf(ln_nmean, s4.w, v3), b.w);
+      } else {
+        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
       }
-      pk[16 * h + 2 * j] = pack_bf16x2(v0 + b.x, v1 + b.y);
-      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2 + b.z, v3 + b.w);
+      pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
+      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
     }
   }
   stage_store_row(stage, lane, pk);
@@ -411,7 +450,8 @@ __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int 
 // Drain NCOLS accumulator columns of this thread's row: two tcgen05.ld in flight per wait.
 template <int EPI, int NCOLS>
 __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int row, int col_base, uint32_t t_row,
-                                                    uint32_t stage, int lane) {
+                                                    uint32_t stage, int lane, int ln_slot = -1,
+                                                    float ln_nmean = 0.f, float ln_rstd = 1.f) {
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
   constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
   constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
@@ -419,13 +459,17 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
                           EPI == EPI_MUL_BF16);  // 16-bit outputs
   const bool staged = ((args.N & 7) == 0) && ((args.ldo & 7) == 0);  // vector validity == column validity
   const int row0 = row - lane;
-  float ln_nmean = 0.f, ln_rstd = 1.f;  // this thread's row statistics when LayerNorm is folded into the GEMM
-  if constexpr (kBf16 || EPI == EPI_QKV_SPLIT) {
-    if (args.ln_stats != nullptr && row < args.M) {
-      const float2 st = __ldg(args.ln_stats + row);
-      ln_nmean = -st.x;
-      ln_rstd = st.y;
-    }
+  // ln_nmean / ln_rstd: this thread's row statistics when LayerNorm is folded into the GEMM (gemm_ln_row_stats)
+  constexpr bool kLnCapable = (EPI == EPI_QKV_SPLIT || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_BIAS_BF16 ||
+                               EPI == EPI_GELU_ERF_BF16);
+  const bool ln = kLnCapable && args.ln_s != nullptr;
+  // LayerNorm fold, producer side: row sums of the new residual stream over this warp's columns (gemm_args.h: ln_part)
+  constexpr bool kStatsCapable = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32);
+  const bool stats = kStatsCapable && staged && args.ln_part != nullptr && ln_slot >= 0;
+  float ps[kStatsCapable ? 8 : 1], pq[kStatsCapable ? 8 : 1];
+  if constexpr (kStatsCapable) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0.f;
   }
 #pragma unroll 1
   for (int c = 0; c < NCOLS; c += 64) {
@@ -436,16 +480,48 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
     tmem_wait_ld();
     if (kF32 && staged) {
       if constexpr (kF32) {
+        if constexpr (kStatsCapable) {
+          if (stats) {
+            gemm_epilogue_f32_staged<EPI, true>(args, row0, col_base + c, r0, stage, lane, ps, pq);
+            if (two) gemm_epilogue_f32_staged<EPI, true>(args, row0, col_base + c + 32, r1, stage, lane, ps, pq);
+            continue;
+          }
+        }
         gemm_epilogue_f32_staged<EPI>(args, row0, col_base + c, r0, stage, lane);
         if (two) gemm_epilogue_f32_staged<EPI>(args, row0, col_base + c + 32, r1, stage, lane);
       }
     } else if (kBf16 && staged && two) {
-      if constexpr (kBf16) gemm_epilogue_bf16_staged<EPI>(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
+      if constexpr (kBf16) {
+        if constexpr (kLnCapable) {
+          if (ln) gemm_epilogue_bf16_staged<EPI, true>(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
+          else gemm_epilogue_bf16_staged<EPI, false>(args, row0, col_base + c, r0, r1, stage, lane);
+        } else {
+          gemm_epilogue_bf16_staged<EPI, false>(args, row0, col_base + c, r0, r1, stage, lane);
+        }
+      }
     } else if (EPI == EPI_QKV_SPLIT && two && (args.N & 7) == 0 && (args.hd & 7) == 0) {
-      if constexpr (EPI == EPI_QKV_SPLIT) gemm_epilogue_qkv_staged(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
+      if constexpr (EPI == EPI_QKV_SPLIT) {
+        if (ln) gemm_epilogue_qkv_staged<true>(args, row0, col_base + c, r0, r1, stage, lane, ln_nmean, ln_rstd);
+        else gemm_epilogue_qkv_staged<false>(args, row0, col_base + c, r0, r1, stage, lane);
+      }
     } else {
       gemm_epilogue_chunk<EPI>(args, row, col_base + c, r0);
       if (two) gemm_epilogue_chunk<EPI>(args, row, col_base + c + 32, r1);
+    }
+  }
+  if constexpr (kStatsCapable) {
+    if (stats) {  // the 8 lanes that share a row (lane bits 0..2 = column group) add up, lane & 7 == 0 writes the slot
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
+          pq[i] += __shfl_xor_sync(0xffffffffu, pq[i], o);
+        }
+        const int grow = row0 + i * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && grow < args.M)
+          args.ln_part[static_cast<size_t>(grow) * args.ln_slots + ln_slot] = make_float2(ps[i], pq[i]);
+      }
     }
   }
 }
@@ -574,8 +650,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
       const int col_base = n_blk * BN + half * (BN / 2);
+      float ln_nmean, ln_rstd;
+      gemm_ln_row_stats(args, row, ln_nmean, ln_rstd);
       gemm_epilogue_drain<EPI, BN / 2>(args, row, col_base, t_row,
-                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane);
+                                       stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes, lane, -1,
+                                       ln_nmean, ln_rstd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

@@ -193,4 +193,4 @@ extern "C" int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_cl
 }
 
 extern "C" const char* radvlm_last_error(void) { return rv::last_error(); }
-extern "C" int radvlm_abi_version(void) { return 2; }
+extern "C" int radvlm_abi_version(void) { return 3; }

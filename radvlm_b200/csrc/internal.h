@@ -29,6 +29,9 @@ int layernorm_bwd_launch(const float* x, const float* gamma, const void* dy, flo
 int pos_embed_grad_launch(const float* dh, float* dpos, int tiles, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, int rows, int D,
                      float eps, cudaStream_t stream);
+int ln_finalize_stats_launch(const void* part, void* stats, int rows, int slots, int D, float eps, cudaStream_t stream);
+// slots of GemmArgs::ln_part the scheduled kernel fills for an [M, N] output; 0 when that kernel does not cover the shape
+int gemm_ln_part_slots(int M, int N);
 int ln_row_stats_launch(const void* x, void* stats, int rows, int D, float eps, cudaStream_t stream);
 int cast_f32_bf16_launch(const float* x, void* y, size_t n, cudaStream_t stream);
 int im2col_launch(const void* pixels, int dtype, void* out, int n_tiles, int C, int S, int ps,

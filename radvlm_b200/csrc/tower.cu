@@ -14,7 +14,7 @@ namespace rv {
 struct EncodeLayout {
   int P, T, seq_pad, hd, hd_pad;
   size_t M;
-  size_t off_hidden, off_xn, off_q, off_k, off_vt, off_h1, total;
+  size_t off_hidden, off_xn, off_xb, off_stats, off_part, off_q, off_k, off_vt, off_h1, total;
   size_t qkv_bytes;
 };
 
@@ -43,6 +43,9 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
   size_t off = 0;
   L->off_hidden = off; off = align_up(off + L->M * D * 4, 1024);
   L->off_xn = off;     off = align_up(off + L->M * xn_cols * 2, 1024);
+  L->off_xb = off;     off = align_up(off + L->M * D * 2, 1024);   // bf16 copy of the residual stream (LayerNorm fold)
+  L->off_stats = off;  off = align_up(off + L->M * 8, 1024);       // (mean, rstd) per row
+  L->off_part = off;   off = align_up(off + L->M * 8 * 2 * ((D + 255) / 256), 1024);  // per-row partial sums (epilogues)
   L->off_q = off;      off = align_up(off + L->qkv_bytes, 1024);
   L->off_k = off;      off = align_up(off + L->qkv_bytes, 1024);
   L->off_vt = off;     off = align_up(off + L->qkv_bytes, 1024);
@@ -108,9 +111,23 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
 
 // `hidden`: inference: the in-place residual stream (= output).  Training (save != nullptr): scratch for the
 // mid-layer residual; layer l reads save->h(l) and writes save->h(l + 1), the output is save->h(num_layers).
+// LayerNorm fold (inference, every layer carries qkv_wf / fc1_wf): no LayerNorm kernel runs.  The residual GEMM
+// epilogues (patch embedding, out_proj, fc2) also write a bf16 copy of the stream, a 2 B/element pass computes the row
+// statistics, and the QKV / fc1 GEMMs multiply the copy by gamma o W and apply (mean, rstd) in their epilogues.  Two
+// bf16 buffers alternate: `xb` holds the stream entering a layer (then, once the QKV GEMM has consumed it, the
+// attention output), `xn` the stream after the attention branch.  *final_bf16 (optional) receives the pointer of the
+// bf16 copy of the tower output (the projector's A operand: no cast pass).
+static bool tower_ln_folded(const radvlm_siglip_weights* tw) {
+  for (int l = 0; l < tw->num_layers; ++l) {
+    const radvlm_vit_layer_weights& w = tw->layers[l];
+    if (!w.qkv_wf || !w.qkv_sf || !w.qkv_bf || !w.fc1_wf || !w.fc1_sf || !w.fc1_bf) return false;
+  }
+  return tw->num_layers > 0;
+}
+
 static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixels, int pixel_dtype,
                               int n_tiles, float* hidden, const EncodeLayout& L, uint8_t* ws,
-                              cudaStream_t stream, const TowerSaved* save = nullptr) {
+                              cudaStream_t stream, const TowerSaved* save = nullptr, const void** final_bf16 = nullptr) {
   const int D = tw->hidden, I = tw->intermediate;
   const int M = static_cast<int>(L.M);
   const int NL = tw->num_layers;
@@ -119,6 +136,28 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   void* k = ws + L.off_k;
   void* vt = ws + L.off_vt;
   void* h1 = ws + L.off_h1;
+  const bool fold = (save == nullptr) && tower_ln_folded(tw);
+  void* xb = ws + L.off_xb;
+  float2* stats = reinterpret_cast<float2*>(ws + L.off_stats);
+  // row statistics: partial sums from the residual epilogues (scheduled GEMM kernel) + a finalize pass over them, or,
+  // when that kernel does not cover the shape, a 2 B/element pass over the bf16 copy
+  float2* part = reinterpret_cast<float2*>(ws + L.off_part);
+  const int part_slots = fold ? gemm_ln_part_slots(M, D) : 0;
+  auto row_stats = [&](const void* xbf) -> int {
+    if (part_slots > 0) return RADVLM_OK;   // the consuming GEMM's epilogue adds the partials up itself
+    ProfScope ps(PROF_LAYERNORM, stream);
+    return ln_row_stats_launch(xbf, stats, M, D, tw->ln_eps, stream);
+  };
+  auto set_consumer_stats = [&](GemmArgs& a, const float* row_sums) {
+    a.ln_s = row_sums;
+    if (part_slots > 0) {
+      a.ln_part = part; a.ln_slots = part_slots;
+      a.ln_inv_dim = 1.0f / static_cast<float>(D); a.ln_eps = tw->ln_eps;
+    } else {
+      a.ln_stats = stats;
+    }
+  };
+  if (final_bf16 != nullptr) *final_bf16 = fold ? xb : nullptr;
   int st;
 
   // padding of q/k/vt must be zero (never written by the QKV epilogue); training uses per-layer slots instead
@@ -140,6 +179,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     a.M = M; a.N = D; a.K = tw->patch_k_pad;
     a.bias = tw->patch_b;
     a.out = save ? save->h(0) : hidden; a.ldo = D;
+    a.out2 = fold ? xb : nullptr;
+    if (part_slots > 0) { a.ln_part = part; a.ln_slots = part_slots; }
     a.aux = tw->pos_embed; a.aux_period = L.T;
     { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, tw->patch_k_pad, tw->patch_w, tw->patch_k_pad, a, EPI_POS_F32, 0, stream); }
     if (st) return st;
@@ -150,7 +191,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     const radvlm_vit_layer_weights& w = tw->layers[l];
     const float* h_in = save ? save->h(l) : hidden;     // residual stream entering the layer
     float* h_out = save ? save->h(l + 1) : hidden;      // ... leaving it
-    void* ao = save ? save->ao(l, NL) : xn;             // attention output (bf16)
+    void* ao = save ? save->ao(l, NL) : (fold ? xb : xn);   // attention output (bf16)
     float* h_mid = save ? save->hmid(l, NL) : hidden;   // residual stream after the attention branch
     if (save != nullptr) {                              // this layer's own q / k / v slots: pads + ones column only
       q = save->qkv(l, 0, NL); k = save->qkv(l, 1, NL); vt = save->qkv(l, 2, NL);
@@ -160,17 +201,19 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     // x = x + out_proj(attn(LN1(x)))
     void* xn1 = save ? save->xn(l, 0, NL) : xn;
     void* xn2 = save ? save->xn(l, 1, NL) : xn;
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream); }
+    if (fold) st = row_stats(xb);
+    else { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_in, w.ln1_gamma, w.ln1_beta, xn1, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
       a.M = M; a.N = 3 * D; a.K = D;
-      a.bias = w.qkv_b;
+      a.bias = fold ? w.qkv_bf : w.qkv_b;
+      if (fold) set_consumer_stats(a, w.qkv_sf);
       a.q = static_cast<__nv_bfloat16*>(q);
       a.k = static_cast<__nv_bfloat16*>(k);
       a.vt = static_cast<__nv_bfloat16*>(vt);
       a.seq = L.T; a.seq_pad = L.seq_pad; a.heads = tw->heads; a.hd = L.hd; a.hd_pad = L.hd_pad;
-      { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(xn1, D, w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
+      { ProfScope ps(PROF_GEMM_QKV, stream); st = gemm_dispatch(fold ? xb : xn1, D, fold ? w.qkv_wf : w.qkv_w, D, a, EPI_QKV_SPLIT, 0, stream); }
       if (st) return st;
     }
     { ProfScope ps(PROF_ATTENTION, stream); st = attention_launch(q, k, vt, ao, save ? save->lse(l, NL) : nullptr, n_tiles, tw->heads, L.T, L.seq_pad, L.hd, L.hd_pad, scale, stream); }
@@ -180,19 +223,23 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
       a.out = h_mid; a.ldo = D; a.aux = h_in;
+      a.out2 = fold ? xn : nullptr;   // bf16 copy of the stream after the attention branch
+      if (part_slots > 0) { a.ln_part = part; a.ln_slots = part_slots; }
       { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
-    { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream); }
+    if (fold) st = row_stats(xn);
+    else { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream); }
     if (st) return st;
     {
       GemmArgs a{};
       a.M = M; a.N = I; a.K = D;
-      a.bias = w.fc1_b;
+      a.bias = fold ? w.fc1_bf : w.fc1_b;
+      if (fold) set_consumer_stats(a, w.fc1_sf);
       a.out = save ? save->act(l, NL) : h1; a.ldo = I;   // training: the activation is kept too (fc2 weight gradient)
       a.out2 = save ? save->u(l, NL) : nullptr;          // training: keep gelu'(u) for the GELU backward
-      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
+      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, fold ? w.fc1_wf : w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
     }
     {
@@ -200,6 +247,8 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       a.M = M; a.N = D; a.K = I;
       a.bias = w.fc2_b;
       a.out = h_out; a.ldo = D; a.aux = h_mid;
+      a.out2 = fold ? xb : nullptr;   // bf16 copy of the stream entering the next layer (or the projector)
+      if (part_slots > 0 && l + 1 < tw->num_layers) { a.ln_part = part; a.ln_slots = part_slots; }
       { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(save ? save->act(l, NL) : h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
@@ -207,20 +256,25 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   return RADVLM_OK;
 }
 
+// hidden_bf16 != nullptr: the bf16 copy of `hidden` already exists (written by the tower's last epilogue)
 static int projector_forward_impl(const radvlm_projector_weights* pw, const float* hidden, int rows,
-                                  void* out, int out_dtype, void* xn, void* h1, cudaStream_t stream) {
+                                  void* out, int out_dtype, void* xn, void* h1, cudaStream_t stream,
+                                  const void* hidden_bf16 = nullptr) {
   RV_CHECK_ARG(out_dtype == RADVLM_DT_BF16 || out_dtype == RADVLM_DT_F32 || out_dtype == RADVLM_DT_F16,
                "projector: out_dtype must be bf16, f16 or f32");
   RV_CHECK_ARG((pw->in_dim % 8) == 0 && (pw->hidden % 8) == 0, "projector: dims must be multiples of 8");
   int st;
-  { ProfScope ps(PROF_MISC, stream); st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream); }
-  if (st) return st;
+  if (hidden_bf16 == nullptr) {
+    { ProfScope ps(PROF_MISC, stream); st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream); }
+    if (st) return st;
+    hidden_bf16 = xn;
+  }
   {
     GemmArgs a{};
     a.M = rows; a.N = pw->hidden; a.K = pw->in_dim;
     a.bias = pw->b1;
     a.out = h1; a.ldo = pw->hidden;
-    { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(xn, pw->in_dim, pw->w1, pw->in_dim, a, EPI_GELU_ERF_BF16, 0, stream); }
+    { ProfScope ps(PROF_GEMM, stream); st = gemm_dispatch(hidden_bf16, pw->in_dim, pw->w1, pw->in_dim, a, EPI_GELU_ERF_BF16, 0, stream); }
     if (st) return st;
   }
   {
@@ -494,10 +548,11 @@ extern "C" int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvl
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* hidden = reinterpret_cast<float*>(ws + L.off_hidden);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  st = tower_forward_impl(tw, pixels, pixel_dtype, n_tiles, hidden, L, ws, s);
+  const void* hidden_bf16 = nullptr;
+  st = tower_forward_impl(tw, pixels, pixel_dtype, n_tiles, hidden, L, ws, s, nullptr, &hidden_bf16);
   if (st) return st;
   return projector_forward_impl(pw, hidden, static_cast<int>(L.M), features_out, out_dtype,
-                                ws + L.off_xn, ws + L.off_h1, s);
+                                ws + L.off_xn, ws + L.off_h1, s, hidden_bf16);
 }
 
 // ------------------------------------------------------------------------------------------------ training mode

@@ -41,7 +41,11 @@ class PackedWeights:
         dev = torch.device(device)
         keep = []       # every device tensor referenced by the structs
         copies = []     # (destination view, source tensor): what refresh() re-copies
+        folds = []      # LayerNorm folded into the QKV / fc1 GEMMs: (W sources, bias sources, gamma, beta, wf, sf, bf)
         self.n_alias = 0
+        # RADVLM_B200_LN=kernel keeps the stand-alone LayerNorm kernels (A/B switch; also the safer choice for a
+        # residual stream whose per-token mean dwarfs its spread: the fold multiplies bf16(x), not bf16(LN(x)))
+        self.ln_fold = os.environ.get("RADVLM_B200_LN", "fold") != "kernel"
 
         def bind(srcs, dtype, pad_cols: int = 0):
             """rows of `srcs` stacked -> one contiguous [sum rows, cols (+ zero padding)] device tensor of `dtype`"""
@@ -99,6 +103,21 @@ class PackedWeights:
             L.fc2_w = w(g("mlp.fc2.weight")).data_ptr()
             L.fc2_b = v(g("mlp.fc2.bias")).data_ptr()
             inter = g("mlp.fc1.weight").shape[0]
+            if self.ln_fold:
+                for tag, ws_, bs_, ln in (
+                        ("qkv", [g("self_attn.%s_proj.weight" % n) for n in "qkv"],
+                         [g("self_attn.%s_proj.bias" % n) for n in "qkv"], "layer_norm1"),
+                        ("fc1", [g("mlp.fc1.weight")], [g("mlp.fc1.bias")], "layer_norm2")):
+                    rows = sum(t.shape[0] for t in ws_)
+                    wf = torch.empty(rows, hidden, dtype=torch.bfloat16, device=dev)
+                    sf = torch.empty(rows, dtype=torch.float32, device=dev)
+                    bf = torch.empty(rows, dtype=torch.float32, device=dev)
+                    keep.extend((wf, sf, bf))
+                    folds.append(([t.detach() for t in ws_], [t.detach() for t in bs_], g(ln + ".weight").detach(),
+                                  g(ln + ".bias").detach(), wf, sf, bf))
+                    setattr(L, tag + "_wf", wf.data_ptr())
+                    setattr(L, tag + "_sf", sf.data_ptr())
+                    setattr(L, tag + "_bf", bf.data_ptr())
         tw = _lib.SiglipWeights()
         tw.hidden, tw.intermediate, tw.heads, tw.num_layers = hidden, int(inter or 0), num_heads, num_layers
         tw.image_size, tw.patch_size, tw.channels, tw.patch_k_pad = image_size, ps, channels, k_pad
@@ -117,6 +136,7 @@ class PackedWeights:
         pj.b2 = v(proj_sd["2.bias"]).data_ptr()
         self.tower, self.projector = tw, pj
         self._layers, self._keep, self._copies = layers, keep, copies
+        self._folds, self._folds_stale = folds, True
         self.device = dev
         self.tokens_per_tile = (image_size // ps) ** 2
         self.patches_per_side = image_size // ps
@@ -126,6 +146,7 @@ class PackedWeights:
     @torch.no_grad()
     def refresh(self) -> None:
         """Re-copy the current values of every non-aliased source into its packed buffer (dtype conversion included)."""
+        self._folds_stale = True
         if not self._copies:
             return
         same = [(d, s) for d, s in self._copies if s.device == d.device]
@@ -134,6 +155,22 @@ class PackedWeights:
         for d, s in self._copies:
             if s.device != d.device:
                 d.copy_(s.reshape(d.shape))
+
+
+    @torch.no_grad()
+    def ensure_folds(self) -> None:
+        """(gamma o W, its row sums, b + W beta) of every folded LayerNorm, recomputed from the CURRENT source values when
+        they may have changed (inference calls only: the training forward keeps the stand-alone LayerNorm kernels).
+        LN(x) W^T + b = rstd (x (gamma o W)^T - mean s) + (b + W beta); siglip_encoder.py:264,266,287,296."""
+        if not self._folds_stale:
+            return
+        dev = self.device
+        for ws_, bs_, gamma, beta, wf, sf, bf in self._folds:
+            W = torch.cat([t.to(dev, torch.float32) for t in ws_], 0)
+            wf.copy_(W * gamma.to(dev, torch.float32)[None, :])
+            sf.copy_(wf.float().sum(1))          # of the bf16 values the tensor core multiplies
+            bf.copy_(torch.cat([t.to(dev, torch.float32) for t in bs_], 0) + W @ beta.to(dev, torch.float32))
+        self._folds_stale = False
 
 
 def _layout_key(tensors) -> tuple:
@@ -254,6 +291,7 @@ class B200VisionEncoder:
             images = images.float()
         images = images.to(dev).contiguous()
         pk = self.packed(dev)
+        pk.ensure_folds()
         lib = _lib.load()
         n = images.shape[0]
         T, Hp = pk.tokens_per_tile, pk.proj_hidden
@@ -281,6 +319,7 @@ class B200VisionEncoder:
             images = images.float()
         images = images.to(dev).contiguous()
         pk = self.packed(dev)
+        pk.ensure_folds()
         lib = _lib.load()
         n = images.shape[0]
         out = torch.empty(n, pk.tokens_per_tile, pk.hidden, dtype=torch.float32, device=dev)

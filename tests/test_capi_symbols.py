@@ -29,7 +29,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.SpliceSegment) == 32
     assert ctypes.sizeof(_lib.MergeImage) == 12 * 4
     assert ctypes.sizeof(_lib.PreprocessImage) == 16 + 10 * 4
-    assert ctypes.sizeof(_lib.VitLayerWeights) == 12 * 8
+    assert ctypes.sizeof(_lib.VitLayerWeights) == 18 * 8
     assert ctypes.sizeof(_lib.VitLayerGrads) == 12 * 8
 
 

@@ -139,6 +139,55 @@ def test_layernorm_and_im2col_vs_torch(lib):
     assert torch.equal(cols[:, :588], ref.bfloat16()) and cols[:, 588:].abs().max() == 0
 
 
+def test_layernorm_folded_into_gemm_vs_torch(lib):
+    """LayerNorm folded into the consuming GEMM (north_star: 'LayerNorm fused into the QKV GEMM prologue'):
+    row statistics of the bf16 stream + (gamma o W, row sums, b + W beta) reproduce LayerNorm(x) W^T + b
+    (siglip_encoder.py:264,266 followed by :207-209 / :252)."""
+    from radvlm_b200 import _lib
+    M, N, K = 1458, 1152, 1152
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(M, K, device="cuda", generator=g) * 2.5 + 0.7
+    x[:, 5] += 40.0                      # an outlier channel, as ViT residual streams have
+    gamma = torch.randn(K, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(K, device="cuda", generator=g) * 0.2
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.03
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    xb = x.bfloat16()
+    stats = torch.empty(M, 2, device="cuda", dtype=torch.float32)
+    _lib.check(lib.radvlm_ln_row_stats_bf16(xb.data_ptr(), stats.data_ptr(), M, K, 1e-6, _stream()))
+    xf = xb.float()
+    torch.testing.assert_close(stats[:, 0], xf.mean(1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(stats[:, 1], torch.rsqrt(xf.var(1, unbiased=False) + 1e-6), rtol=1e-4, atol=1e-6)
+    wf = (W * gamma[None, :]).bfloat16()
+    sf = wf.float().sum(1).contiguous()
+    bf = (b + W @ beta).contiguous()
+    ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-6) @ W.t() + b
+    for epi, fn in ((_lib.EPI_BIAS_BF16, lambda t: t),
+                    (_lib.EPI_GELU_TANH_BF16, lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.radvlm_gemm_bf16_ln(xb.data_ptr(), K, wf.data_ptr(), K, M, N, K, bf.data_ptr(), stats.data_ptr(),
+                                           sf.data_ptr(), epi, out.data_ptr(), N, _stream()))
+        cos, relmax = _metrics(out.float(), fn(ref))
+        assert cos >= 0.9999 and relmax <= 2e-2, "folded LayerNorm GEMM (epilogue %d): cos=%.6f relmax=%.4e" % (epi, cos, relmax)
+
+
+def test_ln_fold_equals_layernorm_kernels(lib, monkeypatch):
+    """The default path (LayerNorm folded into the QKV / fc1 GEMMs, bf16 stream copies written by the residual
+    epilogues) against the same tower with stand-alone LayerNorm kernels (RADVLM_B200_LN=kernel)."""
+    from radvlm_b200 import mm_arch
+    x = gi.encoder_pixels(2, seed=13).cuda()
+    outs = {}
+    for mode in ("kernel", "fold"):
+        monkeypatch.setenv("RADVLM_B200_LN", mode)
+        host = _small_host(torch.float32)
+        enc = mm_arch._encoder_for(host)
+        assert enc.packed("cuda").ln_fold == (mode == "fold")
+        outs[mode] = (enc.tower_forward(x), host.encode_images(x))
+    for i, what in enumerate(("tower", "features")):
+        cos, relmax = _metrics(outs["fold"][i], outs["kernel"][i])
+        assert cos >= 0.9999 and relmax <= 1e-2, "fold vs kernel %s: cos=%.6f relmax=%.4e" % (what, cos, relmax)
+
+
 # ============================================================================ preprocessing (bit-exact)
 @pytest.mark.parametrize("name", sorted(gi.preprocess_cases()))
 def test_preprocess_bit_exact_vs_reference_golden(lib, golden_dir, name):

@@ -209,7 +209,40 @@ static int run_case_ex(int M, int N, int K, int a_layout, int b_layout, int k_sp
   return bad ? 1 : 0;
 }
 
+// LayerNorm-fold epilogue cost: the same GEMM with and without (mean, rstd, row sums) applied in the epilogue
+static void run_ln_cost(int M, int N, int K, int epi) {
+  __nv_bfloat16 *dA, *dW, *dout;
+  float *db, *ds, *dstats;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2)); CK(cudaMalloc(&dW, (size_t)N * K * 2)); CK(cudaMalloc(&dout, (size_t)M * N * 2));
+  CK(cudaMalloc(&db, N * 4)); CK(cudaMalloc(&ds, N * 4)); CK(cudaMalloc(&dstats, (size_t)M * 8));
+  CK(cudaMemset(dA, 0, (size_t)M * K * 2)); CK(cudaMemset(dW, 0, (size_t)N * K * 2));
+  CK(cudaMemset(db, 0, N * 4)); CK(cudaMemset(ds, 0, N * 4)); CK(cudaMemset(dstats, 0, (size_t)M * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int mode = 0; mode < 2; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) {
+      float ms = 0;
+      for (int i = 0; i < 11; ++i) {
+        if (i == 1) cudaEventRecord(e0);
+        int st = mode ? radvlm_gemm_bf16_ln(dA, K, dW, K, M, N, K, db, dstats, ds, epi, dout, N, nullptr)
+                      : radvlm_gemm_bf16(dA, K, dW, K, M, N, K, db, epi, dout, N, nullptr, 0, 0, nullptr);
+        if (st) { printf("API error %s\n", radvlm_last_error()); exit(2); }
+      }
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      cudaEventElapsedTime(&ms, e0, e1);
+      printf("ln-cost M=%d N=%d K=%d epi=%d %s : %.4f ms per launch\n", M, N, K, epi, mode ? "folded" : "plain ", ms / 10);
+    }
+  }
+  cudaFree(dA); cudaFree(dW); cudaFree(dout); cudaFree(db); cudaFree(ds); cudaFree(dstats);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "lncost")) {
+    run_ln_cost(58320, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16);
+    run_ln_cost(58320, 3456, 1152, RADVLM_EPI_BIAS_BF16);
+    return 0;
+  }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   std::vector<Case> cases = {
       {128, 128, 64, RADVLM_EPI_BIAS_F32, 128},    // one tile, one K slab
