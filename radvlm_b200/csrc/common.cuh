@@ -345,6 +345,42 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work).  The GEMM epilogues
+// use them because every instruction the epilogue warps issue slows the MMA pipeline of the same SM (measured,
+// tools/gemm_timeline.cu: +~270 cycles per 256 x 256 tile for each instruction per output element).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_dup(float v) { return f2_make(v, v); }
+__device__ __forceinline__ void f2_get(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t f2_pack_bf16(f32x2 v) {
+  float lo, hi;
+  f2_get(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -354,6 +390,15 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // gelu_pytorch_tanh: 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) )).  One MUFU.TANH (abs error ~5e-4 in
 // tanh, far below the bf16 rounding of the result) instead of the ~40-instruction tanhf().
 __device__ __forceinline__ float gelu_tanh_f(float x) {
+#if defined(RV_GELU_EXPERIMENT) && RV_GELU_EXPERIMENT == 1   // timing experiment: FMA pipe only (wrong values)
+  { const float x2 = x * x; const float u = x * fmaf(0.0356774f, x2, 0.7978845608f); const float hx = 0.5f * x; return fmaf(hx, fminf(fmaxf(u, -1.f), 1.f), hx); }
+#elif defined(RV_GELU_EXPERIMENT) && RV_GELU_EXPERIMENT == 2 // timing experiment: MUFU only (wrong values)
+  return tanh_approx(x);
+#elif defined(RV_GELU_EXPERIMENT) && RV_GELU_EXPERIMENT == 3 // timing experiment: six integer ops instead of six FP ops
+  { uint32_t a = __float_as_uint(x); uint32_t b = a * 2654435761u; b ^= a >> 3; b += 0x9E3779B9u; b = b * 40503u; b ^= b >> 7; b += a; return __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u); }
+#elif defined(RV_GELU_EXPERIMENT) && RV_GELU_EXPERIMENT == 4 // timing experiment: three FP ops
+  { const float x2 = x * x; return x * fmaf(0.0356774f, x2, 0.7978845608f); }
+#endif
   const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
   const float x2 = x * x;
   const float u = x * fmaf(k01, x2, k0);
@@ -370,6 +415,29 @@ __device__ __forceinline__ void gelu_tanh_both_f(float x, float& y, float& dy) {
   const float hx = 0.5f * x;
   y = fmaf(hx, t, hx);
   dy = fmaf(hx * fmaf(-t, t, 1.0f), fmaf(3.0f * k01, x2, k0), fmaf(0.5f, t, 0.5f));
+}
+
+// the same two functions on a pair of values (half the FMA-pipe instructions; the two tanh stay scalar MUFU ops)
+__device__ __forceinline__ f32x2 gelu_tanh_f2(f32x2 x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x2 = f2_mul(x, x);
+  const f32x2 u = f2_mul(x, f2_fma(f2_dup(k01), x2, f2_dup(k0)));
+  float u0, u1;
+  f2_get(u, u0, u1);
+  const f32x2 t = f2_make(tanh_approx(u0), tanh_approx(u1));
+  const f32x2 hx = f2_mul(f2_dup(0.5f), x);
+  return f2_fma(hx, t, hx);
+}
+__device__ __forceinline__ void gelu_tanh_both_f2(f32x2 x, f32x2& y, f32x2& dy) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x2 = f2_mul(x, x);
+  float u0, u1;
+  f2_get(f2_mul(x, f2_fma(f2_dup(k01), x2, f2_dup(k0))), u0, u1);
+  const f32x2 t = f2_make(tanh_approx(u0), tanh_approx(u1));
+  const f32x2 hx = f2_mul(f2_dup(0.5f), x);
+  y = f2_fma(hx, t, hx);
+  const f32x2 one_m_t2 = f2_fma(f2_mul(f2_dup(-1.0f), t), t, f2_dup(1.0f));
+  dy = f2_fma(f2_mul(hx, one_m_t2), f2_fma(f2_dup(3.0f * k01), x2, f2_dup(k0)), f2_fma(f2_dup(0.5f), t, f2_dup(0.5f)));
 }
 
 // exact-erf GELU (nn.GELU()): erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), two MUFU ops.

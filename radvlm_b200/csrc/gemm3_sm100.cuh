@@ -45,6 +45,18 @@ struct Gemm3Cfg {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// (the bulk form, cp.async.bulk.prefetch.L2 with one row segment per lane, was measured too: no shorter drain and
+// ~2400 cycles of issue per tile against ~770; tools/gemm_timeline.cu)
+
+#ifdef RV_GEMM_TIMELINE
+#define RV_GTL(slot)                                                                                      \
+  do {                                                                                                    \
+    if (args.timeline != nullptr && cluster_id == RV_GEMM_TIMELINE && leader && lane == 0 && (e - e_begin) < 24) \
+      args.timeline[(e - e_begin) * 8 + (slot)] = clock64();                                              \
+  } while (0)
+#else
+#define RV_GTL(slot) do { } while (0)
+#endif
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -160,12 +172,15 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
         int m_blk, n0, w;
         tile_of(e, m_blk, n0, w);
         const uint32_t idesc = (w == kSchedBN) ? idesc_full : idesc_half;
+        RV_GTL(0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        RV_GTL(1);
         const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc * kSchedBN);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kb == 0) RV_GTL(2);
           const uint64_t soff = static_cast<uint64_t>((stage * Cfg::kStageBytes) >> 4);
           const uint64_t adesc = desc_k + soff;
           const uint64_t bdesc = b0 + soff + static_cast<uint64_t>(Cfg::kABytes >> 4);
@@ -179,6 +194,7 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
             phase ^= 1u;
           }
         }
+        RV_GTL(3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -213,8 +229,10 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       float ln_nmean, ln_rstd;  // LayerNorm fold: this row's statistics, fetched while the tile's MMAs still run
       gemm_ln_row_stats(args, row, ln_nmean, ln_rstd);
+      if (warp == 2) RV_GTL(4);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (warp == 2) RV_GTL(5);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * kSchedBN + half * (w / 2));
       const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes;
@@ -224,6 +242,7 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       else gemm_epilogue_drain<EPI, 64>(args, row, n0 + half * 64, t_row, stg, lane, ln_slot, ln_nmean, ln_rstd);
       tc_fence_before();
       __syncwarp();
+      if (warp == 2) RV_GTL(6);
       if (lane == 0) {
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_remote(tempty_bar(acc), 0);

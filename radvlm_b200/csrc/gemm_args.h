@@ -54,6 +54,8 @@ struct GemmArgs {
   // Consumer side without a finalize pass: ln_stats == nullptr, ln_s != nullptr and ln_part != nullptr -> every epilogue
   // thread adds up the ln_slots partials of its row itself: mean = sum / ln_dim, rstd = rsqrt(E[x^2] - mean^2 + ln_eps).
   float ln_inv_dim, ln_eps;
+  // tuning builds only (-DRV_GEMM_TIMELINE, tools/gemm_timeline.cu): clock64 stamps of CTA pair 0, [tile][8]
+  long long* timeline;
 };
 
 }  // namespace rv

@@ -127,6 +127,9 @@ static int launch_gemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, 
 }
 
 // Wave-quantisation aware tile-width choice: cost = waves * BN (MMA cycles per K step scale with BN).
+#ifdef RV_GEMM_TIMELINE
+static long long* g_gemm_timeline = nullptr;
+#endif
 static int g_gemm_mode = 0;  // 0 auto, 1 force single-CTA tiles, 2 force CTA-pair tiles
 // scheduled variable-width tiles (gemm3_sm100.cuh) for the pair GEMMs whose A is K-major; RADVLM_B200_GEMM_SCHED=0
 // keeps the round-robin 256 x BN kernel (A/B switch)
@@ -176,6 +179,9 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   int st = require_sm100();
   if (st != RADVLM_OK) return st;
   GemmArgs args = args_in;
+#ifdef RV_GEMM_TIMELINE
+  args.timeline = g_gemm_timeline;
+#endif
   RV_CHECK_ARG(A != nullptr && W != nullptr, "gemm: null operand");
   RV_CHECK_ARG(args.M > 0 && args.N > 0 && args.K > 0, "gemm: bad shape M=%d N=%d K=%d", args.M,
                args.N, args.K);
@@ -306,6 +312,15 @@ extern "C" int radvlm_gemm_bf16(const void* A, int64_t lda, const void* W, int64
   a.aux = aux;
   a.aux_period = aux_period;
   return gemm_dispatch(A, lda, W, ldw, a, epilogue, block_n, static_cast<cudaStream_t>(stream));
+}
+
+// tuning builds (-DRV_GEMM_TIMELINE, tools/gemm_timeline.cu): where the instrumented kernel writes its clock64 stamps
+extern "C" void radvlm_gemm_set_timeline(long long* p) {
+#ifdef RV_GEMM_TIMELINE
+  rv::g_gemm_timeline = p;
+#else
+  (void)p;
+#endif
 }
 
 extern "C" int radvlm_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,

@@ -237,8 +237,8 @@ __device__ __forceinline__ uint4 stage_load_vec(uint32_t stage, int rr, int v) {
 // squares of the values it stores (ps / pq); the caller reduces them over the 8 lanes that share a row once per tile.
 template <int EPI, bool kStats = false>
 __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc,
-                                                         uint32_t stage, int lane, float* ps = nullptr,
-                                                         float* pq = nullptr) {
+                                                         uint32_t stage, int lane, f32x2* ps2 = nullptr,
+                                                         f32x2* pq2 = nullptr) {
   stage_store_row(stage, lane, acc);
   __syncwarp();
   const int v = lane & 7;
@@ -246,6 +246,7 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
   if (gcol < a.N) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(a.bias + gcol));
+    const f32x2 b01 = f2_make(b.x, b.y), b23 = f2_make(b.z, b.w);
     float4 xr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -264,15 +265,16 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
       const int grow = row0 + rr;
       if (grow < a.M) {
         const uint4 t = stage_load_vec(stage, rr, v);
+        // packed pairs (FADD2 / FFMA2): see gemm_epilogue_bf16_staged
+        const f32x2 o01 = f2_add(f2_add(f2_make(__uint_as_float(t.x), __uint_as_float(t.y)), b01), f2_make(xr[i].x, xr[i].y));
+        const f32x2 o23 = f2_add(f2_add(f2_make(__uint_as_float(t.z), __uint_as_float(t.w)), b23), f2_make(xr[i].z, xr[i].w));
         float4 o;
-        o.x = __uint_as_float(t.x) + b.x + xr[i].x;
-        o.y = __uint_as_float(t.y) + b.y + xr[i].y;
-        o.z = __uint_as_float(t.z) + b.z + xr[i].z;
-        o.w = __uint_as_float(t.w) + b.w + xr[i].w;
+        f2_get(o01, o.x, o.y);
+        f2_get(o23, o.z, o.w);
         float* dst = reinterpret_cast<float*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol;
-        if constexpr (kStats) {
-          ps[i] += (o.x + o.y) + (o.z + o.w);
-          pq[i] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, pq[i]))));
+        if constexpr (kStats) {   // ps / pq hold (even column, odd column) partial sums as packed pairs
+          ps2[i] = f2_add(ps2[i], f2_add(o01, o23));
+          pq2[i] = f2_fma(o01, o01, f2_fma(o23, o23, pq2[i]));
         }
         if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32) {
           if (a.out2 != nullptr)  // bf16 copy of the new residual stream (8 lanes x 8 B = 64 contiguous bytes per row)
@@ -311,26 +313,35 @@ __device__ __forceinline__ void gemm_epilogue_bf16_staged(const GemmArgs& a, int
       const int c = col0 + 32 * h + 4 * j;
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
-      float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
+      // two packed pairs per 4 columns (FFMA2 / FADD2 / FMUL2): the epilogue's instruction count, not its latency, is
+      // what the MMA pipeline of the SM feels
+      f32x2 p0 = f2_make(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
+      f32x2 p1 = f2_make(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+      const f32x2 b0 = f2_make(b.x, b.y), b1 = f2_make(b.z, b.w);
       if constexpr (kLn) {  // rstd * (acc - mean * s[n]) + b'[n]
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
-        v0 = fmaf(ln_rstd, fmaf(ln_nmean, s4.x, v0), b.x); v1 = fmaf(ln_rstd, fmaf(ln_nmean, s4.y, v1), b.y);
-        v2 = fmaf(ln_rstd, fmaf(ln_nmean, s4.z, v2), b.z); v3 = fmaf(ln_rstd, fmaf(ln_nmean, s4.w, v3), b.w);
+        const f32x2 nm = f2_dup(ln_nmean), rs = f2_dup(ln_rstd);
+        p0 = f2_fma(rs, f2_fma(nm, f2_make(s4.x, s4.y), p0), b0);
+        p1 = f2_fma(rs, f2_fma(nm, f2_make(s4.z, s4.w), p1), b1);
       } else {
-        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+        p0 = f2_add(p0, b0);
+        p1 = f2_add(p1, b1);
       }
       if constexpr (EPI == EPI_GELU_TANH_BF16) {
-        v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); v2 = gelu_tanh_f(v2); v3 = gelu_tanh_f(v3);
+        p0 = gelu_tanh_f2(p0);
+        p1 = gelu_tanh_f2(p1);
       }
       if constexpr (EPI == EPI_GELU_TANH_DUAL_BF16) {
-        float d0, d1, d2, d3;
-        gelu_tanh_both_f(v0, v0, d0); gelu_tanh_both_f(v1, v1, d1);
-        gelu_tanh_both_f(v2, v2, d2); gelu_tanh_both_f(v3, v3, d3);
-        pk2[16 * h + 2 * j] = pack_bf16x2(d0, d1);
-        pk2[16 * h + 2 * j + 1] = pack_bf16x2(d2, d3);
+        f32x2 d0, d1;
+        gelu_tanh_both_f2(p0, p0, d0);
+        gelu_tanh_both_f2(p1, p1, d1);
+        pk2[16 * h + 2 * j] = f2_pack_bf16(d0);
+        pk2[16 * h + 2 * j + 1] = f2_pack_bf16(d1);
       }
+      float v0, v1, v2, v3;
+      f2_get(p0, v0, v1);
+      f2_get(p1, v2, v3);
       if constexpr (EPI == EPI_GELU_ERF_BF16) {
         v0 = gelu_erf_f(v0); v1 = gelu_erf_f(v1); v2 = gelu_erf_f(v2); v3 = gelu_erf_f(v3);
       }
@@ -407,18 +418,21 @@ __device__ __forceinline__ void gemm_epilogue_qkv_staged(const GemmArgs& a, int 
       const int c = col0 + 32 * h + 4 * j;
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      float v0 = __uint_as_float(acc[4 * j + 0]), v1 = __uint_as_float(acc[4 * j + 1]);
-      float v2 = __uint_as_float(acc[4 * j + 2]), v3 = __uint_as_float(acc[4 * j + 3]);
+      f32x2 p0 = f2_make(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
+      f32x2 p1 = f2_make(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+      const f32x2 b0 = f2_make(b.x, b.y), b1 = f2_make(b.z, b.w);
       if constexpr (kLn) {  // LayerNorm folded into the GEMM: rstd * (acc - mean * s[n]) + b'[n]
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < a.N) s4 = __ldg(reinterpret_cast<const float4*>(a.ln_s + c));
-        v0 = fmaf(ln_rstd, fmaf(ln_nmean, s4.x, v0), b.x); v1 = fmaf(ln_rstd, fmaf(ln_nmean, s4.y, v1), b.y);
-        v2 = fmaf(ln_rstd, fmaf(ln_nmean, s4.z, v2), b.z); v3 = fmaf(ln_rstd, fmaf(ln_nmean, s4.w, v3), b.w);
+        const f32x2 nm = f2_dup(ln_nmean), rs = f2_dup(ln_rstd);
+        p0 = f2_fma(rs, f2_fma(nm, f2_make(s4.x, s4.y), p0), b0);
+        p1 = f2_fma(rs, f2_fma(nm, f2_make(s4.z, s4.w), p1), b1);
       } else {
-        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+        p0 = f2_add(p0, b0);
+        p1 = f2_add(p1, b1);
       }
-      pk[16 * h + 2 * j] = pack_bf16x2(v0, v1);
-      pk[16 * h + 2 * j + 1] = pack_bf16x2(v2, v3);
+      pk[16 * h + 2 * j] = f2_pack_bf16(p0);
+      pk[16 * h + 2 * j + 1] = f2_pack_bf16(p1);
     }
   }
   stage_store_row(stage, lane, pk);
@@ -466,10 +480,10 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
   // LayerNorm fold, producer side: row sums of the new residual stream over this warp's columns (gemm_args.h: ln_part)
   constexpr bool kStatsCapable = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32);
   const bool stats = kStatsCapable && staged && args.ln_part != nullptr && ln_slot >= 0;
-  float ps[kStatsCapable ? 8 : 1], pq[kStatsCapable ? 8 : 1];
+  f32x2 ps[kStatsCapable ? 8 : 1], pq[kStatsCapable ? 8 : 1];   // (even column, odd column) partial sums
   if constexpr (kStatsCapable) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0.f;
+    for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0ull;
   }
 #pragma unroll 1
   for (int c = 0; c < NCOLS; c += 64) {
@@ -513,14 +527,18 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
     if (stats) {  // the 8 lanes that share a row (lane bits 0..2 = column group) add up, lane & 7 == 0 writes the slot
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        float s0, s1, q0, q1;
+        f2_get(ps[i], s0, s1);
+        f2_get(pq[i], q0, q1);
+        float sum = s0 + s1, sq = q0 + q1;
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
-          ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
-          pq[i] += __shfl_xor_sync(0xffffffffu, pq[i], o);
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          sq += __shfl_xor_sync(0xffffffffu, sq, o);
         }
         const int grow = row0 + i * 4 + (lane >> 3);
         if ((lane & 7) == 0 && grow < args.M)
-          args.ln_part[static_cast<size_t>(grow) * args.ln_slots + ln_slot] = make_float2(ps[i], pq[i]);
+          args.ln_part[static_cast<size_t>(grow) * args.ln_slots + ln_slot] = make_float2(sum, sq);
       }
     }
   }
