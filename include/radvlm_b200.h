@@ -346,7 +346,12 @@ int radvlm_plan_splice(const int64_t* input_ids, const uint8_t* attention_mask, 
  * truncate / pad / stack with labels, attention_mask, position_ids (llava_arch.py:495-531) in ONE pass:
  * every output row [b, p, :] is produced once, directly in the padded [B, max_len, H] tensor.
  * ---------------------------------------------------------------------------------------------- */
-#define RADVLM_MERGE_ANYRES 0  /* base tile + unpadded (optionally pooled) grid with newline column */
+#define RADVLM_MERGE_ANYRES 0  /* base tile + unpadded (optionally pooled) grid with newline column; `reserved` holds
+                                * RADVLM_ANYRES_* flags for the other spatial merge types (llava_arch.py:376-404) */
+#define RADVLM_ANYRES_NO_NEWLINE 1 /* no image_newline column: "spatial" without 'unpad' (:398-400), 'maxpool2x2' (:376-380) */
+#define RADVLM_ANYRES_NO_BASE 2    /* 'nobase' in mm_patch_merge_type: the base tile is not prepended (:401-404) */
+/* pool == RADVLM_POOL_MAX in an ANYRES entry: nn.functional.max_pool2d(., 2) of the whole (un-cropped) grid
+ * ('maxpool2x2'): out_h x out_w = floor(S*grid_h / 2) x floor(S*grid_w / 2). */
 #define RADVLM_MERGE_SINGLE 1  /* one tile + one newline token (llava_arch.py:407-412) */
 #define RADVLM_MERGE_FLAT 2    /* tiles*T tokens, no newline ("flat", or a 4-D image batch) */
 /* Video sample (llava_arch.py:171-190 get_2dPool, :222-249 add_token_per_grid / _frame, :310-349): the entry's
@@ -370,7 +375,7 @@ typedef struct radvlm_merge_image {
   int32_t crop_r0, crop_c0, crop_h, crop_w;
   int32_t pool, out_h, out_w;
   int32_t n_tokens;
-  int32_t reserved;  /* RADVLM_MERGE_VIDEO: RADVLM_NEWLINE_* */
+  int32_t reserved;  /* RADVLM_MERGE_VIDEO: RADVLM_NEWLINE_*;  RADVLM_MERGE_ANYRES: RADVLM_ANYRES_* flags */
 } radvlm_merge_image;
 
 /* All pointers are DEVICE pointers.  dtype: element type of features / newline / embed table / out.
@@ -420,11 +425,14 @@ int radvlm_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 
 /* Backward of radvlm_merge_splice (autograd of llava_arch.py:350-531).  d_out_embeds: [B*max_len, H] of `dtype`.
  *   d_features fp32 [tiles*T, H] and d_newline fp32 [H]: accumulated with atomics (zero or running sums on entry);
- *   d_text [n_text, H] of `dtype` (or NULL): gradient rows of the text tokens in text_src order. */
+ *   d_text [n_text, H] of `dtype` (or NULL): gradient rows of the text tokens in text_src order;
+ *   features: the forward's feature tensor ([tiles*T, H] of `dtype`), needed only when an entry pools with
+ *   RADVLM_POOL_MAX (video 'max' pooling, 'maxpool2x2'): the gradient of a window goes to its arg-max, first maximum
+ *   in row-major window order like ATen's max_pool2d backward.  NULL: max-pooled rows get no gradient. */
 int radvlm_merge_splice_backward(const void* d_out_embeds, int dtype, int hidden, int tokens_per_tile,
                                  int patches_per_side, const radvlm_splice_segment* segments, int n_segments,
                                  const radvlm_merge_image* images, int n_images, int64_t total_rows,
-                                 float* d_features, float* d_newline, void* d_text, void* stream);
+                                 float* d_features, float* d_newline, void* d_text, const void* features, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused anyres preprocessing (uint8 -> resize -> pad -> tile -> normalise), bit-exact with

@@ -72,26 +72,41 @@ def encode_images(tower_sd, proj_sd, pixel_values, num_heads=16, eps=1e-6) -> to
 
 
 def merge_image(feat: torch.Tensor, image_size, newline: torch.Tensor, possible_resolutions=None,
-                tile_size: int = 384, unit: int = 27, max_num_patches: Optional[int] = 9) -> torch.Tensor:
-    """llava_arch.py:350-412 for one image (spatial_unpad, anyres / anyres_max_N): [tiles, T, C] -> [N, C]."""
+                tile_size: int = 384, unit: int = 27, max_num_patches: Optional[int] = 9,
+                merge_type: str = "spatial_unpad", anyres: bool = True) -> torch.Tensor:
+    """llava_arch.py:350-412 for one image: [tiles, T, C] -> [N, C].  merge_type is mm_patch_merge_type ("spatial*");
+    anyres = image_aspect_ratio is "anyres" / "anyres_max_N" (otherwise the fixed 2 x 2 grid of :373-374);
+    max_num_patches = N of a matched "anyres_max_N" (None / 0: the un-pooled 'unpad' branch :393-397)."""
     if feat.shape[0] == 1:                                                         # :407-412
-        return torch.cat((feat[0], newline[None]), dim=0)
+        return torch.cat((feat[0], newline[None]), dim=0) if "unpad" in merge_type else feat[0]
     base, rest = feat[0], feat[1:]
-    if possible_resolutions is None:
-        possible_resolutions = po.default_pinpoints(tile_size)
-    gw, gh = po.get_anyres_image_grid_shape(image_size, possible_resolutions, tile_size)
+    if anyres:
+        if possible_resolutions is None:
+            possible_resolutions = po.default_pinpoints(tile_size)
+        gw, gh = po.get_anyres_image_grid_shape(image_size, possible_resolutions, tile_size)   # :366
+    else:
+        gw, gh = 2, 2                                                              # :374
     x = rest.view(gh, gw, unit, unit, -1)                                          # :372
-    x = x.permute(4, 0, 2, 1, 3).contiguous().flatten(1, 2).flatten(2, 3)         # :383-384
-    r0, r1, c0, c1 = po.unpad_window(image_size, x.shape[1], x.shape[2])          # unpad_image :127-159
-    x = x[:, r0:r1, c0:c1]
-    c, h, w = x.shape
-    if max_num_patches:
-        times = math.sqrt(h * w / (max_num_patches * unit ** 2))                   # :387
-        if times > 1.1:
-            x = F.interpolate(x[None], [int(h // times), int(w // times)], mode="bilinear")[0]  # :390
-    x = torch.cat((x, newline[:, None, None].expand(*x.shape[:-1], 1)), dim=-1)    # :391
-    x = x.flatten(1, 2).transpose(0, 1)                                            # :392
-    return torch.cat((base, x), dim=0)                                             # :405
+    if "maxpool2x2" in merge_type:                                                 # :376-380
+        x = x.permute(4, 0, 2, 1, 3).contiguous().flatten(1, 2).flatten(2, 3)
+        x = F.max_pool2d(x, 2)
+        x = x.flatten(1, 2).transpose(0, 1)
+    elif "unpad" in merge_type:                                                    # :381-397
+        x = x.permute(4, 0, 2, 1, 3).contiguous().flatten(1, 2).flatten(2, 3)     # :383-384
+        r0, r1, c0, c1 = po.unpad_window(image_size, x.shape[1], x.shape[2])      # unpad_image :127-159
+        x = x[:, r0:r1, c0:c1]
+        c, h, w = x.shape
+        if max_num_patches and anyres:
+            times = math.sqrt(h * w / (max_num_patches * unit ** 2))               # :387
+            if times > 1.1:
+                x = F.interpolate(x[None], [int(h // times), int(w // times)], mode="bilinear")[0]  # :390
+        x = torch.cat((x, newline[:, None, None].expand(*x.shape[:-1], 1)), dim=-1)    # :391
+        x = x.flatten(1, 2).transpose(0, 1)                                        # :392
+    else:                                                                          # :398-400
+        x = x.permute(0, 2, 1, 3, 4).contiguous().flatten(0, 3)
+    if "nobase" in merge_type:                                                     # :401-402
+        return x
+    return torch.cat((base, x), dim=0)                                             # :404
 
 
 def get_2d_pool(feat: torch.Tensor, mode: str, stride: int = 2, unit: int = 27) -> torch.Tensor:

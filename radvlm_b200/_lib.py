@@ -36,6 +36,7 @@ MERGE_ANYRES, MERGE_SINGLE, MERGE_FLAT, MERGE_VIDEO = 0, 1, 2, 3
 MAX_PEERS = 8
 POOL_NONE, POOL_BILINEAR, POOL_AVERAGE, POOL_MAX = 0, 1, 2, 3
 NEWLINE_NONE, NEWLINE_ONE, NEWLINE_FRAME, NEWLINE_GRID = 0, 1, 2, 3
+ANYRES_NO_NEWLINE, ANYRES_NO_BASE = 1, 2
 
 
 class RadvlmError(RuntimeError):
@@ -163,7 +164,7 @@ SIGNATURES = {
     "radvlm_colsum_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "radvlm_gelu_fwd_bwd_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "radvlm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "radvlm_merge_splice_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    "radvlm_merge_splice_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "radvlm_plan_select_best_resolution": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _pi, _pi]),
     "radvlm_plan_image": (_i, [_i, _i, C.POINTER(C.c_int32), _i, _i, _i, _i, C.POINTER(ImagePlan)]),
     "radvlm_plan_splice": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _i64, _i,

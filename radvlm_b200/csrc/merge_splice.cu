@@ -293,16 +293,33 @@ merge_splice_kernel(const MergeSpliceArgs a) {
             dst.st(i, Vec16<T>::pack(o));
           }
         }
-      } else if (t < a.T) {  // base tile
-        copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
       } else if (im.mode == RADVLM_MERGE_SINGLE) {
-        copy_row(a.newline, dst, a.nvec, lane);
+        if (t < a.T) copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
+        else copy_row(a.newline, dst, a.nvec, lane);
+      } else if (!(im.reserved & RADVLM_ANYRES_NO_BASE) && t < a.T) {  // base tile
+        copy_row(a.features + (static_cast<size_t>(im.tile_base) * a.T + t) * a.nvec, dst, a.nvec, lane);
       } else {
-        const int u = t - a.T;
-        const int r = u / (im.out_w + 1);
-        const int c = u - r * (im.out_w + 1);
+        const int u = t - ((im.reserved & RADVLM_ANYRES_NO_BASE) ? 0 : a.T);
+        const int row_w = im.out_w + ((im.reserved & RADVLM_ANYRES_NO_NEWLINE) ? 0 : 1);
+        const int r = u / row_w;
+        const int c = u - r * row_w;
         if (c == im.out_w) {
           copy_row(a.newline, dst, a.nvec, lane);
+        } else if (im.pool == RADVLM_POOL_MAX) {  // 'maxpool2x2': 2 x 2 windows of the whole grid (llava_arch.py:376-380)
+          const uint4* p00 = a.features + grid_src_row(im, 2 * r, 2 * c, a.S, a.T) * a.nvec;
+          const uint4* p01 = a.features + grid_src_row(im, 2 * r, 2 * c + 1, a.S, a.T) * a.nvec;
+          const uint4* p10 = a.features + grid_src_row(im, 2 * r + 1, 2 * c, a.S, a.T) * a.nvec;
+          const uint4* p11 = a.features + grid_src_row(im, 2 * r + 1, 2 * c + 1, a.S, a.T) * a.nvec;
+          for (int i = lane; i < a.nvec; i += 32) {
+            float f00[Vec16<T>::N], f01[Vec16<T>::N], f10[Vec16<T>::N], f11[Vec16<T>::N], o[Vec16<T>::N];
+            Vec16<T>::unpack(ld_stream(p00 + i), f00);
+            Vec16<T>::unpack(ld_stream(p01 + i), f01);
+            Vec16<T>::unpack(ld_stream(p10 + i), f10);
+            Vec16<T>::unpack(ld_stream(p11 + i), f11);
+#pragma unroll
+            for (int e = 0; e < Vec16<T>::N; ++e) o[e] = fmaxf(fmaxf(f00[e], f01[e]), fmaxf(f10[e], f11[e]));
+            dst.st(i, Vec16<T>::pack(o));
+          }
         } else if (!im.pool) {
           const size_t srow = grid_src_row(im, r + im.crop_r0, c + im.crop_c0, a.S, a.T);
           copy_row(a.features + srow * a.nvec, dst, a.nvec, lane);
@@ -360,7 +377,31 @@ struct MergeSpliceBwdArgs {
   float* dfeat;     // [tiles*T, H] fp32
   float* dnewline;  // [H] fp32
   uint4* dtext;     // [n_text, H] (dtype of dout) or nullptr
+  const uint4* features;  // forward input (max pooling only: the gradient goes to the arg-max of every window)
 };
+
+// Max-pooling backward: every channel's gradient goes to the first maximum of its 2 x 2 window in row-major window
+// order (ATen max_pool2d_with_indices keeps the first value that is not smaller; NaN wins).
+template <typename T>
+__device__ __forceinline__ void scatter_row_max(const uint4* __restrict__ src, const uint4* __restrict__ feat,
+                                                float* __restrict__ dfeat, const size_t* rows, int nvec, int lane) {
+  const size_t H = static_cast<size_t>(nvec) * Vec16<T>::N;
+  for (int i = lane; i < nvec; i += 32) {
+    float g[Vec16<T>::N], f[4][Vec16<T>::N];
+    Vec16<T>::unpack(ld_stream(src + i), g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Vec16<T>::unpack(ld_stream(feat + rows[k] * nvec + i), f[k]);
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) {
+      int best = 0;
+      float bv = f[0][e];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (f[k][e] > bv || f[k][e] != f[k][e]) { best = k; bv = f[k][e]; }
+      atomicAdd(dfeat + rows[best] * H + static_cast<size_t>(i) * Vec16<T>::N + e, g[e]);
+    }
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ void scatter_row(const uint4* __restrict__ src, float* __restrict__ dst, float wgt, int nvec,
@@ -396,10 +437,12 @@ merge_splice_bwd_kernel(const MergeSpliceBwdArgs a) {
     }
     const radvlm_merge_image im = a.images[seg.image];
     const int t = seg.src_off + off;
-    if (im.mode == RADVLM_MERGE_VIDEO) {  // bilinear / average pooling (max pooling has no backward here: see header)
+    if (im.mode == RADVLM_MERGE_VIDEO) {
       const VideoTaps v = video_source(im, t, a.S, a.T);
       if (v.newline) {
         scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+      } else if (im.pool == RADVLM_POOL_MAX) {
+        if (a.features != nullptr) scatter_row_max<T>(src, a.features, a.dfeat, v.row, a.nvec, lane);
       } else if (im.pool == RADVLM_POOL_BILINEAR) {
         const float ly0 = 1.f - v.ly1, lx0 = 1.f - v.lx1;
         scatter_row<T>(src, a.dfeat + v.row[0] * H, ly0 * lx0, a.nvec, lane);
@@ -410,16 +453,26 @@ merge_splice_bwd_kernel(const MergeSpliceBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) scatter_row<T>(src, a.dfeat + v.row[k] * H, 0.25f, a.nvec, lane);
       }
-    } else if (im.mode == RADVLM_MERGE_FLAT || t < a.T) {
+    } else if (im.mode == RADVLM_MERGE_FLAT) {
       scatter_row<T>(src, a.dfeat + (static_cast<size_t>(im.tile_base) * a.T + t) * H, 1.f, a.nvec, lane);
     } else if (im.mode == RADVLM_MERGE_SINGLE) {
-      scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+      if (t < a.T) scatter_row<T>(src, a.dfeat + (static_cast<size_t>(im.tile_base) * a.T + t) * H, 1.f, a.nvec, lane);
+      else scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+    } else if (!(im.reserved & RADVLM_ANYRES_NO_BASE) && t < a.T) {
+      scatter_row<T>(src, a.dfeat + (static_cast<size_t>(im.tile_base) * a.T + t) * H, 1.f, a.nvec, lane);
     } else {
-      const int u = t - a.T;
-      const int r = u / (im.out_w + 1);
-      const int c = u - r * (im.out_w + 1);
+      const int u = t - ((im.reserved & RADVLM_ANYRES_NO_BASE) ? 0 : a.T);
+      const int row_w = im.out_w + ((im.reserved & RADVLM_ANYRES_NO_NEWLINE) ? 0 : 1);
+      const int r = u / row_w;
+      const int c = u - r * row_w;
       if (c == im.out_w) {
         scatter_row<T>(src, a.dnewline, 1.f, a.nvec, lane);
+      } else if (im.pool == RADVLM_POOL_MAX) {
+        if (a.features != nullptr) {
+          const size_t rows[4] = {grid_src_row(im, 2 * r, 2 * c, a.S, a.T), grid_src_row(im, 2 * r, 2 * c + 1, a.S, a.T),
+                                  grid_src_row(im, 2 * r + 1, 2 * c, a.S, a.T), grid_src_row(im, 2 * r + 1, 2 * c + 1, a.S, a.T)};
+          scatter_row_max<T>(src, a.features, a.dfeat, rows, a.nvec, lane);
+        }
       } else if (!im.pool) {
         scatter_row<T>(src, a.dfeat + grid_src_row(im, r + im.crop_r0, c + im.crop_c0, a.S, a.T) * H, 1.f, a.nvec, lane);
       } else {
@@ -642,7 +695,8 @@ extern "C" int radvlm_peer_copy(void* dst, const void* src, size_t bytes, void* 
 extern "C" int radvlm_merge_splice_backward(const void* d_out_embeds, int dtype, int hidden, int tokens_per_tile,
                                             int patches_per_side, const radvlm_splice_segment* segments, int n_segments,
                                             const radvlm_merge_image* images, int n_images, int64_t total_rows,
-                                            float* d_features, float* d_newline, void* d_text, void* stream) {
+                                            float* d_features, float* d_newline, void* d_text, const void* features,
+                                            void* stream) {
   using namespace rv;
   int st = require_sm100();
   if (st) return st;
@@ -662,6 +716,7 @@ extern "C" int radvlm_merge_splice_backward(const void* d_out_embeds, int dtype,
   a.dfeat = d_features;
   a.dnewline = d_newline;
   a.dtext = static_cast<uint4*>(d_text);
+  a.features = static_cast<const uint4*>(features);
   const int threads = 256;
   const int64_t want = (total_rows * 32 + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;

@@ -60,8 +60,12 @@ def _video_entry(self, m, frames: int, S: int, merge_type: str):
     """Merge descriptor of one video sample: get_2dPool with the default stride 2 (llava_arch.py:171-190, 286-288),
     then the newline placement of llava_arch.py:310-349 (add_token_per_grid / add_token_per_frame :222-250)."""
     cfg = self.config
-    if getattr(cfg, "add_faster_video", False):
-        raise NotImplementedError("radvlm_b200: add_faster_video (slow / fast video tokens) is not implemented")
+    if (getattr(cfg, "add_faster_video", False) and merge_type.startswith("spatial")
+            and getattr(cfg, "mm_newline_position", "one_token") == "grid"):
+        # The reference cannot run this configuration either: llava_arch.py:317 reads `all_faster_video_features`, which
+        # only the commented-out encode_multimodals call (:281) would have defined, so it dies with this NameError
+        # after add_token_per_grid.  Every other newline position ignores add_faster_video (:327-349), as does this path.
+        raise NameError("name 'all_faster_video_features' is not defined")
     mode = getattr(cfg, "mm_spatial_pool_mode", None)
     if mode not in _POOL_MODES:
         raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")
@@ -111,33 +115,56 @@ def _merge_table(self, tile_counts: List[int], image_sizes, flat_batch: bool, vi
             m.mode, m.n_tokens = _lib.MERGE_FLAT, tiles * T
         elif merge_type.startswith("spatial"):
             if tiles > 1:
-                if "maxpool2x2" in merge_type or "nobase" in merge_type or "unpad" not in merge_type:
-                    raise NotImplementedError("radvlm_b200 implements mm_patch_merge_type='spatial_unpad' "
-                                              "(RadVLM); got %r" % merge_type)
-                if not (aspect == "anyres" or "anyres_max" in aspect):
-                    raise NotImplementedError("radvlm_b200 implements the anyres / anyres_max_N aspect modes; got %r" % aspect)
                 max_num_patches = 0
-                mt = re.match(r"anyres_max_(\d+)", aspect)
+                mt = re.match(r"anyres_max_(\d+)", aspect) if "anyres_max" in aspect else None
                 if mt:
                     max_num_patches = int(mt.group(1))
-                if not hasattr(tower, "image_size"):
-                    raise ValueError("vision_tower_image_size is not found in the vision tower.")
+                ts = getattr(tower, "image_size", None)
+                if aspect == "anyres" or "anyres_max" in aspect:          # llava_arch.py:362-372
+                    if ts is None:
+                        raise ValueError("vision_tower_image_size is not found in the vision tower.")
+                    pinpoints = cfg.image_grid_pinpoints
+                else:                                                     # :373-374  view(2, 2, h, w, -1)
+                    ts = ts or 384
+                    pinpoints = [[2 * ts, 2 * ts]]
+                unpad = "unpad" in merge_type and "maxpool2x2" not in merge_type
+                # the pooled branch (:381-392) needs 'unpad', an anyres_max aspect and a matched number
+                pool_patches = max_num_patches if (unpad and "anyres_max" in aspect and mt) else 0
                 try:
-                    plan = planner.plan_image(image_sizes[i], cfg.image_grid_pinpoints, tower.image_size, S,
-                                              max_num_patches)
+                    if unpad:
+                        plan = planner.plan_image(image_sizes[i], pinpoints, ts, S, pool_patches)
+                    else:   # no unpad window: only the grid shape depends on the image size
+                        plan = planner.plan_image(image_sizes[i], pinpoints, ts, S, 0)
                 except Exception as e:
+                    if not (aspect == "anyres" or "anyres_max" in aspect):
+                        raise
                     # reference: grid-shape failure falls back to a 2x2 grid (llava_arch.py:367-371); the unpad
                     # window is still computed from image_sizes[i] and raises if that is unusable.
                     print("Error: %s" % e)
-                    ts = tower.image_size
-                    plan = planner.plan_image(image_sizes[i], [[2 * ts, 2 * ts]], ts, S, max_num_patches)
+                    plan = planner.plan_image(image_sizes[i], [[2 * ts, 2 * ts]], ts, S, pool_patches)
                 if plan.grid_w * plan.grid_h != tiles - 1:
                     raise RuntimeError("shape '[%d, %d, %d, %d, -1]' is invalid for input of %d tiles (image %d)"
                                        % (plan.grid_h, plan.grid_w, S, S, tiles - 1, i))
                 m.mode = _lib.MERGE_ANYRES
                 m.grid_w = plan.grid_w
-                m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = plan.crop_r0, plan.crop_c0, plan.crop_h, plan.crop_w
-                m.pool, m.out_h, m.out_w, m.n_tokens = plan.pool, plan.out_h, plan.out_w, plan.n_tokens
+                flags = _lib.ANYRES_NO_BASE if "nobase" in merge_type else 0
+                full_h, full_w = S * plan.grid_h, S * plan.grid_w
+                if "maxpool2x2" in merge_type:                            # :376-380
+                    flags |= _lib.ANYRES_NO_NEWLINE
+                    m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = 0, 0, full_h, full_w
+                    m.pool, m.out_h, m.out_w = _lib.POOL_MAX, full_h // 2, full_w // 2
+                    grid_tokens = m.out_h * m.out_w
+                elif unpad:                                               # :381-397
+                    m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = plan.crop_r0, plan.crop_c0, plan.crop_h, plan.crop_w
+                    m.pool, m.out_h, m.out_w = plan.pool, plan.out_h, plan.out_w
+                    grid_tokens = plan.out_h * (plan.out_w + 1)
+                else:                                                     # :398-400  plain "spatial": tile-row-major scan
+                    flags |= _lib.ANYRES_NO_NEWLINE
+                    m.crop_r0, m.crop_c0, m.crop_h, m.crop_w = 0, 0, full_h, full_w
+                    m.pool, m.out_h, m.out_w = _lib.POOL_NONE, full_h, full_w
+                    grid_tokens = full_h * full_w
+                m.reserved = flags
+                m.n_tokens = grid_tokens + (0 if flags & _lib.ANYRES_NO_BASE else T)
             else:
                 if "unpad" in merge_type:
                     m.mode, m.n_tokens = _lib.MERGE_SINGLE, T + 1
@@ -205,6 +232,8 @@ class _MergeSpliceFn(torch.autograd.Function):
                         # under autograd the result may be kept (saved activations) far beyond the slot's reuse
                         out = out.clone()
         ctx.m = m
+        # max pooling (video 'max', 'maxpool2x2') routes gradients to the arg-max of every window: keep the features
+        ctx.saved_features = features.detach() if m.get("needs_features") and not isinstance(ctx, _NullCtx) else None
         ctx.feat_shape, ctx.feat_dtype = tuple(features.shape), features.dtype
         ctx.newline_dtype, ctx.embed_shape, ctx.embed_dtype = newline.dtype, tuple(embed.shape), embed.dtype
         ctx.mark_non_differentiable(out_labels, out_mask, out_pos)
@@ -231,6 +260,7 @@ class _MergeSpliceFn(torch.autograd.Function):
                     d_out.data_ptr(), _DT[ctx.embed_dtype], H, m["T"], m["S"], tables.data_ptr(), m["n_segments"],
                     tables.data_ptr() + m["off_img"], m["n_images"], m["total_rows"], d_feat.data_ptr(),
                     d_newline.data_ptr(), None if d_text is None else d_text.data_ptr(),
+                    ctx.saved_features.data_ptr() if ctx.saved_features is not None else None,
                     torch.cuda.current_stream(dev).cuda_stream))
             g_feat = d_feat.to(ctx.feat_dtype).reshape(ctx.feat_shape) if need_f else None
             g_newline = d_newline.to(ctx.newline_dtype) if need_n else None
@@ -276,10 +306,6 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
         raise NotImplementedError
     merge_table, image_tokens = _merge_table(self, tile_counts, image_sizes, flat_batch, video_idx)
-    if (video_idx and not flat_batch and getattr(self.config, "mm_spatial_pool_mode", None) == "max"
-            and torch.is_grad_enabled() and features.requires_grad):
-        raise NotImplementedError("radvlm_b200: max-pooled video tokens have no backward (radvlm_merge_splice_backward "
-                                  "covers bilinear and average pooling)")
 
     # ---- splice plan on the host: one D2H of the ids instead of 2 syncs per sample (llava_arch.py:428-493)
     _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask
@@ -321,7 +347,8 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
             T=vision_tower.num_patches_per_side ** 2, S=vision_tower.num_patches_per_side,
             ids_dev=input_ids.detach().to(dev, torch.int64).contiguous(),
             labels_dev=None if labels is None else labels.detach().to(dev, torch.int64).contiguous(),
-            gather=getattr(self, "radvlm_b200_gather", None))
+            gather=getattr(self, "radvlm_b200_gather", None),
+            needs_features=any(int(e.pool) == _lib.POOL_MAX for e in merge_table[:len(tile_counts)]))
     if torch.is_grad_enabled() and (features.requires_grad or newline.requires_grad or embed.requires_grad):
         out, out_labels, out_mask, out_pos = _MergeSpliceFn.apply(features, newline, embed, meta)
     else:

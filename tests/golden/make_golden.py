@@ -72,6 +72,7 @@ def merge_splice_golden():
         host.config.tokenizer_padding_side = case.get("padding_side", "right")
         host.config.tokenizer_model_max_length = case.get("max_length", 32768)
         host.config.image_aspect_ratio = case.get("aspect", "anyres_max_9")
+        host.config.mm_patch_merge_type = case.get("merge_type", "spatial_unpad")
         feats = gi.merge_features(case)
         host.encode_images = lambda images, _f=feats: _f  # stub: tower/projector are not under test here
         images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]

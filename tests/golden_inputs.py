@@ -52,6 +52,17 @@ def merge_cases():
                               images_per_sample=[1, 1], pad_to=50, padding_side="left", max_length=5000),
         "anyres_nopool": dict(seed=4, sizes=[(1536, 1536)], tiles=[17], lengths=[12], images_per_sample=[1],
                               pad_to=12, aspect="anyres"),
+        # the other spatial merge types of llava_arch.py:373-404 (RadVLM itself trains with spatial_unpad)
+        "spatial_plain": dict(seed=5, sizes=[(1024, 1024), (500, 300), (384, 384)], tiles=[10, 3, 1], lengths=[20, 14, 9],
+                              images_per_sample=[1, 1, 1], pad_to=20, merge_type="spatial"),
+        "maxpool2x2": dict(seed=6, sizes=[(1024, 1024), (800, 400)], tiles=[10, 7], lengths=[18, 11],
+                           images_per_sample=[1, 1], pad_to=18, merge_type="spatial_maxpool2x2"),
+        "unpad_nobase": dict(seed=7, sizes=[(1024, 1024), (500, 300)], tiles=[10, 3], lengths=[15, 21],
+                             images_per_sample=[1, 1], pad_to=21, merge_type="spatial_unpad_nobase"),
+        "pad_2x2_unpad": dict(seed=8, sizes=[(500, 300), (640, 480)], tiles=[5, 5], lengths=[13, 17],
+                              images_per_sample=[1, 1], pad_to=17, merge_type="spatial_unpad", aspect="pad"),
+        "pad_2x2_plain_nobase": dict(seed=9, sizes=[(500, 300)], tiles=[5], lengths=[10], images_per_sample=[1],
+                                     pad_to=10, merge_type="spatial_nobase", aspect="pad"),
     }
 
 

@@ -258,6 +258,7 @@ def test_merge_splice_vs_reference_golden(lib, golden_dir, name, dtype):
     host.config.tokenizer_padding_side = case.get("padding_side", "right")
     host.config.tokenizer_model_max_length = case.get("max_length", 32768)
     host.config.image_aspect_ratio = case.get("aspect", "anyres_max_9")
+    host.config.mm_patch_merge_type = case.get("merge_type", "spatial_unpad")
     feats = gi.merge_features(case).to("cuda", dtype)
     host.encode_images = lambda images, _f=feats: _f   # same stub the golden generator used on the reference
     images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
@@ -318,7 +319,38 @@ def test_video_merge_vs_reference_golden(lib, golden_dir, name, dtype):
         assert (got - ref).abs().max() <= tol
 
 
-@pytest.mark.parametrize("pool,newline", [("bilinear", "grid"), ("average", "frame")])
+@pytest.mark.parametrize("merge_type,aspect,size,tiles", [("spatial_maxpool2x2", "anyres_max_9", (800, 400), 7),
+                                                          ("spatial_unpad_nobase", "anyres_max_9", (1024, 1024), 10),
+                                                          ("spatial", "pad", (500, 300), 5)])
+def test_spatial_merge_types_backward_vs_oracle_autograd(lib, merge_type, aspect, size, tiles):
+    """Gradients of the merge gather for the spatial merge types other than spatial_unpad (max-pool arg-max routing,
+    no base tile, no newline column) vs the oracle's fp32 autograd (llava_arch.py:373-404)."""
+    from oracle import encoder_oracle as eo
+    host = _merge_host(torch.float32)
+    host.config.mm_patch_merge_type, host.config.image_aspect_ratio = merge_type, aspect
+    g = torch.Generator().manual_seed(23)
+    feats = torch.randn(tiles, 729, gi.MERGE_HIDDEN, generator=g)
+    nl = host.model.image_newline.detach().cpu().clone().requires_grad_(True)
+    f_ref = feats.clone().requires_grad_(True)
+    merged = eo.merge_image(f_ref, size, nl, gi.PINPOINTS, max_num_patches=9 if aspect == "anyres_max_9" else None,
+                            merge_type=merge_type, anyres="anyres" in aspect)
+    R = torch.randn(merged.shape, generator=g)
+    (merged * R).sum().backward()
+    f_dev = feats.cuda().requires_grad_(True)
+    host.model.image_newline.requires_grad_(True)
+    host.encode_images = lambda images: f_dev
+    ids = torch.tensor([[3, -200, 4]], device="cuda")
+    out = host.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, [torch.zeros(tiles, 3, 2, 2)], ["image"], [size])
+    emb = out[4]
+    assert emb.shape[1] == merged.shape[0] + 2
+    assert torch.equal(emb[0, 1:1 + merged.shape[0]].cpu(), merged.detach()) or "unpad" in merge_type
+    (emb[0, 1:1 + merged.shape[0]] * R.cuda()).sum().backward()
+    assert (f_dev.grad.cpu() - f_ref.grad).abs().max() <= 1e-5
+    if nl.grad is not None:
+        assert (host.model.image_newline.grad.cpu() - nl.grad).abs().max() <= 1e-4
+
+
+@pytest.mark.parametrize("pool,newline", [("bilinear", "grid"), ("average", "frame"), ("max", "one_token")])
 def test_video_merge_backward_vs_oracle_autograd(lib, pool, newline):
     """Gradients of the video gather w.r.t. the visual features and image_newline vs the oracle's fp32 autograd."""
     from oracle import encoder_oracle as eo
@@ -391,9 +423,12 @@ def test_merge_splice_scatter_writes_every_destination(lib):
 
 
 def _is_pooled(size, case):
+    """bilinear anyres_max pooling (the only merge arithmetic that is not a copy or an exact max)"""
     from radvlm_b200 import planner
-    mx = 0 if case.get("aspect", "anyres_max_9") == "anyres" else 9
-    return bool(planner.plan_image(size, gi.PINPOINTS, max_num_patches=mx).pool)
+    mt = case.get("merge_type", "spatial_unpad")
+    if case.get("aspect", "anyres_max_9") != "anyres_max_9" or "unpad" not in mt or "maxpool2x2" in mt:
+        return False
+    return bool(planner.plan_image(size, gi.PINPOINTS, max_num_patches=9).pool)
 
 
 def test_prepare_inputs_early_return_and_none_passthrough(lib):

@@ -68,10 +68,12 @@ def test_merge_splice_oracle_vs_reference(golden_dir, name):
     z = np.load(os.path.join(golden_dir, "merge_splice_golden.npz"))
     feats = gi.merge_features(case)
     newline = gi.merge_newline()
-    mx = None if case.get("aspect", "anyres_max_9") == "anyres" else 9
+    aspect = case.get("aspect", "anyres_max_9")
+    mx = 9 if aspect == "anyres_max_9" else None
     per_image, base = [], 0
     for n, size in zip(case["tiles"], case["sizes"]):
-        per_image.append(eo.merge_image(feats[base:base + n], size, newline, gi.PINPOINTS, max_num_patches=mx))
+        per_image.append(eo.merge_image(feats[base:base + n], size, newline, gi.PINPOINTS, max_num_patches=mx,
+                                        merge_type=case.get("merge_type", "spatial_unpad"), anyres="anyres" in aspect))
         base += n
     ids, mask, labels = gi.merge_ids(case)
     emb, lab, am, pos = eo.prepare_inputs_labels(gi.merge_embed_table(), per_image, ids, mask, labels,

@@ -50,3 +50,32 @@ def test_process_anyres_image_oracle_vs_reference(ref):
         img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
         want = ref.mm_utils.process_anyres_image(Image.fromarray(img), proc, gi.PINPOINTS).numpy()
         assert np.array_equal(ro.process_anyres_image(img, gi.PINPOINTS), want), (w, h)
+
+
+def test_reference_add_faster_video_grid_raises_nameerror():
+    """What `add_faster_video` does in the reference (mirrored by radvlm_b200.mm_arch._video_entry): with
+    mm_newline_position == "grid" prepare_inputs_labels_for_multimodal reads `all_faster_video_features`, which only the
+    commented-out encode_multimodals call would define (llava_arch.py:281, 317) -> NameError; "frame" ignores the flag."""
+    from oracle.ref_loader import build_reference_host
+    host, _ = build_reference_host(vocab=gi.MERGE_VOCAB, hidden_size=gi.MERGE_HIDDEN, seed=0,
+                                   vision_kwargs=dict(hidden_size=16, intermediate_size=16, num_hidden_layers=2,
+                                                      num_attention_heads=1))
+    case = gi.video_cases()["bilinear_grid"]
+    feats = gi.merge_features(case)
+    host.encode_images = lambda images, _f=feats: _f
+    host.config.mm_spatial_pool_mode, host.config.mm_spatial_pool_stride = "bilinear", 2
+    host.config.mm_patch_merge_type, host.config.add_faster_video = "spatial_unpad", True
+    images = [torch.zeros(n, 3, 2, 2) for n in case["tiles"]]
+    ids, mask, labels = gi.merge_ids(case)
+    pos = torch.arange(ids.shape[1])[None].expand(ids.shape[0], -1).contiguous()
+    host.config.mm_newline_position = "grid"
+    with pytest.raises(NameError, match="all_faster_video_features"):
+        host.prepare_inputs_labels_for_multimodal(ids, pos, mask, None, labels, images, modalities=["video"],
+                                                  image_sizes=case["sizes"])
+    host.config.mm_newline_position = "frame"
+    out = host.prepare_inputs_labels_for_multimodal(ids, pos, mask, None, labels, images, modalities=["video"],
+                                                    image_sizes=case["sizes"])
+    host.config.add_faster_video = False
+    ref = host.prepare_inputs_labels_for_multimodal(ids, pos, mask, None, labels, images, modalities=["video"],
+                                                    image_sizes=case["sizes"])
+    assert torch.equal(out[4], ref[4])

@@ -157,6 +157,32 @@ def test_splice_index_error_semantics():
     assert plan.lengths.tolist() == [3, 2 + 4]
 
 
+def test_spatial_merge_types_token_counts_match_oracle():
+    """Host logic of the spatial merge types other than RadVLM's spatial_unpad (llava_arch.py:373-404: plain "spatial",
+    'maxpool2x2', 'nobase', the fixed 2 x 2 grid of the non-anyres aspect modes): token counts equal the oracle's."""
+    import torch
+    import golden_inputs as gi
+    from oracle import encoder_oracle as eo
+    from radvlm_b200 import _lib, mm_arch, synthetic
+    host = synthetic.build_host(hidden_size=8, vocab=16, dtype=torch.float32, device="cpu",
+                                vision_cfg=synthetic.siglip_config(hidden_size=144, intermediate_size=272,
+                                                                   num_hidden_layers=1, num_attention_heads=2))
+    newline = torch.zeros(8)
+    for name, case in gi.merge_cases().items():
+        aspect = case.get("aspect", "anyres_max_9")
+        mt = case.get("merge_type", "spatial_unpad")
+        host.config.image_aspect_ratio, host.config.mm_patch_merge_type = aspect, mt
+        table, tokens = mm_arch._merge_table(host, case["tiles"], case["sizes"], False)
+        for i, (n, size) in enumerate(zip(case["tiles"], case["sizes"])):
+            want = eo.merge_image(torch.zeros(n, 729, 8), size, newline, gi.PINPOINTS,
+                                  max_num_patches=9 if aspect == "anyres_max_9" else None, merge_type=mt,
+                                  anyres="anyres" in aspect).shape[0]
+            assert tokens[i] == want, (name, i, tokens[i], want)
+            if n > 1:
+                assert bool(table[i].reserved & _lib.ANYRES_NO_BASE) == ("nobase" in mt)
+                assert (table[i].pool == _lib.POOL_MAX) == ("maxpool2x2" in mt)
+
+
 def test_video_merge_table_token_counts_match_oracle():
     """Host logic of the video / get_2dPool branch (mm_arch._video_entry) on the CPU: descriptor fields and token
     counts for every pooling mode x newline placement x merge type equal the oracle's merged sequence length."""
@@ -179,10 +205,17 @@ def test_video_merge_table_token_counts_match_oracle():
         assert m.mode == _lib.MERGE_VIDEO and m.grid_w == 3 and m.tile_base == 0
         assert m.out_h == m.out_w == (14 if pool == "bilinear" else 13)
         assert table[1].tile_base == 3 and table[1].mode != _lib.MERGE_VIDEO   # the image after the video
-    host.config.add_faster_video = True
+    # add_faster_video: the reference dies with a NameError for mm_newline_position == "grid" (llava_arch.py:317 reads
+    # `all_faster_video_features`, defined only by the commented-out call at :281) and ignores the flag everywhere else
     import pytest
-    with pytest.raises(NotImplementedError):
+    host.config.add_faster_video = True
+    host.config.mm_spatial_pool_mode, host.config.mm_patch_merge_type = "bilinear", "spatial_unpad"
+    host.config.mm_newline_position = "grid"
+    with pytest.raises(NameError, match="all_faster_video_features"):
         mm_arch._merge_table(host, [3], [(384, 384)], False, {0})
+    host.config.mm_newline_position = "frame"
+    _, tokens = mm_arch._merge_table(host, [3], [(384, 384)], False, {0})
+    assert tokens[0] == eo.merge_video(feat, newline, "bilinear", "frame", "spatial_unpad").shape[0]
     host.config.add_faster_video = False
     host.config.mm_spatial_pool_mode = "median"
     with pytest.raises(ValueError):
