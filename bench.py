@@ -509,6 +509,7 @@ def run_b200_arm(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6545.0))
         total_ms = sum(prof_ms.values()) or 1.0
         rows_step = B * TILES_PER_IMAGE * 729
+        olp_calls = max(prof_n.get("gemm_out", 0), 1) / prof_steps / 26.0   # tower calls per step (weights re-read per call)
         traffic = _ncu_traffic()
 
         def per_launch(cls, work_step):
@@ -538,6 +539,12 @@ def run_b200_arm(args):
         fc2["peak_source"] = "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src
         fc2["measured"] = ("separate profiled pass of %d steps right after the timed regions (CUDA events around every "
                            "launch; the timed regions run with the instrumentation off)" % prof_steps)
+        folded = prof_n.get("layernorm", 0) == 0
+        ob, oms, olps = per_launch("gemm_out", 26 * ((12.0 if folded else 10.0) * rows_step * 1152 + 2.0 * 1152 * 1152 * olp_calls))
+        out_hbm = {"kernel": "out_proj GEMM (fp32 residual epilogue%s)" % (" + bf16 stream copy + row statistics" if folded else ""),
+                   "bound": "hbm", "achieved": ob / (oms * 1e-3) / 1e9 if oms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                   "traffic": traffic_of("gemm_out", olps), "algorithmic_bytes_per_launch": ob, "ms_per_launch": oms}
+        out_hbm["frac"] = out_hbm["achieved"] / hbm_peak
         ln_bytes, ln_ms, ln_lps = per_launch("layernorm", 52 * 6.0 * rows_step * 1152)
         ln_ach = ln_bytes / (ln_ms * 1e-3) / 1e9 if ln_ms > 0 else 0.0
         launches_step = sum(prof_n.values()) / prof_steps
@@ -561,11 +568,19 @@ def run_b200_arm(args):
             "roofline_gemm_fc1": tensor_roofline("gemm_fc1", "fc1 GEMM (GELU-tanh epilogue)", 26 * 2.0 * rows_step * 1152 * 4304),
             "roofline_attention": tensor_roofline("attention", "siglip_attention_pp_kernel (MUFU issue co-limited, DESIGN.md)",
                                                   attn_flops * TILES_PER_IMAGE * B),
-            "roofline_layernorm": {"kernel": "layernorm_f32_to_bf16_kernel", "bound": "hbm", "achieved": ln_ach,
-                                   "peak": hbm_peak, "unit": "GB/s", "frac": ln_ach / hbm_peak,
-                                   "traffic": traffic_of("layernorm", ln_lps),
-                                   "algorithmic_bytes_per_launch": ln_bytes, "ms_per_launch": ln_ms,
-                                   "share_of_step": prof_ms.get("layernorm", 0.0) / total_ms},
+            "roofline_layernorm": ({"kernel": "layernorm_f32_to_bf16_kernel", "bound": "hbm", "achieved": ln_ach,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": ln_ach / hbm_peak,
+                                    "traffic": traffic_of("layernorm", ln_lps),
+                                    "algorithmic_bytes_per_launch": ln_bytes, "ms_per_launch": ln_ms,
+                                    "share_of_step": prof_ms.get("layernorm", 0.0) / total_ms}
+                                   if prof_n.get("layernorm", 0) > 0 else
+                                   {"kernel": "none: LayerNorm is folded into the QKV / fc1 GEMMs (row statistics and the "
+                                              "bf16 copy of the stream come out of the residual GEMM epilogues); "
+                                              "RADVLM_B200_LN=kernel restores the stand-alone kernels",
+                                    "launches_per_step": 0.0, "share_of_step": 0.0}),
+            # out_proj is the one GEMM of a layer that HBM bounds (K = 1152: 155 GFLOP against 12 B per output element:
+            # bf16 A, fp32 residual read + write, bf16 copy of the new stream), so it also gets an HBM roofline
+            "roofline_gemm_out_hbm": out_hbm,
             "kernel_ms_per_step": {k: v / prof_steps for k, v in prof_ms.items()},
             "kernel_launches_per_step": {k: v / prof_steps for k, v in prof_n.items()},
             "profiled_pass": {"steps": prof_steps, "ms_per_step": ms_prof / prof_steps,
@@ -746,11 +761,12 @@ def run_train_arm(args):
 
 
 def _ncu_traffic():
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01b_traffic.json, the latest committed capture); {} if absent."""
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r02_traffic.json, the latest committed capture); {} if absent."""
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
-    p = os.path.join(d, "r01b_traffic.json")
-    if not os.path.exists(p):
-        p = os.path.join(d, "r01_traffic.json")
+    p = os.path.join(d, "r02_traffic.json")
+    for older in ("r01b_traffic.json", "r01_traffic.json"):
+        if not os.path.exists(p):
+            p = os.path.join(d, older)
     try:
         with open(p) as f:
             return json.load(f)
