@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16_tn_2c
     --launch-skip 540 -c 5 -f -o gpurun_out/${R}_full_tower python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 \
     > gpurun_out/${R}_ncu_full_tower.log 2>&1
 ncu --set full --clock-control none -k regex:"merge_splice_kernel|resample_fused|im2col" \
-    --launch-skip 9 -c 3 -f -o gpurun_out/${R}_full_misc python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 \
+    --launch-skip 8 -c 4 -f -o gpurun_out/${R}_full_misc python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 \
     > gpurun_out/${R}_ncu_full_misc.log 2>&1
 # training mode: bench line, then one --set full launch of each backward kernel class
 python bench.py --mode train --batch 4 --steps 3 --warmup 3 > gpurun_out/${R}_bench_train.json 2> gpurun_out/${R}_bench_train.err
