@@ -1,10 +1,12 @@
 // C-ABI launchers for the tcgen05 GEMM (see gemm_sm100.cuh).
 #include <cstdlib>
+#include <cstring>
 
 #include <vector>
 
 #include "gemm2_sm100.cuh"
 #include "gemm3_sm100.cuh"
+#include "gemm4_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
@@ -166,6 +168,101 @@ int gemm_bmn_block_n(int N) {
   static const int force = getenv("RADVLM_B200_BMN_BN") ? atoi(getenv("RADVLM_B200_BMN_BN")) : 0;   // tuning only
   (void)N;
   return force == 128 ? 128 : 256;
+}
+
+// ---- mlp2x_gelu projector as one persistent kernel (gemm4_sm100.cuh) -------------------------------------------------
+static const ChainSched* chain_sched_for(int rows, int n_tiles, int k0_slabs, int k1_slabs, int pairs, int chunk) {
+  struct Item { int rows, n_tiles, k0, k1, pairs, chunk; ChainSched s; };
+  static thread_local std::vector<Item*> cache;
+  for (const Item* it : cache)
+    if (it->rows == rows && it->n_tiles == n_tiles && it->k0 == k0_slabs && it->k1 == k1_slabs && it->pairs == pairs &&
+        it->chunk == chunk)
+      return &it->s;
+  const int num_m = (rows + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const long entries = 2L * num_m * n_tiles;
+  if (entries > kChainMaxEntries || n_tiles > 16 || num_m > 2048 || pairs < 1) return nullptr;
+  const int clusters = static_cast<int>(entries < pairs ? entries : pairs) < kSchedMaxClusters
+                           ? static_cast<int>(entries < pairs ? entries : pairs) : kSchedMaxClusters;
+  std::vector<std::vector<uint16_t>> lists(clusters);
+  std::vector<long> load(clusters, 0);
+  auto deal = [&](int phase, int m0, int m1) {   // tiles of row blocks [m0, m1) of one phase, row-block-major
+    for (int m = m0; m < m1 && m < num_m; ++m)
+      for (int n = 0; n < n_tiles; ++n) {
+        int best = 0;
+        for (int c = 1; c < clusters; ++c)
+          if (load[c] < load[best]) best = c;
+        lists[best].push_back(static_cast<uint16_t>(m * 32 + phase * 16 + n));
+        load[best] += (phase ? k1_slabs : k0_slabs) + 4;   // MMA time in K slabs + a tile's fixed cost
+      }
+  };
+  const int chunks = (num_m + chunk - 1) / chunk;
+  for (int c = 0; c <= chunks; ++c) {   // phase 0 runs one chunk ahead of phase 1
+    if (c < chunks) deal(0, c * chunk, (c + 1) * chunk);
+    if (c > 0) deal(1, (c - 1) * chunk, c * chunk);
+  }
+  Item* it = new Item();
+  it->rows = rows; it->n_tiles = n_tiles; it->k0 = k0_slabs; it->k1 = k1_slabs; it->pairs = pairs; it->chunk = chunk;
+  int pos = 0;
+  for (int c = 0; c <= kSchedMaxClusters; ++c) {
+    it->s.off[c] = static_cast<uint16_t>(pos);
+    if (c < clusters)
+      for (uint16_t v : lists[c]) it->s.ent[pos++] = v;
+  }
+  if (cache.size() >= 16) { delete cache.front(); cache.erase(cache.begin()); }
+  cache.push_back(it);
+  return &it->s;
+}
+
+template <int EPI2>
+static int launch_chain_inst(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& th, const CUtensorMap& tw2,
+                             const ChainArgs& ca, const ChainSched& sched, cudaStream_t stream) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    RV_CUDA(cudaFuncSetAttribute(projector_chain_kernel<EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Gemm3Cfg::kSmemBytes));
+    configured = true;
+  }
+  int clusters = 0;
+  while (clusters < kSchedMaxClusters && sched.off[clusters + 1] > sched.off[clusters]) ++clusters;
+  projector_chain_kernel<EPI2><<<2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream>>>(tx, tw1, th, tw2, ca, sched);
+  RV_CUDA(cudaGetLastError());
+  return RADVLM_OK;
+}
+
+// ready: rows / 256 (rounded up) unsigned ints of scratch.  Returns RADVLM_ERR_UNSUPPORTED_SHAPE when the fused kernel does
+// not cover the shape (the caller then runs the two GEMMs as separate launches).
+int projector_chain_dispatch(const void* X, const void* W1, const float* b1, void* H, const void* W2, const float* b2,
+                             void* out, int out_dtype, int rows, int in_dim, int hidden, void* ready,
+                             cudaStream_t stream) {
+  int st = require_sm100();
+  if (st != RADVLM_OK) return st;
+  static const bool off = getenv("RADVLM_B200_PROJ") && !strcmp(getenv("RADVLM_B200_PROJ"), "split");
+  const int pairs = device_sm_count() / 2;
+  if (off || ready == nullptr || (hidden % kSchedBN) != 0 || (in_dim & 7) != 0 || rows < 4 * kGemmBM || g_gemm_mode == 1)
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  const int k0 = (in_dim + kGemmBK - 1) / kGemmBK, k1 = (hidden + kGemmBK - 1) / kGemmBK;
+  static const int chunk = getenv("RADVLM_B200_PROJ_CHUNK") ? atoi(getenv("RADVLM_B200_PROJ_CHUNK")) : 16;
+  const ChainSched* sched = chain_sched_for(rows, hidden / kSchedBN, k0, k1, pairs, chunk > 0 ? chunk : 16);
+  if (sched == nullptr) return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tx, tw1, th, tw2;
+  if ((st = make_tmap_bf16_2d(&tx, X, in_dim, rows, static_cast<uint64_t>(in_dim) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&tw1, W1, in_dim, hidden, static_cast<uint64_t>(in_dim) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&th, H, hidden, rows, static_cast<uint64_t>(hidden) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&tw2, W2, hidden, hidden, static_cast<uint64_t>(hidden) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  ChainArgs ca{};
+  ca.g[0].M = rows; ca.g[0].N = hidden; ca.g[0].K = in_dim; ca.g[0].bias = b1; ca.g[0].out = H; ca.g[0].ldo = hidden;
+  ca.g[1].M = rows; ca.g[1].N = hidden; ca.g[1].K = hidden; ca.g[1].bias = b2; ca.g[1].out = out; ca.g[1].ldo = hidden;
+  ca.ready = static_cast<unsigned int*>(ready);
+  ca.ready_target = static_cast<unsigned int>(hidden / kSchedBN) * 2u * kGemmEpiWarps;
+  const int num_m = (rows + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  RV_CUDA(cudaMemsetAsync(ready, 0, static_cast<size_t>(num_m) * sizeof(unsigned int), stream));
+  switch (out_dtype) {
+    case RADVLM_DT_BF16: return launch_chain_inst<EPI_BIAS_BF16>(tx, tw1, th, tw2, ca, *sched, stream);
+    case RADVLM_DT_F16: return launch_chain_inst<EPI_BIAS_F16>(tx, tw1, th, tw2, ca, *sched, stream);
+    case RADVLM_DT_F32: return launch_chain_inst<EPI_BIAS_F32>(tx, tw1, th, tw2, ca, *sched, stream);
+  }
+  set_error("projector: out_dtype must be bf16, f16 or f32");
+  return RADVLM_ERR_BAD_ARGUMENT;
 }
 
 int gemm_ln_part_slots(int M, int N) {

@@ -257,9 +257,10 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
 }
 
 // hidden_bf16 != nullptr: the bf16 copy of `hidden` already exists (written by the tower's last epilogue)
+// ready != nullptr (rows / 256 unsigned ints of scratch): both GEMMs run as ONE persistent kernel (gemm4_sm100.cuh)
 static int projector_forward_impl(const radvlm_projector_weights* pw, const float* hidden, int rows,
                                   void* out, int out_dtype, void* xn, void* h1, cudaStream_t stream,
-                                  const void* hidden_bf16 = nullptr) {
+                                  const void* hidden_bf16 = nullptr, void* ready = nullptr) {
   RV_CHECK_ARG(out_dtype == RADVLM_DT_BF16 || out_dtype == RADVLM_DT_F32 || out_dtype == RADVLM_DT_F16,
                "projector: out_dtype must be bf16, f16 or f32");
   RV_CHECK_ARG((pw->in_dim % 8) == 0 && (pw->hidden % 8) == 0, "projector: dims must be multiples of 8");
@@ -268,6 +269,12 @@ static int projector_forward_impl(const radvlm_projector_weights* pw, const floa
     { ProfScope ps(PROF_MISC, stream); st = cast_f32_bf16_launch(hidden, xn, static_cast<size_t>(rows) * pw->in_dim, stream); }
     if (st) return st;
     hidden_bf16 = xn;
+  }
+  if (ready != nullptr) {
+    { ProfScope ps(PROF_GEMM, stream, 2);
+      st = projector_chain_dispatch(hidden_bf16, pw->w1, pw->b1, h1, pw->w2, pw->b2, out, out_dtype, rows, pw->in_dim,
+                                    pw->hidden, ready, stream); }
+    if (st != RADVLM_ERR_UNSUPPORTED_SHAPE) return st;
   }
   {
     GemmArgs a{};
@@ -525,8 +532,11 @@ extern "C" int radvlm_projector_forward(const radvlm_projector_weights* pw, cons
     return RADVLM_ERR_WORKSPACE_TOO_SMALL;
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  // the fused two-GEMM kernel needs rows / 256 counters: taken from the tail of the workspace when the caller left room
+  const size_t ready_bytes = align_up((static_cast<size_t>(rows) / 256 + 2) * 4, 1024);
+  void* ready = workspace_bytes >= xn_bytes + h1_bytes + ready_bytes ? ws + xn_bytes + h1_bytes : nullptr;
   return projector_forward_impl(pw, hidden, rows, features_out, out_dtype, ws, ws + xn_bytes,
-                                static_cast<cudaStream_t>(stream));
+                                static_cast<cudaStream_t>(stream), nullptr, ready);
 }
 
 extern "C" int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvlm_projector_weights* pw,
@@ -552,7 +562,7 @@ extern "C" int radvlm_encode_images(const radvlm_siglip_weights* tw, const radvl
   st = tower_forward_impl(tw, pixels, pixel_dtype, n_tiles, hidden, L, ws, s, nullptr, &hidden_bf16);
   if (st) return st;
   return projector_forward_impl(pw, hidden, static_cast<int>(L.M), features_out, out_dtype,
-                                ws + L.off_xn, ws + L.off_h1, s, hidden_bf16);
+                                ws + L.off_xn, ws + L.off_h1, s, hidden_bf16, ws + L.off_q /* q is dead by now */);
 }
 
 // ------------------------------------------------------------------------------------------------ training mode

@@ -877,3 +877,35 @@ def test_tower_is_deterministic_run_to_run(lib):
     for _ in range(4):
         assert torch.equal(host.encode_images(x), ref)
     assert torch.equal(host.encode_images(torch.cat([x[1:], x[:1]]))[2], ref[0])
+
+
+@pytest.mark.parametrize("rows", [7290, 58320, 1000])
+def test_projector_single_kernel_equals_two_gemms(lib, rows):
+    """north_star 'Projector: a fused two-GEMM kernel': radvlm_projector_forward runs mlp2x_gelu (builder.py:41-48) as
+    ONE persistent launch whose second GEMM waits per row block for the first; it must equal the two stand-alone GEMM
+    launches bit for bit (same tile arithmetic) and the fp32 torch reference within bf16 tolerance."""
+    from radvlm_b200 import _lib
+    D, Hd = 1152, 3584
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, D, device="cuda", generator=g)
+    w1 = (torch.randn(Hd, D, device="cuda", generator=g) * 0.03).bfloat16()
+    w2 = (torch.randn(Hd, Hd, device="cuda", generator=g) * 0.02).bfloat16()
+    b1 = torch.randn(Hd, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(Hd, device="cuda", generator=g) * 0.1
+    pw = _lib.ProjectorWeights()
+    pw.in_dim, pw.hidden = D, Hd
+    pw.w1, pw.b1, pw.w2, pw.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    need = (rows * D * 2 + 1023) // 1024 * 1024 + (rows * Hd * 2 + 1023) // 1024 * 1024
+    out = {}
+    for name, extra in (("fused", 1 << 16), ("split", 0)):   # without room for the counters the two-launch path runs
+        ws = torch.empty(need + extra, dtype=torch.uint8, device="cuda")
+        o = torch.empty(rows, Hd, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.radvlm_projector_forward(C.byref(pw), x.data_ptr(), rows, o.data_ptr(), _lib.DT_BF16, ws.data_ptr(),
+                                                ws.numel(), _stream()))
+        torch.cuda.synchronize()
+        out[name] = o
+    assert torch.equal(out["fused"], out["split"])
+    xb = x.bfloat16().float()
+    ref = torch.nn.functional.gelu(xb @ w1.float().t() + b1).bfloat16().float() @ w2.float().t() + b2
+    cos, relmax = _metrics(out["fused"].float(), ref)
+    assert cos >= 0.9999 and relmax <= 2e-2, "projector: cos=%.6f relmax=%.4e" % (cos, relmax)
