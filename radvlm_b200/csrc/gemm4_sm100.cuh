@@ -15,6 +15,11 @@
 // to the async proxy (fence.proxy.async) before its first bulk-tensor load of H.  In the global tile order every
 // phase-0 tile of a row block precedes its phase-1 tiles and each CTA pair works through its list in that order, so the
 // oldest unfinished tile can always run: no deadlock as long as all pairs are resident (grid <= SM pairs, one CTA per SM).
+//
+// The same kernel chains the two GEMMs of a ViT MLP block (siglip_encoder.py:252-254, 296-298): phase 0 = fc1 with the
+// LayerNorm fold and GELU-tanh, phase 1 = fc2 with the fp32 residual epilogue (+ bf16 stream copy + row statistics); the
+// [rows, 4304] activation is then read back from L2 instead of HBM (1 GB less DRAM traffic per layer and tower call).
+// Phase-1 rows may end in a 128-wide tile like in gemm3_sm100.cuh (N = 1152 = 4 x 256 + 128).
 #pragma once
 
 #include "gemm3_sm100.cuh"
@@ -25,7 +30,7 @@ constexpr int kChainMaxEntries = 8000;  // 80 image tiles: 228 row blocks x (14 
 
 struct ChainSched {
   uint16_t off[kSchedMaxClusters + 1];
-  uint16_t ent[kChainMaxEntries];  // row block * 32 + column tile index (+ 16 for phase 1)
+  uint16_t ent[kChainMaxEntries];  // row block * 64 + phase * 32 + column tile index
 };
 
 struct ChainArgs {
@@ -41,11 +46,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int EPI2>
+// tmap_w2h: W2 with 64-row boxes (128-wide phase-1 tiles); equal to tmap_w2 when phase 1 has none
+template <int EPI1, int EPI2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
-                       const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
-                       const __grid_constant__ ChainArgs ca, const __grid_constant__ ChainSched sched) {
+gemm_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                  const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
+                  const __grid_constant__ CUtensorMap tmap_w2h, const __grid_constant__ ChainArgs ca,
+                  const __grid_constant__ ChainSched sched) {
   using Cfg = Gemm3Cfg;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = 2 * kGemmBM;
@@ -67,11 +74,15 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   const int cluster_id = blockIdx.x >> 1;
   const int e_begin = sched.off[cluster_id], e_end = sched.off[cluster_id + 1];
   const int num_k0 = (ca.g[0].K + kGemmBK - 1) / kGemmBK, num_k1 = (ca.g[1].K + kGemmBK - 1) / kGemmBK;
-  auto tile_of = [&](int e, int& ph, int& m_blk, int& n0) {
+  const int num_n1 = (ca.g[1].N + kSchedBN - 1) / kSchedBN;
+  const int last_w1 = (ca.g[1].N - (num_n1 - 1) * kSchedBN <= 128) ? 128 : kSchedBN;
+  auto tile_of = [&](int e, int& ph, int& m_blk, int& n0, int& w) {
     const int v = sched.ent[e];
-    m_blk = v >> 5;
-    ph = (v >> 4) & 1;
-    n0 = (v & 15) * kSchedBN;
+    m_blk = v >> 6;
+    ph = (v >> 5) & 1;
+    const int n_idx = v & 31;
+    n0 = n_idx * kSchedBN;
+    w = (ph == 1 && n_idx == num_n1 - 1) ? last_w1 : kSchedBN;
   };
 
   if (warp == 0 && lane == 0) {
@@ -79,6 +90,7 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_h);
     tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_w2h);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 2);
       mbar_init(empty_bar(s), 1);
@@ -104,15 +116,15 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      constexpr uint32_t tx = 2u * static_cast<uint32_t>(Cfg::kABytes + Cfg::kBBytes);
       for (int e = e_begin; e < e_end; ++e) {
-        int ph, m_blk, n0;
-        tile_of(e, ph, m_blk, n0);
+        int ph, m_blk, n0, w;
+        tile_of(e, ph, m_blk, n0, w);
         const CUtensorMap* ta = ph ? &tmap_h : &tmap_x;
-        const CUtensorMap* tb = ph ? &tmap_w2 : &tmap_w1;
+        const CUtensorMap* tb = ph ? (w == kSchedBN ? &tmap_w2 : &tmap_w2h) : &tmap_w1;
         const int nk = ph ? num_k1 : num_k0;
         const int row_a = m_blk * kTileM + static_cast<int>(rank) * kGemmBM;
-        const int row_b = n0 + static_cast<int>(rank) * (kSchedBN / 2);
+        const int row_b = n0 + static_cast<int>(rank) * (w / 2);
+        const uint32_t tx = 2u * static_cast<uint32_t>(Cfg::kABytes + (w / 2) * kGemmBK * 2);
         if (ph) {  // H[m_blk] must be complete (and visible to the async proxy) before the first load of it
           const long long t0 = clock64();
           while (ld_acquire_gpu(ca.ready + m_blk) < ca.ready_target) {
@@ -139,7 +151,8 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only; whole warp converged, elect.sync inside) =====================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, kSchedBN);
+      constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, kSchedBN);
+      constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, 128);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t desc_k = make_smem_desc(smem_base, 1024, kLayoutSw128);
       int stage = 0;
@@ -147,8 +160,9 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int e = e_begin; e < e_end; ++e) {
-        int ph, m_blk, n0;
-        tile_of(e, ph, m_blk, n0);
+        int ph, m_blk, n0, w;
+        tile_of(e, ph, m_blk, n0, w);
+        const uint32_t idesc = (w == kSchedBN) ? idesc_full : idesc_half;
         const int nk = ph ? num_k1 : num_k0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -181,18 +195,41 @@ projector_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // phase-1 fp32 residual epilogue: pull this warp's block of the residual into L2 ahead of its use (gemm3_sm100.cuh)
+    auto prefetch_resid = [&](int e) {
+      if constexpr (EPI2 == EPI_RESID_F32) {
+        int ph, m_blk, n0, w;
+        tile_of(e, ph, m_blk, n0, w);
+        if (ph == 0) return;
+        const int row0 = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32;
+        const int col0 = n0 + half * (w / 2);
+        const int lines = w / 64;
+        for (int i = lane; i < 32 * lines; i += 32) {
+          const int r = row0 + i / lines, c = col0 + (i % lines) * 32;
+          if (r < ca.g[1].M && c < ca.g[1].N) prefetch_l2(ca.g[1].aux + static_cast<size_t>(r) * ca.g[1].ldo + c);
+        }
+      }
+    };
     for (int e = e_begin; e < e_end; ++e) {
-      int ph, m_blk, n0;
-      tile_of(e, ph, m_blk, n0);
+      int ph, m_blk, n0, w;
+      tile_of(e, ph, m_blk, n0, w);
+      if (e + 1 < e_end) prefetch_resid(e + 1);
+      const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
+      float ln_nmean = 0.f, ln_rstd = 1.f;   // LayerNorm folded into phase 0: row statistics fetched before the wait
+      if (ph == 0) gemm_ln_row_stats(ca.g[0], row, ln_nmean, ln_rstd);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(acc * kSchedBN + half * (kSchedBN / 2));
+                             static_cast<uint32_t>(acc * kSchedBN + half * (w / 2));
       const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes;
-      const int col = n0 + half * (kSchedBN / 2);
-      if (ph == 0) gemm_epilogue_drain<EPI_GELU_ERF_BF16, kSchedBN / 2>(ca.g[0], row, col, t_row, stg, lane);
-      else gemm_epilogue_drain<EPI2, kSchedBN / 2>(ca.g[1], row, col, t_row, stg, lane);
+      const int col = n0 + half * (w / 2);
+      if (ph == 0) {
+        gemm_epilogue_drain<EPI1, kSchedBN / 2>(ca.g[0], row, col, t_row, stg, lane, -1, ln_nmean, ln_rstd);
+      } else {
+        const int ln_slot = 2 * (n0 / kSchedBN) + half;   // row-statistics slot (gemm_args.h ln_part)
+        if (w == kSchedBN) gemm_epilogue_drain<EPI2, kSchedBN / 2>(ca.g[1], row, col, t_row, stg, lane, ln_slot);
+        else gemm_epilogue_drain<EPI2, 64>(ca.g[1], row, col, t_row, stg, lane, ln_slot);
+      }
       tc_fence_before();
       __syncwarp();
       if (ph == 0) {  // publish this warp's part of H[m_blk]: generic-proxy stores -> async-proxy (TMA) readers elsewhere

@@ -170,29 +170,31 @@ int gemm_bmn_block_n(int N) {
   return force == 128 ? 128 : 256;
 }
 
-// ---- mlp2x_gelu projector as one persistent kernel (gemm4_sm100.cuh) -------------------------------------------------
-static const ChainSched* chain_sched_for(int rows, int n_tiles, int k0_slabs, int k1_slabs, int pairs, int chunk) {
-  struct Item { int rows, n_tiles, k0, k1, pairs, chunk; ChainSched s; };
+// ---- two dependent GEMMs as one persistent kernel (gemm4_sm100.cuh): the projector and the ViT MLP block -------------
+static const ChainSched* chain_sched_for(int rows, int n0_tiles, int n1_tiles, int last_w1, int k0_slabs, int k1_slabs,
+                                         int pairs, int chunk) {
+  struct Item { int key[8]; ChainSched s; };
   static thread_local std::vector<Item*> cache;
+  const int key[8] = {rows, n0_tiles, n1_tiles, last_w1, k0_slabs, k1_slabs, pairs, chunk};
   for (const Item* it : cache)
-    if (it->rows == rows && it->n_tiles == n_tiles && it->k0 == k0_slabs && it->k1 == k1_slabs && it->pairs == pairs &&
-        it->chunk == chunk)
-      return &it->s;
+    if (!memcmp(it->key, key, sizeof(key))) return &it->s;
   const int num_m = (rows + 2 * kGemmBM - 1) / (2 * kGemmBM);
-  const long entries = 2L * num_m * n_tiles;
-  if (entries > kChainMaxEntries || n_tiles > 16 || num_m > 2048 || pairs < 1) return nullptr;
+  const long entries = static_cast<long>(num_m) * (n0_tiles + n1_tiles);
+  if (entries > kChainMaxEntries || n0_tiles > 32 || n1_tiles > 32 || num_m > 1023 || pairs < 1) return nullptr;
   const int clusters = static_cast<int>(entries < pairs ? entries : pairs) < kSchedMaxClusters
                            ? static_cast<int>(entries < pairs ? entries : pairs) : kSchedMaxClusters;
   std::vector<std::vector<uint16_t>> lists(clusters);
   std::vector<long> load(clusters, 0);
   auto deal = [&](int phase, int m0, int m1) {   // tiles of row blocks [m0, m1) of one phase, row-block-major
+    const int nt = phase ? n1_tiles : n0_tiles;
     for (int m = m0; m < m1 && m < num_m; ++m)
-      for (int n = 0; n < n_tiles; ++n) {
+      for (int n = 0; n < nt; ++n) {
         int best = 0;
         for (int c = 1; c < clusters; ++c)
           if (load[c] < load[best]) best = c;
-        lists[best].push_back(static_cast<uint16_t>(m * 32 + phase * 16 + n));
-        load[best] += (phase ? k1_slabs : k0_slabs) + 4;   // MMA time in K slabs + a tile's fixed cost
+        lists[best].push_back(static_cast<uint16_t>(m * 64 + phase * 32 + n));
+        const bool strip = phase == 1 && n == nt - 1 && last_w1 == 128;
+        load[best] += (phase ? k1_slabs : k0_slabs) * (strip ? 82 : 100) + 400;   // MMA time + a tile's fixed cost
       }
   };
   const int chunks = (num_m + chunk - 1) / chunk;
@@ -201,7 +203,7 @@ static const ChainSched* chain_sched_for(int rows, int n_tiles, int k0_slabs, in
     if (c > 0) deal(1, (c - 1) * chunk, c * chunk);
   }
   Item* it = new Item();
-  it->rows = rows; it->n_tiles = n_tiles; it->k0 = k0_slabs; it->k1 = k1_slabs; it->pairs = pairs; it->chunk = chunk;
+  memcpy(it->key, key, sizeof(key));
   int pos = 0;
   for (int c = 0; c <= kSchedMaxClusters; ++c) {
     it->s.off[c] = static_cast<uint16_t>(pos);
@@ -213,56 +215,74 @@ static const ChainSched* chain_sched_for(int rows, int n_tiles, int k0_slabs, in
   return &it->s;
 }
 
-template <int EPI2>
+template <int EPI1, int EPI2>
 static int launch_chain_inst(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& th, const CUtensorMap& tw2,
-                             const ChainArgs& ca, const ChainSched& sched, cudaStream_t stream) {
+                             const CUtensorMap& tw2h, const ChainArgs& ca, const ChainSched& sched, cudaStream_t stream) {
   static thread_local bool configured = false;
   if (!configured) {
-    RV_CUDA(cudaFuncSetAttribute(projector_chain_kernel<EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RV_CUDA(cudaFuncSetAttribute(gemm_chain_kernel<EPI1, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Gemm3Cfg::kSmemBytes));
     configured = true;
   }
   int clusters = 0;
   while (clusters < kSchedMaxClusters && sched.off[clusters + 1] > sched.off[clusters]) ++clusters;
-  projector_chain_kernel<EPI2><<<2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream>>>(tx, tw1, th, tw2, ca, sched);
+  gemm_chain_kernel<EPI1, EPI2><<<2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream>>>(tx, tw1, th, tw2, tw2h, ca, sched);
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }
 
-// ready: rows / 256 (rounded up) unsigned ints of scratch.  Returns RADVLM_ERR_UNSUPPORTED_SHAPE when the fused kernel does
-// not cover the shape (the caller then runs the two GEMMs as separate launches).
+// H = epi0(X W1^T ...) [g0.M, g0.N] bf16 (= g0.out, row pitch g0.ldo), then epi1(H W2^T ...) described by g1 (g1.K == g0.N).
+// ready: g0.M / 256 (rounded up) unsigned ints of scratch.  Returns RADVLM_ERR_UNSUPPORTED_SHAPE when the chained kernel
+// does not cover the case (the caller then launches the two GEMMs separately).
+int gemm_chain_dispatch(const void* X, const void* W1, const void* W2, const GemmArgs& g0, int epi0, const GemmArgs& g1,
+                        int epi1, void* ready, cudaStream_t stream) {
+  int st = require_sm100();
+  if (st != RADVLM_OK) return st;
+  static const int chunk_env = getenv("RADVLM_B200_CHAIN_CHUNK") ? atoi(getenv("RADVLM_B200_CHAIN_CHUNK")) : 0;
+  const int pairs = device_sm_count() / 2;
+  const int rows = g0.M;
+  if (ready == nullptr || g1.M != rows || g1.K != g0.N || (g0.K & 7) || (g0.N & 7) || (g1.N & 7) || (g0.ldo & 7) ||
+      rows < 4 * kGemmBM || g_gemm_mode == 1)
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  const int n0_tiles = (g0.N + kSchedBN - 1) / kSchedBN, n1_tiles = (g1.N + kSchedBN - 1) / kSchedBN;
+  const int last_w1 = (g1.N - (n1_tiles - 1) * kSchedBN <= 128) ? 128 : kSchedBN;
+  const int k0 = (g0.K + kGemmBK - 1) / kGemmBK, k1 = (g1.K + kGemmBK - 1) / kGemmBK;
+  const ChainSched* sched = chain_sched_for(rows, n0_tiles, n1_tiles, last_w1, k0, k1, pairs, chunk_env > 0 ? chunk_env : 16);
+  if (sched == nullptr) return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tx, tw1, th, tw2, tw2h;
+  if ((st = make_tmap_bf16_2d(&tx, X, g0.K, rows, static_cast<uint64_t>(g0.K) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&tw1, W1, g0.K, g0.N, static_cast<uint64_t>(g0.K) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&th, g0.out, g0.N, rows, static_cast<uint64_t>(g0.ldo) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&tw2, W2, g1.K, g1.N, static_cast<uint64_t>(g1.K) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  if ((st = make_tmap_bf16_2d(&tw2h, W2, g1.K, g1.N, static_cast<uint64_t>(g1.K) * 2, kGemmBK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
+  ChainArgs ca{};
+  ca.g[0] = g0;
+  ca.g[1] = g1;
+  ca.ready = static_cast<unsigned int*>(ready);
+  ca.ready_target = static_cast<unsigned int>(n0_tiles) * 2u * kGemmEpiWarps;
+  const int num_m = (rows + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  RV_CUDA(cudaMemsetAsync(ready, 0, static_cast<size_t>(num_m) * sizeof(unsigned int), stream));
+#define RV_CHAIN(E0, E1) if (epi0 == E0 && epi1 == E1) return launch_chain_inst<E0, E1>(tx, tw1, th, tw2, tw2h, ca, *sched, stream)
+  RV_CHAIN(EPI_GELU_ERF_BF16, EPI_BIAS_BF16);
+  RV_CHAIN(EPI_GELU_ERF_BF16, EPI_BIAS_F16);
+  RV_CHAIN(EPI_GELU_ERF_BF16, EPI_BIAS_F32);
+  RV_CHAIN(EPI_GELU_TANH_BF16, EPI_RESID_F32);
+#undef RV_CHAIN
+  return RADVLM_ERR_UNSUPPORTED_SHAPE;
+}
+
 int projector_chain_dispatch(const void* X, const void* W1, const float* b1, void* H, const void* W2, const float* b2,
                              void* out, int out_dtype, int rows, int in_dim, int hidden, void* ready,
                              cudaStream_t stream) {
-  int st = require_sm100();
-  if (st != RADVLM_OK) return st;
   static const bool off = getenv("RADVLM_B200_PROJ") && !strcmp(getenv("RADVLM_B200_PROJ"), "split");
-  const int pairs = device_sm_count() / 2;
-  if (off || ready == nullptr || (hidden % kSchedBN) != 0 || (in_dim & 7) != 0 || rows < 4 * kGemmBM || g_gemm_mode == 1)
-    return RADVLM_ERR_UNSUPPORTED_SHAPE;
-  const int k0 = (in_dim + kGemmBK - 1) / kGemmBK, k1 = (hidden + kGemmBK - 1) / kGemmBK;
-  static const int chunk = getenv("RADVLM_B200_PROJ_CHUNK") ? atoi(getenv("RADVLM_B200_PROJ_CHUNK")) : 16;
-  const ChainSched* sched = chain_sched_for(rows, hidden / kSchedBN, k0, k1, pairs, chunk > 0 ? chunk : 16);
-  if (sched == nullptr) return RADVLM_ERR_UNSUPPORTED_SHAPE;
-  CUtensorMap tx, tw1, th, tw2;
-  if ((st = make_tmap_bf16_2d(&tx, X, in_dim, rows, static_cast<uint64_t>(in_dim) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
-  if ((st = make_tmap_bf16_2d(&tw1, W1, in_dim, hidden, static_cast<uint64_t>(in_dim) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
-  if ((st = make_tmap_bf16_2d(&th, H, hidden, rows, static_cast<uint64_t>(hidden) * 2, kGemmBK, kGemmBM, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
-  if ((st = make_tmap_bf16_2d(&tw2, W2, hidden, hidden, static_cast<uint64_t>(hidden) * 2, kGemmBK, kSchedBN / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return st;
-  ChainArgs ca{};
-  ca.g[0].M = rows; ca.g[0].N = hidden; ca.g[0].K = in_dim; ca.g[0].bias = b1; ca.g[0].out = H; ca.g[0].ldo = hidden;
-  ca.g[1].M = rows; ca.g[1].N = hidden; ca.g[1].K = hidden; ca.g[1].bias = b2; ca.g[1].out = out; ca.g[1].ldo = hidden;
-  ca.ready = static_cast<unsigned int*>(ready);
-  ca.ready_target = static_cast<unsigned int>(hidden / kSchedBN) * 2u * kGemmEpiWarps;
-  const int num_m = (rows + 2 * kGemmBM - 1) / (2 * kGemmBM);
-  RV_CUDA(cudaMemsetAsync(ready, 0, static_cast<size_t>(num_m) * sizeof(unsigned int), stream));
-  switch (out_dtype) {
-    case RADVLM_DT_BF16: return launch_chain_inst<EPI_BIAS_BF16>(tx, tw1, th, tw2, ca, *sched, stream);
-    case RADVLM_DT_F16: return launch_chain_inst<EPI_BIAS_F16>(tx, tw1, th, tw2, ca, *sched, stream);
-    case RADVLM_DT_F32: return launch_chain_inst<EPI_BIAS_F32>(tx, tw1, th, tw2, ca, *sched, stream);
-  }
-  set_error("projector: out_dtype must be bf16, f16 or f32");
-  return RADVLM_ERR_BAD_ARGUMENT;
+  if (off) return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  GemmArgs g0{}, g1{};
+  g0.M = rows; g0.N = hidden; g0.K = in_dim; g0.bias = b1; g0.out = H; g0.ldo = hidden;
+  g1.M = rows; g1.N = hidden; g1.K = hidden; g1.bias = b2; g1.out = out; g1.ldo = hidden;
+  const int epi1 = out_dtype == RADVLM_DT_BF16 ? EPI_BIAS_BF16 : (out_dtype == RADVLM_DT_F16 ? EPI_BIAS_F16 :
+                   (out_dtype == RADVLM_DT_F32 ? EPI_BIAS_F32 : -1));
+  RV_CHECK_ARG(epi1 >= 0, "projector: out_dtype must be bf16, f16 or f32");
+  return gemm_chain_dispatch(X, W1, W2, g0, EPI_GELU_ERF_BF16, g1, epi1, ready, stream);
 }
 
 int gemm_ln_part_slots(int M, int N) {

@@ -13,6 +13,9 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 // mlp2x_gelu projector as one persistent two-GEMM kernel (gemm4_sm100.cuh); RADVLM_ERR_UNSUPPORTED_SHAPE = not covered
 int projector_chain_dispatch(const void* X, const void* W1, const float* b1, void* H, const void* W2, const float* b2,
                              void* out, int out_dtype, int rows, int in_dim, int hidden, void* ready, cudaStream_t stream);
+// two dependent GEMMs as one persistent kernel (gemm4_sm100.cuh): g0 writes the bf16 intermediate, g1 consumes it
+int gemm_chain_dispatch(const void* X, const void* W1, const void* W2, const GemmArgs& g0, int epi0, const GemmArgs& g1,
+                        int epi1, void* ready, cudaStream_t stream);
 int gemm_pick_block_n(int M, int N, int cta_group);
 int gemm_bmn_block_n(int N);  // tile width of the GEMMs whose B operand is MN-major (data / weight gradients)
 int attention_launch(const void* q, const void* k, const void* vt, void* out, float* lse, int tiles, int heads,

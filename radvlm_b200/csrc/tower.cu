@@ -5,6 +5,9 @@
 //   SigLipVisionEmbeddings.forward   siglip_encoder.py:169-174
 //   SigLipEncoderLayer.forward       siglip_encoder.py:285-305
 //   encode_images / mm_projector     llava_arch.py:192-196 ; multimodal_projector/builder.py:41-48
+#include <cstdlib>
+#include <cstring>
+
 #include "host_util.h"
 #include "internal.h"
 
@@ -14,7 +17,7 @@ namespace rv {
 struct EncodeLayout {
   int P, T, seq_pad, hd, hd_pad;
   size_t M;
-  size_t off_hidden, off_xn, off_xb, off_stats, off_part, off_q, off_k, off_vt, off_h1, total;
+  size_t off_hidden, off_xn, off_xb, off_stats, off_part, off_ready, off_q, off_k, off_vt, off_h1, total;
   size_t qkv_bytes;
 };
 
@@ -46,6 +49,7 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
   L->off_xb = off;     off = align_up(off + L->M * D * 2, 1024);   // bf16 copy of the residual stream (LayerNorm fold)
   L->off_stats = off;  off = align_up(off + L->M * 8, 1024);       // (mean, rstd) per row
   L->off_part = off;   off = align_up(off + L->M * 8 * 2 * ((D + 255) / 256), 1024);  // per-row partial sums (epilogues)
+  L->off_ready = off;  off = align_up(off + (L->M / 256 + 2) * 4, 1024);  // row-block counters of the chained GEMM kernels
   L->off_q = off;      off = align_up(off + L->qkv_bytes, 1024);
   L->off_k = off;      off = align_up(off + L->qkv_bytes, 1024);
   L->off_vt = off;     off = align_up(off + L->qkv_bytes, 1024);
@@ -148,6 +152,10 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     ProfScope ps(PROF_LAYERNORM, stream);
     return ln_row_stats_launch(xbf, stats, M, D, tw->ln_eps, stream);
   };
+  // fc1 -> fc2 through the chained kernel (gemm4_sm100.cuh) is opt-in (RADVLM_B200_MLP=chain): measured 55.1-56.2 ms per
+  // step against 54.3 ms for the two launches (profiles/r02j_bench_*: the DRAM traffic it saves is hidden behind tensor
+  // work anyway, the per-warp publish fences are not); the projector, whose second GEMM is 3x longer, does gain (-12 %)
+  static const bool mlp_chain = getenv("RADVLM_B200_MLP") && !strcmp(getenv("RADVLM_B200_MLP"), "chain");
   auto set_consumer_stats = [&](GemmArgs& a, const float* row_sums) {
     a.ln_s = row_sums;
     if (part_slots > 0) {
@@ -232,26 +240,29 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     if (fold) st = row_stats(xn);
     else { ProfScope ps(PROF_LAYERNORM, stream); st = layernorm_launch(h_mid, w.ln2_gamma, w.ln2_beta, xn2, M, D, tw->ln_eps, stream); }
     if (st) return st;
-    {
-      GemmArgs a{};
-      a.M = M; a.N = I; a.K = D;
-      a.bias = fold ? w.fc1_bf : w.fc1_b;
-      if (fold) set_consumer_stats(a, w.fc1_sf);
-      a.out = save ? save->act(l, NL) : h1; a.ldo = I;   // training: the activation is kept too (fc2 weight gradient)
-      a.out2 = save ? save->u(l, NL) : nullptr;          // training: keep gelu'(u) for the GELU backward
-      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, fold ? w.fc1_wf : w.fc1_w, D, a, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
-      if (st) return st;
+    GemmArgs a1{}, a2{};
+    a1.M = M; a1.N = I; a1.K = D;
+    a1.bias = fold ? w.fc1_bf : w.fc1_b;
+    if (fold) set_consumer_stats(a1, w.fc1_sf);
+    a1.out = save ? save->act(l, NL) : h1; a1.ldo = I;   // training: the activation is kept too (fc2 weight gradient)
+    a1.out2 = save ? save->u(l, NL) : nullptr;          // training: keep gelu'(u) for the GELU backward
+    a2.M = M; a2.N = D; a2.K = I;
+    a2.bias = w.fc2_b;
+    a2.out = h_out; a2.ldo = D; a2.aux = h_mid;
+    a2.out2 = fold ? xb : nullptr;   // bf16 copy of the stream entering the next layer (or the projector)
+    if (part_slots > 0 && l + 1 < tw->num_layers) { a2.ln_part = part; a2.ln_slots = part_slots; }
+    st = RADVLM_ERR_UNSUPPORTED_SHAPE;
+    if (save == nullptr && mlp_chain) {   // fc1 and fc2 as ONE persistent kernel: the activation stays in L2
+      ProfScope ps(PROF_GEMM_FC2, stream, 2);
+      st = gemm_chain_dispatch(xn2, fold ? w.fc1_wf : w.fc1_w, w.fc2_w, a1, EPI_GELU_TANH_BF16, a2, EPI_RESID_F32,
+                               ws + L.off_ready, stream);
     }
-    {
-      GemmArgs a{};
-      a.M = M; a.N = D; a.K = I;
-      a.bias = w.fc2_b;
-      a.out = h_out; a.ldo = D; a.aux = h_mid;
-      a.out2 = fold ? xb : nullptr;   // bf16 copy of the stream entering the next layer (or the projector)
-      if (part_slots > 0 && l + 1 < tw->num_layers) { a.ln_part = part; a.ln_slots = part_slots; }
-      { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(save ? save->act(l, NL) : h1, I, w.fc2_w, I, a, EPI_RESID_F32, 0, stream); }
+    if (st == RADVLM_ERR_UNSUPPORTED_SHAPE) {
+      { ProfScope ps(PROF_GEMM_FC1, stream); st = gemm_dispatch(xn2, D, fold ? w.fc1_wf : w.fc1_w, D, a1, save ? EPI_GELU_TANH_DUAL_BF16 : EPI_GELU_TANH_BF16, 0, stream); }
       if (st) return st;
+      { ProfScope ps(PROF_GEMM_FC2, stream); st = gemm_dispatch(save ? save->act(l, NL) : h1, I, w.fc2_w, I, a2, EPI_RESID_F32, 0, stream); }
     }
+    if (st) return st;
   }
   return RADVLM_OK;
 }
