@@ -92,6 +92,12 @@ int radvlm_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, 
  * 1 = force single-CTA 128 x BN tiles, 2 = force CTA-pair tiles.  Process-wide; meant for tests / tuning. */
 int radvlm_gemm_set_mode(int mode);
 
+/* Host-only (no CUDA): the tile schedule of the scheduled GEMM kernel for an [M, N] output on `pairs` CTA pairs (74 on
+ * B200).  A row block of 256 rows is cut into 256-wide column tiles plus ONE 128-wide tile when its remainder is <= 128
+ * columns; tiles are dealt to the pairs by list scheduling (cost 100 / 82).  tiles_per_pair[pairs] (or NULL), *n_tiles,
+ * *max_load, *min_load describe the result; RADVLM_ERR_UNSUPPORTED_SHAPE when the kernel does not cover the shape. */
+int radvlm_gemm_schedule_stats(int M, int N, int pairs, int* tiles_per_pair, int* n_tiles, int* max_load, int* min_load);
+
 /* QKV projection with the head-split scatter fused into the epilogue
  * (siglip_encoder.py:207-213: three Linear + view/transpose).  W is the row-concatenation
  * [q_proj; k_proj; v_proj] = [3*heads*hd, K]; bias likewise.  Outputs (bf16):
@@ -218,7 +224,10 @@ int radvlm_siglip_tower_forward(const radvlm_siglip_weights* tw, const void* pix
                                 int n_tiles, float* hidden_out, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
-/* hidden: fp32 [rows, in_dim] -> features_out: [rows, hidden] of out_dtype (RADVLM_DT_BF16 | RADVLM_DT_F16 | RADVLM_DT_F32) */
+/* hidden: fp32 [rows, in_dim] -> features_out: [rows, hidden] of out_dtype (RADVLM_DT_BF16 | RADVLM_DT_F16 | RADVLM_DT_F32).
+ * workspace: rows*in_dim*2 + rows*hidden*2 bytes (each rounded up to 1 KB).  With (rows/256 + 2)*4 more bytes (rounded
+ * up to 1 KB) both GEMMs run as ONE persistent kernel (the second waits per row block for the first; the intermediate
+ * stays in L2); without them, or for shapes that kernel does not cover, as two launches - same result bit for bit. */
 int radvlm_projector_forward(const radvlm_projector_weights* pw, const float* hidden, int rows,
                              void* features_out, int out_dtype, void* workspace, size_t workspace_bytes,
                              void* stream);

@@ -400,6 +400,46 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 
 }  // namespace rv
 
+// Host-only view of the tile schedule of the scheduled GEMM kernel (no CUDA call: usable in CPU tests).  pairs: CTA
+// pairs of the device (74 on B200).  tiles_per_pair[pairs] (may be NULL) receives the number of tiles of each pair;
+// *n_tiles the total, *max_load / *min_load the largest / smallest summed tile cost (a 256-wide tile = 100, a 128-wide
+// one = 82).  Every (row block, column tile) appears exactly once, in row-block-major order inside every pair's list
+// (checked here: returns RADVLM_ERR_BAD_ARGUMENT otherwise).
+extern "C" int radvlm_gemm_schedule_stats(int M, int N, int pairs, int* tiles_per_pair, int* n_tiles, int* max_load,
+                                          int* min_load) {
+  using namespace rv;
+  RV_CHECK_ARG(M > 0 && N > 0 && pairs > 0 && pairs <= kSchedMaxClusters, "schedule_stats: bad arguments");
+  const GemmSched* s = gemm_sched_for(M, N, pairs);
+  if (s == nullptr) {
+    set_error("schedule_stats: shape [%d, %d] is not covered by the scheduled kernel", M, N);
+    return RADVLM_ERR_UNSUPPORTED_SHAPE;
+  }
+  const int num_m = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int num_n = (N + kSchedBN - 1) / kSchedBN;
+  const bool strip = (N - (num_n - 1) * kSchedBN) <= 128;
+  std::vector<char> seen(static_cast<size_t>(num_m) * num_n, 0);
+  int total = 0, lo = 1 << 30, hi = 0;
+  for (int c = 0; c < pairs; ++c) {
+    int load = 0, prev = -1;
+    for (int e = s->off[c]; e < s->off[c + 1]; ++e) {
+      const int v = s->ent[e], m = v >> 5, n = v & 31;
+      RV_CHECK_ARG(m < num_m && n < num_n && !seen[static_cast<size_t>(m) * num_n + n] && v > prev,
+                   "schedule_stats: corrupt schedule (pair %d entry %d)", c, e);
+      seen[static_cast<size_t>(m) * num_n + n] = 1;
+      prev = v;
+      load += (strip && n == num_n - 1) ? 82 : 100;
+      ++total;
+    }
+    if (tiles_per_pair) tiles_per_pair[c] = s->off[c + 1] - s->off[c];
+    if (s->off[c + 1] > s->off[c]) { lo = load < lo ? load : lo; hi = load > hi ? load : hi; }
+  }
+  RV_CHECK_ARG(total == num_m * num_n, "schedule_stats: %d tiles scheduled, %d expected", total, num_m * num_n);
+  if (n_tiles) *n_tiles = total;
+  if (max_load) *max_load = hi;
+  if (min_load) *min_load = lo;
+  return RADVLM_OK;
+}
+
 extern "C" int radvlm_gemm_set_mode(int mode) {
   if (mode < 0 || mode > 2) {
     rv::set_error("gemm mode must be 0 (auto), 1 (single-CTA tiles) or 2 (CTA-pair tiles)");

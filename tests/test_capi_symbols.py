@@ -48,3 +48,21 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
                                                                    num_hidden_layers=1, num_attention_heads=2))
     with pytest.raises(RuntimeError):
         host.encode_images(torch.zeros(1, 3, 384, 384))
+
+
+def test_scheduled_gemm_tile_lists_cover_every_tile_and_balance():
+    """Host logic of the scheduled GEMM (no GPU): every (row block, column tile) is dealt exactly once, in order inside a
+    pair's list, N = 1152 / 3456 are cut exactly (4 x 256 + 128, 13 x 256 + 128), and list scheduling leaves the pairs
+    within one tile of each other."""
+    import ctypes as C
+    from radvlm_b200 import _lib
+    lib = _lib.load()
+    for M, N, pairs, want_tiles in [(58320, 1152, 74, 228 * 5), (58320, 3456, 74, 228 * 14), (58320, 4304, 74, 228 * 17),
+                                    (7290, 1152, 74, 29 * 5), (1458, 144, 74, 6), (300, 200, 74, 2), (58320, 1152, 10, 1140)]:
+        per = (C.c_int * pairs)()
+        n, hi, lo = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.radvlm_gemm_schedule_stats(M, N, pairs, per, C.byref(n), C.byref(hi), C.byref(lo)))
+        assert n.value == want_tiles == sum(per), (M, N, n.value, want_tiles)
+        assert hi.value - lo.value <= 100, (M, N, hi.value, lo.value)
+    # beyond the parameter block (4000 tiles): not covered, reported as such
+    assert lib.radvlm_gemm_schedule_stats(600000, 4304, 74, None, None, None, None) == _lib.ERR_UNSUPPORTED_SHAPE
