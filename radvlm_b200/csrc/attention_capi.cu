@@ -52,6 +52,8 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
   a.hd = hd;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.lse = lse;
+  static const bool no_trim = [] { const char* e = std::getenv("RADVLM_B200_ATTN_TRIM"); return e && e[0] == '0'; }();
+  a.trim_last = no_trim ? 0 : 1;   // A/B switch: RADVLM_B200_ATTN_TRIM=0 computes the padded last key block 96 wide
   // Tuning switch (bring-up A/B only): RADVLM_B200_ATTN=2cta selects the two-CTAs-per-SM kernel.
   static const bool use_2cta = [] { const char* e = std::getenv("RADVLM_B200_ATTN"); return e && e[0] == '2'; }();
   if (use_2cta) {

@@ -20,6 +20,8 @@
 // O_B += P_B V as the P tiles are published; K / V blocks are loaded once for 256 query rows.
 #pragma once
 
+#include <type_traits>
+
 #include "attention_sm100.cuh"
 
 namespace rv {
@@ -226,7 +228,11 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
   } else if (warp_u == 1) {
     // ===================== MMA issuer (whole warp converged, elect.sync inside the asm blocks) =====================
     constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBKV);
+    constexpr uint32_t idesc_s64 = make_idesc_bf16(kAttnBQ, 64);
     constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnHdPad) | (1u << 16);  // B (= V) is MN-major
+    // The last key block holds seq - (num_kv - 1) * 96 valid keys (57 for 729 tokens): when they fit 64 columns its S is
+    // computed 64 wide and its P V product 64 deep - the other 32 columns are padding (4 % of all score columns)
+    const bool short_last = args.trim_last && (args.seq - (num_kv - 1) * kAttnBKV) <= 64;
     const uint32_t tbase_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t qd128 = make_smem_desc(sQ, 1024, kLayoutSw128);
     const uint64_t qd32 = make_smem_desc(sQ + kAttnQ2Off, 256, kLayoutSw32);
@@ -245,10 +251,11 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
       const uint32_t tS = tbase_u + static_cast<uint32_t>(grp * kPpTmemGroup);
       const uint64_t qoff = static_cast<uint64_t>((qb * kPpGroups + grp) * (kAttnQBytes >> 4));
       const uint64_t koff = static_cast<uint64_t>(s_slot * (kAttnKBytes >> 4));
+      const uint32_t ids = (short_last && j == num_kv - 1) ? idesc_s64 : idesc_s;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        umma_bf16_ss_elect(tS, qd128 + qoff + 2 * c, kd128 + koff + 2 * c, idesc_s, c != 0 ? 1u : 0u);
-      umma_bf16_ss_elect(tS, qd32 + qoff, kd32 + koff, idesc_s, 1u);
+        umma_bf16_ss_elect(tS, qd128 + qoff + 2 * c, kd128 + koff + 2 * c, ids, c != 0 ? 1u : 0u);
+      umma_bf16_ss_elect(tS, qd32 + qoff, kd32 + koff, ids, 1u);
       umma_commit_elect(bar_s + 8 * grp);
       if (grp == kPpGroups - 1) {
         umma_commit_elect(bar_kfree + 8 * s_slot);
@@ -275,9 +282,11 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
           const uint32_t tP = tbase_u + static_cast<uint32_t>(grp * kPpTmemGroup + kPpTmemP);
           const uint32_t tO = tbase_u + static_cast<uint32_t>(grp * kPpTmemGroup + kPpTmemO);
           const uint64_t voff = static_cast<uint64_t>(slot * (kAttnVBytes >> 4));
+          const int pv_steps = (short_last && wrap) ? 4 : kAttnBKV / 16;
 #pragma unroll
           for (int s = 0; s < kAttnBKV / 16; ++s)
-            umma_bf16_ts_elect(tO, tP + static_cast<uint32_t>(s * 8), vd + voff + 32 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
+            if (s < pv_steps)
+              umma_bf16_ts_elect(tO, tP + static_cast<uint32_t>(s * 8), vd + voff + 32 * s, idesc_o, (j | s) != 0 ? 1u : 0u);
           umma_commit_elect(bar_o + 8 * grp);
           if (wrap) umma_commit_elect(bar_ofin + 8 * grp);
           if (grp == kPpGroups - 1) umma_commit_elect(bar_vfree + 8 * slot);
@@ -297,6 +306,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
     const uint32_t b_o = bar_o + 8 * grp;
     const float sc = args.scale_log2e;
     const int total_blocks = num_items * num_kv;
+    const bool short_last = args.trim_last && (args.seq - (num_kv - 1) * kAttnBKV) <= 64;  // see the MMA issuer
 
     if (grp == 1 && total_blocks > 0) turn_pass<1>(0u);  // group A owns the first turn
 
@@ -379,21 +389,27 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
         // drains meanwhile (measured: the burst ran at 65 % of the XU rate).
         uint32_t pk[kAttnBKV / 2];
         uint32_t sign = 0;  // no P is negative: (sign >> 31) == 0
+        const bool short_blk = short_last && j == num_kv - 1;  // 64 score columns only (block-uniform)
+        auto burst = [&](auto nch) {
+          constexpr int kCh = decltype(nch)::value;   // 16-column groups of this block
 #pragma unroll
-        for (int c = 0; c <= kAttnBKV / 16; ++c) {
-          if (c < kAttnBKV / 16) {
+          for (int c = 0; c <= kCh; ++c) {
+            if (c < kCh) {
 #pragma unroll
-            for (int i = 16 * c; i < 16 * c + 16 - RV_PP_POLY_PER_16; ++i)
-              s[i] = __float_as_uint(ex2_approx_v(fmaf(__uint_as_float(s[i]), sc, neg_m2)));
-          }
-          if (c > 0) {
+              for (int i = 16 * c; i < 16 * c + 16 - RV_PP_POLY_PER_16; ++i)
+                s[i] = __float_as_uint(ex2_approx_v(fmaf(__uint_as_float(s[i]), sc, neg_m2)));
+            }
+            if (c > 0) {
 #pragma unroll
-            for (int i = 16 * (c - 1); i < 16 * c; i += 2) {
-              pk[i >> 1] = pack_bf16x2_v(__uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-              sign |= pk[i >> 1];
+              for (int i = 16 * (c - 1); i < 16 * c; i += 2) {
+                pk[i >> 1] = pack_bf16x2_v(__uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                sign |= pk[i >> 1];
+              }
             }
           }
-        }
+        };
+        if (short_blk) burst(std::integral_constant<int, 4>{});
+        else burst(std::integral_constant<int, kAttnBKV / 16>{});
         if (grp == 0) {
           turn_pass<2>(sign >> 31);
         } else if (g + 1 < total_blocks) {
@@ -404,7 +420,7 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
         //      issued a whole block ago)
         if (g > 0) mbar_wait(b_o, static_cast<uint32_t>((g - 1) & 1));
         tmem_st_x32(tP, pk);
-        tmem_st_x16(tP + 32, pk + 32);
+        if (!short_blk) tmem_st_x16(tP + 32, pk + 32);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(b_p);

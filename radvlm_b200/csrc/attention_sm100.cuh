@@ -45,6 +45,7 @@ struct AttnArgs {
   float* lse;          // optional [tiles*heads, seq_pad]: log2-domain log-sum-exp of the scaled scores (for backward)
   int num_qblk;        // ceil(seq / 128) query blocks per (tile, head)
   int total_items;     // tiles * heads * num_qblk
+  int trim_last;       // ping-pong kernel: compute a last key block with <= 64 valid keys 64 wide (default 1)
 };
 
 constexpr int kAttnBQ = 128;       // query rows per work item
