@@ -67,13 +67,16 @@ static const GemmSched* gemm_sched_for(int M, int N, int pairs) {
                            ? static_cast<int>(entries < pairs ? entries : pairs) : kSchedMaxClusters;
   std::vector<std::vector<uint16_t>> lists(clusters);
   std::vector<long> load(clusters, 0);
+  // cost of a 128-wide tile against 100 for a full one: 82 stand-alone (0.112 vs 0.137 ms, tools/test_gemm sched), about
+  // 100 inside a K = 4304 launch (tools/gemm_timeline.cu: its MMAs take as long as a full tile's)
+  static const int strip_cost = getenv("RADVLM_B200_STRIP_COST") ? atoi(getenv("RADVLM_B200_STRIP_COST")) : 82;
   for (int m = 0; m < num_m; ++m)
     for (int n = 0; n < num_n; ++n) {
       int best = 0;
       for (int c = 1; c < clusters; ++c)
         if (load[c] < load[best]) best = c;
       lists[best].push_back(static_cast<uint16_t>(m * 32 + n));
-      load[best] += (n == num_n - 1 && last_w == 128) ? 82 : 100;  // measured: 0.112 vs 0.137 ms (tools/test_gemm sched)
+      load[best] += (n == num_n - 1 && last_w == 128) ? strip_cost : 100;
     }
   Item* it = new Item();
   it->M = M; it->N = N; it->pairs = pairs;

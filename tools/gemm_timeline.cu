@@ -46,6 +46,12 @@ static void run(int M, int N, int K, int epi, bool ln, bool zeros = false) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'o') {   // out_proj shape: residual epilogue vs the same stores without the residual read
+    run(58320, 1152, 1152, RADVLM_EPI_RESID_F32, false);
+    run(58320, 1152, 1152, RADVLM_EPI_BIAS_F32, false);
+    run(58320, 1152, 1152, RADVLM_EPI_BIAS_BF16, false);
+    return 0;
+  }
   if (argc > 1) { run(58320, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, false); return 0; }
   run(58320, 4304, 1152, RADVLM_EPI_GELU_TANH_BF16, false, true);
   run(58320, 4304, 1152, RADVLM_EPI_BIAS_BF16, false, true);
