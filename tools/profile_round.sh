@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: gpurun copies back at most 64 MiB of gpurun_out/: the three --set full reports together exceed that, so run the
+# script once per report (comment the others out) or delete earlier reports first.
 # Round profile capture (run under gpurun): plain bench first, then the ncu launch list and --set full captures of one
 # launch of every kernel class.  Numbers printed by the runs under ncu are never bench values.  Summaries for profiles/
 # are made in the container afterwards (tools/ncu_summary.py launches | full | stalls | traffic).
@@ -8,7 +10,7 @@ python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err || exi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 > gpurun_out/${R}_ncu_list.log 2>&1
 # one launch of each tower kernel class of a middle layer (patch + 26 x [qkv, attention, out, fc1, fc2] per tower call)
-ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16_tn_2cta_sched|siglip_attention_pp" \
+ncu --set full --clock-control none -k regex:"gemm_bf16_tn_2cta_sched|siglip_attention_pp" \
     --launch-skip 540 -c 5 -f -o gpurun_out/${R}_full_tower python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 \
     > gpurun_out/${R}_ncu_full_tower.log 2>&1
 ncu --set full --clock-control none -k regex:"merge_splice_kernel|resample_fused|im2col" \
