@@ -19,6 +19,13 @@ enum GemmEpilogue : int {
                            // kept gelu'(u) = the GELU backward fused into the GEMM (replaces a separate HBM pass)
   EPI_BIAS_F16 = 9,        // out_f16 = acc + bias (projector output when the model serves in fp16,
                            // serve/model_worker.py:124-127, model/builder.py:289-294)
+  EPI_DELTA_BF16 = 11,     // out_proj when LayerNorm is folded (siglip_encoder.py:293): the fp32 stream is NOT rewritten.
+                           //   out_bf16  = d = acc + bias                 (the attention branch, added to the stream by the
+                           //                                               fc2 epilogue of the same layer: aux16 there)
+                           //   out2_bf16 = bf16(aux16 + d)               (aux16 = bf16 copy of the stream entering the layer:
+                           //                                               the LayerNorm-2 input, A operand of fc1)
+                           //   ln_part   : row sums of aux16 + d
+                           // 8 B per element instead of the 12 of EPI_RESID_F32 + copy: out_proj is HBM-bound
 };
 
 struct GemmArgs {
@@ -30,6 +37,8 @@ struct GemmArgs {
                       // operand of the next GEMM when LayerNorm is folded into it (ln_stats below)
   int ldo;
   const float* aux;  // EPI_RESID_F32: residual [M, ldo];  EPI_POS_F32: table [aux_period, N]
+  const __nv_bfloat16* aux16;  // EPI_DELTA_BF16: bf16 residual [M, ldo] (may alias out: read, then written, by the same
+                               // thread);  EPI_RESID_F32: optional second addend [M, ldo] (the bf16 attention branch)
   int aux_period;
   // EPI_QKV_SPLIT
   __nv_bfloat16* q;   // [tiles, heads, seq_pad, hd_pad]

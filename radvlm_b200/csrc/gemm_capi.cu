@@ -308,6 +308,9 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   RV_CHECK_ARG(lda >= (args.a_mn ? args.M : args.K) && ldw >= (args.b_mn ? args.N : args.K),
                "gemm: row pitch smaller than the stored row length");
   RV_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0, "gemm: operand pitches must be multiples of 8 elements");
+  RV_CHECK_ARG(epilogue != EPI_DELTA_BF16 || (args.out2 != nullptr && args.aux16 != nullptr && args.out != nullptr &&
+                                               (args.N & 7) == 0 && (args.ldo & 7) == 0),
+               "gemm: the bf16 branch epilogue needs out, out2, aux16 and N, ldo multiples of 8");
   RV_CHECK_ARG((epilogue != EPI_GELU_TANH_DUAL_BF16 && epilogue != EPI_MUL_BF16) || args.out2 != nullptr,
                "gemm: the dual-output / GELU-backward epilogues need out2");
   const bool general = args.a_mn || args.b_mn || args.k_splits > 1;
@@ -363,6 +366,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_GELU_TANH_DUAL_BF16: return launch_gemm3_inst<EPI_GELU_TANH_DUAL_BF16>(ta, tb, tb64, args, *sched, stream);
       case EPI_BIAS_F16: return launch_gemm3_inst<EPI_BIAS_F16>(ta, tb, tb64, args, *sched, stream);
       case EPI_MUL_BF16: return launch_gemm3_inst<EPI_MUL_BF16>(ta, tb, tb64, args, *sched, stream);
+      case EPI_DELTA_BF16: return launch_gemm3_inst<EPI_DELTA_BF16>(ta, tb, tb64, args, *sched, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -380,6 +384,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       case EPI_GELU_TANH_DUAL_BF16: return launch_gemm2_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
       case EPI_BIAS_F16: return launch_gemm2_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
       case EPI_MUL_BF16: return launch_gemm2_bn<EPI_MUL_BF16>(bn, ta, tb, args, stream);
+      case EPI_DELTA_BF16: return launch_gemm2_bn<EPI_DELTA_BF16>(bn, ta, tb, args, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return RADVLM_ERR_BAD_ARGUMENT;
@@ -396,6 +401,7 @@ int gemm_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     case EPI_GELU_TANH_DUAL_BF16: return launch_gemm_bn<EPI_GELU_TANH_DUAL_BF16>(bn, ta, tb, args, stream);
     case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(bn, ta, tb, args, stream);
     case EPI_MUL_BF16: return launch_gemm_bn<EPI_MUL_BF16>(bn, ta, tb, args, stream);
+    case EPI_DELTA_BF16: return launch_gemm_bn<EPI_DELTA_BF16>(bn, ta, tb, args, stream);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
   return RADVLM_ERR_BAD_ARGUMENT;

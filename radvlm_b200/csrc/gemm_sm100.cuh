@@ -147,6 +147,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
       for (int j = 0; j < 32; ++j)
         if (col0 + j < a.N) o[j] = __float2bfloat16_rn(v[j]);
     }
+  } else if constexpr (EPI == EPI_DELTA_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(row) * a.ldo + col0;
+    const __nv_bfloat16* x = a.aux16 + static_cast<size_t>(row) * a.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < a.N) {
+        const float r = __bfloat162float(x[j]);
+        o[j] = __float2bfloat16_rn(v[j]);
+        o2[j] = __float2bfloat16_rn(r + v[j]);
+      }
   } else if constexpr (EPI == EPI_ATOMIC_F32) {
     float* o = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldo + col0;
 #pragma unroll
@@ -157,7 +168,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
     const float* x = nullptr;
     if constexpr (EPI == EPI_RESID_F32) x = a.aux + static_cast<size_t>(row) * a.ldo + col0;
     if constexpr (EPI == EPI_POS_F32) x = a.aux + static_cast<size_t>(row % a.aux_period) * a.N + col0;
-    if (full) {
+    if (full && !(EPI == EPI_RESID_F32 && a.aux16 != nullptr)) {
       float4* o4 = reinterpret_cast<float4*>(o);
       if constexpr (EPI != EPI_BIAS_F32) {
         const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -181,6 +192,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& a, int row, 
         if (col0 + j < a.N) {
           float r = v[j];
           if constexpr (EPI != EPI_BIAS_F32) r += x[j];
+          if constexpr (EPI == EPI_RESID_F32)
+            if (a.aux16 != nullptr) r += __bfloat162float(a.aux16[static_cast<size_t>(row) * a.ldo + col0 + j]);
           o[j] = r;
         }
     }
@@ -248,10 +261,16 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
     if (a.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(a.bias + gcol));
     const f32x2 b01 = f2_make(b.x, b.y), b23 = f2_make(b.z, b.w);
     float4 xr[8];
+    uint2 x16[(EPI == EPI_RESID_F32 || EPI == EPI_DELTA_BF16) ? 8 : 1];   // the bf16 addend / residual (aux16)
+    const bool has16 = (EPI == EPI_DELTA_BF16) || (EPI == EPI_RESID_F32 && a.aux16 != nullptr);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int grow = row0 + i * 4 + (lane >> 3);
       xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DELTA_BF16) {
+        x16[i] = make_uint2(0u, 0u);
+        if (has16 && grow < a.M) x16[i] = *reinterpret_cast<const uint2*>(a.aux16 + static_cast<size_t>(grow) * a.ldo + gcol);
+      }
       if (grow < a.M) {
         if constexpr (EPI == EPI_RESID_F32)
           xr[i] = *reinterpret_cast<const float4*>(a.aux + static_cast<size_t>(grow) * a.ldo + gcol);
@@ -266,8 +285,20 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
       if (grow < a.M) {
         const uint4 t = stage_load_vec(stage, rr, v);
         // packed pairs (FADD2 / FFMA2): see gemm_epilogue_bf16_staged
-        const f32x2 o01 = f2_add(f2_add(f2_make(__uint_as_float(t.x), __uint_as_float(t.y)), b01), f2_make(xr[i].x, xr[i].y));
-        const f32x2 o23 = f2_add(f2_add(f2_make(__uint_as_float(t.z), __uint_as_float(t.w)), b23), f2_make(xr[i].z, xr[i].w));
+        f32x2 o01 = f2_add(f2_add(f2_make(__uint_as_float(t.x), __uint_as_float(t.y)), b01), f2_make(xr[i].x, xr[i].y));
+        f32x2 o23 = f2_add(f2_add(f2_make(__uint_as_float(t.z), __uint_as_float(t.w)), b23), f2_make(xr[i].z, xr[i].w));
+        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DELTA_BF16) {
+          if (has16) {
+            const f32x2 a01 = f2_make(__uint_as_float(x16[i].x << 16), __uint_as_float(x16[i].x & 0xFFFF0000u));
+            const f32x2 a23 = f2_make(__uint_as_float(x16[i].y << 16), __uint_as_float(x16[i].y & 0xFFFF0000u));
+            if constexpr (EPI == EPI_DELTA_BF16) {   // the branch itself goes out in bf16, the stream copy is residual + branch
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(grow) * a.ldo + gcol) =
+                  make_uint2(f2_pack_bf16(o01), f2_pack_bf16(o23));
+            }
+            o01 = f2_add(o01, a01);
+            o23 = f2_add(o23, a23);
+          }
+        }
         float4 o;
         f2_get(o01, o.x, o.y);
         f2_get(o23, o.z, o.w);
@@ -276,7 +307,7 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
           ps2[i] = f2_add(ps2[i], f2_add(o01, o23));
           pq2[i] = f2_fma(o01, o01, f2_fma(o23, o23, pq2[i]));
         }
-        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32) {
+        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_DELTA_BF16) {
           if (a.out2 != nullptr)  // bf16 copy of the new residual stream (8 lanes x 8 B = 64 contiguous bytes per row)
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + static_cast<size_t>(grow) * a.ldo + gcol) =
                 make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
@@ -284,7 +315,7 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
         if constexpr (EPI == EPI_ATOMIC_F32) {   // one 16-byte vector reduction instead of four scalar atomics
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
                        : "memory");
-        } else {
+        } else if constexpr (EPI != EPI_DELTA_BF16) {
           *reinterpret_cast<float4*>(dst) = o;
         }
       }
@@ -467,7 +498,8 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
                                                     uint32_t stage, int lane, int ln_slot = -1,
                                                     float ln_nmean = 0.f, float ln_rstd = 1.f) {
   static_assert(NCOLS % 32 == 0, "column span must be a multiple of 32");
-  constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32);
+  constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_ATOMIC_F32 ||
+                         EPI == EPI_DELTA_BF16);   // epilogues that work on fp32 values after the transposition
   constexpr bool kBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_GELU_ERF_BF16 ||
                           EPI == EPI_GELU_TANH_DUAL_BF16 || EPI == EPI_BIAS_F16 ||
                           EPI == EPI_MUL_BF16);  // 16-bit outputs
@@ -478,7 +510,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmArgs& args, int ro
                                EPI == EPI_GELU_ERF_BF16);
   const bool ln = kLnCapable && args.ln_s != nullptr;
   // LayerNorm fold, producer side: row sums of the new residual stream over this warp's columns (gemm_args.h: ln_part)
-  constexpr bool kStatsCapable = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32);
+  constexpr bool kStatsCapable = (EPI == EPI_RESID_F32 || EPI == EPI_POS_F32 || EPI == EPI_DELTA_BF16);
   const bool stats = kStatsCapable && staged && args.ln_part != nullptr && ln_slot >= 0;
   f32x2 ps[kStatsCapable ? 8 : 1], pq[kStatsCapable ? 8 : 1];   // (even column, odd column) partial sums
   if constexpr (kStatsCapable) {

@@ -17,7 +17,7 @@ namespace rv {
 struct EncodeLayout {
   int P, T, seq_pad, hd, hd_pad;
   size_t M;
-  size_t off_hidden, off_xn, off_xb, off_stats, off_part, off_ready, off_q, off_k, off_vt, off_h1, total;
+  size_t off_hidden, off_xn, off_xb, off_ao, off_stats, off_part, off_ready, off_q, off_k, off_vt, off_h1, total;
   size_t qkv_bytes;
 };
 
@@ -47,6 +47,7 @@ static int make_layout(const radvlm_siglip_weights* tw, const radvlm_projector_w
   L->off_hidden = off; off = align_up(off + L->M * D * 4, 1024);
   L->off_xn = off;     off = align_up(off + L->M * xn_cols * 2, 1024);
   L->off_xb = off;     off = align_up(off + L->M * D * 2, 1024);   // bf16 copy of the residual stream (LayerNorm fold)
+  L->off_ao = off;     off = align_up(off + L->M * D * 2, 1024);   // attention output (LayerNorm fold: xb stays live)
   L->off_stats = off;  off = align_up(off + L->M * 8, 1024);       // (mean, rstd) per row
   L->off_part = off;   off = align_up(off + L->M * 8 * 2 * ((D + 255) / 256), 1024);  // per-row partial sums (epilogues)
   L->off_ready = off;  off = align_up(off + (L->M / 256 + 2) * 4, 1024);  // row-block counters of the chained GEMM kernels
@@ -115,12 +116,14 @@ static TowerSaved make_saved(const radvlm_siglip_weights* tw, const EncodeLayout
 
 // `hidden`: inference: the in-place residual stream (= output).  Training (save != nullptr): scratch for the
 // mid-layer residual; layer l reads save->h(l) and writes save->h(l + 1), the output is save->h(num_layers).
-// LayerNorm fold (inference, every layer carries qkv_wf / fc1_wf): no LayerNorm kernel runs.  The residual GEMM
-// epilogues (patch embedding, out_proj, fc2) also write a bf16 copy of the stream, a 2 B/element pass computes the row
-// statistics, and the QKV / fc1 GEMMs multiply the copy by gamma o W and apply (mean, rstd) in their epilogues.  Two
-// bf16 buffers alternate: `xb` holds the stream entering a layer (then, once the QKV GEMM has consumed it, the
-// attention output), `xn` the stream after the attention branch.  *final_bf16 (optional) receives the pointer of the
-// bf16 copy of the tower output (the projector's A operand: no cast pass).
+// LayerNorm fold (inference, every layer carries qkv_wf / fc1_wf): no LayerNorm kernel runs.  The epilogues that
+// produce the stream (patch embedding, fc2) also write a bf16 copy of it (`xb`) and per-row partial sums; the QKV / fc1
+// GEMMs multiply the copy by gamma o W and apply (mean, rstd) in their epilogues.  out_proj does NOT rewrite the fp32
+// stream (it is the one HBM-bound GEMM): it reads `xb`, writes the attention branch d = acc + bias over it in bf16 and
+// the LayerNorm-2 input bf16(xb + d) to `xn` (EPI_DELTA_BF16, 8 B per element instead of 12); the fc2 epilogue of the same
+// layer then forms  stream += d + mlp  in fp32, so the fp32 stream is read and written once per layer, and only the
+// branch - not the stream - is rounded to bf16.  *final_bf16 (optional) receives the pointer of the bf16 copy of the
+// tower output (the projector's A operand: no cast pass).
 static bool tower_ln_folded(const radvlm_siglip_weights* tw) {
   for (int l = 0; l < tw->num_layers; ++l) {
     const radvlm_vit_layer_weights& w = tw->layers[l];
@@ -156,6 +159,9 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
   // step against 54.3 ms for the two launches (profiles/r02j_bench_*: the DRAM traffic it saves is hidden behind tensor
   // work anyway, the per-warp publish fences are not); the projector, whose second GEMM is 3x longer, does gain (-12 %)
   static const bool mlp_chain = getenv("RADVLM_B200_MLP") && !strcmp(getenv("RADVLM_B200_MLP"), "chain");
+  // A/B switch: RADVLM_B200_OUTPROJ=f32 lets out_proj rewrite the fp32 stream itself (12 B per element) as before
+  static const bool outproj_f32 = getenv("RADVLM_B200_OUTPROJ") && !strcmp(getenv("RADVLM_B200_OUTPROJ"), "f32");
+  const bool delta = fold && !outproj_f32;
   auto set_consumer_stats = [&](GemmArgs& a, const float* row_sums) {
     a.ln_s = row_sums;
     if (part_slots > 0) {
@@ -199,7 +205,7 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     const radvlm_vit_layer_weights& w = tw->layers[l];
     const float* h_in = save ? save->h(l) : hidden;     // residual stream entering the layer
     float* h_out = save ? save->h(l + 1) : hidden;      // ... leaving it
-    void* ao = save ? save->ao(l, NL) : (fold ? xb : xn);   // attention output (bf16)
+    void* ao = save ? save->ao(l, NL) : (fold ? (delta ? static_cast<void*>(ws + L.off_ao) : xb) : xn);   // attention output (bf16)
     float* h_mid = save ? save->hmid(l, NL) : hidden;   // residual stream after the attention branch
     if (save != nullptr) {                              // this layer's own q / k / v slots: pads + ones column only
       q = save->qkv(l, 0, NL); k = save->qkv(l, 1, NL); vt = save->qkv(l, 2, NL);
@@ -230,10 +236,15 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
       GemmArgs a{};
       a.M = M; a.N = D; a.K = D;
       a.bias = w.out_b;
-      a.out = h_mid; a.ldo = D; a.aux = h_in;
-      a.out2 = fold ? xn : nullptr;   // bf16 copy of the stream after the attention branch
+      if (delta) {   // branch in bf16 over xb, LayerNorm-2 input to xn, the fp32 stream is left to the fc2 epilogue
+        a.out = xb; a.ldo = D; a.aux16 = static_cast<const __nv_bfloat16*>(xb);
+        a.out2 = xn;
+      } else {
+        a.out = h_mid; a.ldo = D; a.aux = h_in;
+        a.out2 = fold ? xn : nullptr;   // bf16 copy of the stream after the attention branch
+      }
       if (part_slots > 0) { a.ln_part = part; a.ln_slots = part_slots; }
-      { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(ao, D, w.out_w, D, a, EPI_RESID_F32, 0, stream); }
+      { ProfScope ps(PROF_GEMM_OUT, stream); st = gemm_dispatch(ao, D, w.out_w, D, a, delta ? EPI_DELTA_BF16 : EPI_RESID_F32, 0, stream); }
       if (st) return st;
     }
     // x = x + fc2(gelu_tanh(fc1(LN2(x))))
@@ -248,8 +259,9 @@ static int tower_forward_impl(const radvlm_siglip_weights* tw, const void* pixel
     a1.out2 = save ? save->u(l, NL) : nullptr;          // training: keep gelu'(u) for the GELU backward
     a2.M = M; a2.N = D; a2.K = I;
     a2.bias = w.fc2_b;
-    a2.out = h_out; a2.ldo = D; a2.aux = h_mid;
+    a2.out = h_out; a2.ldo = D; a2.aux = fold ? h_in : h_mid;
     a2.out2 = fold ? xb : nullptr;   // bf16 copy of the stream entering the next layer (or the projector)
+    if (delta) a2.aux16 = static_cast<const __nv_bfloat16*>(xb);   // + the attention branch out_proj left there
     if (part_slots > 0 && l + 1 < tw->num_layers) { a2.ln_part = part; a2.ln_slots = part_slots; }
     st = RADVLM_ERR_UNSUPPORTED_SHAPE;
     if (save == nullptr && mlp_chain) {   // fc1 and fc2 as ONE persistent kernel: the activation stays in L2
