@@ -490,6 +490,22 @@ def run_b200_arm(args):
               "path_frac_of_peak": flops_per_tile() * TILES_PER_IMAGE / (ms_b1 / reps1 / 1e3) / 1e12 / pk1,
               "what": "one 1024x1024 image per call through preprocess + prepare_inputs_labels_for_multimodal, device "
                       "resident, per rank (no exchange)"}
+        # encode_images alone on those 10 tiles: eager launches (~140 kernel launches + their TMA descriptors per call)
+        # against ONE replay of the call captured in a CUDA graph (B200VisionEncoder.capture)
+        if world == 1:   # N = 1 only: a rank-local failure inside `timed` (barrier + all-reduce) would hang the others
+            try:
+                from radvlm_b200 import mm_arch
+                t1, _, _, _ = mm_utils.preprocess_anyres_batch(list(one[0]), gi.PINPOINTS, device=dev, dtype=torch.bfloat16)
+                with torch.no_grad():
+                    ref1 = host.encode_images(t1)
+                    ms_eager, _, _, _ = timed(lambda i: host.encode_images(t1), reps1)
+                    graphed = mm_arch._encoder_for(host).capture(int(t1.shape[0]), in_dtype=torch.bfloat16)
+                    same = bool(torch.equal(graphed(t1), ref1))
+                    ms_graph, _, _, _ = timed(lambda i: graphed(t1), reps1)
+                b1["encode_only"] = {"eager_ms": ms_eager / reps1, "cuda_graph_ms": ms_graph / reps1, "graph_equals_eager": same,
+                                     "tma_descriptor_cache": dict(zip(("hits", "misses"), _lib.tmap_cache_stats()))}
+            except Exception as e:   # a failed capture must not cost the bench line
+                b1["encode_only"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     line = None
     if rank == 0:

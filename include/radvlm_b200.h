@@ -47,6 +47,12 @@ int radvlm_abi_version(void);
 int radvlm_profile_enable(int on);
 int radvlm_profile_read(float* ms_per_class, int64_t* launches_per_class, int n_classes);
 
+/* TMA descriptors (CUtensorMap) are cached per calling thread, keyed on the full argument tuple of
+ * cuTensorMapEncodeTiled (base address, dims, pitches, box, swizzle): a step re-uses the descriptors of its
+ * workspace / weight buffers instead of re-encoding ~600 of them.  Returns the calling thread's hit / miss counts
+ * (host only, no device needed).  RADVLM_B200_TMAP_CACHE=0 disables the cache. */
+int radvlm_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM building block:  out[M,N] = A[M,K](bf16) * W[N,K]^T(bf16)  (+ fused epilogue), fp32 accumulate
  * in TMEM (tcgen05.mma, TMA-fed).  Replaces nn.Linear.forward at

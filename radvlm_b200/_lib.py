@@ -132,6 +132,7 @@ SIGNATURES = {
     "radvlm_abi_version": (_i, []),
     "radvlm_profile_enable": (_i, [_i]),
     "radvlm_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int64), _i]),
+    "radvlm_tmap_cache_stats": (_i, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "radvlm_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_bf16_ex": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp]),
     "radvlm_gemm_bf16_ln": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
@@ -222,6 +223,13 @@ def profile_read():
     cnt = (C.c_int64 * n)()
     check(load().radvlm_profile_read(ms, cnt, n))
     return dict(zip(PROF_CLASSES, [float(v) for v in ms])), dict(zip(PROF_CLASSES, [int(v) for v in cnt]))
+
+
+def tmap_cache_stats():
+    """-> (hits, misses) of the calling thread's TMA-descriptor cache (host_util.cu)."""
+    h, m = C.c_uint64(0), C.c_uint64(0)
+    check(load().radvlm_tmap_cache_stats(C.byref(h), C.byref(m)))
+    return int(h.value), int(m.value)
 
 
 def last_error() -> str:

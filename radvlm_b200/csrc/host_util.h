@@ -47,6 +47,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                       uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
+// Hit / miss counts of the calling thread's descriptor cache (host_util.cu).
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses);
+
 // Optional per-kernel-class device timing (CUDA events recorded on the launch stream).  Off by default;
 // bench.py turns it on to report the live duration / launch count of each kernel class.
 enum ProfClass : int {

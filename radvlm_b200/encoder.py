@@ -331,6 +331,70 @@ class B200VisionEncoder:
         return out
 
 
+    def capture(self, n_tiles: int, in_dtype: torch.dtype = torch.bfloat16, out_dtype: Optional[torch.dtype] = None,
+                channels: int = 3) -> "GraphedEncode":
+        """``encode_images`` for a fixed tile count as ONE CUDA graph (see ``GraphedEncode``)."""
+        return GraphedEncode(self, n_tiles, in_dtype, out_dtype, channels)
+
+
+class GraphedEncode:
+    """One ``encode_images`` call of ``n_tiles`` tiles captured in a CUDA graph and replayed.
+
+    The C entry point allocates nothing, never synchronises and takes its stream as an argument, so the whole call
+    (im2col, ~135 GEMM / attention launches, the projector) records into a graph as is; the kernel parameters — TMA
+    descriptors and tile schedules included — are frozen in the graph nodes, a replay costs one launch on the host.
+    Serving-side use (model_worker.py:124-127: the same tile count per request shape): small calls, where the host-side
+    launch path (~5 us per kernel) is comparable with the kernels themselves.
+
+    * ``images`` (static input) / ``features`` (static output, overwritten by the next replay) belong to the object;
+      ``__call__(x)`` copies ``x`` in, replays and returns ``features``.
+    * The graph reads the packed weights at their addresses: in-place refreshes (``PackedWeights.refresh``, aliases of
+      bf16 Parameters) are seen by later replays; a REBUILD of the packed weights (new storage: checkpoint load,
+      ``.to()``) invalidates the graph and ``__call__`` raises.  Refreshes are not part of the graph: call
+      ``encoder.packed(device)`` before a replay if weights may have changed through ``p.data``.
+    * Inference only (no autograd), per-launch profiling must be off while capturing."""
+
+    def __init__(self, enc: B200VisionEncoder, n_tiles: int, in_dtype: torch.dtype = torch.bfloat16,
+                 out_dtype: Optional[torch.dtype] = None, channels: int = 3):
+        if n_tiles < 1 or n_tiles > enc.max_tiles_per_call:
+            raise ValueError("capture: 1 <= n_tiles <= max_tiles_per_call (%d), got %d" % (enc.max_tiles_per_call, n_tiles))
+        dev = next(enc.projector_module.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("radvlm_b200: CUDA-graph capture needs the modules on a CUDA device")
+        self.enc, self.device = enc, dev
+        S = enc.image_size
+        self.images = torch.zeros(n_tiles, channels, S, S, dtype=in_dtype, device=dev)
+        # eager warm-up: packs / refreshes the weights, sizes the workspace, sets the kernels' shared-memory attributes
+        enc.encode_images(self.images, out_dtype)
+        torch.cuda.synchronize(dev)
+        self._pk = enc._packed
+        self._ws = enc._ws[dev]       # the graph holds its address: keep it alive even if the encoder grows a new one
+        self.graph = torch.cuda.CUDAGraph()
+        frozen = enc._frozen
+        enc._frozen = True            # no weight refresh (a multi-tensor copy) inside the captured region
+        try:
+            with torch.cuda.graph(self.graph):
+                self.features = enc.encode_images(self.images, out_dtype)
+        finally:
+            enc._frozen = frozen
+        if enc._ws[dev] is not self._ws:
+            raise RuntimeError("radvlm_b200: the workspace was re-allocated during capture")
+
+    def replay(self) -> torch.Tensor:
+        if self.enc._packed is not self._pk:
+            raise RuntimeError("radvlm_b200: the packed weights were rebuilt (new parameter storage) after this graph "
+                               "was captured; capture again")
+        self.graph.replay()
+        return self.features
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        if tuple(images.shape) != tuple(self.images.shape):
+            raise ValueError("graph captured for %s, got %s" % (tuple(self.images.shape), tuple(images.shape)))
+        self.images.copy_(images, non_blocking=True)
+        return self.replay()
+
+
 # =================================================================================================
 # Training mode: encode_images under autograd (BASELINE config 5; mm_tunable_parts = vision tower + projector,
 # train.py:1642-1665).  The forward keeps what radvlm_siglip_tower_forward_train saves; the backward runs

@@ -274,6 +274,30 @@ class _MergeSpliceFn(torch.autograd.Function):
         return g_feat, g_newline, g_embed, None
 
 
+def _concat_tiles(images_list) -> torch.Tensor:
+    """``torch.cat(images, 0)`` of llava_arch.py:272 without the copy when the per-image tile blocks already lie back to
+    back in one allocation (what ``mm_utils.preprocess_anyres_batch(...)[0].split(splits)`` and the DataLoader collate of
+    ``radvlm_b200.data`` hand over): the blocks are then one strided view.  Anything else is concatenated as usual."""
+    first = images_list[0]
+    if len(images_list) == 1:
+        return first
+    tile_shape, stride = tuple(first.shape[1:]), first.stride()
+    if first.is_contiguous() and first.shape[0] > 0:
+        base, off, ok = first.untyped_storage().data_ptr(), first.storage_offset(), True
+        per_tile = first[0].numel()
+        for im in images_list:
+            if (tuple(im.shape[1:]) != tile_shape or im.dtype != first.dtype or im.device != first.device
+                    or not im.is_contiguous() or im.untyped_storage().data_ptr() != base or im.storage_offset() != off
+                    or im.requires_grad):
+                ok = False
+                break
+            off += im.shape[0] * per_tile
+        if ok:
+            n = sum(int(im.shape[0]) for im in images_list)
+            return first.as_strided((n,) + tile_shape, stride, first.storage_offset())
+    return torch.cat([im for im in images_list], dim=0)
+
+
 def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
                                          images, modalities=["image"], image_sizes=None):
     """llava_arch.py:251-555.  Returns (None, position_ids, attention_mask, past_key_values, inputs_embeds, labels)."""
@@ -290,7 +314,7 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         if type(images) is list:
             images = [x.unsqueeze(0) if x.ndim == 3 else x for x in images]
         images_list = [im if im.ndim == 4 else im.unsqueeze(0) for im in images]
-        concat_images = torch.cat([im for im in images_list], dim=0)
+        concat_images = _concat_tiles(images_list)
         tile_counts = [int(im.shape[0]) for im in images_list]
         flat_batch = False
     else:

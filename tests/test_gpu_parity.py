@@ -919,3 +919,56 @@ def test_projector_single_kernel_equals_two_gemms(lib, rows):
     ref = torch.nn.functional.gelu(xb @ w1.float().t() + b1).bfloat16().float() @ w2.float().t() + b2
     cos, relmax = _metrics(out["fused"].float(), ref)
     assert cos >= 0.9999 and relmax <= 2e-2, "projector: cos=%.6f relmax=%.4e" % (cos, relmax)
+
+
+def test_encode_images_captured_in_a_cuda_graph_replays_bit_exact(lib):
+    """The encode call allocates nothing and never synchronises: it records into ONE CUDA graph
+    (``B200VisionEncoder.capture``) whose replays equal the eager call bit for bit, for new inputs too."""
+    from radvlm_b200 import mm_arch
+    host = _small_host(torch.float32)
+    enc = mm_arch._encoder_for(host)
+    x1 = gi.encoder_pixels(3, seed=21).cuda()
+    x2 = gi.encoder_pixels(3, seed=22).cuda()
+    eager1, eager2 = host.encode_images(x1), host.encode_images(x2)
+    g = enc.capture(3, in_dtype=torch.float32)
+    assert torch.equal(g(x1), eager1)
+    assert torch.equal(g(x2), eager2)
+    assert torch.equal(g(x1), eager1)
+    assert torch.equal(host.encode_images(x2), eager2)        # eager calls still work beside the graph
+    with pytest.raises(ValueError):
+        g(x1[:2])
+
+
+def test_tma_descriptor_cache_hits_on_repeated_calls(lib):
+    """host_util.cu: a repeated call re-uses its CUtensorMaps (keyed on the full encode argument tuple) and gives the
+    same bits; new buffers miss."""
+    from radvlm_b200 import _lib
+    M, N, K = 512, 384, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.rand(M, K, device="cuda", generator=g) - 0.5).bfloat16()
+    W = (torch.rand(N, K, device="cuda", generator=g) - 0.5).bfloat16()
+    b = torch.rand(N, device="cuda", generator=g) - 0.5
+    outs = []
+
+    def run(a):
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        _lib.check(lib.radvlm_gemm_bf16(a.data_ptr(), K, W.data_ptr(), K, M, N, K, b.data_ptr(), _lib.EPI_BIAS_F32,
+                                        out.data_ptr(), N, None, 0, 0, _stream()))
+        torch.cuda.synchronize()
+        return out
+
+    h0, m0 = _lib.tmap_cache_stats()
+    outs.append(run(A))
+    h1, m1 = _lib.tmap_cache_stats()
+    outs.append(run(A))
+    h2, m2 = _lib.tmap_cache_stats()
+    per_call = (m1 - m0) + (h1 - h0)
+    assert per_call >= 2, "a GEMM call asks for at least the A and W descriptors"
+    assert m2 == m1 and h2 - h1 == per_call, "second call must be served from the cache"
+    assert torch.equal(outs[0], outs[1])
+    A2 = A.clone()
+    outs.append(run(A2))
+    h3, m3 = _lib.tmap_cache_stats()
+    assert (m3 - m2) + (h3 - h2) == per_call and torch.equal(outs[2], outs[0])
+    ref = A.float() @ W.float().t() + b
+    assert float((outs[0] - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3
