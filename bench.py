@@ -419,8 +419,14 @@ def run_b200_arm(args):
 
     # ---- device-resident arm: the headline `value`.  The per-class CUDA-event instrumentation is OFF here.
     clocks = ClockSampler(local) if rank == 0 else None
+    from radvlm_b200 import mm_arch as _mm_arch
+    _enc = _mm_arch._encoder_for(host)
+    g0 = (_enc.n_graph_replays, _enc.n_graph_captures, _enc.n_eager_launches)
     ms, tw0, tw1, _ = timed(lambda i: step(dev_imgs[i % n_buf]), args.steps)
     clk = clocks.stop(tw0, tw1) if clocks else None
+    # how the encode calls of the timed region were issued: replays of captured CUDA graphs / captures / eager launches
+    graph_stats = {"enabled": bool(_enc.graph_mode), "encode_calls_replayed": _enc.n_graph_replays - g0[0],
+                   "graphs_captured": _enc.n_graph_captures - g0[1], "encode_calls_eager": _enc.n_eager_launches - g0[2]}
 
     # ---- end-to-end arm: pinned host uint8 in, slice of the result out, every step
     for i in range(min(2, args.warmup)):
@@ -496,13 +502,21 @@ def run_b200_arm(args):
             try:
                 from radvlm_b200 import mm_arch
                 t1, _, _, _ = mm_utils.preprocess_anyres_batch(list(one[0]), gi.PINPOINTS, device=dev, dtype=torch.bfloat16)
+                enc1 = mm_arch._encoder_for(host)
                 with torch.no_grad():
+                    mode1, enc1.graph_mode = enc1.graph_mode, False
                     ref1 = host.encode_images(t1)
                     ms_eager, _, _, _ = timed(lambda i: host.encode_images(t1), reps1)
-                    graphed = mm_arch._encoder_for(host).capture(int(t1.shape[0]), in_dtype=torch.bfloat16)
+                    enc1.graph_mode = mode1
+                    for _ in range(3):
+                        same_auto = bool(torch.equal(host.encode_images(t1), ref1))
+                    ms_auto, _, _, _ = timed(lambda i: host.encode_images(t1), reps1)
+                    graphed = enc1.capture(int(t1.shape[0]), in_dtype=torch.bfloat16)
                     same = bool(torch.equal(graphed(t1), ref1))
                     ms_graph, _, _, _ = timed(lambda i: graphed(t1), reps1)
-                b1["encode_only"] = {"eager_ms": ms_eager / reps1, "cuda_graph_ms": ms_graph / reps1, "graph_equals_eager": same,
+                b1["encode_only"] = {"eager_ms": ms_eager / reps1, "auto_graph_ms": ms_auto / reps1,
+                                     "auto_graph_equals_eager": same_auto,
+                                     "cuda_graph_ms": ms_graph / reps1, "graph_equals_eager": same,
                                      "tma_descriptor_cache": dict(zip(("hits", "misses"), _lib.tmap_cache_stats()))}
             except Exception as e:   # a failed capture must not cost the bench line
                 b1["encode_only"] = {"error": "%s: %s" % (type(e).__name__, e)}
@@ -556,8 +570,13 @@ def run_b200_arm(args):
         fc2["measured"] = ("separate profiled pass of %d steps right after the timed regions (CUDA events around every "
                            "launch; the timed regions run with the instrumentation off)" % prof_steps)
         folded = prof_n.get("layernorm", 0) == 0
-        ob, oms, olps = per_launch("gemm_out", 26 * ((12.0 if folded else 10.0) * rows_step * 1152 + 2.0 * 1152 * 1152 * olp_calls))
-        out_hbm = {"kernel": "out_proj GEMM (fp32 residual epilogue%s)" % (" + bf16 stream copy + row statistics" if folded else ""),
+        # bytes per output element: bf16 A 2 + (delta epilogue, the default with the fold: bf16 stream copy in 2, bf16
+        # branch out 2, bf16 LayerNorm-2 input out 2 = 8 | fp32 stream in / out + bf16 copy = 12 | without the fold 10)
+        delta = folded and os.environ.get("RADVLM_B200_OUTPROJ", "") != "f32"
+        out_bpe = 8.0 if delta else (12.0 if folded else 10.0)
+        ob, oms, olps = per_launch("gemm_out", 26 * (out_bpe * rows_step * 1152 + 2.0 * 1152 * 1152 * olp_calls))
+        out_hbm = {"kernel": "out_proj GEMM (%s)" % ("bf16 branch + LayerNorm-2 input + row statistics out, %g B per element" % out_bpe
+                                                     if delta else "fp32 residual epilogue%s" % (" + bf16 stream copy + row statistics" if folded else "")),
                    "bound": "hbm", "achieved": ob / (oms * 1e-3) / 1e9 if oms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                    "traffic": traffic_of("gemm_out", olps), "algorithmic_bytes_per_launch": ob, "ms_per_launch": oms}
         out_hbm["frac"] = out_hbm["achieved"] / hbm_peak
@@ -594,8 +613,8 @@ def run_b200_arm(args):
                                               "bf16 copy of the stream come out of the residual GEMM epilogues); "
                                               "RADVLM_B200_LN=kernel restores the stand-alone kernels",
                                     "launches_per_step": 0.0, "share_of_step": 0.0}),
-            # out_proj is the one GEMM of a layer that HBM bounds (K = 1152: 155 GFLOP against 12 B per output element:
-            # bf16 A, fp32 residual read + write, bf16 copy of the new stream), so it also gets an HBM roofline
+            # out_proj is the GEMM of a layer closest to the HBM bound (K = 1152: 155 GFLOP against 8 B per output
+            # element, 12 B with RADVLM_B200_OUTPROJ=f32), so it also gets an HBM roofline
             "roofline_gemm_out_hbm": out_hbm,
             "kernel_ms_per_step": {k: v / prof_steps for k, v in prof_ms.items()},
             "kernel_launches_per_step": {k: v / prof_steps for k, v in prof_n.items()},
@@ -604,6 +623,7 @@ def run_b200_arm(args):
             "path_tflops": flops_per_tile() * TILES_PER_IMAGE * B * world / (ms / args.steps / 1e3) / 1e12,
             "path_frac_of_peak": flops_per_tile() * TILES_PER_IMAGE * B / (ms / args.steps / 1e3) / 1e12 / peak,
         }
+        line["cuda_graph"] = graph_stats
         if gather_check is not None:
             line["gather_check"] = gather_check
         if c3 is not None:

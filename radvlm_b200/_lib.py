@@ -212,8 +212,13 @@ PROF_CLASSES = ("gemm_patch_proj", "attention", "layernorm", "misc", "preprocess
                 "bwd_recompute", "bwd_dgrad", "bwd_wgrad", "bwd_attention", "bwd_elementwise")
 
 
+PROFILING = False   # per-launch CUDA-event instrumentation on: the encoder then launches eagerly (no graph replay)
+
+
 def profile_enable(on: bool):
+    global PROFILING
     load().radvlm_profile_enable(1 if on else 0)
+    PROFILING = bool(on)
 
 
 def profile_read():

@@ -972,3 +972,41 @@ def test_tma_descriptor_cache_hits_on_repeated_calls(lib):
     assert (m3 - m2) + (h3 - h2) == per_call and torch.equal(outs[2], outs[0])
     ref = A.float() @ W.float().t() + b
     assert float((outs[0] - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3
+
+
+def test_encode_images_auto_graph_replay_equals_eager_and_follows_weight_updates(lib):
+    """Inference calls whose (weights, input / output / workspace addresses, tile count, dtypes) tuple has been seen before
+    are replayed from a CUDA graph (encoder._launch_encode): bit-equal with eager launches; an in-place weight update is
+    refreshed into the same packed buffers, so replays compute with the new values."""
+    from radvlm_b200 import mm_arch
+    host = _small_host(torch.float32)
+    host.requires_grad_(False)
+    enc = mm_arch._encoder_for(host)
+    x = gi.encoder_pixels(3, seed=31).cuda()
+    enc.graph_mode = False
+    ref = host.encode_images(x)
+    enc.graph_mode = True
+    r0, c0 = enc.n_graph_replays, enc.n_graph_captures
+    for _ in range(6):
+        o = host.encode_images(x)
+        assert torch.equal(o, ref)
+        del o            # the caching allocator hands the same output address to the next call
+    assert enc.n_graph_captures > c0 and enc.n_graph_replays - r0 >= 3
+    w = host.model.mm_projector[2].weight
+    with torch.no_grad():
+        w.mul_(1.5)      # bumps _version: refreshed in place before the next launch
+    got = host.encode_images(x)
+    enc.graph_mode = False
+    want = host.encode_images(x)
+    enc.graph_mode = True
+    assert torch.equal(got, want) and not torch.equal(got, ref)
+    # under an outer capture (GraphedEncode) and with the per-launch profiler on the call is launched eagerly
+    from radvlm_b200 import _lib
+    e0 = enc.n_eager_launches
+    _lib.profile_enable(True)
+    try:
+        assert torch.equal(host.encode_images(x), want)
+    finally:
+        _lib.profile_read()
+        _lib.profile_enable(False)
+    assert enc.n_eager_launches == e0 + 1

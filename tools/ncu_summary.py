@@ -91,7 +91,7 @@ def traffic(dst, tiles_per_launch, *summaries):
     every kernel class found in them.  usage: traffic <out.json> <tiles per launch> <summary.csv> ..."""
     import json
     classes = [("gemm_qkv", "sched_kernel<5>"), ("gemm_fc1", "sched_kernel<1>"), ("attention", "siglip_attention_pp_kernel"),
-               ("layernorm", "layernorm_f32_to_bf16_kernel"), ("merge_splice", "merge_splice_kernel"),
+               ("gemm_out", "sched_kernel<11>"), ("layernorm", "layernorm_f32_to_bf16_kernel"), ("merge_splice", "merge_splice_kernel"),
                ("preprocess", "resample_fused_kernel")]
     res = {"_source": "ncu --set full --clock-control none, one launch per kernel class of bench.py --steps 1 --warmup 3 "
                       "(tools/profile_round.sh): " + ", ".join(summaries), "tiles_per_launch": int(tiles_per_launch)}
@@ -117,9 +117,11 @@ def traffic(dst, tiles_per_launch, *summaries):
             for cls, pat in classes:
                 if pat in r[0]:
                     res[cls] = e
-    if resid:
-        resid.sort(key=lambda e: e["duration_us_under_ncu"])
-        res["gemm_out"], res["gemm_fc2"] = resid[0], resid[-1]
+    if resid:   # EPI_RESID_F32 (<3>): fc2, and out_proj too when RADVLM_B200_OUTPROJ=f32 (the shorter launch, K = 1152);
+        resid.sort(key=lambda e: e["duration_us_under_ncu"])   # the default out_proj is <11> (EPI_DELTA_BF16)
+        res["gemm_fc2"] = resid[-1]
+        if len(resid) > 1 and "gemm_out" not in res:
+            res["gemm_out"] = resid[0]
     with open(dst, "w") as f:
         json.dump(res, f, indent=1)
     print(open(dst).read())
