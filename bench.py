@@ -39,6 +39,7 @@ TOKENS_PER_IMAGE = 7371          # 729 + 81 * 82 for a 1024x1024 image (SURVEY.m
 TILES_PER_IMAGE = 10
 IMG = 1024
 METRIC = "visual tokens/sec (anyres_max_9, SigLIP+projector)"
+STEP_TIMES = os.environ.get("RADVLM_BENCH_STEP_TIMES", "0") == "1"   # diagnostics: per-step device / host times on stderr
 
 
 def _peaks():
@@ -393,19 +394,41 @@ def run_b200_arm(args):
 
     def timed(fn, steps, read_back=False):
         """device time of `steps` calls of fn(i), bracketed by barrier + synchronize, max over ranks"""
+        rb_slots = [(torch.empty(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)] if read_back else None
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
         e0.record()
         chk = 0.0
+        marks = []
+        pending = None
         for i in range(steps):
             emb = fn(i)
             if read_back:
-                chk += float(emb[0, -1, :8].float().sum().item())   # D2H read of a slice of the result
+                # D2H read of a value computed from every step's result: copied asynchronously into pinned memory and
+                # consumed one step later (after the next step has been enqueued), so the read does not drain the stream
+                slot = rb_slots[i & 1]
+                slot[0].copy_(emb[0, -1, :8].float().sum().reshape(1), non_blocking=True)
+                slot[1].record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    chk += float(pending[0][0])
+                pending = slot
+            if STEP_TIMES:
+                marks.append((torch.cuda.Event(enable_timing=True), time.time()))
+                marks[-1][0].record()
+        if pending is not None:
+            pending[1].synchronize()
+            chk += float(pending[0][0])
         drain_gathers()   # the timed region ends when the last exchange has landed
         e1.record()
         sync()
         ms = e0.elapsed_time(e1)
+        if STEP_TIMES and marks:   # diagnostics: device time and host enqueue time of every step of this region
+            dev_ms = [e0.elapsed_time(marks[0][0])] + [marks[k - 1][0].elapsed_time(marks[k][0]) for k in range(1, len(marks))]
+            host_ms = [(marks[0][1] - t_wall0) * 1e3] + [(marks[k][1] - marks[k - 1][1]) * 1e3 for k in range(1, len(marks))]
+            print("step times: device ms %s | host enqueue ms %s" % (" ".join("%.1f" % v for v in dev_ms),
+                                                                     " ".join("%.1f" % v for v in host_ms)), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -426,7 +449,8 @@ def run_b200_arm(args):
     clk = clocks.stop(tw0, tw1) if clocks else None
     # how the encode calls of the timed region were issued: replays of captured CUDA graphs / captures / eager launches
     graph_stats = {"enabled": bool(_enc.graph_mode), "encode_calls_replayed": _enc.n_graph_replays - g0[0],
-                   "graphs_captured": _enc.n_graph_captures - g0[1], "encode_calls_eager": _enc.n_eager_launches - g0[2]}
+                   "graphs_captured": _enc.n_graph_captures - g0[1], "encode_calls_eager": _enc.n_eager_launches - g0[2],
+                   "graphs_captured_before": g0[1], "capture_host_ms_total": _enc.graph_capture_seconds * 1e3}
 
     # ---- end-to-end arm: pinned host uint8 in, slice of the result out, every step
     for i in range(min(2, args.warmup)):
@@ -508,7 +532,7 @@ def run_b200_arm(args):
                     ref1 = host.encode_images(t1)
                     ms_eager, _, _, _ = timed(lambda i: host.encode_images(t1), reps1)
                     enc1.graph_mode = mode1
-                    for _ in range(3):
+                    for _ in range(6):
                         same_auto = bool(torch.equal(host.encode_images(t1), ref1))
                     ms_auto, _, _, _ = timed(lambda i: host.encode_images(t1), reps1)
                     graphed = enc1.capture(int(t1.shape[0]), in_dtype=torch.bfloat16)
@@ -589,7 +613,10 @@ def run_b200_arm(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _workload_config(args, world),
             "e2e": {"value": e2e, "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * IMG * IMG * 3 + B * 128 + 4096,
-                    "d2h_bytes_per_step": B * Lp * 8 + 4},
+                    "d2h_bytes_per_step": B * Lp * 8 + B * Lp + 4,
+                    "how": "pinned-host uint8 images H2D on a copy stream every step; input_ids / attention_mask D2H for the "
+                           "splice plan (enqueued before the encode kernels, waited for after them); a checksum of every "
+                           "step's inputs_embeds slice D2H into pinned memory, consumed one step later"},
             "gpu_launches": int(round(launches_step * args.steps)),
             "clocks": clk,
             "roofline": fc2,
@@ -814,7 +841,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import math
+import time
 import warnings
 from collections import OrderedDict
 from typing import Dict, Mapping, Optional
@@ -224,6 +225,10 @@ class B200VisionEncoder:
         # RADVLM_B200_GRAPH=0 launches every kernel eagerly (A/B switch).
         self.graph_mode = os.environ.get("RADVLM_B200_GRAPH", "1") != "0"
         self.graph_capacity = 16
+        self.graph_min_sightings = 2          # eager launches of a key before it is captured
+        self.graph_free_captures = 2
+        self.graph_replays_per_capture = 48
+        self.graph_capture_seconds = 0.0      # host time spent capturing (diagnostics)
         self._graphs: "OrderedDict[tuple, torch.cuda.CUDAGraph]" = OrderedDict()
         self._graph_seen: "OrderedDict[tuple, int]" = OrderedDict()
         self._graph_streams: Dict[torch.device, torch.cuda.Stream] = {}
@@ -331,7 +336,7 @@ class B200VisionEncoder:
 
         The C entry point allocates nothing and never synchronises, and everything it does is a function of (packed
         weights, input / output / workspace addresses, tile count, dtypes): that tuple is the graph key.  In a steady
-        loop the caching allocator hands the same addresses back every step, so after the second sighting of a key the
+        loop the caching allocator hands the same addresses back every step, so once a key has come back a few times the
         call costs ONE graph launch: the kernels then follow each other over graph edges instead of stream order
         (measured on B200: 8.07 -> 7.55 ms for a 10-tile image, profiles/r02q_bench_final.json).  A key seen for the
         first time is launched eagerly; weight refreshes keep the addresses (replays read the new values), a rebuild of
@@ -346,13 +351,22 @@ class B200VisionEncoder:
         key = (self._pk_serial, dev.index, in_ptr, in_dt, m, out_ptr, out_dt, ws.data_ptr(), ws.numel())
         g = self._graphs.get(key)
         if g is None:
-            if key not in self._graph_seen:
-                self._graph_seen[key] = 1
-                if len(self._graph_seen) > 8 * self.graph_capacity:
-                    self._graph_seen.popitem(last=False)
+            # A capture (record + instantiate + first upload) costs the host about as much as 30-40 replays save, so it has
+            # to be earned: the key must have come back `graph_min_sightings` times (a steady loop, not a one-off set of
+            # addresses), and beyond the first `graph_free_captures` every capture must be covered by
+            # `graph_replays_per_capture` replays already served — a caller whose addresses never repeat pays for two
+            # captures at most and is then launched eagerly for good.
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            self._graph_seen.move_to_end(key)
+            if len(self._graph_seen) > 8 * self.graph_capacity:
+                self._graph_seen.popitem(last=False)
+            allowed = self.graph_free_captures + self.n_graph_replays // self.graph_replays_per_capture
+            if seen <= self.graph_min_sightings or self.n_graph_captures >= allowed:
                 self.n_eager_launches += 1
                 _lib.check(lib.radvlm_encode_images(*args, cur.cuda_stream))
                 return
+            t_cap = time.perf_counter()
             side = self._graph_streams.get(dev)
             if side is None:
                 side = self._graph_streams[dev] = torch.cuda.Stream(dev)
@@ -380,6 +394,7 @@ class B200VisionEncoder:
                 _lib.check(lib.radvlm_encode_images(*args, cur.cuda_stream))
                 return
             self.n_graph_captures += 1
+            self.graph_capture_seconds += time.perf_counter() - t_cap
             self._graphs[key] = g
             if len(self._graphs) > self.graph_capacity:
                 self._graphs.popitem(last=False)

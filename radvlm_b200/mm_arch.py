@@ -274,6 +274,32 @@ class _MergeSpliceFn(torch.autograd.Function):
         return g_feat, g_newline, g_embed, None
 
 
+def _to_host_async(t: torch.Tensor, dtype: torch.dtype):
+    """Start copying a (small) integer / mask tensor to the host without blocking: -> (host tensor, event or None).
+    uint8 means "as a mask": non-zero -> 1.  A synchronous ``.to("cpu")`` issued after the encode kernels would block
+    the host until the whole tower has run and leave the GPU idle while the host then plans the splice (measured: host
+    and device in lock-step, ~1.3 ms of idle stream per 16-image step)."""
+    t = t.detach()
+    if dtype == torch.uint8:
+        t = t if t.dtype == torch.bool else t.ne(0)
+    if t.device.type != "cuda":
+        return t.to(dtype).contiguous(), None
+    with torch.cuda.device(t.device):
+        src = t.to(dtype).contiguous()
+        host = torch.empty(src.shape, dtype=dtype, pin_memory=True)
+        host.copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+    return host, ev
+
+
+def _host_result(fetch) -> np.ndarray:
+    host, ev = fetch
+    if ev is not None:
+        ev.synchronize()
+    return host.numpy()
+
+
 def _concat_tiles(images_list) -> torch.Tensor:
     """``torch.cat(images, 0)`` of llava_arch.py:272 without the copy when the per-image tile blocks already lie back to
     back in one allocation (what ``mm_utils.preprocess_anyres_batch(...)[0].split(splits)`` and the DataLoader collate of
@@ -321,6 +347,11 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
         concat_images = images
         tile_counts = [1] * int(images.shape[0])
         flat_batch = True
+    # The splice plan needs input_ids / attention_mask on the host.  Their D2H copies are enqueued BEFORE the encode
+    # kernels and waited for AFTER (see _to_host_async): the host plans and enqueues the merge kernel while the GPU runs
+    # the tower, and the next call's kernels are queued before this call's have finished — the stream never runs dry.
+    ids_fetch = _to_host_async(input_ids, torch.int64)
+    mask_fetch = None if attention_mask is None else _to_host_async(attention_mask, torch.uint8)
     features = self.encode_images(concat_images)            # [tiles, T, H]  (llava_arch.py:279)
     embed = self.get_model().embed_tokens.weight
     dev = embed.device
@@ -335,8 +366,8 @@ def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attentio
     _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask
     B, L = input_ids.shape
     B_eff = min(B, len(modalities))  # the reference's zip(new_input_embeds, modalities) truncates (llava_arch.py:499-500)
-    ids_host = input_ids.detach().to("cpu", torch.int64).numpy()
-    mask_host = None if attention_mask is None else attention_mask.detach().to("cpu").bool().numpy().astype(np.uint8)
+    ids_host = _host_result(ids_fetch)
+    mask_host = None if mask_fetch is None else _host_result(mask_fetch)
     max_length = getattr(self.config, "tokenizer_model_max_length", None)
     left_pad = getattr(self.config, "tokenizer_padding_side", "right") == "left"
     plan = planner.plan_splice(ids_host, mask_host, image_tokens, max_length, left_pad)

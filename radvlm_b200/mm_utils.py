@@ -37,6 +37,9 @@ def _to_uint8_hwc(image) -> torch.Tensor:
     return t.contiguous()
 
 
+_COPY_STREAMS = {}   # device -> the H2D stream of preprocess_anyres_batch
+
+
 def preprocess_anyres_batch(images: Sequence, grid_pinpoints, device=None, dtype: torch.dtype = torch.float32,
                             tile_size: int = 384, patches_per_side: int = 27,
                             max_num_patches: Optional[int] = 9):
@@ -55,8 +58,22 @@ def preprocess_anyres_batch(images: Sequence, grid_pinpoints, device=None, dtype
     scratch_off = tile_base = 0
     sizes, splits = [], []
     with torch.cuda.device(device):
-        # host images go H2D straight from their own (ideally pinned) storage; device images are used in place
-        dev_srcs = [t if t.device == device else t.to(device, non_blocking=True) for t in srcs]
+        # host images go H2D straight from their own (ideally pinned) storage; device images are used in place.  The
+        # copies run on a copy stream of their own, so a caller that enqueues ahead of the GPU (the encode path never
+        # blocks the host) gets the next batch's transfer under the current batch's kernels instead of in between them.
+        if any(t.device != device for t in srcs):
+            cur = torch.cuda.current_stream(device)
+            cs = _COPY_STREAMS.get(device)
+            if cs is None:
+                cs = _COPY_STREAMS[device] = torch.cuda.Stream(device)
+            with torch.cuda.stream(cs):
+                dev_srcs = [t if t.device == device else t.to(device, non_blocking=True) for t in srcs]
+            cur.wait_stream(cs)
+            for t, d in zip(srcs, dev_srcs):
+                if d is not t:
+                    d.record_stream(cur)     # allocated on the copy stream, consumed by the kernel on `cur`
+        else:
+            dev_srcs = srcs
         base_ptr = min(t.data_ptr() for t in dev_srcs)
         for i, t in enumerate(dev_srcs):
             H, W = int(t.shape[0]), int(t.shape[1])

@@ -1,19 +1,23 @@
+#!/bin/bash
+# Round-end check (run under gpurun): the full GPU test suite, the plain bench line, then an interleaved A/B of the
+# CUDA-graph replay of encode_images (RADVLM_B200_GRAPH=0 launches every kernel eagerly).
 set -x
-cd $GRAFT_REPO_ROOT
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r02q_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02q_pytest_gpu.log
-tail -5 gpurun_out/r02q_pytest_gpu.log
-( time python bench.py ) > gpurun_out/r02q_bench_final.json 2> gpurun_out/r02q_bench_final.err; echo "bench rc=$?"
-tail -3 gpurun_out/r02q_bench_final.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/r02q_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 > gpurun_out/r02q_ncu_list.log 2>&1
-ncu --set full --clock-control none -k regex:"gemm_bf16_tn_2cta_sched|siglip_attention_pp" \
-    --launch-skip 540 -c 5 -f -o gpurun_out/r02q_full_tower python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c3 --no-batch1 --train-steps 0 \
-    > gpurun_out/r02q_ncu_full_tower.log 2>&1
-ls -la gpurun_out | tail -12
-python -c "
-import json
-l=[x for x in open('gpurun_out/r02q_bench_final.json') if x.startswith('{')][-1]
-d=json.loads(l)
-print({k:d[k] for k in ('value','ms_per_step','e2e','batch1','clocks','path_frac_of_peak') if k in d})
-print(d.get('roofline',{}).get('frac'))
-"
+cd ${GRAFT_REPO_ROOT:-.}
+R=${1:-r02r}
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${R}_pytest_gpu.log
+tail -4 gpurun_out/${R}_pytest_gpu.log
+( time python bench.py ) > gpurun_out/${R}_bench_final.json 2> gpurun_out/${R}_bench_final.err; echo "bench rc=$?"
+for i in 1 2; do
+  RADVLM_B200_GRAPH=0 python bench.py --no-cpu-baseline --no-c3 --train-steps 0 > gpurun_out/${R}_bench_graph0_$i.json 2>> gpurun_out/${R}_ab.err
+  RADVLM_B200_GRAPH=1 python bench.py --no-cpu-baseline --no-c3 --train-steps 0 > gpurun_out/${R}_bench_graph1_$i.json 2>> gpurun_out/${R}_ab.err
+done
+python - <<PY
+import json,glob
+for f in sorted(glob.glob('gpurun_out/${R}_bench_*.json')):
+    try:
+        d=json.loads([x for x in open(f) if x.startswith('{')][-1])
+    except Exception as e:
+        print(f, 'unreadable', e); continue
+    b=d.get('batch1') or {}
+    print(f, round(d['ms_per_step'],2), round(d['e2e']['ms_per_step'],2), d.get('cuda_graph'), round(b.get('ms_per_image',0),3), b.get('encode_only'), d['clocks']['sm_mhz'])
+PY
