@@ -70,7 +70,8 @@ int attention_launch(const void* q, const void* k, const void* vt, void* out, fl
     st = make_tmap_bf16_3d(&tout, out, static_cast<uint64_t>(heads) * hd, seq, tiles, row_bytes, row_bytes * seq, hd,
                            kAttnBQ, 1);
     if (st != RADVLM_OK) return st;
-    siglip_attention_pp_kernel<<<grid, kPpThreads, kPpSmemBytes, stream>>>(tq, tq2, tk, tk2, tv, tout, a);
+    RV_CUDA(launch_kernel_pdl(siglip_attention_pp_kernel, grid, kPpThreads, kPpSmemBytes, stream, pdl_enabled(), tq, tq2, tk,
+                              tk2, tv, tout, a));
   }
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;

@@ -188,6 +188,9 @@ siglip_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,    // Q  
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // PDL: the prologue above ran under the previous kernel's tail; from here on global memory is touched
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp_u < kPpFirstSoftmaxWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPpRegsIo));

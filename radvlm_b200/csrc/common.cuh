@@ -81,6 +81,14 @@ __device__ __forceinline__ void tc_fence_after() {
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running: everything before griddep_wait() (barrier
+// initialisation, TMEM allocation, descriptor prefetch - nothing that touches global memory) overlaps the predecessor's
+// tail; griddep_wait() returns once the predecessor has completed and its writes are visible.  Both are no-ops for a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

@@ -120,6 +120,9 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // PDL: the prologue above ran under the previous kernel's tail; from here on global memory is touched
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

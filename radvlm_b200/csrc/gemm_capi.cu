@@ -102,7 +102,8 @@ static int launch_gemm3_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
   }
   int clusters = 0;
   while (clusters < kSchedMaxClusters && sched.off[clusters + 1] > sched.off[clusters]) ++clusters;
-  gemm_bf16_tn_2cta_sched_kernel<EPI><<<2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream>>>(ta, tb, tb64, args, sched);
+  RV_CUDA(launch_kernel_pdl(gemm_bf16_tn_2cta_sched_kernel<EPI>, 2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream,
+                            pdl_enabled(), ta, tb, tb64, args, sched));
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;
 }

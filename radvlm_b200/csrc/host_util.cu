@@ -42,6 +42,11 @@ int require_sm100() {
   return cached_ok ? RADVLM_OK : RADVLM_ERR_UNSUPPORTED_DEVICE;
 }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("RADVLM_B200_PDL") && atoi(getenv("RADVLM_B200_PDL")) == 0);
+  return on;
+}
+
 int device_sm_count() {
   static thread_local int cached_dev = -1;
   static thread_local int sms = 0;

@@ -47,6 +47,27 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                       uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
+// RADVLM_B200_PDL (default on; 0 = ordinary launches): programmatic dependent launch of the persistent tensor-core
+// kernels (common.cuh griddep_wait).
+bool pdl_enabled();
+
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute when `pdl` is set.
+template <typename... Params, typename... Args>
+static inline cudaError_t launch_kernel_pdl(void (*kernel)(Params...), unsigned grid, unsigned block, size_t smem,
+                                            cudaStream_t stream, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 // Hit / miss counts of the calling thread's descriptor cache (host_util.cu).
 void tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 
