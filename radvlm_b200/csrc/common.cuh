@@ -81,6 +81,14 @@ __device__ __forceinline__ void tc_fence_after() {
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ---------------------------------------------------------------------------------------------
+// Ampere-style asynchronous copies (LDGSTS): 16 bytes global -> shared per thread, L2 only; src_bytes = 0 zero-fills.
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // become resident while its predecessor in the stream is still running: everything before griddep_wait() (barrier
 // initialisation, TMEM allocation, descriptor prefetch - nothing that touches global memory) overlaps the predecessor's

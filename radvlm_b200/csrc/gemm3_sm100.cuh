@@ -42,6 +42,89 @@ struct Gemm3Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kGemmStagingBytes + 1024 + 256;
 };
 
+// Residual prefetch of the bf16-delta epilogue (out_proj).  Its drain was a chain of four dependent chunks per warp, each
+// TMEM load -> transpose -> residual load from global memory -> store: 17.7 K cycles per 256 x 256 tile against a
+// 9.2 K-cycle main loop (profiles/r02q_ncu_full_tower_summary.csv: 53 % tensor pipe, 41 % DRAM - neither roofline).
+// With RV_DELTA_PF every epilogue warp owns a ring of four 2 KB chunk slots ([32 rows][64 B] of the bf16 residual) filled
+// by cp.async: chunk q of the NEXT tile is requested as soon as chunk q of the current tile has been consumed, so the
+// loads fly under the other chunks' work and across the tile boundary, and the drain no longer waits for DRAM.  The
+// 64 KB come out of the operand ring (4 stages instead of 6: K = 1152 is 18 slabs, the kernel is not load-bound).
+#ifndef RV_DELTA_PF
+#define RV_DELTA_PF 1
+#endif
+constexpr int kResidChunkBytes = 32 * 64;                  // 32 rows x 32 bf16 columns
+constexpr int kResidWarpBytes = 4 * kResidChunkBytes;      // chunks 0..3 of a warp's 32 x 128 block
+template <int EPI>
+struct Gemm3CfgT : Gemm3Cfg {
+  static constexpr bool kResidPf = (RV_DELTA_PF != 0) && (EPI == EPI_DELTA_BF16);
+  static constexpr int kStages = kResidPf ? 4 : Gemm3Cfg::kStages;
+  static constexpr int kResidBytes = kResidPf ? kGemmEpiWarps * kResidWarpBytes : 0;
+  static constexpr int kSmemBytes = kStages * Gemm3Cfg::kStageBytes + kGemmStagingBytes + kResidBytes + 1024 + 256;
+};
+static_assert(Gemm3CfgT<EPI_DELTA_BF16>::kSmemBytes <= 232448, "shared memory of the delta epilogue variant");
+
+// One chunk ([32 rows][32 columns] bf16) of the residual block of a warp: 128 x 16 B, four per lane.
+__device__ __forceinline__ void delta_prefetch_chunk(const GemmArgs& a, int row0, int col0, uint32_t slot, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = lane + 32 * j;
+    const int grow = row0 + (idx >> 2), gcol = col0 + (idx & 3) * 8;
+    const bool ok = grow < a.M && gcol < a.N;
+    const __nv_bfloat16* src = ok ? a.aux16 + static_cast<size_t>(grow) * a.ldo + gcol : a.aux16;
+    cp_async_16(slot + static_cast<uint32_t>(idx) * 16u, src, ok ? 16u : 0u);
+  }
+}
+
+// Drain of one tile of the bf16-delta epilogue with the residual ring (see above).  cur / nxt = 32-column chunks of this
+// warp's block in this / the next tile (4 for a full tile, 2 for the 128-wide one, 0 = no next tile).  Four cp.async
+// groups are committed per tile whatever its width, so exactly three groups are younger than the chunk being consumed.
+__device__ __forceinline__ void gemm_epilogue_drain_delta_pf(const GemmArgs& args, int row, int col_base, int cur,
+                                                             int nxt_row0, int nxt_col_base, int nxt, uint32_t t_row,
+                                                             uint32_t stage, uint32_t ring, int lane, int ln_slot) {
+  const int row0 = row - lane;
+  const bool stats = args.ln_part != nullptr && ln_slot >= 0;
+  f32x2 ps[8], pq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0ull;
+  uint32_t r0[32], r1[32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t slot = ring + static_cast<uint32_t>(q) * kResidChunkBytes;
+    if (q < cur) {
+      if ((q & 1) == 0) {
+        tmem_ld_x32(t_row + 32 * q, r0);
+        if (q + 1 < cur) tmem_ld_x32(t_row + 32 * (q + 1), r1);
+        tmem_wait_ld();
+      }
+      cp_async_wait_group<3>();
+      __syncwarp();
+      const uint32_t* acc = (q & 1) ? r1 : r0;
+      if (stats) gemm_epilogue_f32_staged<EPI_DELTA_BF16, true, true>(args, row0, col_base + 32 * q, acc, stage, lane, ps, pq, slot);
+      else gemm_epilogue_f32_staged<EPI_DELTA_BF16, false, true>(args, row0, col_base + 32 * q, acc, stage, lane, nullptr, nullptr, slot);
+      // (ends with __syncwarp: every lane has read the slot)
+    }
+    if (q < nxt) delta_prefetch_chunk(args, nxt_row0, nxt_col_base + 32 * q, slot, lane);
+    cp_async_commit();
+  }
+  if (stats) {  // as in gemm_epilogue_drain: the 8 lanes that share a row add up, lane & 7 == 0 writes the slot
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s0, s1, q0, q1;
+      f2_get(ps[i], s0, s1);
+      f2_get(pq[i], q0, q1);
+      float sum = s0 + s1, sq = q0 + q1;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      const int grow = row0 + i * 4 + (lane >> 3);
+      if ((lane & 7) == 0 && grow < args.M)
+        args.ln_part[static_cast<size_t>(grow) * args.ln_slots + ln_slot] = make_float2(sum, sq);
+    }
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -63,14 +146,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                const __grid_constant__ CUtensorMap tmap_b64, const GemmArgs args,
                                const __grid_constant__ GemmSched sched) {
-  using Cfg = Gemm3Cfg;
+  using Cfg = Gemm3CfgT<EPI>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = 2 * kGemmBM;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base + kStages * Cfg::kStageBytes;  // epilogue transpose buffers
-  const uint32_t bar_base = stage_base + kGemmStagingBytes;
+  const uint32_t resid_base = stage_base + kGemmStagingBytes;          // residual rings of the delta epilogue (or empty)
+  const uint32_t bar_base = resid_base + Cfg::kResidBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -225,6 +309,21 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       }
     };
     if (e_begin < e_end) prefetch_resid(e_begin);
+    // delta epilogue with the residual ring: works on full 16-byte vectors only (N, ldo multiples of 8: always, in the tower)
+    const bool delta_pf = Cfg::kResidPf && ((args.N & 7) == 0) && ((args.ldo & 7) == 0);
+    const uint32_t ring = resid_base + static_cast<uint32_t>(warp - 2) * kResidWarpBytes;
+    if constexpr (Cfg::kResidPf) {
+      if (delta_pf) {   // the first tile's four chunk groups
+        int m_blk = 0, n0 = 0, w = 0;
+        if (e_begin < e_end) tile_of(e_begin, m_blk, n0, w);
+        const int r0w = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32, c0w = n0 + half * (w / 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e_begin < e_end && q < w / 64) delta_prefetch_chunk(args, r0w, c0w + 32 * q, ring + q * kResidChunkBytes, lane);
+          cp_async_commit();
+        }
+      }
+    }
     for (int e = e_begin; e < e_end; ++e) {
       int m_blk, n0, w;
       tile_of(e, m_blk, n0, w);
@@ -240,9 +339,22 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
                              static_cast<uint32_t>(acc * kSchedBN + half * (w / 2));
       const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 2) * kGemmStageWarpBytes;
       const int ln_slot = 2 * (n0 / kSchedBN) + half;  // one statistics slot per (column tile, half): gemm_args.h ln_part
-      if (w == kSchedBN) gemm_epilogue_drain<EPI, kSchedBN / 2>(args, row, n0 + half * (kSchedBN / 2), t_row, stg, lane, ln_slot,
-                                                                ln_nmean, ln_rstd);
-      else gemm_epilogue_drain<EPI, 64>(args, row, n0 + half * 64, t_row, stg, lane, ln_slot, ln_nmean, ln_rstd);
+      bool drained = false;
+      if constexpr (Cfg::kResidPf) {
+        if (delta_pf) {
+          int m2 = 0, n2 = 0, w2 = 0;
+          if (e + 1 < e_end) tile_of(e + 1, m2, n2, w2);
+          gemm_epilogue_drain_delta_pf(args, row, n0 + half * (w / 2), w / 64,
+                                       m2 * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32, n2 + half * (w2 / 2), w2 / 64,
+                                       t_row, stg, ring, lane, ln_slot);
+          drained = true;
+        }
+      }
+      if (!drained) {
+        if (w == kSchedBN) gemm_epilogue_drain<EPI, kSchedBN / 2>(args, row, n0 + half * (kSchedBN / 2), t_row, stg, lane, ln_slot,
+                                                                  ln_nmean, ln_rstd);
+        else gemm_epilogue_drain<EPI, 64>(args, row, n0 + half * 64, t_row, stg, lane, ln_slot, ln_nmean, ln_rstd);
+      }
       tc_fence_before();
       __syncwarp();
       if (warp == 2) RV_GTL(6);

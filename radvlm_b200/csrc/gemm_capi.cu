@@ -97,12 +97,12 @@ static int launch_gemm3_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
   static thread_local bool configured = false;
   if (!configured) {
     RV_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_sched_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Gemm3Cfg::kSmemBytes));
+                                 Gemm3CfgT<EPI>::kSmemBytes));
     configured = true;
   }
   int clusters = 0;
   while (clusters < kSchedMaxClusters && sched.off[clusters + 1] > sched.off[clusters]) ++clusters;
-  RV_CUDA(launch_kernel_pdl(gemm_bf16_tn_2cta_sched_kernel<EPI>, 2 * clusters, kGemmThreads, Gemm3Cfg::kSmemBytes, stream,
+  RV_CUDA(launch_kernel_pdl(gemm_bf16_tn_2cta_sched_kernel<EPI>, 2 * clusters, kGemmThreads, Gemm3CfgT<EPI>::kSmemBytes, stream,
                             pdl_enabled(), ta, tb, tb64, args, sched));
   RV_CUDA(cudaGetLastError());
   return RADVLM_OK;

@@ -248,10 +248,12 @@ __device__ __forceinline__ uint4 stage_load_vec(uint32_t stage, int rr, int v) {
 // fp32 outputs (EPI_RESID_F32 / EPI_POS_F32 / EPI_BIAS_F32): one 32-column chunk, requires N % 4 == 0
 // kStats: also accumulate, per output row this thread touches (8 of them: rows i * 4 + lane / 8), the sum and the sum of
 // squares of the values it stores (ps / pq); the caller reduces them over the 8 lanes that share a row once per tile.
-template <int EPI, bool kStats = false>
+// kResidSmem (EPI_DELTA_BF16, gemm3_sm100.cuh): the bf16 residual chunk has been prefetched into shared memory at
+// `resid_smem` as [32 rows][64 B] (rows beyond M zero-filled) instead of being loaded from a.aux16 here.
+template <int EPI, bool kStats = false, bool kResidSmem = false>
 __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int row0, int col0, const uint32_t* acc,
                                                          uint32_t stage, int lane, f32x2* ps2 = nullptr,
-                                                         f32x2* pq2 = nullptr) {
+                                                         f32x2* pq2 = nullptr, uint32_t resid_smem = 0) {
   stage_store_row(stage, lane, acc);
   __syncwarp();
   const int v = lane & 7;
@@ -269,7 +271,12 @@ __device__ __forceinline__ void gemm_epilogue_f32_staged(const GemmArgs& a, int 
       xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DELTA_BF16) {
         x16[i] = make_uint2(0u, 0u);
-        if (has16 && grow < a.M) x16[i] = *reinterpret_cast<const uint2*>(a.aux16 + static_cast<size_t>(grow) * a.ldo + gcol);
+        if constexpr (kResidSmem) {
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x16[i].x), "=r"(x16[i].y)
+                       : "r"(resid_smem + static_cast<uint32_t>(i * 4 + (lane >> 3)) * 64u + static_cast<uint32_t>(v) * 8u));
+        } else {
+          if (has16 && grow < a.M) x16[i] = *reinterpret_cast<const uint2*>(a.aux16 + static_cast<size_t>(grow) * a.ldo + gcol);
+        }
       }
       if (grow < a.M) {
         if constexpr (EPI == EPI_RESID_F32)
