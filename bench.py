@@ -626,7 +626,7 @@ def run_b200_arm(args):
                                    "algorithmic_flops_per_step": gemm_flops_step, "kernel_ms_per_step": gemm_ms_step,
                                    "share_of_step": gemm_total_ms / total_ms},
             "roofline_gemm_qkv": tensor_roofline("gemm_qkv", "QKV GEMM (head-split epilogue)", 26 * 2.0 * rows_step * 1152 * 3456),
-            "roofline_gemm_out": tensor_roofline("gemm_out", "out_proj GEMM (fp32 residual epilogue)", 26 * 2.0 * rows_step * 1152 * 1152),
+            "roofline_gemm_out": tensor_roofline("gemm_out", "out_proj GEMM (bf16-delta epilogue with the residual prefetch ring; fp32 residual epilogue with RADVLM_B200_OUTPROJ=f32)", 26 * 2.0 * rows_step * 1152 * 1152),
             "roofline_gemm_fc1": tensor_roofline("gemm_fc1", "fc1 GEMM (GELU-tanh epilogue)", 26 * 2.0 * rows_step * 1152 * 4304),
             "roofline_attention": tensor_roofline("attention", "siglip_attention_pp_kernel (MUFU issue co-limited, DESIGN.md)",
                                                   attn_flops * TILES_PER_IMAGE * B),
