@@ -49,20 +49,11 @@ struct Gemm3Cfg {
 // by cp.async: chunk q of the NEXT tile is requested as soon as chunk q of the current tile has been consumed, so the
 // loads fly under the other chunks' work and across the tile boundary, and the drain no longer waits for DRAM.  The
 // 64 KB come out of the operand ring (4 stages instead of 6: K = 1152 is 18 slabs, the kernel is not load-bound).
-//
-// RV_DELTA_PF = 2 (default) also changes the shape of the pass: the fp32-staged epilogue handles 32 columns per pass (two
-// transposition passes, 8-byte global accesses); here a pass covers 64 columns: the row-owning thread forms
-// d = acc + bias and packs it to bf16, ONE transposition, then every lane holds 8 consecutive columns of d and of the
-// residual (16 bytes each), forms bf16(x + d) and the row statistics, and stores two full 16-byte vectors (128-byte lines
-// per row) - half the shared-memory and global instructions per element.  x + d uses the bf16-rounded d, exactly the
-// value the fc2 epilogue later adds to the fp32 stream (the reference adds the bf16 attention output too,
-// siglip_encoder.py:293).  RV_DELTA_PF = 1: the 32-column ring on the unchanged arithmetic; 0: no ring.
 #ifndef RV_DELTA_PF
-#define RV_DELTA_PF 2
+#define RV_DELTA_PF 1
 #endif
-constexpr int kResidChunkCols = (RV_DELTA_PF == 2) ? 64 : 32;
-constexpr int kResidChunkBytes = 32 * kResidChunkCols * 2;                   // 32 rows x chunk columns of bf16
-constexpr int kResidWarpBytes = (128 / kResidChunkCols) * kResidChunkBytes;  // a warp's 32 x 128 block: 8 KB
+constexpr int kResidChunkBytes = 32 * 64;                  // 32 rows x 32 bf16 columns
+constexpr int kResidWarpBytes = 4 * kResidChunkBytes;      // chunks 0..3 of a warp's 32 x 128 block
 template <int EPI>
 struct Gemm3CfgT : Gemm3Cfg {
   static constexpr bool kResidPf = (RV_DELTA_PF != 0) && (EPI == EPI_DELTA_BF16);
@@ -116,118 +107,6 @@ __device__ __forceinline__ void gemm_epilogue_drain_delta_pf(const GemmArgs& arg
     cp_async_commit();
   }
   if (stats) {  // as in gemm_epilogue_drain: the 8 lanes that share a row add up, lane & 7 == 0 writes the slot
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float s0, s1, q0, q1;
-      f2_get(ps[i], s0, s1);
-      f2_get(pq[i], q0, q1);
-      float sum = s0 + s1, sq = q0 + q1;
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      }
-      const int grow = row0 + i * 4 + (lane >> 3);
-      if ((lane & 7) == 0 && grow < args.M)
-        args.ln_part[static_cast<size_t>(grow) * args.ln_slots + ln_slot] = make_float2(sum, sq);
-    }
-  }
-}
-
-// ---- RV_DELTA_PF == 2: 64-column chunks ([32 rows][128 B]) ------------------------------------------------------------
-__device__ __forceinline__ void delta_prefetch_chunk64(const GemmArgs& a, int row0, int col0, uint32_t slot, int lane) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int idx = lane + 32 * j;
-    const int grow = row0 + (idx >> 3), gcol = col0 + (idx & 7) * 8;
-    const bool ok = grow < a.M && gcol < a.N;
-    const __nv_bfloat16* src = ok ? a.aux16 + static_cast<size_t>(grow) * a.ldo + gcol : a.aux16;
-    cp_async_16(slot + static_cast<uint32_t>(idx) * 16u, src, ok ? 16u : 0u);
-  }
-}
-
-// One 64-column pass.  acc0 / acc1: this thread's row, columns [0,32) / [32,64) of the pass; resid: the chunk slot.
-template <bool kStats>
-__device__ __forceinline__ void gemm_epilogue_delta64(const GemmArgs& a, int row0, int col0, const uint32_t* acc0,
-                                                      const uint32_t* acc1, uint32_t stage, uint32_t resid, int lane,
-                                                      f32x2* ps2, f32x2* pq2) {
-  uint32_t pk[32];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint32_t* acc = h ? acc1 : acc0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col0 + 32 * h + 4 * j;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.bias != nullptr && c < a.N) b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      pk[16 * h + 2 * j] = f2_pack_bf16(f2_add(f2_make(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1])),
-                                               f2_make(b.x, b.y)));
-      pk[16 * h + 2 * j + 1] = f2_pack_bf16(f2_add(f2_make(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])),
-                                                   f2_make(b.z, b.w)));
-    }
-  }
-  stage_store_row(stage, lane, pk);
-  __syncwarp();
-  const int v = lane & 7;
-  const int gcol = col0 + 8 * v;
-  if (gcol < a.N) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + (lane >> 3);
-      const int grow = row0 + rr;
-      if (grow < a.M) {
-        const uint4 t = stage_load_vec(stage, rr, v);   // bf16 d, columns gcol .. gcol + 7 of row grow
-        uint4 x;                                        // the residual at the same place
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                     : "r"(resid + static_cast<uint32_t>(rr) * 128u + static_cast<uint32_t>(v) * 16u));
-        const uint32_t tw[4] = {t.x, t.y, t.z, t.w}, xw[4] = {x.x, x.y, x.z, x.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const f32x2 o = f2_add(f2_make(__uint_as_float(tw[q] << 16), __uint_as_float(tw[q] & 0xFFFF0000u)),
-                                 f2_make(__uint_as_float(xw[q] << 16), __uint_as_float(xw[q] & 0xFFFF0000u)));
-          if constexpr (kStats) {
-            ps2[i] = f2_add(ps2[i], o);
-            pq2[i] = f2_fma(o, o, pq2[i]);
-          }
-          ow[q] = f2_pack_bf16(o);
-        }
-        const size_t off = static_cast<size_t>(grow) * a.ldo + gcol;
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + off) = t;
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-    }
-  }
-  __syncwarp();
-}
-
-// Drain of one tile, 64-column chunks: cur / nxt = chunks of this warp's block in this / the next tile (2 for a full tile,
-// 1 for the 128-wide one, 0 = no next tile); two cp.async groups per tile, one group younger than the chunk consumed.
-__device__ __forceinline__ void gemm_epilogue_drain_delta_pf64(const GemmArgs& args, int row, int col_base, int cur,
-                                                               int nxt_row0, int nxt_col_base, int nxt, uint32_t t_row,
-                                                               uint32_t stage, uint32_t ring, int lane, int ln_slot) {
-  const int row0 = row - lane;
-  const bool stats = args.ln_part != nullptr && ln_slot >= 0;
-  f32x2 ps[8], pq[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0ull;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint32_t slot = ring + static_cast<uint32_t>(q) * kResidChunkBytes;
-    if (q < cur) {
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32(t_row + 64 * q, r0);
-      tmem_ld_x32(t_row + 64 * q + 32, r1);
-      tmem_wait_ld();
-      cp_async_wait_group<1>();
-      __syncwarp();
-      if (stats) gemm_epilogue_delta64<true>(args, row0, col_base + 64 * q, r0, r1, stage, slot, lane, ps, pq);
-      else gemm_epilogue_delta64<false>(args, row0, col_base + 64 * q, r0, r1, stage, slot, lane, ps, pq);
-    }
-    if (q < nxt) delta_prefetch_chunk64(args, nxt_row0, nxt_col_base + 64 * q, slot, lane);
-    cp_async_commit();
-  }
-  if (stats) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float s0, s1, q0, q1;
@@ -438,19 +317,11 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
         int m_blk = 0, n0 = 0, w = 0;
         if (e_begin < e_end) tile_of(e_begin, m_blk, n0, w);
         const int r0w = m_blk * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32, c0w = n0 + half * (w / 2);
-#if RV_DELTA_PF == 2
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (e_begin < e_end && q < w / 128) delta_prefetch_chunk64(args, r0w, c0w + 64 * q, ring + q * kResidChunkBytes, lane);
-          cp_async_commit();
-        }
-#else
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (e_begin < e_end && q < w / 64) delta_prefetch_chunk(args, r0w, c0w + 32 * q, ring + q * kResidChunkBytes, lane);
           cp_async_commit();
         }
-#endif
       }
     }
     for (int e = e_begin; e < e_end; ++e) {
@@ -473,15 +344,9 @@ gemm_bf16_tn_2cta_sched_kernel(const __grid_constant__ CUtensorMap tmap_a, const
         if (delta_pf) {
           int m2 = 0, n2 = 0, w2 = 0;
           if (e + 1 < e_end) tile_of(e + 1, m2, n2, w2);
-#if RV_DELTA_PF == 2
-          gemm_epilogue_drain_delta_pf64(args, row, n0 + half * (w / 2), w / 128,
-                                         m2 * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32, n2 + half * (w2 / 2),
-                                         w2 / 128, t_row, stg, ring, lane, ln_slot);
-#else
           gemm_epilogue_drain_delta_pf(args, row, n0 + half * (w / 2), w / 64,
                                        m2 * kTileM + static_cast<int>(rank) * kGemmBM + quad * 32, n2 + half * (w2 / 2), w2 / 64,
                                        t_row, stg, ring, lane, ln_slot);
-#endif
           drained = true;
         }
       }
